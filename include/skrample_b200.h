@@ -1,0 +1,144 @@
+/*
+ * skrample_b200 - C ABI of the B200-native sampler-step library.
+ *
+ * The reference (Beinsezii/skrample) is pure Python and has no FFI: its hot
+ * path is a chain of ATen elementwise ops issued from
+ *   skrample/sampling/models.py:53-83      (forward / backward)
+ *   skrample/sampling/models.py:92-212     (to_x / from_x conversions)
+ *   skrample/sampling/structured.py:167-577 (Euler, DPM, Adams, UniP, UniPC, SPC)
+ *   skrample/sampling/functional.py:55-105  (step_tableau)
+ *   skrample/common.py:32-40               (Point.add_noise / remove_noise)
+ *   skrample/pytorch/noise.py:36-425       (Random / Offset / Pyramid / Colored)
+ * Every entry point below replaces one of those call sites with ONE launch of a
+ * hand-written sm_100a kernel.  Plain pointers and sizes only; no torch types.
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, < 0 = bad argument (see SKR_E_*),
+ *     > 0 = a cudaError_t from the launch.  skr_last_error() gives the text
+ *     (thread-local).  No C++ exception crosses this boundary.
+ *   - launches are asynchronous on the caller's stream (`stream` is a
+ *     cudaStream_t passed as void*), on the current device, and never
+ *     synchronise, allocate, free or retain device memory.
+ *   - tensors are dense, contiguous, element-count `numel`; all tensors of one
+ *     call have the same numel.  16-byte aligned bases take the TMA fast path,
+ *     anything else a slower but correct element-wise path.
+ *   - scalars are float64; the library rounds them to the compute type
+ *     (fp32, or fp64 when any tensor is fp64) exactly once, like torch does
+ *     with a Python scalar operand.
+ */
+#ifndef SKRAMPLE_B200_H
+#define SKRAMPLE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SKR_VERSION 1
+
+#define SKR_MAX_OPS 64
+#define SKR_MAX_INPUTS 32
+#define SKR_MAX_OUTPUTS 8
+
+/* element types */
+enum { SKR_F32 = 0, SKR_F64 = 1, SKR_BF16 = 2, SKR_F16 = 3 };
+
+/* error codes */
+enum {
+    SKR_E_NULL = -1,      /* null program / pointer            */
+    SKR_E_RANGE = -2,     /* count or index out of range        */
+    SKR_E_DTYPE = -3,     /* unknown element type               */
+    SKR_E_OPCODE = -4,    /* unknown op code                    */
+    SKR_E_SHAPE = -5,     /* inconsistent shape description     */
+    SKR_E_UNSUPPORTED = -6
+};
+
+/* registers of the step machine (each holds one value per latent element) */
+enum { SKR_X = 0, SKR_P = 1, SKR_B = 2, SKR_A = 3, SKR_S = 4, SKR_R = 5, SKR_T = 6, SKR_U = 7 };
+
+/*
+ * Op codes.  "in" is the op's input tensor element, c0..c3 its scalars.  Each
+ * binary operation is individually rounded (no FMA contraction) in the order
+ * written, which is the reference's evaluation order.
+ */
+enum {
+    SKR_OP_END = 0,
+    SKR_OP_LOAD = 1,   /* reg[a] = (b&1) ? -in : in                                             */
+    SKR_OP_MOV = 2,    /* reg[a] = reg[b]                                                       */
+    SKR_OP_STORE = 3,  /* out[dst] = round_to_dtype(reg[a])                                     */
+    SKR_OP_CONV = 4,   /* P = conv(X, y), y = in (b==0) or P (b==1); a = SKR_CONV_* flags:
+                          USE_X: v = (MUL_X ? c0*X : X) - (MUL_Y ? c1*y : y) else v = MUL_Y ? y*c1 : y;
+                          DIV: v = v / c2                           models.py:92-212            */
+    SKR_OP_ACC0 = 5,   /* A = 0 + s*c0, s = in (a==0) or reg[a-1]    math.sumprod head          */
+    SKR_OP_ACC = 6,    /* A = A + s*c0                                                          */
+    SKR_OP_DIVA = 7,   /* A = A / c0                                 functional.py:84           */
+    SKR_OP_UNI = 8,    /* A = (a ? 0 : A) + ((in - B)/c0)*c1         structured.py:390-428      */
+    SKR_OP_UNIC = 9,   /* A = (a ? 0 : A) + (P - B)*c1               structured.py:403          */
+    SKR_OP_ADDB = 10,  /* A = B + (a ? 0 : A)                        structured.py:428          */
+    SKR_OP_DPM2 = 11,  /* A = B + c1*(c0*(B - in))                   structured.py:243,269      */
+    SKR_OP_DPM3A = 12, /* T = in; U = c0*(B - in)                    structured.py:243          */
+    SKR_OP_DPM3B = 13, /* d11 = c0*(T - in); d = U - d11; T = U + c1*d; U = c2*d   :254-256     */
+    SKR_OP_DPM3C = 14, /* A = (B + c0*T) + c1*U                      structured.py:268          */
+    SKR_OP_FWD = 15,   /* R = ((0 + X*c0) + reg[a]*c1) [+ in*c2 if b&1]    models.py:53-67      */
+    SKR_OP_BACK = 16,  /* P = ((R - X*c0) [- in*c2 if b&1]) / c1           models.py:69-83      */
+    SKR_OP_BLEND = 17, /* a==0: X = S*c0 + R*c1; a==1: signed-power blend, c2 = pw, c3 = 1/pw
+                                                                      structured.py:568-575     */
+    SKR_OP_AXPBY = 18, /* a==0: R = X*c0 + in*c1; a==1: R = (X - in*c0)/c1   common.py:32-40    */
+    SKR_OP__COUNT = 19
+};
+
+enum { SKR_CONV_USE_X = 1, SKR_CONV_MUL_X = 2, SKR_CONV_MUL_Y = 4, SKR_CONV_DIV = 8 };
+
+typedef struct skr_op {
+    uint8_t code;
+    uint8_t a;
+    uint8_t b;
+    uint8_t reserved;
+    int16_t src; /* input index, -1 if the op reads no tensor  */
+    int16_t dst; /* output index, -1 if the op writes no tensor */
+    double c[4];
+} skr_op;
+
+typedef struct skr_tensor {
+    void* ptr;     /* device pointer */
+    int32_t dtype; /* SKR_F32 ...    */
+    int32_t reserved;
+} skr_tensor;
+
+typedef struct skr_program {
+    int32_t n_ops;
+    int32_t n_inputs;
+    int32_t n_outputs;
+    int32_t reserved;
+    skr_op ops[SKR_MAX_OPS];
+    skr_tensor inputs[SKR_MAX_INPUTS];
+    skr_tensor outputs[SKR_MAX_OUTPUTS];
+} skr_program;
+
+/* Library identification / diagnostics. */
+int skr_version(void);
+const char* skr_last_error(void);
+/* Number of kernels this library has launched in this process (bench bookkeeping). */
+int64_t skr_launch_count(void);
+
+/*
+ * The fused solver step: run `program` over `numel` elements as ONE kernel.
+ * Replaces the whole per-step ATen op chain of a structured sampler
+ * (structured.py:167-577), an RK stage (functional.py:80-105), a model
+ * conversion (models.py:215-239) or forward/backward (models.py:53-83).
+ */
+int skr_program_launch(const skr_program* program, int64_t numel, void* stream);
+
+/*
+ * Point.add_noise / remove_noise (common.py:32-40):
+ *   remove == 0: out = sample*alpha + noise*sigma
+ *   remove != 0: out = (sample - noise*sigma) / alpha
+ */
+int skr_axpby(const void* sample, const void* noise, void* out, int32_t dtype, int64_t numel, double sigma,
+              double alpha, int32_t remove, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKRAMPLE_B200_H */

@@ -1,0 +1,619 @@
+// skrample_b200 - fused solver-step kernel for sm_100a (B200).
+//
+// One launch executes a whole step program (include/skrample_b200.h) over a latent batch:
+//   * a persistent grid (one or two CTAs per SM) walks 1024-element tiles;
+//   * the inputs of a tile are staged into shared memory by 1-D TMA bulk copies
+//     (cp.async.bulk + mbarrier complete_tx), several tiles ahead, so the memory-level
+//     parallelism that saturates HBM3e does not depend on register count or occupancy;
+//   * 256 threads interpret the program with eight named per-element registers held in
+//     real registers (4 elements per thread), reading operands from the staged tile;
+//   * every arithmetic op is an individually rounded IEEE op (__fmul_rn / __fadd_rn /
+//     __fdiv_rn, no FMA contraction) in the reference's evaluation order, so fp32/fp64
+//     results are bit-identical to the reference torch-CPU path;
+//   * results are rounded once to the storage dtype and written with 128-bit stores.
+//
+// The op loop is driven from kernel parameters (constant bank, uniform across the grid):
+// all control flow is warp-uniform.  Tail elements and unaligned tensors run through a
+// guarded element-wise path of the same interpreter.
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/skrample_b200.h"
+#include "common.cuh"
+
+namespace skr {
+
+constexpr int kThreads = 256;
+constexpr int kVec = 4;                    // elements per thread per tile
+constexpr int kTile = kThreads * kVec;     // elements per tile
+constexpr int kMaxStages = 8;
+
+template <typename CT>
+struct KOp {
+    uint8_t code, a, b, pad;
+    int16_t src, dst;
+    CT c[4];
+};
+
+template <typename CT>
+struct KProgram {
+    int32_t n_ops, n_inputs, n_outputs, stages;
+    int64_t numel;
+    uint32_t stage_bytes;   // bytes of one staged tile (all inputs)
+    uint32_t use_tma;       // 0: every tile goes through the guarded element-wise path
+    KOp<CT> ops[SKR_MAX_OPS];
+    const void* in_ptr[SKR_MAX_INPUTS];
+    void* out_ptr[SKR_MAX_OUTPUTS];
+    uint32_t in_off[SKR_MAX_INPUTS];  // byte offset of input i inside a stage
+    uint8_t in_dtype[SKR_MAX_INPUTS];
+    uint8_t out_dtype[SKR_MAX_OUTPUTS];
+};
+
+// ------------------------------------------------------------------------------------------
+// individually rounded arithmetic
+
+template <typename CT> struct Arith;
+template <> struct Arith<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ float spow(float x, float f) {
+        // |x|^f * sign(x); torch's tensor-scalar pow has exact special cases (reference: common.py:187-190)
+        const float m = fabsf(x);
+        float r;
+        if (f == 2.0f) r = __fmul_rn(m, m);
+        else if (f == 3.0f) r = __fmul_rn(__fmul_rn(m, m), m);
+        else if (f == 0.5f) r = __fsqrt_rn(m);
+        else if (f == -0.5f) r = __fdiv_rn(1.0f, __fsqrt_rn(m));
+        else if (f == -1.0f) r = __fdiv_rn(1.0f, m);
+        else if (f == -2.0f) r = __fdiv_rn(1.0f, __fmul_rn(m, m));
+        else r = (float)pow((double)m, (double)f);
+        return x < 0.0f ? -r : r;
+    }
+};
+template <> struct Arith<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ double spow(double x, double f) {
+        const double m = fabs(x);
+        double r;
+        if (f == 2.0) r = __dmul_rn(m, m);
+        else if (f == 3.0) r = __dmul_rn(__dmul_rn(m, m), m);
+        else if (f == 0.5) r = __dsqrt_rn(m);
+        else if (f == -0.5) r = __ddiv_rn(1.0, __dsqrt_rn(m));
+        else if (f == -1.0) r = __ddiv_rn(1.0, m);
+        else if (f == -2.0) r = __ddiv_rn(1.0, __dmul_rn(m, m));
+        else r = pow(m, f);
+        return x < 0.0 ? -r : r;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// operand fetch / result store
+
+// Staged path: this thread's 4 consecutive elements of input `i` from the shared-memory tile.
+template <typename CT>
+__device__ __forceinline__ void fetch_staged(const unsigned char* stage, uint32_t off, int dtype, int tid, CT (&v)[kVec]) {
+    const unsigned char* base = stage + off;
+    switch (dtype) {
+        case SKR_F32: {
+            const float4 q = *reinterpret_cast<const float4*>(base + tid * 16);
+            v[0] = (CT)q.x; v[1] = (CT)q.y; v[2] = (CT)q.z; v[3] = (CT)q.w;
+        } break;
+        case SKR_BF16: {
+            const uint2 q = *reinterpret_cast<const uint2*>(base + tid * 8);
+            v[0] = (CT)__uint_as_float(q.x << 16); v[1] = (CT)__uint_as_float(q.x & 0xffff0000u);
+            v[2] = (CT)__uint_as_float(q.y << 16); v[3] = (CT)__uint_as_float(q.y & 0xffff0000u);
+        } break;
+        case SKR_F16: {
+            const uint2 q = *reinterpret_cast<const uint2*>(base + tid * 8);
+            const __half2 lo = *reinterpret_cast<const __half2*>(&q.x);
+            const __half2 hi = *reinterpret_cast<const __half2*>(&q.y);
+            const float2 a = __half22float2(lo), b = __half22float2(hi);
+            v[0] = (CT)a.x; v[1] = (CT)a.y; v[2] = (CT)b.x; v[3] = (CT)b.y;
+        } break;
+        default: {  // SKR_F64
+            const double2 q0 = *reinterpret_cast<const double2*>(base + tid * 32);
+            const double2 q1 = *reinterpret_cast<const double2*>(base + tid * 32 + 16);
+            v[0] = (CT)q0.x; v[1] = (CT)q0.y; v[2] = (CT)q1.x; v[3] = (CT)q1.y;
+        } break;
+    }
+}
+
+// Guarded path: element-wise loads straight from global memory (tail tile / unaligned tensors).
+template <typename CT>
+__device__ __forceinline__ void fetch_direct(const void* ptr, int dtype, int64_t first, int64_t numel, CT (&v)[kVec]) {
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+        const int64_t e = first + j;
+        CT x = (CT)0;
+        if (e < numel) {
+            switch (dtype) {
+                case SKR_F32: x = (CT) reinterpret_cast<const float*>(ptr)[e]; break;
+                case SKR_BF16: x = (CT)__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(ptr)[e]); break;
+                case SKR_F16: x = (CT)__half2float(reinterpret_cast<const __half*>(ptr)[e]); break;
+                default: x = (CT) reinterpret_cast<const double*>(ptr)[e]; break;
+            }
+        }
+        v[j] = x;
+    }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&p);
+}
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+    const __half2 p = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&p);
+}
+// double -> bf16/f16 goes through one rounding only (to-odd trick is not needed: these outputs
+// are produced from fp32 compute in every supported program; fp64 compute with 16-bit storage
+// rounds double->float->half, documented in DESIGN.md).
+
+template <typename CT, bool DIRECT>
+__device__ __forceinline__ void store_vec(void* ptr, int dtype, int64_t first, int64_t numel, const CT (&v)[kVec]) {
+    if constexpr (!DIRECT) {
+        switch (dtype) {
+            case SKR_F32:
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(ptr) + first) =
+                    make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+                break;
+            case SKR_BF16:
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ptr) + first) =
+                    make_uint2(pack_bf16((float)v[0], (float)v[1]), pack_bf16((float)v[2], (float)v[3]));
+                break;
+            case SKR_F16:
+                *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ptr) + first) =
+                    make_uint2(pack_f16((float)v[0], (float)v[1]), pack_f16((float)v[2], (float)v[3]));
+                break;
+            default: {
+                double* p = reinterpret_cast<double*>(ptr) + first;
+                *reinterpret_cast<double2*>(p) = make_double2((double)v[0], (double)v[1]);
+                *reinterpret_cast<double2*>(p + 2) = make_double2((double)v[2], (double)v[3]);
+            } break;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) {
+            const int64_t e = first + j;
+            if (e < numel) {
+                switch (dtype) {
+                    case SKR_F32: reinterpret_cast<float*>(ptr)[e] = (float)v[j]; break;
+                    case SKR_BF16: reinterpret_cast<__nv_bfloat16*>(ptr)[e] = __float2bfloat16_rn((float)v[j]); break;
+                    case SKR_F16: reinterpret_cast<__half*>(ptr)[e] = __float2half_rn((float)v[j]); break;
+                    default: reinterpret_cast<double*>(ptr)[e] = (double)v[j]; break;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// register file access by run-time id (uniform switch, the registers themselves stay static)
+
+#define SKR_REG_SWITCH(id, STMT)                                                                      \
+    switch (id) {                                                                                     \
+        case 0: { auto& reg = r0; STMT; } break;                                                      \
+        case 1: { auto& reg = r1; STMT; } break;                                                      \
+        case 2: { auto& reg = r2; STMT; } break;                                                      \
+        case 3: { auto& reg = r3; STMT; } break;                                                      \
+        case 4: { auto& reg = r4; STMT; } break;                                                      \
+        case 5: { auto& reg = r5; STMT; } break;                                                      \
+        case 6: { auto& reg = r6; STMT; } break;                                                      \
+        default: { auto& reg = r7; STMT; } break;                                                     \
+    }
+
+template <typename CT, bool DIRECT>
+__device__ __forceinline__ void run_tile(const KProgram<CT>& prog, int64_t tile, const unsigned char* stage, int tid) {
+    using Ar = Arith<CT>;
+    // X, P, B, A, S, R, T, U
+    CT r0[kVec], r1[kVec], r2[kVec], r3[kVec], r4[kVec], r5[kVec], r6[kVec], r7[kVec];
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+        r0[j] = r1[j] = r2[j] = r3[j] = r4[j] = r5[j] = r6[j] = r7[j] = (CT)0;
+    }
+    CT(&rX)[kVec] = r0; CT(&rP)[kVec] = r1; CT(&rB)[kVec] = r2; CT(&rA)[kVec] = r3;
+    CT(&rS)[kVec] = r4; CT(&rR)[kVec] = r5; CT(&rT)[kVec] = r6; CT(&rU)[kVec] = r7;
+
+    const int64_t first = tile * kTile + (int64_t)tid * kVec;
+    const int64_t numel = prog.numel;
+    const int n_ops = prog.n_ops;
+
+    for (int pc = 0; pc < n_ops; ++pc) {
+        const KOp<CT>& op = prog.ops[pc];
+        const int code = op.code, a = op.a, b = op.b, src = op.src;
+        const CT c0 = op.c[0], c1 = op.c[1], c2 = op.c[2], c3 = op.c[3];
+
+        CT in[kVec];
+        if (src >= 0) {
+            if constexpr (DIRECT) fetch_direct<CT>(prog.in_ptr[src], prog.in_dtype[src], first, numel, in);
+            else fetch_staged<CT>(stage, prog.in_off[src], prog.in_dtype[src], tid, in);
+        } else {
+#pragma unroll
+            for (int j = 0; j < kVec; ++j) in[j] = (CT)0;
+        }
+
+        switch (code) {
+            case SKR_OP_LOAD: {
+                if (b & 1) {
+#pragma unroll
+                    for (int j = 0; j < kVec; ++j) in[j] = -in[j];
+                }
+                SKR_REG_SWITCH(a, _Pragma("unroll") for (int j = 0; j < kVec; ++j) reg[j] = in[j]);
+            } break;
+            case SKR_OP_MOV: {
+                CT t[kVec];
+                SKR_REG_SWITCH(b, _Pragma("unroll") for (int j = 0; j < kVec; ++j) t[j] = reg[j]);
+                SKR_REG_SWITCH(a, _Pragma("unroll") for (int j = 0; j < kVec; ++j) reg[j] = t[j]);
+            } break;
+            case SKR_OP_STORE: {
+                CT t[kVec];
+                SKR_REG_SWITCH(a, _Pragma("unroll") for (int j = 0; j < kVec; ++j) t[j] = reg[j]);
+                store_vec<CT, DIRECT>(prog.out_ptr[op.dst], prog.out_dtype[op.dst], first, numel, t);
+            } break;
+            case SKR_OP_CONV: {
+#pragma unroll
+                for (int j = 0; j < kVec; ++j) {
+                    const CT y = (b == 0) ? in[j] : rP[j];
+                    CT v;
+                    if (a & SKR_CONV_USE_X) {
+                        const CT lhs = (a & SKR_CONV_MUL_X) ? Ar::mul(c0, rX[j]) : rX[j];
+                        const CT rhs = (a & SKR_CONV_MUL_Y) ? Ar::mul(c1, y) : y;
+                        v = Ar::sub(lhs, rhs);
+                    } else {
+                        v = (a & SKR_CONV_MUL_Y) ? Ar::mul(y, c1) : y;
+                    }
+                    rP[j] = (a & SKR_CONV_DIV) ? Ar::div(v, c2) : v;
+                }
+            } break;
+            case SKR_OP_ACC0:
+            case SKR_OP_ACC: {
+                if (a != 0) {
+                    SKR_REG_SWITCH(a - 1, _Pragma("unroll") for (int j = 0; j < kVec; ++j) in[j] = reg[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < kVec; ++j) {
+                    const CT base = (code == SKR_OP_ACC0) ? (CT)0 : rA[j];
+                    rA[j] = Ar::add(base, Ar::mul(in[j], c0));
+                }
+            } break;
+            case SKR_OP_DIVA: {
+#pragma unroll
+                for (int j = 0; j < kVec; ++j) rA[j] = Ar::div(rA[j], c0);
+            } break;
+            case SKR_OP_UNI: {
+#pragma unroll
+                for (int j = 0; j < kVec; ++j) {
+                    const CT term = Ar::mul(Ar::div(Ar::sub(in[j], rB[j]), c0), c1);
+                    rA[j] = Ar::add(a ? (CT)0 : rA[j], term);
+                }
+            } break;
+            case SKR_OP_UNIC: {
+#pragma unroll
+                for (int j = 0; j < kVec; ++j) {
+                    const CT term = Ar::mul(Ar::sub(rP[j], rB[j]), c1);
+                    rA[j] = Ar::add(a ? (CT)0 : rA[j], term);
+                }
+            } break;
+            case SKR_OP_ADDB: {
+#pragma unroll
+                for (int j = 0; j < kVec; ++j) rA[j] = Ar::add(rB[j], a ? (CT)0 : rA[j]);
+            } break;
+            case SKR_OP_DPM2: {
+#pragma unroll
+                for (int j = 0; j < kVec; ++j)
+                    rA[j] = Ar::add(rB[j], Ar::mul(c1, Ar::mul(c0, Ar::sub(rB[j], in[j]))));
+            } break;
+            case SKR_OP_DPM3A: {
+#pragma unroll
+                for (int j = 0; j < kVec; ++j) {
+                    rT[j] = in[j];
+                    rU[j] = Ar::mul(c0, Ar::sub(rB[j], in[j]));
+                }
+            } break;
+            case SKR_OP_DPM3B: {
+#pragma unroll
+                for (int j = 0; j < kVec; ++j) {
+                    const CT d11 = Ar::mul(c0, Ar::sub(rT[j], in[j]));
+                    const CT d10 = rU[j];
+                    const CT d = Ar::sub(d10, d11);
+                    rT[j] = Ar::add(d10, Ar::mul(c1, d));
+                    rU[j] = Ar::mul(c2, d);
+                }
+            } break;
+            case SKR_OP_DPM3C: {
+#pragma unroll
+                for (int j = 0; j < kVec; ++j)
+                    rA[j] = Ar::add(Ar::add(rB[j], Ar::mul(c0, rT[j])), Ar::mul(c1, rU[j]));
+            } break;
+            case SKR_OP_FWD: {
+                CT p[kVec];
+                SKR_REG_SWITCH(a, _Pragma("unroll") for (int j = 0; j < kVec; ++j) p[j] = reg[j]);
+#pragma unroll
+                for (int j = 0; j < kVec; ++j) {
+                    CT v = Ar::add((CT)0, Ar::mul(rX[j], c0));
+                    v = Ar::add(v, Ar::mul(p[j], c1));
+                    if (b & 1) v = Ar::add(v, Ar::mul(in[j], c2));
+                    rR[j] = v;
+                }
+            } break;
+            case SKR_OP_BACK: {
+#pragma unroll
+                for (int j = 0; j < kVec; ++j) {
+                    CT v = Ar::sub(rR[j], Ar::mul(rX[j], c0));
+                    if (b & 1) v = Ar::sub(v, Ar::mul(in[j], c2));
+                    rP[j] = Ar::div(v, c1);
+                }
+            } break;
+            case SKR_OP_BLEND: {
+#pragma unroll
+                for (int j = 0; j < kVec; ++j) {
+                    if (a == 0) {
+                        rX[j] = Ar::add(Ar::mul(rS[j], c0), Ar::mul(rR[j], c1));
+                    } else {
+                        const CT mixed = Ar::add(Ar::mul(Ar::spow(rS[j], c2), c0), Ar::mul(Ar::spow(rR[j], c2), c1));
+                        rX[j] = Ar::spow(mixed, c3);
+                    }
+                }
+            } break;
+            case SKR_OP_AXPBY: {
+#pragma unroll
+                for (int j = 0; j < kVec; ++j) {
+                    if (a == 0) rR[j] = Ar::add(Ar::mul(rX[j], c0), Ar::mul(in[j], c1));
+                    else rR[j] = Ar::div(Ar::sub(rX[j], Ar::mul(in[j], c0)), c1);
+                }
+            } break;
+            default: break;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// the kernel
+
+template <typename CT>
+__global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ KProgram<CT> prog) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+
+    const int tid = threadIdx.x;
+    const int64_t numel = prog.numel;
+    const int64_t n_full = prog.use_tma ? numel / kTile : 0;
+    const int64_t n_tiles = (numel + kTile - 1) / kTile;
+    const int stages = prog.stages;
+    const uint32_t stage_bytes = prog.stage_bytes;
+
+    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const int64_t mine = n_full > (int64_t)blockIdx.x ? (n_full - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (mine > 0) {
+        if (tid == 0) {
+            for (int s = 0; s < stages; ++s) mbar_init(&full_bar[s], 1);
+            fence_barrier_init();
+        }
+        __syncthreads();
+
+        auto issue = [&](int64_t k) {
+            const int s = (int)(k % stages);
+            const int64_t tile = blockIdx.x + k * (int64_t)gridDim.x;
+            unsigned char* dst = smem + (size_t)s * stage_bytes;
+            mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+            for (int i = 0; i < prog.n_inputs; ++i) {
+                const uint32_t esize = dtype_size(prog.in_dtype[i]);
+                const unsigned char* srcp = reinterpret_cast<const unsigned char*>(prog.in_ptr[i]) + (size_t)tile * kTile * esize;
+                tma_load_1d(dst + prog.in_off[i], srcp, kTile * esize, &full_bar[s]);
+            }
+        };
+
+        if (tid == 0) {
+            const int64_t ahead = mine < stages - 1 ? mine : stages - 1;
+            for (int64_t k = 0; k < ahead; ++k) issue(k);
+        }
+        for (int64_t k = 0; k < mine; ++k) {
+            if (tid == 0 && k + stages - 1 < mine) issue(k + stages - 1);
+            const int s = (int)(k % stages);
+            mbar_wait(&full_bar[s], (uint32_t)((k / stages) & 1));
+            run_tile<CT, false>(prog, blockIdx.x + k * (int64_t)gridDim.x, smem + (size_t)s * stage_bytes, tid);
+            __syncthreads();  // everyone is done with stage s before it is refilled
+        }
+    }
+
+    // remaining tiles (the ragged tail, or everything when TMA staging is off): guarded path
+    for (int64_t tile = n_full + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        run_tile<CT, true>(prog, tile, nullptr, tid);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+
+static thread_local char g_error[512] = "";
+static int64_t g_launches = 0;
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+struct DeviceInfo {
+    int sm_count = 0;
+    int max_smem = 0;
+    bool attr_set[2] = {false, false};
+};
+static DeviceInfo g_devices[64];
+
+static DeviceInfo* device_info(int* err) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess || dev < 0 || dev >= 64) { *err = e ? (int)e : 1; return nullptr; }
+    DeviceInfo& d = g_devices[dev];
+    if (d.sm_count == 0) {
+        cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&d.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    }
+    *err = 0;
+    return &d;
+}
+
+template <typename CT>
+static int launch_typed(const skr_program* p, int64_t numel, cudaStream_t stream, bool aligned) {
+    KProgram<CT> k;
+    memset(&k, 0, sizeof(k));
+    k.n_ops = p->n_ops;
+    k.n_inputs = p->n_inputs;
+    k.n_outputs = p->n_outputs;
+    k.numel = numel;
+    for (int i = 0; i < p->n_ops; ++i) {
+        const skr_op& o = p->ops[i];
+        KOp<CT>& d = k.ops[i];
+        d.code = o.code; d.a = o.a; d.b = o.b; d.pad = 0; d.src = o.src; d.dst = o.dst;
+        for (int j = 0; j < 4; ++j) d.c[j] = (CT)o.c[j];  // the one rounding of each scalar
+    }
+    uint32_t off = 0;
+    for (int i = 0; i < p->n_inputs; ++i) {
+        k.in_ptr[i] = p->inputs[i].ptr;
+        k.in_dtype[i] = (uint8_t)p->inputs[i].dtype;
+        k.in_off[i] = off;
+        off += kTile * dtype_size_host(p->inputs[i].dtype);
+    }
+    for (int i = 0; i < p->n_outputs; ++i) {
+        k.out_ptr[i] = p->outputs[i].ptr;
+        k.out_dtype[i] = (uint8_t)p->outputs[i].dtype;
+    }
+    k.stage_bytes = off;
+
+    int err = 0;
+    DeviceInfo* dev = device_info(&err);
+    if (!dev) return fail(err, "cudaGetDevice failed");
+
+    const int64_t n_tiles = (numel + kTile - 1) / kTile;
+    const int64_t n_full = numel / kTile;
+
+    // Pipeline depth: keep >= ~48 KB of loads in flight per SM, two CTAs per SM when a stage is small.
+    int stages = 2;
+    int ctas_per_sm = 2;
+    size_t smem = 0;
+    k.use_tma = (aligned && n_full > 0 && off > 0) ? 1u : 0u;
+    if (k.use_tma) {
+        const uint32_t budget2 = 100u * 1024u;  // per CTA when two CTAs share an SM
+        const uint32_t budget1 = (uint32_t)dev->max_smem - 1024u;
+        if (2u * off <= budget2) {
+            stages = (int)(budget2 / off);
+            ctas_per_sm = 2;
+        } else if (2u * off <= budget1) {
+            stages = (int)(budget1 / off);
+            ctas_per_sm = 1;
+        } else {
+            k.use_tma = 0;  // a single tile of all inputs does not fit twice: element-wise path
+        }
+        if (stages > kMaxStages) stages = kMaxStages;
+        if (stages > 4 && (uint32_t)stages * off > 64u * 1024u) {
+            // enough bytes in flight already; do not hoard shared memory
+            stages = (int)((64u * 1024u + off - 1) / off);
+            if (stages < 3) stages = 3;
+        }
+    }
+    k.stages = stages;
+    if (k.use_tma) smem = (size_t)stages * off;
+
+    int64_t grid = (int64_t)dev->sm_count * ctas_per_sm;
+    const int64_t work = k.use_tma ? (n_full > 0 ? n_full : 1) : n_tiles;
+    if (grid > work) grid = work;
+    if (!k.use_tma) {
+        grid = n_tiles < (int64_t)dev->sm_count * 8 ? n_tiles : (int64_t)dev->sm_count * 8;
+    }
+    if (grid < 1) grid = 1;
+
+    const int which = sizeof(CT) == 8 ? 1 : 0;
+    if (!dev->attr_set[which]) {
+        cudaError_t e = cudaFuncSetAttribute(step_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev->max_smem);
+        if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        dev->attr_set[which] = true;
+    }
+    step_kernel<CT><<<(unsigned)grid, kThreads, smem, stream>>>(k);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail((int)e, "step kernel launch: %s", cudaGetErrorString(e));
+    ++g_launches;
+    return 0;
+}
+
+}  // namespace skr
+
+extern "C" {
+
+int skr_version(void) { return SKR_VERSION; }
+const char* skr_last_error(void) { return skr::g_error; }
+int64_t skr_launch_count(void) { return skr::g_launches; }
+
+int skr_program_launch(const skr_program* p, int64_t numel, void* stream) {
+    using namespace skr;
+    if (!p) return fail(SKR_E_NULL, "null program");
+    if (numel < 0) return fail(SKR_E_RANGE, "negative numel");
+    if (p->n_ops < 0 || p->n_ops > SKR_MAX_OPS) return fail(SKR_E_RANGE, "n_ops %d out of range", p->n_ops);
+    if (p->n_inputs < 0 || p->n_inputs > SKR_MAX_INPUTS) return fail(SKR_E_RANGE, "n_inputs %d out of range", p->n_inputs);
+    if (p->n_outputs < 0 || p->n_outputs > SKR_MAX_OUTPUTS) return fail(SKR_E_RANGE, "n_outputs %d out of range", p->n_outputs);
+    bool any64 = false, aligned = true;
+    for (int i = 0; i < p->n_inputs; ++i) {
+        const skr_tensor& t = p->inputs[i];
+        if (t.dtype < 0 || t.dtype > SKR_F16) return fail(SKR_E_DTYPE, "input %d: unknown dtype %d", i, t.dtype);
+        if (!t.ptr && numel > 0) return fail(SKR_E_NULL, "input %d: null pointer", i);
+        any64 |= t.dtype == SKR_F64;
+        aligned &= (reinterpret_cast<uintptr_t>(t.ptr) & 15u) == 0;
+    }
+    for (int i = 0; i < p->n_outputs; ++i) {
+        const skr_tensor& t = p->outputs[i];
+        if (t.dtype < 0 || t.dtype > SKR_F16) return fail(SKR_E_DTYPE, "output %d: unknown dtype %d", i, t.dtype);
+        if (!t.ptr && numel > 0) return fail(SKR_E_NULL, "output %d: null pointer", i);
+        any64 |= t.dtype == SKR_F64;
+        aligned &= (reinterpret_cast<uintptr_t>(t.ptr) & 15u) == 0;
+    }
+    for (int i = 0; i < p->n_ops; ++i) {
+        const skr_op& o = p->ops[i];
+        if (o.code >= SKR_OP__COUNT) return fail(SKR_E_OPCODE, "op %d: unknown code %d", i, (int)o.code);
+        if (o.src >= p->n_inputs) return fail(SKR_E_RANGE, "op %d: input index %d out of range", i, (int)o.src);
+        if (o.dst >= p->n_outputs) return fail(SKR_E_RANGE, "op %d: output index %d out of range", i, (int)o.dst);
+        if (o.code == SKR_OP_STORE && o.dst < 0) return fail(SKR_E_RANGE, "op %d: STORE without an output", i);
+        const bool reads = o.code == SKR_OP_LOAD || o.code == SKR_OP_UNI || o.code == SKR_OP_DPM2 || o.code == SKR_OP_DPM3A ||
+                           o.code == SKR_OP_DPM3B || o.code == SKR_OP_AXPBY ||
+                           ((o.code == SKR_OP_ACC0 || o.code == SKR_OP_ACC) && o.a == 0) ||
+                           (o.code == SKR_OP_CONV && o.b == 0) || ((o.code == SKR_OP_FWD || o.code == SKR_OP_BACK) && (o.b & 1));
+        if (reads && o.src < 0) return fail(SKR_E_RANGE, "op %d (code %d) needs an input tensor", i, (int)o.code);
+        if ((o.code == SKR_OP_LOAD || o.code == SKR_OP_MOV || o.code == SKR_OP_STORE || o.code == SKR_OP_FWD) && o.a > 7)
+            return fail(SKR_E_RANGE, "op %d: register %d out of range", i, (int)o.a);
+        if (o.code == SKR_OP_MOV && o.b > 7) return fail(SKR_E_RANGE, "op %d: register %d out of range", i, (int)o.b);
+        if ((o.code == SKR_OP_ACC0 || o.code == SKR_OP_ACC) && o.a > 8) return fail(SKR_E_RANGE, "op %d: register out of range", i);
+    }
+    if (numel == 0 || p->n_ops == 0) return 0;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    return any64 ? launch_typed<double>(p, numel, s, aligned) : launch_typed<float>(p, numel, s, aligned);
+}
+
+int skr_axpby(const void* sample, const void* noise, void* out, int32_t dtype, int64_t numel, double sigma, double alpha,
+              int32_t remove, void* stream) {
+    skr_program p;
+    memset(&p, 0, sizeof(p));
+    p.n_ops = 3; p.n_inputs = 2; p.n_outputs = 1;
+    p.inputs[0].ptr = const_cast<void*>(sample); p.inputs[0].dtype = dtype;
+    p.inputs[1].ptr = const_cast<void*>(noise); p.inputs[1].dtype = dtype;
+    p.outputs[0].ptr = out; p.outputs[0].dtype = dtype;
+    p.ops[0].code = SKR_OP_LOAD; p.ops[0].a = SKR_X; p.ops[0].src = 0; p.ops[0].dst = -1;
+    p.ops[1].code = SKR_OP_AXPBY; p.ops[1].a = remove ? 1 : 0; p.ops[1].src = 1; p.ops[1].dst = -1;
+    p.ops[1].c[0] = remove ? sigma : alpha; p.ops[1].c[1] = remove ? alpha : sigma;
+    p.ops[2].code = SKR_OP_STORE; p.ops[2].a = SKR_R; p.ops[2].src = -1; p.ops[2].dst = 0;
+    return skr_program_launch(&p, numel, stream);
+}
+
+}  // extern "C"

@@ -95,11 +95,12 @@ class _View:
 class _Ctx:
     "One program under construction plus the outputs the caller wants back."
 
-    __slots__ = ("depth", "preserve_p", "prog", "xhat_key", "xhat_slot")
+    __slots__ = ("depth", "out_dtype", "preserve_p", "prog", "xhat_key", "xhat_slot")
 
-    def __init__(self) -> None:
+    def __init__(self, like: Any = None) -> None:
         self.prog = Program()
         self.depth = 0
+        self.out_dtype = getattr(like, "dtype", None) if pg.is_cuda_tensor(like) else None  # results follow the sample
         self.preserve_p = False  # a later block of the same program still needs P as it is
         self.xhat_slot: int | None = None
         self.xhat_key: Any = None
@@ -207,7 +208,7 @@ class StatedSampler(StructuredSampler):
         schedule: SkrampleSchedule,
         previous: Sequence[SKSamples[T]] = (),
     ) -> SKSamples[T]:
-        ctx = _Ctx()
+        ctx = _Ctx(packed.sample)
         try:
             self._emit(ctx, _View(packed.sample, packed.prediction, packed.step, packed.noise), model_transform, schedule, previous)
         except CannotFuse:
@@ -215,7 +216,7 @@ class StatedSampler(StructuredSampler):
                 raise
             final = self._sample_packed(packed, model_transform, schedule, previous)
             return SKSamples(packed.sample, packed.prediction, packed.step, packed.noise, final)
-        final_slot = ctx.prog.store(R)
+        final_slot = ctx.prog.store(R, ctx.out_dtype)
         outs = ctx.prog.run()
         result = SKSamples(packed.sample, packed.prediction, packed.step, packed.noise, outs[final_slot])
         if ctx.xhat_slot is not None:
@@ -519,7 +520,7 @@ class UniP(StructuredUnified, StatedSampler):
         prediction_next: Sample | None = None,
     ) -> T:
         "Passing ``prediction_next`` makes this UniC, otherwise UniP. reference: structured.py:344-436"
-        ctx = _Ctx()
+        ctx = _Ctx(packed.sample)
         ctx.depth = 1  # standalone solve: no x-hat cache side output
         self._emit_uni(
             ctx,
@@ -529,7 +530,7 @@ class UniP(StructuredUnified, StatedSampler):
             previous,
             prediction_next,
         )
-        slot = ctx.prog.store(R)
+        slot = ctx.prog.store(R, ctx.out_dtype)
         return ctx.prog.run()[slot]
 
     def _emit(self, ctx, view, model_transform, schedule, previous) -> None:  # noqa: ANN001
@@ -587,7 +588,7 @@ class UniPC(UniP):
         convert = models.ModelConvert(model_transform, self.derivative_transform) if self.derivative_transform else None
         inner_model = convert.transform_to if convert is not None else model_transform
         try:
-            ctx = _Ctx()
+            ctx = _Ctx(packed.sample)
             ctx.depth = 1
             prog = ctx.prog
             origin = _point_from(packed.step, schedule)
@@ -598,14 +599,14 @@ class UniPC(UniP):
                 self._emit_uni(
                     ctx, _View(last.sample, last.prediction, last.step, last.noise), inner_model, schedule, previous[:-1], IN_P
                 )
-                sample_slot = prog.store(R)
+                sample_slot = prog.store(R, COMPUTE)  # solver state stays in compute precision
                 prog.mov(X, R)
             view = _View(IN_X, IN_P, packed.step, packed.noise)
             if self.predictor is None:
                 UniP._emit(self, ctx, view, inner_model, schedule, previous)
             else:
                 self.predictor._emit(ctx, view, inner_model, schedule, previous)
-            final_slot = prog.store(R)
+            final_slot = prog.store(R, ctx.out_dtype)
             outs = prog.run()
             return SKSamples(
                 packed.sample if sample_slot is None else outs[sample_slot],
@@ -667,7 +668,7 @@ class SPC(traits.DerivativeTransform, StructuredSampler):
         inner_model = convert.transform_to if convert is not None else model_transform
         origin = _point_from(packed.step, schedule)
         try:
-            ctx = _Ctx()
+            ctx = _Ctx(packed.sample)
             ctx.depth = 1
             prog = ctx.prog
             xhat_slot = _converted_current(ctx, packed, convert, origin)
@@ -680,9 +681,9 @@ class SPC(traits.DerivativeTransform, StructuredSampler):
                 self.corrector._emit(ctx, _View(last.sample, IN_P, last.step, last.noise), inner_model, schedule, shifted)
                 ctx.preserve_p = False
                 prog.blend(*self._weights(origin), self.power)
-                sample_slot = prog.store(X)
+                sample_slot = prog.store(X, COMPUTE)  # solver state stays in compute precision
             self.predictor._emit(ctx, _View(IN_X, IN_P, packed.step, packed.noise), inner_model, schedule, previous)
-            final_slot = prog.store(R)
+            final_slot = prog.store(R, ctx.out_dtype)
             outs = prog.run()
             return SKSamples(
                 packed.sample if sample_slot is None else outs[sample_slot],

@@ -1,0 +1,112 @@
+"""Shared parity-case definitions.
+
+The same case table drives (a) the golden-vector generator that runs the reference
+(``tests/golden/make_golden.py``), (b) the CPU tests of the oracle and of the host
+layer, and (c) the GPU parity tests.  Inputs are regenerated from seeds so fixtures
+only hold expected outputs.
+"""
+
+from __future__ import annotations
+
+import itertools
+from typing import Any
+
+import numpy as np
+
+N_GOLDEN = 1024 + 5  # one full TMA tile + a ragged tail
+
+
+def _case(sampler: str, kw: dict, schedule: str, model: str, dtype: str, steps: int, seed: int) -> dict:
+    kw_id = ",".join(f"{k}={v}" for k, v in sorted(kw.items(), key=lambda kv: kv[0]))
+    return {
+        "id": f"{sampler}({kw_id})|{schedule}|{model}|{dtype}|{steps}",
+        "sampler": sampler,
+        "kw": kw,
+        "schedule": schedule,
+        "model": model,
+        "dtype": dtype,
+        "steps": steps,
+        "seed": seed,
+        "numel": N_GOLDEN,
+    }
+
+
+def _structured_cases() -> list[dict]:
+    table: list[tuple[str, dict]] = [
+        ("Euler", {}),
+        ("Euler", {"stochasticity": 1}),
+        ("DPM", {"order": 1, "stochasticity": 1}),
+        ("DPM", {"order": 2}),
+        ("DPM", {"order": 3, "stochasticity": 0.5}),
+        ("Adams", {"order": 4}),
+        ("Adams", {"order": 9, "stochasticity": 1}),
+        ("UniP", {"order": 3}),
+        ("UniP", {"order": 2, "fast_solve": True, "stochasticity": 1}),
+        ("UniPC", {"order": 3, "stochasticity": 1}),
+        ("UniPC", {"order": 9}),
+        ("UniPC", {"order": 2, "predictor": ["Adams", {"order": 3}]}),
+        ("SPC", {}),
+        ("SPC", {"predictor": ["DPM", {"order": 2, "stochasticity": 1}], "corrector": ["UniP", {"order": 3}]}),
+        ("Adams", {"order": 3, "derivative_transform": "FlowModel"}),
+        ("DPM", {"order": 3, "derivative_transform": None}),
+        ("UniPC", {"order": 3, "derivative_transform": "VelocityModel", "stochasticity": 1}),
+    ]
+    out: list[dict] = []
+    seed = 1000
+    for (sampler, kw), (schedule, model) in itertools.product(
+        table, [("scaled", "NoiseModel"), ("flow", "FlowModel"), ("scaled", "VelocityModel"), ("karras", "DataModel")]
+    ):
+        for dtype in ("f32", "f64"):
+            seed += 1
+            out.append(_case(sampler, kw, schedule, model, dtype, 12, seed))
+    return out
+
+
+STRUCTURED_CASES = _structured_cases()
+
+
+def make_schedule(mod: Any, name: str) -> Any:
+    if name == "scaled":
+        return mod.Scaled()
+    if name == "flow":
+        return mod.FlowShift(mod.Linear())
+    if name == "karras":
+        return mod.Karras(mod.Scaled())
+    if name == "linear":
+        return mod.Linear()
+    if name == "hyper_linear":
+        return mod.Hyper(mod.Linear())
+    if name == "hyper_scaled":
+        return mod.Hyper(mod.Scaled())
+    if name == "sinner_linear":
+        return mod.Sinner(mod.Linear())
+    raise KeyError(name)
+
+
+def make_model(mod: Any, name: str | None) -> Any:
+    return None if name is None else getattr(mod, name)()
+
+
+def make_sampler(mod_structured: Any, mod_models: Any, case: dict) -> Any:
+    kw = dict(case["kw"])
+    for key in ("predictor", "corrector"):
+        if key in kw:
+            name, sub = kw[key]
+            kw[key] = getattr(mod_structured, name)(**sub)
+    if "derivative_transform" in kw:
+        kw["derivative_transform"] = make_model(mod_models, kw["derivative_transform"])
+    return getattr(mod_structured, case["sampler"])(**kw)
+
+
+def trajectory_inputs(case: dict) -> tuple[np.ndarray, list[np.ndarray], list[np.ndarray]]:
+    "(x0, network outputs per step, noises per step) as float32-exact float64 arrays."
+    rng = np.random.default_rng(case["seed"])
+    n = case["numel"]
+
+    def draw(scale: float = 1.0) -> np.ndarray:
+        return (rng.standard_normal(n).astype(np.float32) * np.float32(scale)).astype(np.float64)
+
+    x0 = draw()
+    outs = [draw(0.5) for _ in range(case["steps"])]
+    noises = [draw() for _ in range(case["steps"])]
+    return x0, outs, noises

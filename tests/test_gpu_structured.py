@@ -1,0 +1,196 @@
+"""GPU parity: the fused sm_100a step kernel (through the C ABI) vs golden tensors and the oracle."""
+
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import oracle_run
+from oracle import skrample_oracle as O
+from test_host_layer import run_product
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+STRUCTURED = np.load(GOLDEN / "structured.npz")
+STRUCTURED_INDEX = json.loads((GOLDEN / "structured.json").read_text())
+
+
+def test_native_library_is_the_path() -> None:
+    from skrample_b200 import native
+    from skrample_b200.common import Point
+
+    before = native.launch_count()
+    x = torch.randn(4096, device="cuda")
+    n = torch.randn(4096, device="cuda")
+    got = Point(10.0, 0.6, 0.8).add_noise(x, n)
+    assert native.launch_count() == before + 1
+    want = (x.cpu().numpy() * np.float32(0.8)) + (n.cpu().numpy() * np.float32(0.6))
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("case", STRUCTURED_INDEX, ids=lambda c: c["id"])
+def test_cuda_matches_reference_golden(case: dict) -> None:
+    "fp32 and fp64 trajectories are bit-identical to the reference's torch-CPU results."
+    from skrample_b200 import native
+
+    before = native.launch_count()
+    result = run_product(case, device="cuda")
+    assert native.launch_count() > before
+    for field in ("final", "sample", "prediction"):
+        want = STRUCTURED[f"{case['id']}/{field}"]
+        got = getattr(result, field).cpu().numpy()
+        assert got.dtype == want.dtype
+        assert np.array_equal(got, want, equal_nan=True), f"{field}: max abs diff {np.nanmax(np.abs(got - want))}"
+
+
+SIZES = [1, 3, 1023, 1024, 1025, 4096 + 17, 148 * 2 * 1024 * 3 + 5]
+
+
+def _size_case(sampler: str, kw: dict, numel: int, dtype: str = "f32", schedule: str = "scaled", model: str = "NoiseModel") -> dict:
+    return {"id": "x", "sampler": sampler, "kw": kw, "schedule": schedule, "model": model, "dtype": dtype, "steps": 5, "seed": numel + 7, "numel": numel}
+
+
+@pytest.mark.parametrize("numel", SIZES)
+@pytest.mark.parametrize(("sampler", "kw"), [("Euler", {"stochasticity": 1}), ("Adams", {"order": 4}), ("UniPC", {"order": 3, "stochasticity": 1}), ("DPM", {"order": 3})])
+def test_sizes_and_tails_vs_oracle(sampler: str, kw: dict, numel: int) -> None:
+    "Empty-ish, ragged and multi-wave sizes: TMA tiles, the guarded tail and the persistent loop."
+    case = _size_case(sampler, kw, numel)
+    got = run_product(case, device="cuda")
+    want = oracle_run.run_structured(case)
+    assert np.array_equal(got.final.cpu().numpy(), want.final)
+    assert np.array_equal(got.sample.cpu().numpy(), np.asarray(want.sample))
+    assert np.array_equal(got.prediction.cpu().numpy(), np.asarray(want.prediction))
+
+
+def test_empty_tensor() -> None:
+    from skrample_b200 import scheduling
+    from skrample_b200.sampling import models, structured
+
+    x = torch.empty(0, device="cuda")
+    out = structured.Euler().sample(x, x, (0.0, 0.1), models.FlowModel(), scheduling.Linear())
+    assert out.final.shape == (0,)
+
+
+@pytest.mark.parametrize("offset", [1, 2, 3])
+def test_unaligned_views_vs_oracle(offset: int) -> None:
+    "Tensors whose base is not 16-byte aligned take the element-wise path and still match bit for bit."
+    from skrample_b200 import scheduling
+    from skrample_b200.common import Step
+    from skrample_b200.sampling import models, structured
+
+    n = 5000
+    rng = np.random.default_rng(offset)
+    host = [rng.standard_normal(n + 8).astype(np.float32) for _ in range(3)]
+    dev = [torch.from_numpy(h).cuda()[offset : offset + n] for h in host]
+    step = Step.from_int(3, 10)
+    got = structured.Euler(stochasticity=1).sample(dev[0], dev[1], step, models.NoiseModel(), scheduling.Scaled(), dev[2])
+    cur = O.Rec(host[0][offset : offset + n], host[1][offset : offset + n], O.St(*step), host[2][offset : offset + n])
+    want = O.euler_step(cur, O.Model("noise"), O.scaled(), 1)
+    assert np.array_equal(got.final.cpu().numpy(), want)
+
+
+def test_non_contiguous_inputs() -> None:
+    from skrample_b200 import scheduling
+    from skrample_b200.sampling import models, structured
+
+    x = torch.randn(64, 96, device="cuda").t()
+    o = torch.randn(96, 64, device="cuda")
+    got = structured.Euler().sample(x, o, (0.2, 0.3), models.FlowModel(), scheduling.Linear())
+    want = structured.Euler().sample(x.cpu(), o.cpu(), (0.2, 0.3), models.FlowModel(), scheduling.Linear())
+    assert got.final.shape == (96, 64)
+    assert torch.equal(got.final.cpu(), want.final)
+
+
+@pytest.mark.parametrize(("sampler", "kw"), [("Euler", {"stochasticity": 1}), ("DPM", {"order": 2}), ("Adams", {"order": 9, "stochasticity": 1}), ("UniPC", {"order": 3, "stochasticity": 1}), ("SPC", {})])
+@pytest.mark.parametrize("half", ["bf16", "f16"])
+def test_half_storage_fp32_compute(sampler: str, kw: dict, half: str) -> None:
+    """16-bit storage: inputs are read as stored, all arithmetic is fp32 in the reference's op order, results are
+    rounded ONCE to the storage type.  Against the same model in the oracle this is exact (0 ulp); it is the
+    numerics of the reference's diffusers wrapper with compute_scale=float32 (reference: diffusers.py:575-599).
+    Stated bound vs a pure-fp32 run: <= 2^-8 relative per step for bf16 (one rounding of the result)."""
+    tdtype = {"bf16": torch.bfloat16, "f16": torch.float16}[half]
+    case = _size_case(sampler, kw, 3 * 1024 + 11, "f32", "flow", "FlowModel")
+
+    def to_half_exact(a: np.ndarray) -> np.ndarray:
+        return torch.from_numpy(a).to(tdtype).to(torch.float32).numpy()
+
+    need_noise, need_prev = oracle_run.require(case)
+    from skrample_b200 import scheduling
+    from skrample_b200.common import Step
+    from skrample_b200.sampling import models, structured
+
+    sampler_obj = cases.make_sampler(structured, models, case)
+    x0, outs, noises = cases.trajectory_inputs(case)
+    x_host = to_half_exact(x0.astype(np.float32))
+    x_dev = torch.from_numpy(x_host).cuda().to(tdtype)
+    prev_dev: list = []
+    prev_host: list[O.Rec] = []
+    sch_o, model_o = oracle_run.schedule("flow"), oracle_run.MODELS["FlowModel"]
+    for n in range(case["steps"]):
+        out_host = to_half_exact(outs[n].astype(np.float32))
+        noise_host = to_half_exact(noises[n].astype(np.float32)) if need_noise else None
+        res = sampler_obj.sample(
+            x_dev,
+            torch.from_numpy(out_host).cuda().to(tdtype),
+            Step.from_int(n, case["steps"]),
+            models.FlowModel(),
+            scheduling.FlowShift(scheduling.Linear()),
+            torch.from_numpy(noise_host).cuda().to(tdtype) if need_noise else None,
+            prev_dev,
+        )
+        prev_dev.append(res)
+        prev_dev = prev_dev[max(len(prev_dev) - sampler_obj.require_previous, 0) :]
+        rec = oracle_run.one_step(case, O.Rec(x_host, out_host, O.St.from_int(n, case["steps"]), noise_host), prev_host, model_o, sch_o)
+        prev_host.append(rec)
+        prev_host = prev_host[max(len(prev_host) - need_prev, 0) :]
+        want_final = to_half_exact(np.asarray(rec.final, dtype=np.float32))
+        assert res.final.dtype == tdtype
+        assert np.array_equal(res.final.float().cpu().numpy(), want_final), f"step {n}"
+        x_dev, x_host = res.final, want_final
+        rec.final = want_final
+
+
+def test_full_size_flux_latent_subset_vs_oracle() -> None:
+    """BASELINE config 3 shape (16x16x128x128): the step is elementwise, so the oracle on a random subset of
+    elements must equal the kernel's output at those elements, and a sharded run must equal the whole run."""
+    from skrample_b200 import scheduling
+    from skrample_b200.common import Step
+    from skrample_b200.sampling import models, structured
+
+    shape = (16, 16, 128, 128)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    steps = 6
+    sampler = structured.Adams(order=4, stochasticity=1)
+    schedule, model = scheduling.FlowShift(scheduling.Linear()), models.FlowModel()
+    x = torch.randn(shape, device="cuda", generator=g)
+    pick = torch.randint(0, x.numel(), (4096,), device="cuda", generator=g)
+    prev: list = []
+    prev_lo: list = []
+    prev_o: list[O.Rec] = []
+    x_o = x.flatten()[pick].cpu().numpy()
+    case = {"sampler": "Adams", "kw": {"order": 4, "stochasticity": 1}}
+    for n in range(steps):
+        out = torch.randn(shape, device="cuda", generator=g) * 0.5
+        noise = torch.randn(shape, device="cuda", generator=g)
+        step = Step.from_int(n, steps)
+        res = sampler.sample(x, out, step, model, schedule, noise, prev)
+        lo = sampler.sample(x[:8], out[:8], step, model, schedule, noise[:8], prev_lo)  # a 2-way batch shard
+        assert torch.equal(lo.final, res.final[:8])
+        prev = (prev + [res])[-sampler.require_previous :]
+        prev_lo = (prev_lo + [lo])[-sampler.require_previous :]
+        rec = oracle_run.one_step(
+            case,
+            O.Rec(x_o, out.flatten()[pick].cpu().numpy(), O.St(*step), noise.flatten()[pick].cpu().numpy()),
+            prev_o,
+            O.Model("flow"),
+            O.flow_shift(O.linear()),
+        )
+        prev_o = (prev_o + [rec])[-3:]
+        assert np.array_equal(res.final.flatten()[pick].cpu().numpy(), rec.final), f"step {n}"
+        x, x_o = res.final, rec.final

@@ -1,0 +1,54 @@
+"""Host scalar layer + generic executor of skrample_b200 against the reference's golden tensors (CPU)."""
+
+from __future__ import annotations
+
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from skrample_b200 import scheduling
+from skrample_b200.common import Step
+from skrample_b200.sampling import models, structured
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+STRUCTURED = np.load(GOLDEN / "structured.npz")
+STRUCTURED_INDEX = json.loads((GOLDEN / "structured.json").read_text())
+
+
+def run_product(case: dict, device: str = "cpu", dtype: torch.dtype | None = None):
+    sampler = cases.make_sampler(structured, models, case)
+    schedule = cases.make_schedule(scheduling, case["schedule"])
+    model = cases.make_model(models, case["model"])
+    dtype = dtype or {"f32": torch.float32, "f64": torch.float64}[case["dtype"]]
+    x0, outs, noises = cases.trajectory_inputs(case)
+    x = torch.from_numpy(x0).to(device=device, dtype=dtype)
+    previous: list = []
+    result = None
+    for n in range(case["steps"]):
+        result = sampler.sample(
+            x,
+            torch.from_numpy(outs[n]).to(device=device, dtype=dtype),
+            Step.from_int(n, case["steps"]),
+            model,
+            schedule,
+            torch.from_numpy(noises[n]).to(device=device, dtype=dtype) if sampler.require_noise else None,
+            previous,
+        )
+        previous.append(result)
+        previous = previous[max(len(previous) - sampler.require_previous, 0) :]
+        x = result.final
+    return result
+
+
+@pytest.mark.parametrize("case", STRUCTURED_INDEX, ids=lambda c: c["id"])
+def test_cpu_tensors_match_reference(case: dict) -> None:
+    result = run_product(case)
+    for field in ("final", "sample", "prediction"):
+        want = STRUCTURED[f"{case['id']}/{field}"]
+        got = getattr(result, field).numpy()
+        assert got.dtype == want.dtype
+        assert np.array_equal(got, want, equal_nan=True), field

@@ -121,6 +121,8 @@ int skr_version(void);
 const char* skr_last_error(void);
 /* Number of kernels this library has launched in this process (bench bookkeeping). */
 int64_t skr_launch_count(void);
+/* Same, split by kernel: kind 0 = structured block kernel (fast path), 1 = interpreter (general path). */
+int64_t skr_launch_count_kind(int32_t kind);
 
 /*
  * The fused solver step: run `program` over `numel` elements as ONE kernel.
@@ -129,6 +131,12 @@ int64_t skr_launch_count(void);
  * conversion (models.py:215-239) or forward/backward (models.py:53-83).
  */
 int skr_program_launch(const skr_program* program, int64_t numel, void* stream);
+
+/*
+ * Which kernel would run `program`: 0 = structured block kernel, 1 = interpreter, < 0 = error.
+ * Pure host logic (no device needed); used by tests and tooling.
+ */
+int skr_program_classify(const skr_program* program);
 
 /*
  * Point.add_noise / remove_noise (common.py:32-40):

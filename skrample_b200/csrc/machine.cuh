@@ -1,0 +1,159 @@
+// skrample_b200 - per-element arithmetic and operand fetch/store shared by the step kernels.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace skr {
+
+constexpr int kThreads = 256;             // consumer threads per CTA
+constexpr int kVec = 4;                   // elements per thread per tile
+constexpr int kTile = kThreads * kVec;    // elements per tile
+constexpr int kMaxStages = 8;
+
+// ------------------------------------------------------------------------------------------
+// individually rounded arithmetic
+
+template <typename CT> struct Arith;
+template <> struct Arith<float> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ float spow(float x, float f) {
+        // |x|^f * sign(x); torch's tensor-scalar pow has exact special cases (reference: common.py:187-190)
+        const float m = fabsf(x);
+        float r;
+        if (f == 2.0f) r = __fmul_rn(m, m);
+        else if (f == 3.0f) r = __fmul_rn(__fmul_rn(m, m), m);
+        else if (f == 0.5f) r = __fsqrt_rn(m);
+        else if (f == -0.5f) r = __fdiv_rn(1.0f, __fsqrt_rn(m));
+        else if (f == -1.0f) r = __fdiv_rn(1.0f, m);
+        else if (f == -2.0f) r = __fdiv_rn(1.0f, __fmul_rn(m, m));
+        else r = (float)pow((double)m, (double)f);
+        return x < 0.0f ? -r : r;
+    }
+};
+template <> struct Arith<double> {
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ double spow(double x, double f) {
+        const double m = fabs(x);
+        double r;
+        if (f == 2.0) r = __dmul_rn(m, m);
+        else if (f == 3.0) r = __dmul_rn(__dmul_rn(m, m), m);
+        else if (f == 0.5) r = __dsqrt_rn(m);
+        else if (f == -0.5) r = __ddiv_rn(1.0, __dsqrt_rn(m));
+        else if (f == -1.0) r = __ddiv_rn(1.0, m);
+        else if (f == -2.0) r = __ddiv_rn(1.0, __dmul_rn(m, m));
+        else r = pow(m, f);
+        return x < 0.0 ? -r : r;
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// operand fetch / result store
+
+// Staged path: this thread's 4 consecutive elements of input `i` from the shared-memory tile.
+template <typename CT>
+__device__ __forceinline__ void fetch_staged(const unsigned char* stage, uint32_t off, int dtype, int tid, CT (&v)[kVec]) {
+    const unsigned char* base = stage + off;
+    switch (dtype) {
+        case SKR_F32: {
+            const float4 q = *reinterpret_cast<const float4*>(base + tid * 16);
+            v[0] = (CT)q.x; v[1] = (CT)q.y; v[2] = (CT)q.z; v[3] = (CT)q.w;
+        } break;
+        case SKR_BF16: {
+            const uint2 q = *reinterpret_cast<const uint2*>(base + tid * 8);
+            v[0] = (CT)__uint_as_float(q.x << 16); v[1] = (CT)__uint_as_float(q.x & 0xffff0000u);
+            v[2] = (CT)__uint_as_float(q.y << 16); v[3] = (CT)__uint_as_float(q.y & 0xffff0000u);
+        } break;
+        case SKR_F16: {
+            const uint2 q = *reinterpret_cast<const uint2*>(base + tid * 8);
+            const __half2 lo = *reinterpret_cast<const __half2*>(&q.x);
+            const __half2 hi = *reinterpret_cast<const __half2*>(&q.y);
+            const float2 a = __half22float2(lo), b = __half22float2(hi);
+            v[0] = (CT)a.x; v[1] = (CT)a.y; v[2] = (CT)b.x; v[3] = (CT)b.y;
+        } break;
+        default: {  // SKR_F64
+            const double2 q0 = *reinterpret_cast<const double2*>(base + tid * 32);
+            const double2 q1 = *reinterpret_cast<const double2*>(base + tid * 32 + 16);
+            v[0] = (CT)q0.x; v[1] = (CT)q0.y; v[2] = (CT)q1.x; v[3] = (CT)q1.y;
+        } break;
+    }
+}
+
+// Guarded path: element-wise loads straight from global memory (tail tile / unaligned tensors).
+template <typename CT>
+__device__ __forceinline__ void fetch_direct(const void* ptr, int dtype, int64_t first, int64_t numel, CT (&v)[kVec]) {
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+        const int64_t e = first + j;
+        CT x = (CT)0;
+        if (e < numel) {
+            switch (dtype) {
+                case SKR_F32: x = (CT) reinterpret_cast<const float*>(ptr)[e]; break;
+                case SKR_BF16: x = (CT)__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(ptr)[e]); break;
+                case SKR_F16: x = (CT)__half2float(reinterpret_cast<const __half*>(ptr)[e]); break;
+                default: x = (CT) reinterpret_cast<const double*>(ptr)[e]; break;
+            }
+        }
+        v[j] = x;
+    }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&p);
+}
+__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
+    const __half2 p = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t*>(&p);
+}
+// double -> bf16/f16 goes through one rounding only (to-odd trick is not needed: these outputs
+// are produced from fp32 compute in every supported program; fp64 compute with 16-bit storage
+// rounds double->float->half, documented in DESIGN.md).
+
+template <typename CT, bool DIRECT>
+__device__ __forceinline__ void store_vec(void* ptr, int dtype, int64_t first, int64_t numel, const CT (&v)[kVec]) {
+    if constexpr (!DIRECT) {
+        switch (dtype) {
+            case SKR_F32:
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(ptr) + first) =
+                    make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+                break;
+            case SKR_BF16:
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ptr) + first) =
+                    make_uint2(pack_bf16((float)v[0], (float)v[1]), pack_bf16((float)v[2], (float)v[3]));
+                break;
+            case SKR_F16:
+                *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ptr) + first) =
+                    make_uint2(pack_f16((float)v[0], (float)v[1]), pack_f16((float)v[2], (float)v[3]));
+                break;
+            default: {
+                double* p = reinterpret_cast<double*>(ptr) + first;
+                *reinterpret_cast<double2*>(p) = make_double2((double)v[0], (double)v[1]);
+                *reinterpret_cast<double2*>(p + 2) = make_double2((double)v[2], (double)v[3]);
+            } break;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kVec; ++j) {
+            const int64_t e = first + j;
+            if (e < numel) {
+                switch (dtype) {
+                    case SKR_F32: reinterpret_cast<float*>(ptr)[e] = (float)v[j]; break;
+                    case SKR_BF16: reinterpret_cast<__nv_bfloat16*>(ptr)[e] = __float2bfloat16_rn((float)v[j]); break;
+                    case SKR_F16: reinterpret_cast<__half*>(ptr)[e] = __float2half_rn((float)v[j]); break;
+                    default: reinterpret_cast<double*>(ptr)[e] = (double)v[j]; break;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace skr

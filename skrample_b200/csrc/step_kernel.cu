@@ -22,17 +22,15 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/skrample_b200.h"
 #include "common.cuh"
+#include "machine.cuh"
+#include "block_kernel.cuh"
 
 namespace skr {
-
-constexpr int kThreads = 256;
-constexpr int kVec = 4;                    // elements per thread per tile
-constexpr int kTile = kThreads * kVec;     // elements per tile
-constexpr int kMaxStages = 8;
 
 template <typename CT>
 struct KOp {
@@ -54,149 +52,6 @@ struct KProgram {
     uint8_t in_dtype[SKR_MAX_INPUTS];
     uint8_t out_dtype[SKR_MAX_OUTPUTS];
 };
-
-// ------------------------------------------------------------------------------------------
-// individually rounded arithmetic
-
-template <typename CT> struct Arith;
-template <> struct Arith<float> {
-    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
-    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
-    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
-    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
-    static __device__ __forceinline__ float spow(float x, float f) {
-        // |x|^f * sign(x); torch's tensor-scalar pow has exact special cases (reference: common.py:187-190)
-        const float m = fabsf(x);
-        float r;
-        if (f == 2.0f) r = __fmul_rn(m, m);
-        else if (f == 3.0f) r = __fmul_rn(__fmul_rn(m, m), m);
-        else if (f == 0.5f) r = __fsqrt_rn(m);
-        else if (f == -0.5f) r = __fdiv_rn(1.0f, __fsqrt_rn(m));
-        else if (f == -1.0f) r = __fdiv_rn(1.0f, m);
-        else if (f == -2.0f) r = __fdiv_rn(1.0f, __fmul_rn(m, m));
-        else r = (float)pow((double)m, (double)f);
-        return x < 0.0f ? -r : r;
-    }
-};
-template <> struct Arith<double> {
-    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
-    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
-    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
-    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
-    static __device__ __forceinline__ double spow(double x, double f) {
-        const double m = fabs(x);
-        double r;
-        if (f == 2.0) r = __dmul_rn(m, m);
-        else if (f == 3.0) r = __dmul_rn(__dmul_rn(m, m), m);
-        else if (f == 0.5) r = __dsqrt_rn(m);
-        else if (f == -0.5) r = __ddiv_rn(1.0, __dsqrt_rn(m));
-        else if (f == -1.0) r = __ddiv_rn(1.0, m);
-        else if (f == -2.0) r = __ddiv_rn(1.0, __dmul_rn(m, m));
-        else r = pow(m, f);
-        return x < 0.0 ? -r : r;
-    }
-};
-
-// ------------------------------------------------------------------------------------------
-// operand fetch / result store
-
-// Staged path: this thread's 4 consecutive elements of input `i` from the shared-memory tile.
-template <typename CT>
-__device__ __forceinline__ void fetch_staged(const unsigned char* stage, uint32_t off, int dtype, int tid, CT (&v)[kVec]) {
-    const unsigned char* base = stage + off;
-    switch (dtype) {
-        case SKR_F32: {
-            const float4 q = *reinterpret_cast<const float4*>(base + tid * 16);
-            v[0] = (CT)q.x; v[1] = (CT)q.y; v[2] = (CT)q.z; v[3] = (CT)q.w;
-        } break;
-        case SKR_BF16: {
-            const uint2 q = *reinterpret_cast<const uint2*>(base + tid * 8);
-            v[0] = (CT)__uint_as_float(q.x << 16); v[1] = (CT)__uint_as_float(q.x & 0xffff0000u);
-            v[2] = (CT)__uint_as_float(q.y << 16); v[3] = (CT)__uint_as_float(q.y & 0xffff0000u);
-        } break;
-        case SKR_F16: {
-            const uint2 q = *reinterpret_cast<const uint2*>(base + tid * 8);
-            const __half2 lo = *reinterpret_cast<const __half2*>(&q.x);
-            const __half2 hi = *reinterpret_cast<const __half2*>(&q.y);
-            const float2 a = __half22float2(lo), b = __half22float2(hi);
-            v[0] = (CT)a.x; v[1] = (CT)a.y; v[2] = (CT)b.x; v[3] = (CT)b.y;
-        } break;
-        default: {  // SKR_F64
-            const double2 q0 = *reinterpret_cast<const double2*>(base + tid * 32);
-            const double2 q1 = *reinterpret_cast<const double2*>(base + tid * 32 + 16);
-            v[0] = (CT)q0.x; v[1] = (CT)q0.y; v[2] = (CT)q1.x; v[3] = (CT)q1.y;
-        } break;
-    }
-}
-
-// Guarded path: element-wise loads straight from global memory (tail tile / unaligned tensors).
-template <typename CT>
-__device__ __forceinline__ void fetch_direct(const void* ptr, int dtype, int64_t first, int64_t numel, CT (&v)[kVec]) {
-#pragma unroll
-    for (int j = 0; j < kVec; ++j) {
-        const int64_t e = first + j;
-        CT x = (CT)0;
-        if (e < numel) {
-            switch (dtype) {
-                case SKR_F32: x = (CT) reinterpret_cast<const float*>(ptr)[e]; break;
-                case SKR_BF16: x = (CT)__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(ptr)[e]); break;
-                case SKR_F16: x = (CT)__half2float(reinterpret_cast<const __half*>(ptr)[e]); break;
-                default: x = (CT) reinterpret_cast<const double*>(ptr)[e]; break;
-            }
-        }
-        v[j] = x;
-    }
-}
-
-__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-    const __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
-    return *reinterpret_cast<const uint32_t*>(&p);
-}
-__device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
-    const __half2 p = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<const uint32_t*>(&p);
-}
-// double -> bf16/f16 goes through one rounding only (to-odd trick is not needed: these outputs
-// are produced from fp32 compute in every supported program; fp64 compute with 16-bit storage
-// rounds double->float->half, documented in DESIGN.md).
-
-template <typename CT, bool DIRECT>
-__device__ __forceinline__ void store_vec(void* ptr, int dtype, int64_t first, int64_t numel, const CT (&v)[kVec]) {
-    if constexpr (!DIRECT) {
-        switch (dtype) {
-            case SKR_F32:
-                *reinterpret_cast<float4*>(reinterpret_cast<float*>(ptr) + first) =
-                    make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
-                break;
-            case SKR_BF16:
-                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ptr) + first) =
-                    make_uint2(pack_bf16((float)v[0], (float)v[1]), pack_bf16((float)v[2], (float)v[3]));
-                break;
-            case SKR_F16:
-                *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ptr) + first) =
-                    make_uint2(pack_f16((float)v[0], (float)v[1]), pack_f16((float)v[2], (float)v[3]));
-                break;
-            default: {
-                double* p = reinterpret_cast<double*>(ptr) + first;
-                *reinterpret_cast<double2*>(p) = make_double2((double)v[0], (double)v[1]);
-                *reinterpret_cast<double2*>(p + 2) = make_double2((double)v[2], (double)v[3]);
-            } break;
-        }
-    } else {
-#pragma unroll
-        for (int j = 0; j < kVec; ++j) {
-            const int64_t e = first + j;
-            if (e < numel) {
-                switch (dtype) {
-                    case SKR_F32: reinterpret_cast<float*>(ptr)[e] = (float)v[j]; break;
-                    case SKR_BF16: reinterpret_cast<__nv_bfloat16*>(ptr)[e] = __float2bfloat16_rn((float)v[j]); break;
-                    case SKR_F16: reinterpret_cast<__half*>(ptr)[e] = __float2half_rn((float)v[j]); break;
-                    default: reinterpret_cast<double*>(ptr)[e] = (double)v[j]; break;
-                }
-            }
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------
 // register file access by run-time id (uniform switch, the registers themselves stay static)
@@ -439,6 +294,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
 
 static thread_local char g_error[512] = "";
 static int64_t g_launches = 0;
+static int64_t g_launches_kind[2] = {0, 0};  // [0] structured block kernel, [1] interpreter
 
 static int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -451,8 +307,13 @@ static int fail(int code, const char* fmt, ...) {
 struct DeviceInfo {
     int sm_count = 0;
     int max_smem = 0;
-    bool attr_set[2] = {false, false};
+    bool attr_set[4] = {false, false, false, false};
 };
+
+static int env_int(const char* name, int fallback) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : fallback;
+}
 static DeviceInfo g_devices[64];
 
 static DeviceInfo* device_info(int* err) {
@@ -509,7 +370,7 @@ static int launch_typed(const skr_program* p, int64_t numel, cudaStream_t stream
     k.use_tma = (aligned && n_full > 0 && off > 0) ? 1u : 0u;
     if (k.use_tma) {
         const uint32_t budget2 = 100u * 1024u;  // per CTA when two CTAs share an SM
-        const uint32_t budget1 = (uint32_t)dev->max_smem - 1024u;
+        const uint32_t budget1 = (uint32_t)dev->max_smem - 2048u;  // leave room for the static barriers
         if (2u * off <= budget2) {
             stages = (int)(budget2 / off);
             ctas_per_sm = 2;
@@ -539,7 +400,11 @@ static int launch_typed(const skr_program* p, int64_t numel, cudaStream_t stream
 
     const int which = sizeof(CT) == 8 ? 1 : 0;
     if (!dev->attr_set[which]) {
-        cudaError_t e = cudaFuncSetAttribute(step_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev->max_smem);
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, step_kernel<CT>);
+        if (e != cudaSuccess) return fail((int)e, "cudaFuncGetAttributes: %s", cudaGetErrorString(e));
+        e = cudaFuncSetAttribute(step_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 dev->max_smem - (int)fa.sharedSizeBytes);
         if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         dev->attr_set[which] = true;
     }
@@ -547,7 +412,100 @@ static int launch_typed(const skr_program* p, int64_t numel, cudaStream_t stream
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, "step kernel launch: %s", cudaGetErrorString(e));
     ++g_launches;
+    ++g_launches_kind[1];
     return 0;
+}
+
+// Pipeline shape for the block kernel: stages per CTA and CTAs per SM from the size of one staged tile.
+struct Shape {
+    int stages;
+    int ctas_per_sm;
+    bool ok;
+};
+
+static Shape pick_shape(uint32_t stage_bytes, int max_smem) {
+    // keep roughly 64-96 KB of bulk loads in flight per SM; more CTAs per SM when a stage is small
+    Shape sh{2, 1, true};
+    const uint32_t usable = (uint32_t)max_smem - 4096u;
+    if (stage_bytes == 0 || 2u * stage_bytes > usable) { sh.ok = false; return sh; }
+    int ctas = 4;
+    while (ctas > 1 && 2u * stage_bytes * (uint32_t)ctas > usable) --ctas;
+    uint32_t per_cta = usable / (uint32_t)ctas;
+    int stages = (int)(per_cta / stage_bytes);
+    const int want = (int)((96u * 1024u / (uint32_t)ctas + stage_bytes - 1) / stage_bytes) + 1;
+    if (stages > want) stages = want;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) stages = 2;
+    sh.stages = env_int("SKR_STAGES", stages);
+    sh.ctas_per_sm = env_int("SKR_CTAS", ctas);
+    if (sh.stages < 2) sh.stages = 2;
+    if (sh.stages > kMaxStages) sh.stages = kMaxStages;
+    if ((uint32_t)sh.stages * stage_bytes > usable) sh.stages = (int)(usable / stage_bytes);
+    return sh;
+}
+
+template <typename CT>
+static int launch_block(const skr_program* p, BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned) {
+    k.numel = numel;
+    k.n_inputs = p->n_inputs;
+    uint32_t off = 0;
+    for (int i = 0; i < p->n_inputs; ++i) {
+        k.in_ptr[i] = p->inputs[i].ptr;
+        k.in_dtype[i] = (uint8_t)p->inputs[i].dtype;
+        k.in_off[i] = off;
+        off += kTile * dtype_size_host(p->inputs[i].dtype);
+    }
+    for (int i = 0; i < p->n_outputs; ++i) {
+        k.out_ptr[i] = p->outputs[i].ptr;
+        k.out_dtype[i] = (uint8_t)p->outputs[i].dtype;
+    }
+    k.stage_bytes = off;
+
+    int err = 0;
+    DeviceInfo* dev = device_info(&err);
+    if (!dev) return fail(err, "cudaGetDevice failed");
+
+    const int64_t n_tiles = (numel + kTile - 1) / kTile;
+    const int64_t n_full = numel / kTile;
+    Shape sh = pick_shape(off, dev->max_smem);
+    k.use_tma = (aligned && n_full > 0 && sh.ok) ? 1u : 0u;
+    k.stages = sh.stages;
+    size_t smem = k.use_tma ? (size_t)sh.stages * off : 0;
+
+    int64_t grid;
+    if (k.use_tma) {
+        grid = (int64_t)dev->sm_count * sh.ctas_per_sm;
+        if (grid > n_full) grid = n_full;
+    } else {
+        grid = n_tiles < (int64_t)dev->sm_count * 8 ? n_tiles : (int64_t)dev->sm_count * 8;
+    }
+    if (grid < 1) grid = 1;
+
+    const int which = 2 + (sizeof(CT) == 8 ? 1 : 0);
+    if (!dev->attr_set[which]) {
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, block_kernel<CT>);
+        if (e != cudaSuccess) return fail((int)e, "cudaFuncGetAttributes: %s", cudaGetErrorString(e));
+        e = cudaFuncSetAttribute(block_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev->max_smem - (int)fa.sharedSizeBytes);
+        if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        dev->attr_set[which] = true;
+    }
+    block_kernel<CT><<<(unsigned)grid, kThreads + kProducerThreads, smem, stream>>>(k);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail((int)e, "block kernel launch: %s", cudaGetErrorString(e));
+    ++g_launches;
+    ++g_launches_kind[0];
+    return 0;
+}
+
+template <typename CT>
+static int launch_any(const skr_program* p, int64_t numel, cudaStream_t stream, bool aligned) {
+    if (!env_int("SKR_FORCE_INTERP", 0)) {
+        BProgram<CT> b;
+        memset(&b, 0, sizeof(b));
+        if (parse_block_program<CT>(p, b)) return launch_block<CT>(p, b, numel, stream, aligned);
+    }
+    return launch_typed<CT>(p, numel, stream, aligned);
 }
 
 }  // namespace skr
@@ -557,6 +515,16 @@ extern "C" {
 int skr_version(void) { return SKR_VERSION; }
 const char* skr_last_error(void) { return skr::g_error; }
 int64_t skr_launch_count(void) { return skr::g_launches; }
+int64_t skr_launch_count_kind(int32_t kind) { return (kind == 0 || kind == 1) ? skr::g_launches_kind[kind] : -1; }
+
+int skr_program_classify(const skr_program* p) {
+    using namespace skr;
+    if (!p) return fail(SKR_E_NULL, "null program");
+    if (p->n_ops < 0 || p->n_ops > SKR_MAX_OPS) return fail(SKR_E_RANGE, "n_ops %d out of range", p->n_ops);
+    BProgram<double> b;
+    memset(&b, 0, sizeof(b));
+    return parse_block_program<double>(p, b) ? 0 : 1;
+}
 
 int skr_program_launch(const skr_program* p, int64_t numel, void* stream) {
     using namespace skr;
@@ -598,7 +566,7 @@ int skr_program_launch(const skr_program* p, int64_t numel, void* stream) {
     }
     if (numel == 0 || p->n_ops == 0) return 0;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    return any64 ? launch_typed<double>(p, numel, s, aligned) : launch_typed<float>(p, numel, s, aligned);
+    return any64 ? launch_any<double>(p, numel, s, aligned) : launch_any<float>(p, numel, s, aligned);
 }
 
 int skr_axpby(const void* sample, const void* noise, void* out, int32_t dtype, int64_t numel, double sigma, double alpha,

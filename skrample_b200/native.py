@@ -65,7 +65,9 @@ EXPORTS = (
     "skr_version",
     "skr_last_error",
     "skr_launch_count",
+    "skr_launch_count_kind",
     "skr_program_launch",
+    "skr_program_classify",
     "skr_axpby",
 )
 
@@ -86,8 +88,12 @@ def load() -> ctypes.CDLL:
     lib.skr_version.restype = ctypes.c_int
     lib.skr_last_error.restype = ctypes.c_char_p
     lib.skr_launch_count.restype = ctypes.c_int64
+    lib.skr_launch_count_kind.restype = ctypes.c_int64
+    lib.skr_launch_count_kind.argtypes = [ctypes.c_int32]
     lib.skr_program_launch.restype = ctypes.c_int
     lib.skr_program_launch.argtypes = [ctypes.POINTER(SkrProgram), ctypes.c_int64, ctypes.c_void_p]
+    lib.skr_program_classify.restype = ctypes.c_int
+    lib.skr_program_classify.argtypes = [ctypes.POINTER(SkrProgram)]
     lib.skr_axpby.restype = ctypes.c_int
     lib.skr_axpby.argtypes = [
         ctypes.c_void_p,
@@ -112,6 +118,11 @@ def check(status: int, what: str) -> None:
 
 def launch_count() -> int:
     return int(load().skr_launch_count())
+
+
+def launch_count_kind(kind: int) -> int:
+    "kind 0 = structured block kernel, 1 = interpreter"
+    return int(load().skr_launch_count_kind(kind))
 
 
 def promoted_dtype(tensors: list[torch.Tensor]) -> torch.dtype:

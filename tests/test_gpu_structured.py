@@ -34,14 +34,26 @@ def test_native_library_is_the_path() -> None:
     assert np.array_equal(got.cpu().numpy(), want)
 
 
+@pytest.fixture(params=["block", "interpreter"])
+def kernel_kind(request: pytest.FixtureRequest, monkeypatch: pytest.MonkeyPatch) -> int:
+    "Run a test once per kernel: the structured block kernel (default) and the general interpreter."
+    if request.param == "interpreter":
+        monkeypatch.setenv("SKR_FORCE_INTERP", "1")
+        return 1
+    monkeypatch.delenv("SKR_FORCE_INTERP", raising=False)
+    return 0
+
+
 @pytest.mark.parametrize("case", STRUCTURED_INDEX, ids=lambda c: c["id"])
-def test_cuda_matches_reference_golden(case: dict) -> None:
-    "fp32 and fp64 trajectories are bit-identical to the reference's torch-CPU results."
+def test_cuda_matches_reference_golden(case: dict, kernel_kind: int) -> None:
+    "fp32 and fp64 trajectories are bit-identical to the reference's torch-CPU results, on both kernels."
     from skrample_b200 import native
 
-    before = native.launch_count()
+    before = native.launch_count_kind(kernel_kind)
+    other = native.launch_count_kind(1 - kernel_kind)
     result = run_product(case, device="cuda")
-    assert native.launch_count() > before
+    assert native.launch_count_kind(kernel_kind) > before
+    assert native.launch_count_kind(1 - kernel_kind) == other, "a step fell off the expected kernel"
     for field in ("final", "sample", "prediction"):
         want = STRUCTURED[f"{case['id']}/{field}"]
         got = getattr(result, field).cpu().numpy()
@@ -58,7 +70,7 @@ def _size_case(sampler: str, kw: dict, numel: int, dtype: str = "f32", schedule:
 
 @pytest.mark.parametrize("numel", SIZES)
 @pytest.mark.parametrize(("sampler", "kw"), [("Euler", {"stochasticity": 1}), ("Adams", {"order": 4}), ("UniPC", {"order": 3, "stochasticity": 1}), ("DPM", {"order": 3})])
-def test_sizes_and_tails_vs_oracle(sampler: str, kw: dict, numel: int) -> None:
+def test_sizes_and_tails_vs_oracle(sampler: str, kw: dict, numel: int, kernel_kind: int) -> None:
     "Empty-ish, ragged and multi-wave sizes: TMA tiles, the guarded tail and the persistent loop."
     case = _size_case(sampler, kw, numel)
     got = run_product(case, device="cuda")

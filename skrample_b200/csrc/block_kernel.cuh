@@ -10,9 +10,14 @@
 // optionally followed by a link (X = R, SPC blend, or the RK backward stage).  This kernel runs
 // that skeleton with *static* control flow: the only loops are the history-term loops, whose
 // operands are read from the TMA-staged shared-memory tile, so there is no per-op dispatch and the
-// eight state vectors live in fixed registers.  A dedicated producer warp issues the bulk copies
+// six state vectors live in fixed registers.  A dedicated producer warp issues the bulk copies
 // (one lane per input tensor) and runs ahead of the eight consumer warps through a full/empty
 // mbarrier ring; consumers never synchronise with each other.
+//
+// Instantiations: storage mode of the inputs (all fp32 / all bf16 / all fp16 / mixed, chosen per
+// launch) x elements per thread (4, or 8 for 16-bit storage so every shared-memory read is
+// 128-bit) x compute type (fp32, fp64).  The descriptor is plain int32/float fields in the
+// kernel-parameter constant bank so every test is a uniform-datapath compare.
 //
 // Arithmetic is identical to the interpreter (machine.cuh): individually rounded ops in the
 // reference's order.  A program that does not fit the skeleton is executed by the interpreter.
@@ -25,29 +30,33 @@ namespace skr {
 constexpr int kMaxTerms = 36;
 constexpr int kProducerThreads = 32;
 
-enum BlockKind : uint8_t { BK_NONE = 0, BK_ACC = 1, BK_UNI = 2, BK_DPM2 = 3, BK_DPM3 = 4 };
-enum BlockLink : uint8_t { BL_NONE = 0, BL_X_FROM_R = 1, BL_BLEND = 2, BL_BACK = 3 };
+enum BlockKind : int32_t { BK_NONE = 0, BK_ACC = 1, BK_UNI = 2, BK_DPM2 = 3, BK_DPM3 = 4 };
+enum BlockLink : int32_t { BL_NONE = 0, BL_X_FROM_R = 1, BL_BLEND = 2, BL_BACK = 3 };
+enum InMode : int { IN_MIXED = 0, IN_F32 = 1, IN_BF16 = 2, IN_F16 = 3 };
 
 template <typename CT>
 struct BTerm {
     CT c0, c1;
     int32_t in;  // input index
+    int32_t pad;
 };
 
 template <typename CT>
 struct BBlock {
-    uint8_t enabled, kind, save_s, p_mode;       // p_mode: ACC 1 = P first, 2 = P last; UNI 1 = UniC term
-    uint8_t has_div, pred_is_p, has_noise, link;
-    uint8_t n_terms, empty_sum, pad0, pad1;
-    int8_t sample_in, base_in, noise_in, store_r, store_link, pad2, pad3, pad4;  // -1 = not used
+    int32_t enabled, kind, save_s, p_mode;  // p_mode: ACC 1 = P first, 2 = P last; UNI 1 = UniC term
+    int32_t has_div, pred_is_p, has_noise, link;
+    int32_t n_terms, empty_sum;
+    int32_t sample_in, base_in, noise_in, store_r, store_link;  // -1 = not used
+    int32_t pad;
     CT p_coef, div, gamma, delta, zeta, l0, l1, e0, e1, e2;
     BTerm<CT> terms[kMaxTerms];
 };
 
 template <typename CT>
 struct BHead {
-    int8_t x_in, y_in, store_p, n_conv;
-    uint8_t neg, conv_flags[2], pad;
+    int32_t x_in, y_in, store_p, n_conv, neg;
+    int32_t conv_flags[2];
+    int32_t pad;
     CT conv_c[2][3];
 };
 
@@ -56,68 +65,173 @@ struct BProgram {
     int64_t numel;
     int32_t n_inputs, stages;
     uint32_t stage_bytes, use_tma;
+    int32_t n_full_tiles, pad;
     const void* in_ptr[SKR_MAX_INPUTS];
     void* out_ptr[SKR_MAX_OUTPUTS];
     uint32_t in_off[SKR_MAX_INPUTS];
-    uint8_t in_dtype[SKR_MAX_INPUTS];
-    uint8_t out_dtype[SKR_MAX_OUTPUTS];
+    int32_t in_dtype[SKR_MAX_INPUTS];
+    int32_t out_dtype[SKR_MAX_OUTPUTS];
     BHead<CT> head;
     BBlock<CT> blk[2];
 };
 
-template <typename CT, bool DIRECT>
-struct Fetcher {
+// ---- staged operand fetch, V elements per thread ---------------------------------------------------
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+template <typename CT, int MODE, int V>
+__device__ __forceinline__ void fetch_tile(const unsigned char* stage, uint32_t off, int dtype, int tid, CT (&v)[V]) {
+    const unsigned char* base = stage + off;
+    if constexpr (MODE == IN_F32) {
+        static_assert(V == 4, "fp32 tiles use 4 elements per thread");
+        const float4 q = *reinterpret_cast<const float4*>(base + tid * 16);
+        v[0] = (CT)q.x; v[1] = (CT)q.y; v[2] = (CT)q.z; v[3] = (CT)q.w;
+    } else if constexpr (MODE == IN_BF16) {
+        static_assert(V == 8, "16-bit tiles use 8 elements per thread");
+        const uint4 q = *reinterpret_cast<const uint4*>(base + tid * 16);
+        v[0] = (CT)bf16_lo(q.x); v[1] = (CT)bf16_hi(q.x); v[2] = (CT)bf16_lo(q.y); v[3] = (CT)bf16_hi(q.y);
+        v[4] = (CT)bf16_lo(q.z); v[5] = (CT)bf16_hi(q.z); v[6] = (CT)bf16_lo(q.w); v[7] = (CT)bf16_hi(q.w);
+    } else if constexpr (MODE == IN_F16) {
+        static_assert(V == 8, "16-bit tiles use 8 elements per thread");
+        const uint4 q = *reinterpret_cast<const uint4*>(base + tid * 16);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            v[2 * i] = (CT)f.x;
+            v[2 * i + 1] = (CT)f.y;
+        }
+    } else {
+        static_assert(V == 4, "mixed tiles use 4 elements per thread");
+        fetch_staged<CT>(stage, off, dtype, tid, v);
+    }
+}
+
+template <typename CT, int V>
+__device__ __forceinline__ void store_tile(void* ptr, int dtype, int64_t first, const CT (&v)[V]) {
+    switch (dtype) {
+        case SKR_F32: {
+            float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(ptr) + first);
+#pragma unroll
+            for (int i = 0; i < V / 4; ++i) p[i] = make_float4((float)v[4 * i], (float)v[4 * i + 1], (float)v[4 * i + 2], (float)v[4 * i + 3]);
+        } break;
+        case SKR_BF16: {
+            uint32_t w[V / 2];
+#pragma unroll
+            for (int i = 0; i < V / 2; ++i) w[i] = pack_bf16((float)v[2 * i], (float)v[2 * i + 1]);
+            if constexpr (V == 8) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(ptr) + first) = make_uint4(w[0], w[1], w[2], w[3]);
+            else *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ptr) + first) = make_uint2(w[0], w[1]);
+        } break;
+        case SKR_F16: {
+            uint32_t w[V / 2];
+#pragma unroll
+            for (int i = 0; i < V / 2; ++i) w[i] = pack_f16((float)v[2 * i], (float)v[2 * i + 1]);
+            if constexpr (V == 8) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(ptr) + first) = make_uint4(w[0], w[1], w[2], w[3]);
+            else *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ptr) + first) = make_uint2(w[0], w[1]);
+        } break;
+        default: {
+            double2* p = reinterpret_cast<double2*>(reinterpret_cast<double*>(ptr) + first);
+#pragma unroll
+            for (int i = 0; i < V / 2; ++i) p[i] = make_double2((double)v[2 * i], (double)v[2 * i + 1]);
+        } break;
+    }
+}
+
+// Guarded element-wise variants for the ragged tail / unaligned tensors.
+template <typename CT, int V>
+__device__ __forceinline__ void fetch_guarded(const void* ptr, int dtype, int64_t first, int64_t numel, CT (&v)[V]) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int64_t e = first + j;
+        CT x = (CT)0;
+        if (e < numel) {
+            switch (dtype) {
+                case SKR_F32: x = (CT) reinterpret_cast<const float*>(ptr)[e]; break;
+                case SKR_BF16: x = (CT)__bfloat162float(reinterpret_cast<const __nv_bfloat16*>(ptr)[e]); break;
+                case SKR_F16: x = (CT)__half2float(reinterpret_cast<const __half*>(ptr)[e]); break;
+                default: x = (CT) reinterpret_cast<const double*>(ptr)[e]; break;
+            }
+        }
+        v[j] = x;
+    }
+}
+
+template <typename CT, int V>
+__device__ __forceinline__ void store_guarded(void* ptr, int dtype, int64_t first, int64_t numel, const CT (&v)[V]) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int64_t e = first + j;
+        if (e < numel) {
+            switch (dtype) {
+                case SKR_F32: reinterpret_cast<float*>(ptr)[e] = (float)v[j]; break;
+                case SKR_BF16: reinterpret_cast<__nv_bfloat16*>(ptr)[e] = __float2bfloat16_rn((float)v[j]); break;
+                case SKR_F16: reinterpret_cast<__half*>(ptr)[e] = __float2half_rn((float)v[j]); break;
+                default: reinterpret_cast<double*>(ptr)[e] = (double)v[j]; break;
+            }
+        }
+    }
+}
+
+// ---- one tile of the skeleton -------------------------------------------------------------------------
+
+template <typename CT, int MODE, int V, bool GUARDED>
+struct TileIO {
     const BProgram<CT>& prog;
     const unsigned char* stage;
     int tid;
     int64_t first;
-    __device__ __forceinline__ void operator()(int in, CT (&v)[kVec]) const {
-        if constexpr (DIRECT) fetch_direct<CT>(prog.in_ptr[in], prog.in_dtype[in], first, prog.numel, v);
-        else fetch_staged<CT>(stage, prog.in_off[in], prog.in_dtype[in], tid, v);
+    __device__ __forceinline__ void load(int in, CT (&v)[V]) const {
+        if constexpr (GUARDED) fetch_guarded<CT, V>(prog.in_ptr[in], prog.in_dtype[in], first, prog.numel, v);
+        else fetch_tile<CT, MODE, V>(stage, prog.in_off[in], prog.in_dtype[in], tid, v);
+    }
+    __device__ __forceinline__ void store(int out, const CT (&v)[V]) const {
+        if constexpr (GUARDED) store_guarded<CT, V>(prog.out_ptr[out], prog.out_dtype[out], first, prog.numel, v);
+        else store_tile<CT, V>(prog.out_ptr[out], prog.out_dtype[out], first, v);
     }
 };
 
-template <typename CT, bool DIRECT>
-__device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t tile, const unsigned char* stage, int tid) {
+template <typename CT, int MODE, int V, bool GUARDED>
+__device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t first, const unsigned char* stage, int tid) {
     using Ar = Arith<CT>;
-    const int64_t first = tile * kTile + (int64_t)tid * kVec;
-    const Fetcher<CT, DIRECT> fetch{prog, stage, tid, first};
-    const int64_t numel = prog.numel;
+    const TileIO<CT, MODE, V, GUARDED> io{prog, stage, tid, first};
 
-    CT X[kVec], P[kVec], B[kVec], A[kVec], S[kVec], R[kVec];
+    CT X[V], P[V], B[V], A[V], S[V], R[V];
 #pragma unroll
-    for (int j = 0; j < kVec; ++j) X[j] = P[j] = B[j] = A[j] = S[j] = R[j] = (CT)0;
+    for (int j = 0; j < V; ++j) X[j] = P[j] = B[j] = A[j] = S[j] = R[j] = (CT)0;
 
     // ---- head ---------------------------------------------------------------------------------
     const BHead<CT>& h = prog.head;
-    if (h.x_in >= 0) fetch(h.x_in, X);
+    if (h.x_in >= 0) io.load(h.x_in, X);
     if (h.y_in >= 0) {
-        fetch(h.y_in, P);
+        io.load(h.y_in, P);
         if (h.neg) {
 #pragma unroll
-            for (int j = 0; j < kVec; ++j) P[j] = -P[j];
+            for (int j = 0; j < V; ++j) P[j] = -P[j];
         }
     }
+    if (h.n_conv > 0) {
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        if (c < h.n_conv) {
-            const int f = h.conv_flags[c];
-            const CT c0 = h.conv_c[c][0], c1 = h.conv_c[c][1], c2 = h.conv_c[c][2];
+        for (int c = 0; c < 2; ++c) {
+            if (c < h.n_conv) {
+                const int f = h.conv_flags[c];
+                const CT c0 = h.conv_c[c][0], c1 = h.conv_c[c][1], c2 = h.conv_c[c][2];
 #pragma unroll
-            for (int j = 0; j < kVec; ++j) {
-                CT v;
-                if (f & SKR_CONV_USE_X) {
-                    const CT lhs = (f & SKR_CONV_MUL_X) ? Ar::mul(c0, X[j]) : X[j];
-                    const CT rhs = (f & SKR_CONV_MUL_Y) ? Ar::mul(c1, P[j]) : P[j];
-                    v = Ar::sub(lhs, rhs);
-                } else {
-                    v = (f & SKR_CONV_MUL_Y) ? Ar::mul(P[j], c1) : P[j];
+                for (int j = 0; j < V; ++j) {
+                    CT v;
+                    if (f & SKR_CONV_USE_X) {
+                        const CT lhs = (f & SKR_CONV_MUL_X) ? Ar::mul(c0, X[j]) : X[j];
+                        const CT rhs = (f & SKR_CONV_MUL_Y) ? Ar::mul(c1, P[j]) : P[j];
+                        v = Ar::sub(lhs, rhs);
+                    } else {
+                        v = (f & SKR_CONV_MUL_Y) ? Ar::mul(P[j], c1) : P[j];
+                    }
+                    P[j] = (f & SKR_CONV_DIV) ? Ar::div(v, c2) : v;
                 }
-                P[j] = (f & SKR_CONV_DIV) ? Ar::div(v, c2) : v;
             }
         }
     }
-    if (h.store_p >= 0) store_vec<CT, DIRECT>(prog.out_ptr[h.store_p], prog.out_dtype[h.store_p], first, numel, P);
+    if (h.store_p >= 0) io.store(h.store_p, P);
 
     // ---- blocks -------------------------------------------------------------------------------
 #pragma unroll
@@ -126,75 +240,84 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
         if (!k.enabled) continue;
         if (k.save_s) {
 #pragma unroll
-            for (int j = 0; j < kVec; ++j) S[j] = X[j];
+            for (int j = 0; j < V; ++j) S[j] = X[j];
         }
-        if (k.sample_in >= 0) fetch(k.sample_in, X);
-        if (k.base_in >= 0) fetch(k.base_in, B);
-        else {
-#pragma unroll
-            for (int j = 0; j < kVec; ++j) B[j] = P[j];
-        }
+        if (k.sample_in >= 0) io.load(k.sample_in, X);
 
-        const int n_terms = k.n_terms;
-        CT in[kVec];
-        switch (k.kind) {
-            case BK_ACC: {
+        CT in[V];
+        const int kind = k.kind;
+        if (kind != BK_NONE) {
+            const int n_terms = k.n_terms;
+            if (kind != BK_ACC) {
+                if (k.base_in >= 0) io.load(k.base_in, B);
+                else {
+#pragma unroll
+                    for (int j = 0; j < V; ++j) B[j] = P[j];
+                }
+            }
+            if (kind == BK_ACC) {
                 int t = 0;
                 if (k.p_mode == 1 || n_terms == 0) {
+                    const CT c = k.p_coef;
 #pragma unroll
-                    for (int j = 0; j < kVec; ++j) A[j] = Ar::add((CT)0, Ar::mul(P[j], k.p_coef));
+                    for (int j = 0; j < V; ++j) A[j] = Ar::add((CT)0, Ar::mul(P[j], c));
                 } else {
-                    fetch(k.terms[0].in, in);
+                    io.load(k.terms[0].in, in);
                     const CT c = k.terms[0].c0;
 #pragma unroll
-                    for (int j = 0; j < kVec; ++j) A[j] = Ar::add((CT)0, Ar::mul(in[j], c));
+                    for (int j = 0; j < V; ++j) A[j] = Ar::add((CT)0, Ar::mul(in[j], c));
                     t = 1;
                 }
                 for (; t < n_terms; ++t) {
-                    fetch(k.terms[t].in, in);
+                    io.load(k.terms[t].in, in);
                     const CT c = k.terms[t].c0;
 #pragma unroll
-                    for (int j = 0; j < kVec; ++j) A[j] = Ar::add(A[j], Ar::mul(in[j], c));
+                    for (int j = 0; j < V; ++j) A[j] = Ar::add(A[j], Ar::mul(in[j], c));
                 }
                 if (k.p_mode == 2 && n_terms > 0) {
+                    const CT c = k.p_coef;
 #pragma unroll
-                    for (int j = 0; j < kVec; ++j) A[j] = Ar::add(A[j], Ar::mul(P[j], k.p_coef));
+                    for (int j = 0; j < V; ++j) A[j] = Ar::add(A[j], Ar::mul(P[j], c));
                 }
-            } break;
-            case BK_UNI: {
+                if (k.has_div) {
+                    const CT d = k.div;
+#pragma unroll
+                    for (int j = 0; j < V; ++j) A[j] = Ar::div(A[j], d);
+                }
+            } else if (kind == BK_UNI) {
                 for (int t = 0; t < n_terms; ++t) {
-                    fetch(k.terms[t].in, in);
+                    io.load(k.terms[t].in, in);
                     const CT rk = k.terms[t].c0, rho = k.terms[t].c1;
 #pragma unroll
-                    for (int j = 0; j < kVec; ++j) {
+                    for (int j = 0; j < V; ++j) {
                         const CT term = Ar::mul(Ar::div(Ar::sub(in[j], B[j]), rk), rho);
                         A[j] = Ar::add(t == 0 ? (CT)0 : A[j], term);
                     }
                 }
                 if (k.p_mode == 1) {
+                    const CT rho = k.p_coef;
 #pragma unroll
-                    for (int j = 0; j < kVec; ++j) {
-                        const CT term = Ar::mul(Ar::sub(P[j], B[j]), k.p_coef);
+                    for (int j = 0; j < V; ++j) {
+                        const CT term = Ar::mul(Ar::sub(P[j], B[j]), rho);
                         A[j] = Ar::add(n_terms == 0 ? (CT)0 : A[j], term);
                     }
                 }
+                const bool empty = k.empty_sum != 0;
 #pragma unroll
-                for (int j = 0; j < kVec; ++j) A[j] = Ar::add(B[j], k.empty_sum ? (CT)0 : A[j]);
-            } break;
-            case BK_DPM2: {
-                fetch(k.terms[0].in, in);
+                for (int j = 0; j < V; ++j) A[j] = Ar::add(B[j], empty ? (CT)0 : A[j]);
+            } else if (kind == BK_DPM2) {
+                io.load(k.terms[0].in, in);
                 const CT inv_r = k.terms[0].c0, half = k.terms[0].c1;
 #pragma unroll
-                for (int j = 0; j < kVec; ++j) A[j] = Ar::add(B[j], Ar::mul(half, Ar::mul(inv_r, Ar::sub(B[j], in[j]))));
-            } break;
-            case BK_DPM3: {
-                CT in2[kVec];
-                fetch(k.terms[0].in, in);
-                fetch(k.terms[1].in, in2);
+                for (int j = 0; j < V; ++j) A[j] = Ar::add(B[j], Ar::mul(half, Ar::mul(inv_r, Ar::sub(B[j], in[j]))));
+            } else {  // BK_DPM3
+                CT in2[V];
+                io.load(k.terms[0].in, in);
+                io.load(k.terms[1].in, in2);
                 const CT inv_r = k.terms[0].c0, inv_r2 = k.terms[1].c0, mix = k.terms[1].c1;
                 const CT inv_sum = k.e0, w1 = k.e1, w2 = k.e2;
 #pragma unroll
-                for (int j = 0; j < kVec; ++j) {
+                for (int j = 0; j < V; ++j) {
                     const CT d10 = Ar::mul(inv_r, Ar::sub(B[j], in[j]));
                     const CT d11 = Ar::mul(inv_r2, Ar::sub(in[j], in2[j]));
                     const CT d = Ar::sub(d10, d11);
@@ -202,53 +325,67 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
                     const CT d2 = Ar::mul(inv_sum, d);
                     A[j] = Ar::add(Ar::add(B[j], Ar::mul(w1, d1)), Ar::mul(w2, d2));
                 }
-            } break;
-            default: break;
+            }
         }
-        if (k.has_div) {
-#pragma unroll
-            for (int j = 0; j < kVec; ++j) A[j] = Ar::div(A[j], k.div);
-        }
-        if (k.has_noise) fetch(k.noise_in, in);
-#pragma unroll
-        for (int j = 0; j < kVec; ++j) {
-            const CT pred = k.pred_is_p ? P[j] : A[j];
-            CT v = Ar::add((CT)0, Ar::mul(X[j], k.gamma));
-            v = Ar::add(v, Ar::mul(pred, k.delta));
-            if (k.has_noise) v = Ar::add(v, Ar::mul(in[j], k.zeta));
-            R[j] = v;
-        }
-        if (k.store_r >= 0) store_vec<CT, DIRECT>(prog.out_ptr[k.store_r], prog.out_dtype[k.store_r], first, numel, R);
 
-        if (k.link == BL_X_FROM_R) {
+        const CT gamma = k.gamma, delta = k.delta;
+        if (k.pred_is_p) {
 #pragma unroll
-            for (int j = 0; j < kVec; ++j) X[j] = R[j];
-        } else if (k.link == BL_BLEND) {
+            for (int j = 0; j < V; ++j) R[j] = Ar::add(Ar::add((CT)0, Ar::mul(X[j], gamma)), Ar::mul(P[j], delta));
+        } else {
 #pragma unroll
-            for (int j = 0; j < kVec; ++j) X[j] = Ar::add(Ar::mul(S[j], k.l0), Ar::mul(R[j], k.l1));
-            if (k.store_link >= 0) store_vec<CT, DIRECT>(prog.out_ptr[k.store_link], prog.out_dtype[k.store_link], first, numel, X);
-        } else if (k.link == BL_BACK) {
+            for (int j = 0; j < V; ++j) R[j] = Ar::add(Ar::add((CT)0, Ar::mul(X[j], gamma)), Ar::mul(A[j], delta));
+        }
+        if (k.has_noise) {
+            io.load(k.noise_in, in);
+            const CT zeta = k.zeta;
 #pragma unroll
-            for (int j = 0; j < kVec; ++j) P[j] = Ar::div(Ar::sub(R[j], Ar::mul(X[j], k.l0)), k.l1);
-            if (k.store_link >= 0) store_vec<CT, DIRECT>(prog.out_ptr[k.store_link], prog.out_dtype[k.store_link], first, numel, P);
+            for (int j = 0; j < V; ++j) R[j] = Ar::add(R[j], Ar::mul(in[j], zeta));
+        }
+        if (k.store_r >= 0) io.store(k.store_r, R);
+
+        const int link = k.link;
+        if (link != BL_NONE) {
+            if (link == BL_X_FROM_R) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) X[j] = R[j];
+            } else if (link == BL_BLEND) {
+                const CT l0 = k.l0, l1 = k.l1;
+#pragma unroll
+                for (int j = 0; j < V; ++j) X[j] = Ar::add(Ar::mul(S[j], l0), Ar::mul(R[j], l1));
+                if (k.store_link >= 0) io.store(k.store_link, X);
+            } else {  // BL_BACK
+                const CT l0 = k.l0, l1 = k.l1;
+#pragma unroll
+                for (int j = 0; j < V; ++j) P[j] = Ar::div(Ar::sub(R[j], Ar::mul(X[j], l0)), l1);
+                if (k.store_link >= 0) io.store(k.store_link, P);
+            }
         }
     }
 }
 
-template <typename CT>
+// The ragged tail (and unaligned launches) run out of line so the pipelined loop stays compact.
+template <typename CT, int MODE, int V>
+__device__ __noinline__ void run_guarded_tiles(const BProgram<CT>& prog, int64_t first_tile, int64_t n_tiles, int tid) {
+    for (int64_t tile = first_tile + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        run_block_tile<CT, MODE, V, true>(prog, tile * (kThreads * V) + (int64_t)tid * V, nullptr, tid);
+    }
+}
+
+template <typename CT, int MODE, int V>
 __global__ void __launch_bounds__(kThreads + kProducerThreads) block_kernel(const __grid_constant__ BProgram<CT> prog) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
 
+    constexpr int TILE = kThreads * V;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int64_t numel = prog.numel;
-    const int64_t n_full = prog.use_tma ? numel / kTile : 0;
-    const int64_t n_tiles = (numel + kTile - 1) / kTile;
+    const int n_full = prog.use_tma ? prog.n_full_tiles : 0;
     const int stages = prog.stages;
     const uint32_t stage_bytes = prog.stage_bytes;
-    const int64_t mine = n_full > (int64_t)blockIdx.x ? (n_full - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int grid = (int)gridDim.x, cta = (int)blockIdx.x;
+    const int mine = n_full > cta ? (n_full - cta + grid - 1) / grid : 0;
     const bool producer = warp == kThreads / 32;
 
     if (mine > 0) {
@@ -266,29 +403,38 @@ __global__ void __launch_bounds__(kThreads + kProducerThreads) block_kernel(cons
             const bool active = lane < prog.n_inputs;
             const uint32_t esize = active ? dtype_size(prog.in_dtype[lane]) : 0u;
             const unsigned char* src = active ? reinterpret_cast<const unsigned char*>(prog.in_ptr[lane]) : nullptr;
-            const uint32_t off = active ? prog.in_off[lane] : 0u;
-            for (int64_t k = 0; k < mine; ++k) {
-                const int s = (int)(k % stages);
-                if (k >= stages) mbar_wait(&empty_bar[s], (uint32_t)(((k / stages) - 1) & 1));
+            unsigned char* dst = smem + (active ? prog.in_off[lane] : 0u);
+            const uint32_t bytes = TILE * esize;
+            src += (size_t)cta * bytes;
+            const size_t stride = (size_t)grid * bytes;
+            int s = 0;
+            uint32_t phase = 1;  // a fresh "empty" barrier counts as already released
+            for (int k = 0; k < mine; ++k) {
+                mbar_wait(&empty_bar[s], phase);
                 if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
                 __syncwarp();
-                if (active) {
-                    const int64_t tile = blockIdx.x + k * (int64_t)gridDim.x;
-                    tma_load_1d(smem + (size_t)s * stage_bytes + off, src + (size_t)tile * kTile * esize, kTile * esize, &full_bar[s]);
-                }
+                if (active) tma_load_1d(dst + (size_t)s * stage_bytes, src, bytes, &full_bar[s]);
+                src += stride;
+                if (++s == stages) { s = 0; phase ^= 1u; }
             }
         } else {
-            for (int64_t k = 0; k < mine; ++k) {
-                const int s = (int)(k % stages);
-                mbar_wait(&full_bar[s], (uint32_t)((k / stages) & 1));
-                run_block_tile<CT, false>(prog, blockIdx.x + k * (int64_t)gridDim.x, smem + (size_t)s * stage_bytes, tid);
+            int s = 0;
+            uint32_t phase = 0;
+            int64_t first = (int64_t)cta * TILE + (int64_t)tid * V;
+            const int64_t stride = (int64_t)grid * TILE;
+            for (int k = 0; k < mine; ++k) {
+                mbar_wait(&full_bar[s], phase);
+                run_block_tile<CT, MODE, V, false>(prog, first, smem + (size_t)s * stage_bytes, tid);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[s]);
+                first += stride;
+                if (++s == stages) { s = 0; phase ^= 1u; }
             }
         }
     }
     if (!producer) {
-        for (int64_t tile = n_full + blockIdx.x; tile < n_tiles; tile += gridDim.x) run_block_tile<CT, true>(prog, tile, nullptr, tid);
+        const int64_t n_tiles = (prog.numel + TILE - 1) / TILE;
+        if ((int64_t)n_full < n_tiles) run_guarded_tiles<CT, MODE, V>(prog, n_full, n_tiles, tid);
     }
 }
 
@@ -307,7 +453,7 @@ struct OpCursor {
 };
 
 template <typename CT>
-static bool parse_block(OpCursor& cur, BBlock<CT>& k, bool first_block) {
+static bool parse_block(OpCursor& cur, BBlock<CT>& k) {
     memset(&k, 0, sizeof(k));
     k.sample_in = k.base_in = k.noise_in = k.store_r = k.store_link = -1;
     if (!cur.peek()) return true;  // no (more) blocks
@@ -317,18 +463,14 @@ static bool parse_block(OpCursor& cur, BBlock<CT>& k, bool first_block) {
     if (cur.is_load(SKR_X)) {
         const skr_op* o = cur.take();
         if (o->b & 1) return false;
-        k.sample_in = (int8_t)o->src;
+        k.sample_in = o->src;
     }
-    bool base_set = false;
-    if (cur.is_mov(SKR_B, SKR_P)) { cur.take(); base_set = true; }
+    if (cur.is_mov(SKR_B, SKR_P)) cur.take();
     else if (cur.is_load(SKR_B)) {
         const skr_op* o = cur.take();
         if (o->b & 1) return false;
-        k.base_in = (int8_t)o->src;
-        base_set = true;
+        k.base_in = o->src;
     }
-    (void)base_set;
-    (void)first_block;
 
     const skr_op* o = cur.peek();
     if (!o) return false;
@@ -355,6 +497,7 @@ static bool parse_block(OpCursor& cur, BBlock<CT>& k, bool first_block) {
             head = false;
             cur.take();
         }
+        if (k.base_in >= 0) return false;  // ACC never reads B
         pred_from_a = true;
     } else if (o->code == SKR_OP_UNI || o->code == SKR_OP_UNIC || o->code == SKR_OP_ADDB) {
         k.kind = BK_UNI;
@@ -421,9 +564,9 @@ static bool parse_block(OpCursor& cur, BBlock<CT>& k, bool first_block) {
         else return false;
         k.gamma = (CT)t->c[0];
         k.delta = (CT)t->c[1];
-        if (t->b & 1) { k.has_noise = 1; k.noise_in = (int8_t)t->src; k.zeta = (CT)t->c[2]; }
+        if (t->b & 1) { k.has_noise = 1; k.noise_in = t->src; k.zeta = (CT)t->c[2]; }
     }
-    if (cur.is_store(SKR_R)) k.store_r = (int8_t)cur.take()->dst;
+    if (cur.is_store(SKR_R)) k.store_r = cur.take()->dst;
 
     if (cur.is_mov(SKR_X, SKR_R)) { cur.take(); k.link = BL_X_FROM_R; }
     else if (cur.is(SKR_OP_BLEND)) {
@@ -432,16 +575,21 @@ static bool parse_block(OpCursor& cur, BBlock<CT>& k, bool first_block) {
         k.link = BL_BLEND;
         k.l0 = (CT)t->c[0];
         k.l1 = (CT)t->c[1];
-        if (cur.is_store(SKR_X)) k.store_link = (int8_t)cur.take()->dst;
+        if (cur.is_store(SKR_X)) k.store_link = cur.take()->dst;
     } else if (cur.is(SKR_OP_BACK)) {
         const skr_op* t = cur.take();
         if (t->b & 1) return false;
         k.link = BL_BACK;
         k.l0 = (CT)t->c[0];
         k.l1 = (CT)t->c[1];
-        if (cur.is_store(SKR_P)) k.store_link = (int8_t)cur.take()->dst;
+        if (cur.is_store(SKR_P)) k.store_link = cur.take()->dst;
     }
     return true;
+}
+
+template <typename CT>
+static bool block_reads_p(const BBlock<CT>& k) {
+    return k.enabled && (k.pred_is_p || k.p_mode != 0 || (k.kind != BK_NONE && k.kind != BK_ACC && k.base_in < 0));
 }
 
 // Returns true when `p` matches the skeleton; fills head/blk of `out`.
@@ -455,15 +603,15 @@ static bool parse_block_program(const skr_program* p, BProgram<CT>& out) {
     if (cur.is_load(SKR_X)) {
         const skr_op* o = cur.take();
         if (o->b & 1) return false;
-        h.x_in = (int8_t)o->src;
+        h.x_in = o->src;
     }
     if (cur.is_load(SKR_P)) {
         const skr_op* o = cur.take();
-        h.y_in = (int8_t)o->src;
+        h.y_in = o->src;
         h.neg = o->b & 1;
     } else if (cur.is(SKR_OP_CONV) && cur.peek()->b == 0) {
         const skr_op* o = cur.take();
-        h.y_in = (int8_t)o->src;
+        h.y_in = o->src;
         h.conv_flags[0] = o->a;
         for (int j = 0; j < 3; ++j) h.conv_c[0][j] = (CT)o->c[j];
         h.n_conv = 1;
@@ -475,14 +623,15 @@ static bool parse_block_program(const skr_program* p, BProgram<CT>& out) {
         for (int j = 0; j < 3; ++j) h.conv_c[h.n_conv][j] = (CT)o->c[j];
         ++h.n_conv;
     }
-    if (cur.is_store(SKR_P)) h.store_p = (int8_t)cur.take()->dst;
+    for (int c = 0; c < h.n_conv; ++c)
+        if ((h.conv_flags[c] & SKR_CONV_USE_X) && h.x_in < 0) return false;
+    if (cur.is_store(SKR_P)) h.store_p = cur.take()->dst;
 
-    if (!parse_block<CT>(cur, out.blk[0], true)) return false;
-    if (!parse_block<CT>(cur, out.blk[1], false)) return false;
+    if (!parse_block<CT>(cur, out.blk[0])) return false;
+    if (!parse_block<CT>(cur, out.blk[1])) return false;
     if (cur.peek()) return false;  // trailing ops the skeleton cannot express
-    // a block that uses X needs it to come from somewhere
-    if (out.blk[0].enabled && h.x_in < 0 && out.blk[0].sample_in < 0) return false;
-    if ((out.blk[0].enabled && (out.blk[0].kind == BK_NONE || out.blk[0].base_in < 0)) && h.y_in < 0) return false;
+    if (out.blk[0].enabled && h.x_in < 0 && out.blk[0].sample_in < 0) return false;  // X must come from somewhere
+    if ((block_reads_p(out.blk[0]) || block_reads_p(out.blk[1]) || h.store_p >= 0) && h.y_in < 0) return false;
     return out.blk[0].enabled || h.store_p >= 0;
 }
 

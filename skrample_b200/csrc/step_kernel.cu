@@ -307,7 +307,7 @@ static int fail(int code, const char* fmt, ...) {
 struct DeviceInfo {
     int sm_count = 0;
     int max_smem = 0;
-    bool attr_set[4] = {false, false, false, false};
+    bool attr_set[8] = {false, false, false, false, false, false, false, false};
 };
 
 static int env_int(const char* name, int fallback) {
@@ -423,12 +423,12 @@ struct Shape {
     bool ok;
 };
 
-static Shape pick_shape(uint32_t stage_bytes, int max_smem) {
+static Shape pick_shape(uint32_t stage_bytes, int max_smem, int max_ctas) {
     // keep roughly 64-96 KB of bulk loads in flight per SM; more CTAs per SM when a stage is small
     Shape sh{2, 1, true};
     const uint32_t usable = (uint32_t)max_smem - 4096u;
     if (stage_bytes == 0 || 2u * stage_bytes > usable) { sh.ok = false; return sh; }
-    int ctas = 4;
+    int ctas = max_ctas;
     while (ctas > 1 && 2u * stage_bytes * (uint32_t)ctas > usable) --ctas;
     uint32_t per_cta = usable / (uint32_t)ctas;
     int stages = (int)(per_cta / stage_bytes);
@@ -444,20 +444,21 @@ static Shape pick_shape(uint32_t stage_bytes, int max_smem) {
     return sh;
 }
 
-template <typename CT>
-static int launch_block(const skr_program* p, BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned) {
+template <typename CT, int MODE, int V>
+static int launch_block_inst(const skr_program* p, BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned, int slot) {
+    constexpr int TILE = kThreads * V;
     k.numel = numel;
     k.n_inputs = p->n_inputs;
     uint32_t off = 0;
     for (int i = 0; i < p->n_inputs; ++i) {
         k.in_ptr[i] = p->inputs[i].ptr;
-        k.in_dtype[i] = (uint8_t)p->inputs[i].dtype;
+        k.in_dtype[i] = p->inputs[i].dtype;
         k.in_off[i] = off;
-        off += kTile * dtype_size_host(p->inputs[i].dtype);
+        off += TILE * dtype_size_host(p->inputs[i].dtype);
     }
     for (int i = 0; i < p->n_outputs; ++i) {
         k.out_ptr[i] = p->outputs[i].ptr;
-        k.out_dtype[i] = (uint8_t)p->outputs[i].dtype;
+        k.out_dtype[i] = p->outputs[i].dtype;
     }
     k.stage_bytes = off;
 
@@ -465,10 +466,12 @@ static int launch_block(const skr_program* p, BProgram<CT>& k, int64_t numel, cu
     DeviceInfo* dev = device_info(&err);
     if (!dev) return fail(err, "cudaGetDevice failed");
 
-    const int64_t n_tiles = (numel + kTile - 1) / kTile;
-    const int64_t n_full = numel / kTile;
-    Shape sh = pick_shape(off, dev->max_smem);
+    const int64_t n_tiles = (numel + TILE - 1) / TILE;
+    const int64_t n_full = numel / TILE;
+    if (n_full > 0x7fffffff) return fail(SKR_E_RANGE, "numel too large");
+    Shape sh = pick_shape(off, dev->max_smem, V == 8 || sizeof(CT) == 8 ? 2 : 4);
     k.use_tma = (aligned && n_full > 0 && sh.ok) ? 1u : 0u;
+    k.n_full_tiles = (int32_t)n_full;
     k.stages = sh.stages;
     size_t smem = k.use_tma ? (size_t)sh.stages * off : 0;
 
@@ -481,21 +484,41 @@ static int launch_block(const skr_program* p, BProgram<CT>& k, int64_t numel, cu
     }
     if (grid < 1) grid = 1;
 
-    const int which = 2 + (sizeof(CT) == 8 ? 1 : 0);
-    if (!dev->attr_set[which]) {
+    if (!dev->attr_set[slot]) {
         cudaFuncAttributes fa;
-        cudaError_t e = cudaFuncGetAttributes(&fa, block_kernel<CT>);
+        cudaError_t e = cudaFuncGetAttributes(&fa, block_kernel<CT, MODE, V>);
         if (e != cudaSuccess) return fail((int)e, "cudaFuncGetAttributes: %s", cudaGetErrorString(e));
-        e = cudaFuncSetAttribute(block_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, dev->max_smem - (int)fa.sharedSizeBytes);
+        e = cudaFuncSetAttribute(block_kernel<CT, MODE, V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 dev->max_smem - (int)fa.sharedSizeBytes);
         if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        dev->attr_set[which] = true;
+        dev->attr_set[slot] = true;
     }
-    block_kernel<CT><<<(unsigned)grid, kThreads + kProducerThreads, smem, stream>>>(k);
+    block_kernel<CT, MODE, V><<<(unsigned)grid, kThreads + kProducerThreads, smem, stream>>>(k);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, "block kernel launch: %s", cudaGetErrorString(e));
     ++g_launches;
     ++g_launches_kind[0];
     return 0;
+}
+
+template <typename CT>
+static int launch_block(const skr_program* p, BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned) {
+    if constexpr (sizeof(CT) == 8) {
+        return launch_block_inst<double, IN_MIXED, 4>(p, k, numel, stream, aligned, 2);
+    } else {
+        bool all_f32 = true, all_bf16 = true, all_f16 = true;
+        for (int i = 0; i < p->n_inputs; ++i) {
+            all_f32 &= p->inputs[i].dtype == SKR_F32;
+            all_bf16 &= p->inputs[i].dtype == SKR_BF16;
+            all_f16 &= p->inputs[i].dtype == SKR_F16;
+        }
+        const int force = env_int("SKR_IN_MODE", -1);  // development switch: 0 forces the mixed instantiation
+        if (force == 0) return launch_block_inst<float, IN_MIXED, 4>(p, k, numel, stream, aligned, 3);
+        if (all_f32) return launch_block_inst<float, IN_F32, 4>(p, k, numel, stream, aligned, 4);
+        if (all_bf16) return launch_block_inst<float, IN_BF16, 8>(p, k, numel, stream, aligned, 5);
+        if (all_f16) return launch_block_inst<float, IN_F16, 8>(p, k, numel, stream, aligned, 6);
+        return launch_block_inst<float, IN_MIXED, 4>(p, k, numel, stream, aligned, 3);
+    }
 }
 
 template <typename CT>

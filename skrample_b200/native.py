@@ -73,6 +73,9 @@ EXPORTS = (
 
 _lib: ctypes.CDLL | None = None
 
+ACCOUNT = {"on": False, "bytes": 0, "launches": 0}
+"Opt-in byte accounting of launched programs (bench.py derives algorithmic bytes per step from it)."
+
 
 def load() -> ctypes.CDLL:
     "Load the shared library once; raise loudly if it is not there."
@@ -181,6 +184,9 @@ def launch_program(program: "Program") -> list[Any]:
             dtype = want
         outputs.append(torch.empty(first.shape, dtype=dtype, device=first.device))
 
+    if ACCOUNT["on"]:
+        ACCOUNT["launches"] += 1
+        ACCOUNT["bytes"] += sum(t.numel() * t.element_size() for t in inputs) + sum(t.numel() * t.element_size() for t in outputs)
     packed = pack_program(program, inputs, outputs)
     device = first.device
     if torch.cuda.current_device() != device.index:

@@ -126,7 +126,7 @@ def _trivial(specs: tuple | None) -> bool:
 
 def _point_from(step: Step, schedule: SkrampleSchedule) -> Point:
     "Origin of a step, evaluated the way ``SampleInput.delta_point`` does (both ends in one call)."
-    return schedule.ipoints(step)[0]
+    return schedule._ipoints_memo(tuple(step))[0]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -353,7 +353,7 @@ class Euler(StructuredStochastic, StatedSampler):
             prog.load(X, view.sample)
         if view.prediction is not IN_P:
             prog.load(P, view.prediction)
-        delta = DeltaPoint(*schedule.ipoints(view.step))
+        delta = DeltaPoint(*schedule._ipoints_memo(tuple(view.step)))
         _finish(prog, model_transform, delta, self.stochasticity, P, view.noise)
 
 
@@ -370,7 +370,7 @@ class DPM(StructuredUnified, StatedSampler):
 
     def _emit(self, ctx, view, model_transform, schedule, previous) -> None:  # noqa: ANN001
         prog = ctx.prog
-        delta = DeltaPoint(*schedule.ipoints(view.step))
+        delta = DeltaPoint(*schedule._ipoints_memo(tuple(view.step)))
         order = self.effective_order(view.step, previous)
         model, history = self._head(ctx, view, model_transform, schedule, previous, order, delta.point_from)
 
@@ -378,11 +378,11 @@ class DPM(StructuredUnified, StatedSampler):
         if order >= 2:
             lam = _lambda(delta.point_from)
             h = abs(_lambda(delta.point_to) - lam)
-            lam_prev = _lambda(schedule.ipoint(previous[-1].step.time_from))
+            lam_prev = _lambda(schedule._ipoint_memo(previous[-1].step.time_from))
             r = (lam - lam_prev) / h
             prog.mov(B, P)
             if order >= 3:
-                lam_prev2 = _lambda(schedule.ipoint(previous[-2].step.time_from))
+                lam_prev2 = _lambda(schedule._ipoint_memo(previous[-2].step.time_from))
                 r2 = (lam_prev - lam_prev2) / h
                 hh = -h
                 e = math.expm1(hh)
@@ -406,7 +406,7 @@ class Adams(StructuredUnified, StatedSampler):
     def _emit(self, ctx, view, model_transform, schedule, previous) -> None:  # noqa: ANN001
         prog = ctx.prog
         order = self.effective_order(view.step, previous)
-        delta = DeltaPoint(*schedule.ipoints(view.step))
+        delta = DeltaPoint(*schedule._ipoints_memo(tuple(view.step)))
         model, history = self._head(ctx, view, model_transform, schedule, previous, order, delta.point_from)
 
         weights = common.bashforth(order)
@@ -453,7 +453,7 @@ class UniP(StructuredUnified, StatedSampler):
     ) -> None:
         """UniP (``prediction_next`` None) or UniC (``prediction_next`` = IN_P or a value) into R."""
         prog = ctx.prog
-        delta = DeltaPoint(*schedule.ipoints(view.step))
+        delta = DeltaPoint(*schedule._ipoints_memo(tuple(view.step)))
         order = self.effective_order(view.step, previous)
         corrector = prediction_next is not None
 

@@ -136,6 +136,38 @@ class SkrampleSchedule(ABC):
         "The all-noise end of the curve."
         return self.point(1)
 
+    def _ipoints_memo(self, times: tuple[float, ...]) -> tuple[Point, ...]:
+        """``ipoints`` memoised on the instance (schedules are immutable, so this is a pure function).
+
+        The samplers ask for the same handful of step boundaries again and again while building step
+        programs; the reference recomputes the NumPy curve every time (reference: structured.py:33-34).
+        """
+        try:
+            memo = self.__dict__["_skr_ipoints"]
+        except KeyError:
+            memo = {}
+            object.__setattr__(self, "_skr_ipoints", memo)
+        found = memo.get(times)
+        if found is None:
+            if len(memo) > 4096:
+                memo.clear()
+            found = memo[times] = tuple(self.ipoints(times))
+        return found
+
+    def _ipoint_memo(self, time: float) -> Point:
+        "``ipoint`` memoised on the instance (scalar evaluation path, kept separate from the vector one)."
+        try:
+            memo = self.__dict__["_skr_ipoint"]
+        except KeyError:
+            memo = {}
+            object.__setattr__(self, "_skr_ipoint", memo)
+        found = memo.get(time)
+        if found is None:
+            if len(memo) > 4096:
+                memo.clear()
+            found = memo[time] = self.ipoint(time)
+        return found
+
     def step(self, step: Step) -> DeltaPoint:
         return DeltaPoint(*self.points(step))
 

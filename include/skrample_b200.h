@@ -40,6 +40,8 @@ extern "C" {
 #define SKR_MAX_OPS 64
 #define SKR_MAX_INPUTS 32
 #define SKR_MAX_OUTPUTS 8
+#define SKR_MAX_DIMS 8
+#define SKR_MAX_LEVELS 16
 
 /* element types */
 enum { SKR_F32 = 0, SKR_F64 = 1, SKR_BF16 = 2, SKR_F16 = 3 };
@@ -121,7 +123,8 @@ int skr_version(void);
 const char* skr_last_error(void);
 /* Number of kernels this library has launched in this process (bench bookkeeping). */
 int64_t skr_launch_count(void);
-/* Same, split by kernel: kind 0 = structured block kernel (fast path), 1 = interpreter (general path). */
+/* Same, split by kernel: kind 0 = structured block kernel (fast path), 1 = interpreter (general path),
+ * 2 = noise kernels. */
 int64_t skr_launch_count_kind(int32_t kind);
 
 /*
@@ -145,6 +148,73 @@ int skr_program_classify(const skr_program* program);
  */
 int skr_axpby(const void* sample, const void* noise, void* out, int32_t dtype, int64_t numel, double sigma,
               double alpha, int32_t remove, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Noise generation (skrample/pytorch/noise.py).  Counter-based Philox4x32-10: the value at element e of
+ * stream (seed, stream) depends on nothing else, so shards of a batch reproduce the unsharded values.
+ */
+
+/* Offset term of noise.py:104-113: out += normal(offset stream)[index reduced to the kept axes] * scale */
+typedef struct skr_offset {
+    int32_t ndim;
+    int32_t reserved;
+    int64_t shape[SKR_MAX_DIMS]; /* full shape of the unit tensor (product == numel)          */
+    int32_t keep[SKR_MAX_DIMS];  /* 1: the offset varies along this axis, 0: broadcast         */
+    uint64_t stream;             /* Philox stream of the offset draw                           */
+    double scale;                /* strength^2                                                 */
+} skr_offset;
+
+/*
+ * Random / Offset (noise.py:73-74,104-113): out[e] = normal(seed, stream)[e] (+ offset term).
+ * `moments` (optional, device double[2], pre-zeroed) accumulates sum and sum of squares of the values written.
+ */
+int skr_noise_fill(void* out, int32_t dtype, int64_t numel, uint64_t seed, uint64_t stream, const skr_offset* offset,
+                   double* moments, void* cuda_stream);
+
+/* sum / sum^2 of a tensor into device double[2] (pre-zeroed), for Tensor.std() (noise.py:207,365,401). */
+int skr_noise_moments(const void* in, int32_t dtype, int64_t numel, double* moments, void* cuda_stream);
+
+/*
+ * out = in * s, s = numerator [* std(num_moments, num_count)] [/ std(moments, count)], each factor applied when
+ * its pointer is given (unbiased std from device double[2] accumulators); s stays 1 when the denominator std
+ * is <= min_std.  In place allowed; casts in_dtype -> out_dtype.  (noise.py:207, 369, 402-405)
+ */
+int skr_noise_scale(const void* in, int32_t in_dtype, void* out, int32_t out_dtype, int64_t numel, double numerator,
+                    const double* num_moments, int64_t num_count, const double* moments, int64_t count, double min_std,
+                    void* cuda_stream);
+
+typedef struct skr_pyramid_level {
+    uint64_t stream;     /* Philox stream of this level's normal draw                               */
+    const float* buffer; /* non-null: read the level (fp32, level shape, row-major) instead          */
+    int64_t extent[2];   /* extents of the resized axes at this level, in axis order                  */
+    double weight;       /* strength^level; 0 skips the level                                         */
+} skr_pyramid_level;
+
+typedef struct skr_pyramid {
+    int32_t ndim;
+    int32_t n_levels;
+    int64_t shape[SKR_MAX_DIMS];  /* unit tensor shape                                                */
+    int32_t masked[SKR_MAX_DIMS]; /* 1: axis is resized by the pyramid (1 or 2 axes)                  */
+    uint64_t seed;
+    uint64_t base_stream;         /* the plain randn(shape) term                                      */
+    const float* base_buffer;     /* non-null: supplied base draw                                     */
+    skr_pyramid_level levels[SKR_MAX_LEVELS];
+} skr_pyramid;
+
+/*
+ * Pyramid (noise.py:146-207): out = (base + sum_l weight_l * upsample(level_l)) / std, bilinear/linear
+ * upsampling with align_corners=False semantics, unbiased std over the whole tensor.  Two kernels: moments,
+ * then regenerate + normalise + write.  `moments` = device double[2], pre-zeroed.
+ */
+int skr_noise_pyramid(void* out, int32_t dtype, const skr_pyramid* desc, double* moments, void* cuda_stream);
+
+/*
+ * Colored (noise.py:285-335,379-394): multiply an rfftn half-spectrum in place by
+ * clamp(normalised radial frequency, 0.5 / max(mean(dims), 4)) ** (-exponent / 2).
+ * `spectrum`: complex64 (complex_dtype SKR_F32) or complex128 (SKR_F64), shape dims[0..n-2] x (dims[n-1]/2+1).
+ */
+int skr_colored_shape(void* spectrum, int32_t complex_dtype, const int64_t* dims, int32_t ndim, double exponent,
+                      void* cuda_stream);
 
 #ifdef __cplusplus
 }

@@ -694,3 +694,42 @@ def colorize(white: np.ndarray, exponent: float, energy: float | None = None) ->
     if cstd > 1e-8:
         colored = colored * (wstd / cstd if energy is None else energy / cstd)
     return colored.reshape(white.shape).astype(white.dtype)
+
+
+def pyramid_level_shapes(shape: Sequence[int], mask: Sequence[bool], ratios: Sequence[float]) -> list[tuple[int, ...]]:
+    "Level shapes for given per-level ratios r (reference draws r = rand()*2+2). reference: noise.py:158-162,197-198"
+    running = list(shape)
+    out: list[tuple[int, ...]] = []
+    for level, r in enumerate(ratios):
+        running = [max(1, int(s / (r**level))) if m else s for m, s in zip(mask, running)]
+        out.append(tuple(running))
+        if any(s <= 1 for m, s in zip(mask, running) if m):
+            break
+    return out
+
+
+def upsample_linear(level: np.ndarray, shape: Sequence[int], mask: Sequence[bool]) -> np.ndarray:
+    "F.interpolate(mode linear/bilinear, align_corners=False) of `level` to `shape` along the masked axes."
+    out = level.astype(np.float32)
+    for axis in reversed([d for d, m in enumerate(mask) if m]):  # innermost resized axis first
+        i0, i1, w1 = bilinear_axis_index(shape[axis], out.shape[axis])
+        lo = np.take(out, i0, axis=axis)
+        hi = np.take(out, i1, axis=axis)
+        wshape = [1] * out.ndim
+        wshape[axis] = -1
+        w = w1.reshape(wshape)
+        out = (np.float32(1) - w) * lo + w * hi
+    return out
+
+
+def pyramid_compose(base: np.ndarray, levels: Sequence[np.ndarray], mask: Sequence[bool], strength: float = 0.3, depth: int = 99) -> np.ndarray:
+    "(base + sum_l strength^l * upsample(level_l)) / std. reference: noise.py:146-207"
+    top = len(levels) - 1
+    skip = min(top, max(0, top - depth))
+    total = np.zeros(base.shape, dtype=np.float32)
+    for l, level in enumerate(levels):
+        if l < skip:
+            continue
+        total = total + upsample_linear(level, base.shape, mask) * np.float32(strength**l)
+    noise = base.astype(np.float32) + total
+    return noise / noise.std(ddof=1)

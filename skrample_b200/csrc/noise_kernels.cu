@@ -1,0 +1,549 @@
+// skrample_b200 - noise generation kernels for sm_100a (B200).
+//
+// Replaces the ATen op chains of skrample/pytorch/noise.py (reference lines cited per kernel):
+//   skr_noise_fill      Random / Offset: counter-based Philox4x32-10 normals written straight in the
+//                       storage dtype, 128-bit stores, optional running sum / sum-of-squares.
+//   skr_noise_pyramid   Pyramid: base + full-resolution level + bilinear-upsampled coarse levels, evaluated
+//                       per element from Philox streams (or supplied buffers), two passes: moments, then
+//                       regenerate + normalise + write - the N-sized intermediate is never stored.
+//   skr_noise_moments   sum / sum^2 of a tensor (for std), warp-shuffle + block reduction, fp64 partials.
+//   skr_noise_scale     out = in * scale (in place allowed), storage-dtype aware.
+//   skr_colored_shape   in-place spectral shaping of an rfftn half-spectrum: multiply each complex bin by
+//                       clamp(radial_frequency, eps)^(-exponent/2); the radial grid is computed from indices.
+//
+// Philox streams are keyed (seed, stream id) with the counter = element index / 4, so any batch sharding
+// over GPUs reproduces the same values for the same (seed, stream, index).
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+
+#include "../../include/skrample_b200.h"
+#include "common.cuh"
+
+namespace skr {
+
+extern int fail(int code, const char* fmt, ...);
+extern void count_launch(int kind);
+extern int sm_count_or(int fallback);
+
+// ---------------------------------------------------------------------------------------------------------
+// Philox4x32-10
+
+struct Philox {
+    uint32_t k0, k1;
+    __device__ __forceinline__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+    __device__ __forceinline__ uint4 operator()(uint64_t index, uint64_t stream) const {
+        uint32_t c0 = (uint32_t)index, c1 = (uint32_t)(index >> 32), c2 = (uint32_t)stream, c3 = (uint32_t)(stream >> 32);
+        uint32_t a = k0, b = k1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            c0 = hi1 ^ c1 ^ a;
+            c1 = lo1;
+            c2 = hi0 ^ c3 ^ b;
+            c3 = lo0;
+            a += 0x9E3779B9u;
+            b += 0xBB67AE85u;
+        }
+        return make_uint4(c0, c1, c2, c3);
+    }
+};
+
+__device__ __forceinline__ float u01(uint32_t x) { return (float)x * 2.3283064365386963e-10f + 1.1641532182693481e-10f; }  // (0, 1]
+
+// four standard normals from one Philox block (two Box-Muller pairs)
+__device__ __forceinline__ void normal4(const uint4 r, float (&z)[4]) {
+    const float r0 = sqrtf(-2.0f * logf(u01(r.x)));
+    const float r1 = sqrtf(-2.0f * logf(u01(r.z)));
+    float s0, c0, s1, c1;
+    sincospif(2.0f * u01(r.y), &s0, &c0);
+    sincospif(2.0f * u01(r.w), &s1, &c1);
+    z[0] = r0 * s0;
+    z[1] = r0 * c0;
+    z[2] = r1 * s1;
+    z[3] = r1 * c1;
+}
+
+// the normal at element `e` of stream (seed, stream)
+__device__ __forceinline__ float normal_at(const Philox& ph, uint64_t e, uint64_t stream) {
+    float z[4];
+    normal4(ph(e >> 2, stream), z);
+    const int lane = (int)(e & 3);
+    return lane == 0 ? z[0] : lane == 1 ? z[1] : lane == 2 ? z[2] : z[3];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// store helpers
+
+__device__ __forceinline__ void store4(void* out, int dtype, int64_t first, const float (&v)[4]) {
+    switch (dtype) {
+        case SKR_F32: *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + first) = make_float4(v[0], v[1], v[2], v[3]); break;
+        case SKR_BF16: {
+            const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + first) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+        } break;
+        case SKR_F16: {
+            const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + first) =
+                make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+        } break;
+        default: {
+            double* p = reinterpret_cast<double*>(out) + first;
+            *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+            *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+        } break;
+    }
+}
+
+__device__ __forceinline__ void store1(void* out, int dtype, int64_t e, float v) {
+    switch (dtype) {
+        case SKR_F32: reinterpret_cast<float*>(out)[e] = v; break;
+        case SKR_BF16: reinterpret_cast<__nv_bfloat16*>(out)[e] = __float2bfloat16_rn(v); break;
+        case SKR_F16: reinterpret_cast<__half*>(out)[e] = __float2half_rn(v); break;
+        default: reinterpret_cast<double*>(out)[e] = (double)v; break;
+    }
+}
+
+__device__ __forceinline__ float load1(const void* in, int dtype, int64_t e) {
+    switch (dtype) {
+        case SKR_F32: return reinterpret_cast<const float*>(in)[e];
+        case SKR_BF16: return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(in)[e]);
+        case SKR_F16: return __half2float(reinterpret_cast<const __half*>(in)[e]);
+        default: return (float)reinterpret_cast<const double*>(in)[e];
+    }
+}
+
+// block-wide sum of two doubles; result valid in thread 0
+__device__ __forceinline__ void block_sum2(double& a, double& b) {
+    __shared__ double sa[32], sb[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, o);
+        b += __shfl_down_sync(0xffffffffu, b, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sa[warp] = a; sb[warp] = b; }
+    __syncthreads();
+    if (warp == 0) {
+        const int n = (blockDim.x + 31) >> 5;
+        a = lane < n ? sa[lane] : 0.0;
+        b = lane < n ? sb[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_down_sync(0xffffffffu, a, o);
+            b += __shfl_down_sync(0xffffffffu, b, o);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Random / Offset fill   (reference: noise.py:36-42,73-74,104-113)
+
+struct FillParams {
+    void* out;
+    int64_t numel;
+    uint64_t seed, stream, offset_stream;
+    float offset_scale;  // strength^2; 0 disables the offset term
+    int32_t dtype, ndim, aligned;
+    int64_t shape[SKR_MAX_DIMS];
+    int32_t keep[SKR_MAX_DIMS];  // 1: axis indexes the offset tensor, 0: broadcast
+    double* moments;             // optional [sum, sum^2] accumulators
+};
+
+__device__ __forceinline__ int64_t reduced_index(const FillParams& p, int64_t e) {
+    // linear index into the offset tensor (shape = shape[d] if keep[d] else 1), row-major
+    int64_t idx[SKR_MAX_DIMS];
+    for (int d = p.ndim - 1; d >= 0; --d) { idx[d] = e % p.shape[d]; e /= p.shape[d]; }
+    int64_t r = 0;
+    for (int d = 0; d < p.ndim; ++d) if (p.keep[d]) r = r * p.shape[d] + idx[d];
+    return r;
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(const __grid_constant__ FillParams p) {
+    const Philox ph(p.seed);
+    double s1 = 0.0, s2 = 0.0;
+    const int64_t groups = (p.numel + 3) >> 2;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+        float z[4];
+        normal4(ph((uint64_t)g, p.stream), z);
+        const int64_t first = g << 2;
+        if (p.offset_scale != 0.0f) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (first + j < p.numel) z[j] = z[j] + normal_at(ph, (uint64_t)reduced_index(p, first + j), p.offset_stream) * p.offset_scale;
+            }
+        }
+        if (p.aligned && first + 4 <= p.numel) {
+            store4(p.out, p.dtype, first, z);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { s1 += z[j]; s2 += (double)z[j] * z[j]; }
+        } else {
+            for (int j = 0; j < 4 && first + j < p.numel; ++j) {
+                store1(p.out, p.dtype, first + j, z[j]);
+                s1 += z[j];
+                s2 += (double)z[j] * z[j];
+            }
+        }
+    }
+    if (p.moments) {
+        block_sum2(s1, s2);
+        if (threadIdx.x == 0) { atomicAdd(&p.moments[0], s1); atomicAdd(&p.moments[1], s2); }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// moments / scale   (reference: noise.py:207,365,401-403 - Tensor.std())
+
+struct MomentParams {
+    const void* in;
+    int64_t numel;
+    int32_t dtype;
+    double* moments;
+};
+
+__global__ void __launch_bounds__(256) moments_kernel(const __grid_constant__ MomentParams p) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.numel; e += (int64_t)gridDim.x * blockDim.x) {
+        const double v = p.dtype == SKR_F64 ? reinterpret_cast<const double*>(p.in)[e] : (double)load1(p.in, p.dtype, e);
+        s1 += v;
+        s2 += v * v;
+    }
+    block_sum2(s1, s2);
+    if (threadIdx.x == 0) { atomicAdd(&p.moments[0], s1); atomicAdd(&p.moments[1], s2); }
+}
+
+struct ScaleParams {
+    const void* in;
+    void* out;
+    int64_t numel;
+    int32_t in_dtype, out_dtype;
+    // scale = numerator [* std(num_moments)] [/ std(moments)], each std unbiased over its count
+    double numerator;
+    const double* num_moments;
+    int64_t num_count;
+    const double* moments;
+    int64_t count;
+    double min_std;  // leave the data unscaled when the denominator std <= min_std (reference: `if cstd > 1e-8`)
+};
+
+__device__ __forceinline__ double std_from(const double* m, int64_t n) {
+    const double mean = m[0] / (double)n;
+    const double var = (m[1] - (double)n * mean * mean) / (double)(n > 1 ? n - 1 : 1);
+    return sqrt(var > 0.0 ? var : 0.0);
+}
+
+__global__ void __launch_bounds__(256) scale_kernel(const __grid_constant__ ScaleParams p) {
+    double scale = p.numerator;
+    if (p.num_moments) scale *= std_from(p.num_moments, p.num_count);
+    if (p.moments) {
+        const double sd = std_from(p.moments, p.count);
+        scale = sd > p.min_std ? scale / sd : 1.0;
+    }
+    const float fs = (float)scale;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.numel; e += (int64_t)gridDim.x * blockDim.x) {
+        if (p.in_dtype == SKR_F64 || p.out_dtype == SKR_F64) {
+            const double v = p.in_dtype == SKR_F64 ? reinterpret_cast<const double*>(p.in)[e] : (double)load1(p.in, p.in_dtype, e);
+            if (p.out_dtype == SKR_F64) reinterpret_cast<double*>(p.out)[e] = v * scale;
+            else store1(p.out, p.out_dtype, e, (float)(v * scale));
+        } else {
+            store1(p.out, p.out_dtype, e, load1(p.in, p.in_dtype, e) * fs);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Pyramid   (reference: noise.py:146-207)
+
+struct PyramidParams {
+    void* out;
+    int64_t numel;
+    int32_t dtype, ndim, n_levels, mode;  // mode 0: accumulate moments only, 1: write out = value / std
+    uint64_t seed;
+    int64_t shape[SKR_MAX_DIMS];
+    int32_t masked[SKR_MAX_DIMS];           // 1: axis is resized by the pyramid
+    // level l: source (Philox stream or supplied fp32 buffer), resized extents along the masked axes, weight
+    uint64_t stream[SKR_MAX_LEVELS];
+    const float* buffer[SKR_MAX_LEVELS];    // non-null: read the level from this tensor instead of Philox
+    int64_t extent[SKR_MAX_LEVELS][2];      // size of the (up to two) masked axes at this level, in axis order
+    float weight[SKR_MAX_LEVELS];           // strength^l (0 for skipped levels)
+    uint64_t base_stream;
+    const float* base_buffer;
+    double* moments;
+};
+
+// F.interpolate(align_corners=False) source position along one axis (ATen area_pixel_compute_source_index)
+__device__ __forceinline__ void source_index(int64_t dst, int64_t in_size, int64_t out_size, int64_t& i0, int64_t& i1, float& w1) {
+    const float scale = (float)in_size / (float)out_size;
+    float src = scale * ((float)dst + 0.5f) - 0.5f;
+    src = src < 0.0f ? 0.0f : src;
+    i0 = (int64_t)src;
+    if (i0 > in_size - 1) i0 = in_size - 1;
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    w1 = src - (float)i0;
+}
+
+__device__ __forceinline__ float level_value(const PyramidParams& p, const Philox& ph, int l, int64_t linear) {
+    return p.buffer[l] ? p.buffer[l][linear] : normal_at(ph, (uint64_t)linear, p.stream[l]);
+}
+
+__device__ __forceinline__ float pyramid_value(const PyramidParams& p, const Philox& ph, int64_t e) {
+    int64_t idx[SKR_MAX_DIMS];
+    int64_t rem = e;
+    for (int d = p.ndim - 1; d >= 0; --d) { idx[d] = rem % p.shape[d]; rem /= p.shape[d]; }
+    int m_axis[2] = {-1, -1};
+    int n_masked = 0;
+    for (int d = 0; d < p.ndim; ++d) if (p.masked[d] && n_masked < 2) m_axis[n_masked++] = d;
+
+    float pyramid = 0.0f;  // the reference starts from a zero tensor and adds the kept levels in order
+    for (int l = 0; l < p.n_levels; ++l) {
+        const float wl = p.weight[l];
+        if (wl == 0.0f) continue;
+        // linear index of a level element given coordinates along the masked axes
+        auto at = [&](int64_t a0, int64_t a1) {
+            int64_t lin = 0;
+            int seen = 0;
+            for (int d = 0; d < p.ndim; ++d) {
+                int64_t size = p.shape[d], coord = idx[d];
+                if (p.masked[d]) { size = p.extent[l][seen]; coord = seen == 0 ? a0 : a1; ++seen; }
+                lin = lin * size + coord;
+            }
+            return level_value(p, ph, l, lin);
+        };
+        float v;
+        if (n_masked == 1) {
+            int64_t i0, i1; float w1;
+            source_index(idx[m_axis[0]], p.extent[l][0], p.shape[m_axis[0]], i0, i1, w1);
+            v = (1.0f - w1) * at(i0, 0) + w1 * at(i1, 0);
+        } else {
+            int64_t h0, h1, w0, w1i; float wh, ww;
+            source_index(idx[m_axis[0]], p.extent[l][0], p.shape[m_axis[0]], h0, h1, wh);
+            source_index(idx[m_axis[1]], p.extent[l][1], p.shape[m_axis[1]], w0, w1i, ww);
+            const float top = (1.0f - ww) * at(h0, w0) + ww * at(h0, w1i);
+            const float bot = (1.0f - ww) * at(h1, w0) + ww * at(h1, w1i);
+            v = (1.0f - wh) * top + wh * bot;
+        }
+        pyramid += v * wl;
+    }
+    const float base = p.base_buffer ? p.base_buffer[e] : normal_at(ph, (uint64_t)e, p.base_stream);
+    return base + pyramid;
+}
+
+__global__ void __launch_bounds__(256) pyramid_kernel(const __grid_constant__ PyramidParams p) {
+    const Philox ph(p.seed);
+    double s1 = 0.0, s2 = 0.0;
+    float inv_std = 1.0f;
+    if (p.mode == 1) inv_std = (float)(1.0 / std_from(p.moments, p.numel));
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.numel; e += (int64_t)gridDim.x * blockDim.x) {
+        const float v = pyramid_value(p, ph, e);
+        if (p.mode == 0) { s1 += v; s2 += (double)v * v; }
+        else store1(p.out, p.dtype, e, v * inv_std);
+    }
+    if (p.mode == 0) {
+        block_sum2(s1, s2);
+        if (threadIdx.x == 0) { atomicAdd(&p.moments[0], s1); atomicAdd(&p.moments[1], s2); }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Colored: spectral shaping of an rfftn half spectrum, in place   (reference: noise.py:285-335,379-394)
+
+struct ShapeParams {
+    float2* spectrum;     // complex64, shape = dims[0..ndim-2] x (dims[ndim-1]/2 + 1)
+    double2* spectrum64;  // complex128 alternative (exactly one of the two is non-null)
+    int64_t bins;         // number of complex elements
+    int32_t ndim;
+    int64_t dims[SKR_MAX_DIMS];  // real-space extents of the transformed axes
+    float exponent_half_neg;     // -exponent / 2
+    float eps_clip;
+    float r_max;
+};
+
+__global__ void __launch_bounds__(256) colored_shape_kernel(const __grid_constant__ ShapeParams p) {
+    const int last = p.ndim - 1;
+    const int64_t last_bins = p.dims[last] / 2 + 1;
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < p.bins; b += (int64_t)gridDim.x * blockDim.x) {
+        int64_t rem = b;
+        float r2 = 0.0f;
+        {
+            const int64_t k = rem % last_bins;
+            rem /= last_bins;
+            const float f = (float)k / (float)p.dims[last];
+            r2 = f * f;
+        }
+        for (int d = last - 1; d >= 0; --d) {
+            const int64_t n = p.dims[d];
+            const int64_t k = rem % n;
+            rem /= n;
+            // |fftfreq(n)|: k/n for k < ceil(n/2), else (n-k)/n
+            const int64_t kk = k < (n + 1) / 2 ? k : n - k;
+            const float f = (float)kk / (float)n;
+            r2 += f * f;
+        }
+        float r = sqrtf(r2);
+        if (p.r_max > 0.0f) r = r / p.r_max;
+        r = r < p.eps_clip ? p.eps_clip : r;
+        const float w = powf(r, p.exponent_half_neg);
+        if (p.spectrum) {
+            float2 v = p.spectrum[b];
+            v.x *= w;
+            v.y *= w;
+            p.spectrum[b] = v;
+        } else {
+            double2 v = p.spectrum64[b];
+            v.x *= (double)w;
+            v.y *= (double)w;
+            p.spectrum64[b] = v;
+        }
+    }
+}
+
+static unsigned grid_for(int64_t work_items, int threads) {
+    const int64_t sms = sm_count_or(148);
+    int64_t blocks = (work_items + threads - 1) / threads;
+    const int64_t cap = sms * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+static int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail((int)e, "%s launch: %s", what, cudaGetErrorString(e));
+    count_launch(2);
+    return 0;
+}
+
+}  // namespace skr
+
+extern "C" {
+
+int skr_noise_fill(void* out, int32_t dtype, int64_t numel, uint64_t seed, uint64_t stream, const skr_offset* offset, double* moments,
+                   void* cuda_stream) {
+    using namespace skr;
+    if (numel < 0) return fail(SKR_E_RANGE, "negative numel");
+    if (dtype < 0 || dtype > SKR_F16) return fail(SKR_E_DTYPE, "unknown dtype %d", dtype);
+    if (numel == 0) return 0;
+    if (!out) return fail(SKR_E_NULL, "null output");
+    FillParams p;
+    memset(&p, 0, sizeof(p));
+    p.out = out; p.numel = numel; p.seed = seed; p.stream = stream; p.dtype = dtype; p.moments = moments;
+    p.aligned = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+    if (offset && offset->scale != 0.0) {
+        if (offset->ndim < 1 || offset->ndim > SKR_MAX_DIMS) return fail(SKR_E_SHAPE, "offset ndim %d out of range", offset->ndim);
+        int64_t total = 1;
+        for (int d = 0; d < offset->ndim; ++d) {
+            if (offset->shape[d] < 1) return fail(SKR_E_SHAPE, "offset shape[%d] < 1", d);
+            p.shape[d] = offset->shape[d];
+            p.keep[d] = offset->keep[d] ? 1 : 0;
+            total *= offset->shape[d];
+        }
+        if (total != numel) return fail(SKR_E_SHAPE, "offset shape does not multiply to numel");
+        p.ndim = offset->ndim;
+        p.offset_scale = (float)offset->scale;
+        p.offset_stream = offset->stream;
+    }
+    fill_kernel<<<grid_for((numel + 3) / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
+    return check_launch("noise fill");
+}
+
+int skr_noise_moments(const void* in, int32_t dtype, int64_t numel, double* moments, void* cuda_stream) {
+    using namespace skr;
+    if (numel < 0) return fail(SKR_E_RANGE, "negative numel");
+    if (dtype < 0 || dtype > SKR_F16) return fail(SKR_E_DTYPE, "unknown dtype %d", dtype);
+    if (!moments) return fail(SKR_E_NULL, "null moments");
+    if (numel == 0) return 0;
+    if (!in) return fail(SKR_E_NULL, "null input");
+    MomentParams p{in, numel, dtype, moments};
+    moments_kernel<<<grid_for(numel, 256 * 4), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
+    return check_launch("noise moments");
+}
+
+int skr_noise_scale(const void* in, int32_t in_dtype, void* out, int32_t out_dtype, int64_t numel, double numerator,
+                    const double* num_moments, int64_t num_count, const double* moments, int64_t count, double min_std, void* cuda_stream) {
+    using namespace skr;
+    if (numel < 0) return fail(SKR_E_RANGE, "negative numel");
+    if (in_dtype < 0 || in_dtype > SKR_F16 || out_dtype < 0 || out_dtype > SKR_F16) return fail(SKR_E_DTYPE, "unknown dtype");
+    if (numel == 0) return 0;
+    if (!in || !out) return fail(SKR_E_NULL, "null tensor");
+    ScaleParams p{in, out, numel, in_dtype, out_dtype, numerator, num_moments, num_count, moments, count, min_std};
+    scale_kernel<<<grid_for(numel, 256 * 4), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
+    return check_launch("noise scale");
+}
+
+int skr_noise_pyramid(void* out, int32_t dtype, const skr_pyramid* desc, double* moments, void* cuda_stream) {
+    using namespace skr;
+    if (!desc || !moments) return fail(SKR_E_NULL, "null descriptor / moments");
+    if (dtype < 0 || dtype > SKR_F16) return fail(SKR_E_DTYPE, "unknown dtype %d", dtype);
+    if (desc->ndim < 1 || desc->ndim > SKR_MAX_DIMS) return fail(SKR_E_SHAPE, "ndim %d out of range", desc->ndim);
+    if (desc->n_levels < 0 || desc->n_levels > SKR_MAX_LEVELS) return fail(SKR_E_SHAPE, "n_levels %d out of range", desc->n_levels);
+    PyramidParams p;
+    memset(&p, 0, sizeof(p));
+    int64_t numel = 1;
+    int masked = 0;
+    for (int d = 0; d < desc->ndim; ++d) {
+        if (desc->shape[d] < 1) return fail(SKR_E_SHAPE, "shape[%d] < 1", d);
+        p.shape[d] = desc->shape[d];
+        p.masked[d] = desc->masked[d] ? 1 : 0;
+        masked += p.masked[d];
+        numel *= desc->shape[d];
+    }
+    if (masked < 1 || masked > 2) return fail(SKR_E_UNSUPPORTED, "pyramid needs 1 or 2 resized axes, got %d", masked);
+    if (!out) return fail(SKR_E_NULL, "null output");
+    p.out = out; p.numel = numel; p.dtype = dtype; p.ndim = desc->ndim; p.n_levels = desc->n_levels; p.seed = desc->seed;
+    for (int l = 0; l < desc->n_levels; ++l) {
+        p.stream[l] = desc->levels[l].stream;
+        p.buffer[l] = desc->levels[l].buffer;
+        p.extent[l][0] = desc->levels[l].extent[0];
+        p.extent[l][1] = desc->levels[l].extent[1];
+        p.weight[l] = (float)desc->levels[l].weight;
+        if (p.extent[l][0] < 1 || (masked == 2 && p.extent[l][1] < 1)) return fail(SKR_E_SHAPE, "level %d has an empty extent", l);
+    }
+    p.base_stream = desc->base_stream;
+    p.base_buffer = desc->base_buffer;
+    p.moments = moments;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+    p.mode = 0;
+    pyramid_kernel<<<grid_for(numel, 256), 256, 0, s>>>(p);
+    int rc = check_launch("pyramid moments");
+    if (rc) return rc;
+    p.mode = 1;
+    pyramid_kernel<<<grid_for(numel, 256), 256, 0, s>>>(p);
+    return check_launch("pyramid write");
+}
+
+int skr_colored_shape(void* spectrum, int32_t complex_dtype, const int64_t* dims, int32_t ndim, double exponent, void* cuda_stream) {
+    using namespace skr;
+    if (!spectrum || !dims) return fail(SKR_E_NULL, "null spectrum / dims");
+    if (ndim < 1 || ndim > SKR_MAX_DIMS) return fail(SKR_E_SHAPE, "ndim %d out of range", ndim);
+    if (complex_dtype != SKR_F32 && complex_dtype != SKR_F64) return fail(SKR_E_DTYPE, "spectrum must be complex64 or complex128");
+    ShapeParams p;
+    memset(&p, 0, sizeof(p));
+    p.ndim = ndim;
+    int64_t bins = 1;
+    double sum = 0.0, rmax2 = 0.0;
+    for (int d = 0; d < ndim; ++d) {
+        if (dims[d] < 1) return fail(SKR_E_SHAPE, "dims[%d] < 1", d);
+        p.dims[d] = dims[d];
+        sum += (double)dims[d];
+        bins *= d == ndim - 1 ? dims[d] / 2 + 1 : dims[d];
+        const float fmax = (float)(dims[d] / 2) / (float)dims[d];  // largest |frequency| along the axis
+        rmax2 += (double)(fmax * fmax);
+    }
+    p.bins = bins;
+    if (complex_dtype == SKR_F32) p.spectrum = reinterpret_cast<float2*>(spectrum);
+    else p.spectrum64 = reinterpret_cast<double2*>(spectrum);
+    const double n_eff = sum / (double)ndim;
+    p.eps_clip = (float)(0.5 / (n_eff > 4.0 ? n_eff : 4.0));
+    p.r_max = sqrtf((float)rmax2);
+    p.exponent_half_neg = (float)(-exponent / 2.0);
+    colored_shape_kernel<<<grid_for(bins, 256), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
+    return check_launch("colored shape");
+}
+
+}  // extern "C"

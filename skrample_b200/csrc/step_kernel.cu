@@ -294,9 +294,9 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
 
 static thread_local char g_error[512] = "";
 static int64_t g_launches = 0;
-static int64_t g_launches_kind[2] = {0, 0};  // [0] structured block kernel, [1] interpreter
+static int64_t g_launches_kind[3] = {0, 0, 0};  // [0] structured block kernel, [1] interpreter, [2] noise kernels
 
-static int fail(int code, const char* fmt, ...) {
+int fail(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_error, sizeof(g_error), fmt, ap);
@@ -327,6 +327,17 @@ static DeviceInfo* device_info(int* err) {
     }
     *err = 0;
     return &d;
+}
+
+void count_launch(int kind) {
+    ++g_launches;
+    if (kind >= 0 && kind < 3) ++g_launches_kind[kind];
+}
+
+int sm_count_or(int fallback) {
+    int err = 0;
+    DeviceInfo* dev = device_info(&err);
+    return dev && dev->sm_count > 0 ? dev->sm_count : fallback;
 }
 
 template <typename CT>
@@ -538,7 +549,7 @@ extern "C" {
 int skr_version(void) { return SKR_VERSION; }
 const char* skr_last_error(void) { return skr::g_error; }
 int64_t skr_launch_count(void) { return skr::g_launches; }
-int64_t skr_launch_count_kind(int32_t kind) { return (kind == 0 || kind == 1) ? skr::g_launches_kind[kind] : -1; }
+int64_t skr_launch_count_kind(int32_t kind) { return (kind >= 0 && kind <= 2) ? skr::g_launches_kind[kind] : -1; }
 
 int skr_program_classify(const skr_program* p) {
     using namespace skr;

@@ -1,0 +1,634 @@
+"""Noise generators for stochastic samplers, with in-kernel Philox on CUDA generators.
+
+Public surface follows reference: skrample/pytorch/noise.py:11-466 (``Random``, ``Offset``, ``Pyramid``,
+``Colored``, ``Brownian``, ``BatchTensorNoise`` and their ``*Props``).  The result lives on the device of the
+``torch.Generator`` handed in, exactly like the reference:
+
+* **CUDA generator** - everything is generated on the device by hand-written kernels
+  (``csrc/noise_kernels.cu``): counter-based Philox4x32-10 normals written directly in the storage dtype, the
+  Offset broadcast folded into the same kernel, the Pyramid evaluated per element from Philox streams with
+  on-the-fly bilinear upsampling and a two-pass (moments, regenerate+normalise) scheme, and the Colored
+  spectrum shaped in place around ``torch.fft`` (cuFFT).  No host synchronisation anywhere: the ``rand().item()``
+  per pyramid level and the ``if std > eps`` tests of the reference are evaluated on the host RNG / on device.
+  Streams are keyed ``(generator.initial_seed(), philox offset)`` and the generator's offset is advanced, so
+  draws are reproducible, independent between calls, and independent of how a batch is sharded over GPUs.
+* **CPU generator** - the values come from the generator's own stream in the reference's draw order, so a
+  seeded CPU generator reproduces the reference's noise bit for bit (this is what its parity tests use).
+"""
+
+from __future__ import annotations
+
+import ctypes
+import math
+from abc import ABC, abstractmethod
+from dataclasses import dataclass
+from typing import Any, Self
+
+import torch
+
+from skrample_b200.common import Step, divf, rescale_positive
+
+_SUBSTREAMS = 64
+"Philox offset units consumed per generate() call on a CUDA generator."
+
+
+@dataclass(frozen=True)
+class TensorNoiseProps:
+    "Immutable settings of a generator; share these, not the generator."
+
+
+@dataclass
+class SkrampleTensorNoise(ABC):
+    @abstractmethod
+    def generate(self, step: Step | None) -> torch.Tensor:
+        "Next noise tensor of the sequence (stateful: one generator per job)."
+        raise NotImplementedError
+
+
+# ------------------------------------------------------------------------------------------------------------
+# native plumbing
+
+
+def _native() -> Any:
+    from skrample_b200 import native
+
+    return native
+
+
+class _SkrOffset(ctypes.Structure):
+    _fields_ = [
+        ("ndim", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("shape", ctypes.c_int64 * 8),
+        ("keep", ctypes.c_int32 * 8),
+        ("stream", ctypes.c_uint64),
+        ("scale", ctypes.c_double),
+    ]
+
+
+class _SkrPyramidLevel(ctypes.Structure):
+    _fields_ = [
+        ("stream", ctypes.c_uint64),
+        ("buffer", ctypes.c_void_p),
+        ("extent", ctypes.c_int64 * 2),
+        ("weight", ctypes.c_double),
+    ]
+
+
+class _SkrPyramid(ctypes.Structure):
+    _fields_ = [
+        ("ndim", ctypes.c_int32),
+        ("n_levels", ctypes.c_int32),
+        ("shape", ctypes.c_int64 * 8),
+        ("masked", ctypes.c_int32 * 8),
+        ("seed", ctypes.c_uint64),
+        ("base_stream", ctypes.c_uint64),
+        ("base_buffer", ctypes.c_void_p),
+        ("levels", _SkrPyramidLevel * 16),
+    ]
+
+
+_bound = False
+
+
+def _lib() -> Any:
+    global _bound
+    native = _native()
+    lib = native.load()
+    if not _bound:
+        vp, i32, i64, u64, dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double
+        lib.skr_noise_fill.restype = ctypes.c_int
+        lib.skr_noise_fill.argtypes = [vp, i32, i64, u64, u64, ctypes.POINTER(_SkrOffset), vp, vp]
+        lib.skr_noise_moments.restype = ctypes.c_int
+        lib.skr_noise_moments.argtypes = [vp, i32, i64, vp, vp]
+        lib.skr_noise_scale.restype = ctypes.c_int
+        lib.skr_noise_scale.argtypes = [vp, i32, vp, i32, i64, dbl, vp, i64, vp, i64, dbl, vp]
+        lib.skr_noise_pyramid.restype = ctypes.c_int
+        lib.skr_noise_pyramid.argtypes = [vp, i32, ctypes.POINTER(_SkrPyramid), vp, vp]
+        lib.skr_colored_shape.restype = ctypes.c_int
+        lib.skr_colored_shape.argtypes = [vp, i32, ctypes.POINTER(i64), i32, dbl, vp]
+        _bound = True
+    return lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _code(dtype: torch.dtype) -> int:
+    try:
+        return _native().DTYPE_CODE[dtype]
+    except KeyError:
+        raise TypeError(f"skrample_b200 noise kernels support fp32/fp64/bf16/fp16, not {dtype}") from None
+
+
+class _DeviceGuard:
+    "Make ``device`` current for the launches inside (no-op when it already is)."
+
+    def __init__(self, device: torch.device) -> None:
+        self.ctx = torch.cuda.device(device) if torch.cuda.current_device() != device.index else None
+
+    def __enter__(self) -> None:
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc: object) -> None:
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+
+
+def _host_uniform(seed: int, stream: int, index: int) -> float:
+    "Counter-based U[0,1) on the host (SplitMix64 of the key) - the pyramid's per-level ratio, without a device sync."
+    z = (seed * 0x9E3779B97F4A7C15 + stream * 0xBF58476D1CE4E5B9 + index * 0x94D049BB133111EB + 0x632BE59BD9B4E019) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    z ^= z >> 31
+    return (z >> 11) / float(1 << 53)
+
+
+@dataclass
+class TensorNoiseCommon[T: TensorNoiseProps | None](SkrampleTensorNoise):
+    "Shape / seed / dtype / props shared by the base generators. reference: noise.py:27-55"
+
+    shape: tuple[int, ...]
+    seed: torch.Generator
+    dtype: torch.dtype
+    props: T
+
+    @property
+    def on_device(self) -> bool:
+        return self.seed.device.type == "cuda"
+
+    def _randn(self, shape: tuple[int, ...] | None = None) -> torch.Tensor:
+        "A plain normal draw from this generator (reference-compatible helper)."
+        shape = tuple(self.shape if shape is None else shape)
+        if self.on_device:
+            out = torch.empty(shape, dtype=self.dtype, device=self.seed.device)
+            self._fill(out, self._tick())
+            return out
+        return torch.randn(shape, generator=self.seed, dtype=self.dtype, device=self.seed.device)
+
+    # -- device helpers
+    def _tick(self) -> int:
+        "Reserve this call's block of Philox streams by advancing the generator's offset."
+        at = int(self.seed.get_offset())
+        self.seed.set_offset(at + 4 * _SUBSTREAMS)
+        return at // 4
+
+    def _key(self) -> int:
+        return int(self.seed.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+
+    def _fill(self, out: torch.Tensor, stream: int, offset: _SkrOffset | None = None, moments: torch.Tensor | None = None) -> None:
+        with _DeviceGuard(out.device):
+            status = _lib().skr_noise_fill(
+                out.data_ptr(),
+                _code(out.dtype),
+                out.numel(),
+                self._key(),
+                stream,
+                ctypes.byref(offset) if offset is not None else None,
+                moments.data_ptr() if moments is not None else None,
+                _stream(),
+            )
+        _native().check(status, "skr_noise_fill")
+
+    def generate_into(self, out: torch.Tensor, step: Step | None) -> None:
+        "Write the next draw into ``out`` (used by the batch helper to avoid a stack copy)."
+        out.copy_(self.generate(step))
+
+    @classmethod
+    @abstractmethod
+    def from_inputs(
+        cls,
+        shape: tuple[int, ...],
+        seed: torch.Generator,
+        props: T = None,  # type: ignore[assignment]
+        dtype: torch.dtype = torch.float32,
+    ) -> Self:
+        "Build the generator from what is at hand during inference."
+        raise NotImplementedError
+
+
+# ------------------------------------------------------------------------------------------------------------
+
+
+@dataclass
+class Random(TensorNoiseCommon[None]):
+    "Independent standard normals. reference: noise.py:58-74"
+
+    @classmethod
+    def from_inputs(cls, shape: tuple[int, ...], seed: torch.Generator, props: None = None, dtype: torch.dtype = torch.float32) -> Self:
+        return cls(shape, seed, dtype, props)
+
+    def generate(self, step: Step | None) -> torch.Tensor:
+        return self._randn()
+
+    def generate_into(self, out: torch.Tensor, step: Step | None) -> None:
+        if self.on_device and out.is_cuda and out.is_contiguous():
+            self._fill(out, self._tick())
+        else:
+            out.copy_(self.generate(step))
+
+
+@dataclass(frozen=True)
+class OffsetProps(TensorNoiseProps):
+    dims: tuple[int, ...] = (0,)
+    strength: float = 0.2
+    static: bool = False
+
+
+@dataclass
+class Offset(TensorNoiseCommon[OffsetProps]):
+    "Normal noise plus one random offset per slice along ``dims``. reference: noise.py:84-113"
+
+    @classmethod
+    def from_inputs(
+        cls, shape: tuple[int, ...], seed: torch.Generator, props: OffsetProps = OffsetProps(), dtype: torch.dtype = torch.float32
+    ) -> Self:
+        return cls(shape, seed, dtype, props)
+
+    def __post_init__(self) -> None:
+        self.static_offset: torch.Tensor | None = None
+        self._static_stream: int | None = None
+        if self.props.static:
+            if self.on_device:
+                self._static_stream = self._tick() + 1
+            else:
+                self.static_offset = self.offset()
+
+    def _offset_shape(self) -> tuple[int, ...]:
+        return tuple(d if n in self.props.dims else 1 for n, d in enumerate(self.shape))
+
+    def offset(self) -> torch.Tensor:
+        return self._randn(self._offset_shape()) * self.props.strength**2
+
+    def _descriptor(self, stream: int) -> _SkrOffset:
+        desc = _SkrOffset()
+        desc.ndim = len(self.shape)
+        for n, d in enumerate(self.shape):
+            desc.shape[n] = d
+            desc.keep[n] = int(n in self.props.dims)
+        desc.stream = stream
+        desc.scale = self.props.strength**2
+        return desc
+
+    def generate_into(self, out: torch.Tensor, step: Step | None) -> None:
+        if self.on_device and out.is_cuda and out.is_contiguous() and len(self.shape) <= 8:
+            base = self._tick()
+            offset_stream = self._static_stream if self._static_stream is not None else base + 1
+            self._fill(out, base, self._descriptor(offset_stream))
+        else:
+            out.copy_(self.generate(step))
+
+    def generate(self, step: Step | None) -> torch.Tensor:
+        if self.on_device and len(self.shape) <= 8:
+            out = torch.empty(tuple(self.shape), dtype=self.dtype, device=self.seed.device)
+            self.generate_into(out, step)
+            return out
+        offset = self.static_offset if self.props.static and self.static_offset is not None else self.offset()
+        return self._randn() + offset
+
+
+@dataclass(frozen=True)
+class PyramidProps(OffsetProps):
+    dims: tuple[int] | tuple[int, int] | tuple[int, int, int] = (-1, -2)
+    strength: float = 0.3
+    depth: int = 99
+    "Maximum number of pyramid levels kept, counted from the coarsest"
+
+
+@dataclass
+class Pyramid(TensorNoiseCommon[PyramidProps]):
+    "Multi-resolution noise: progressively coarser normal fields upsampled and summed. reference: noise.py:125-207"
+
+    @classmethod
+    def from_inputs(
+        cls, shape: tuple[int, ...], seed: torch.Generator, props: PyramidProps = PyramidProps(), dtype: torch.dtype = torch.float32
+    ) -> Self:
+        return cls(shape, seed, dtype, props)
+
+    def __post_init__(self) -> None:
+        self._static_pyramid: torch.Tensor | None = None
+        self._static_plan: tuple[int, list[tuple[int, ...]]] | None = None
+        if self.props.static:
+            if self.on_device:
+                tick = self._tick()
+                self._static_plan = (tick, self._level_shapes(lambda level: _host_uniform(self._key(), tick, level)))
+            else:
+                self._static_pyramid = self.pyramid()
+
+    def _mask(self) -> list[bool]:
+        rank = len(self.shape)
+        axes = [rank + d if d < 0 else d for d in self.props.dims]
+        return [n in axes for n in range(rank)]
+
+    def _level_shapes(self, uniform: Any) -> list[tuple[int, ...]]:
+        "Shapes of the pyramid levels: every level shrinks the running shape by r**level, r ~ U[2, 4)."
+        mask = self._mask()
+        running = list(self.shape)
+        shapes: list[tuple[int, ...]] = []
+        for level in range(99):
+            ratio = uniform(level) * 2 + 2
+            running = [max(1, int(s / (ratio**level))) if m else s for m, s in zip(mask, running)]
+            shapes.append(tuple(running))
+            if any(s <= 1 for m, s in zip(mask, running) if m):
+                break
+        return shapes
+
+    def _kept(self, count: int) -> int:
+        "Index of the first level that is kept (``depth`` counts from the coarsest)."
+        top = count - 1
+        return min(top, max(0, top - self.props.depth))
+
+    # -- reference-exact path (CPU generator): same draws in the same order
+    def pyramid(self) -> torch.Tensor:
+        "Just the summed pyramid component."
+        if self.on_device:
+            raise RuntimeError("Pyramid.pyramid() is only materialised for CPU generators; use generate() on CUDA")
+        mask = self._mask()
+        target = tuple(s for m, s in zip(mask, self.shape) if m)
+        mode = ["linear", "bilinear", "bicubic"][len(target) - 1]
+        order = [n for n, m in enumerate(mask) if not m] + [n for n, m in enumerate(mask) if m]
+        inverse = [order.index(n) for n in range(len(order))]
+        lead = len(order) - len(target)
+        device = self.seed.device
+
+        levels: list[torch.Tensor] = []
+        running = list(self.shape)
+        for level in range(99):
+            ratio = torch.rand([1], dtype=self.dtype, device=device, generator=self.seed).item() * 2 + 2
+            running = [max(1, int(s / (ratio**level))) if m else s for m, s in zip(mask, running)]
+            field = torch.randn(running, dtype=self.dtype, device=device, generator=self.seed)
+            moved = field.permute(order)
+            lead_shape = moved.shape[:lead]
+            stacked = moved.reshape(-1, 1, *moved.shape[lead:])  # every leading slice is an independent image
+            grown = torch.nn.functional.interpolate(stacked, target, mode=mode)
+            levels.append(grown.reshape(*lead_shape, *target).permute(inverse).reshape(self.shape) * self.props.strength**level)
+            if any(s <= 1 for m, s in zip(mask, running) if m):
+                break
+        total = torch.zeros(self.shape, dtype=self.dtype, device=device)
+        return total + sum(levels[self._kept(len(levels)) :])
+
+    # -- device path
+    def _generate_device(self, out: torch.Tensor) -> None:
+        rank = len(self.shape)
+        if rank > 8:
+            raise ValueError("Pyramid on CUDA supports unit shapes of rank <= 8")
+        mask = self._mask()
+        if not 1 <= sum(mask) <= 2:
+            raise NotImplementedError("Pyramid resizes 1 or 2 axes (3 is broken in the reference too: bicubic on 5-D)")
+        base = self._tick()
+        if self._static_plan is not None:
+            level_tick, shapes = self._static_plan
+        else:
+            level_tick = base
+            shapes = self._level_shapes(lambda level: _host_uniform(self._key(), base, level))
+        if len(shapes) > 16:
+            shapes = shapes[:16]
+        first = self._kept(len(shapes))
+
+        desc = _SkrPyramid()
+        desc.ndim = rank
+        desc.n_levels = len(shapes)
+        desc.seed = self._key()
+        desc.base_stream = base
+        for n, d in enumerate(self.shape):
+            desc.shape[n] = d
+            desc.masked[n] = int(mask[n])
+        for level, shape in enumerate(shapes):
+            slot = desc.levels[level]
+            slot.stream = level_tick + 2 + level
+            extents = [s for m, s in zip(mask, shape) if m]
+            slot.extent[0] = extents[0]
+            slot.extent[1] = extents[1] if len(extents) > 1 else 1
+            slot.weight = self.props.strength**level if level >= first else 0.0
+        moments = torch.zeros(2, dtype=torch.float64, device=out.device)
+        with _DeviceGuard(out.device):
+            status = _lib().skr_noise_pyramid(out.data_ptr(), _code(out.dtype), ctypes.byref(desc), moments.data_ptr(), _stream())
+        _native().check(status, "skr_noise_pyramid")
+
+    def generate_into(self, out: torch.Tensor, step: Step | None) -> None:
+        if self.on_device and out.is_cuda and out.is_contiguous():
+            self._generate_device(out)
+        else:
+            out.copy_(self.generate(step))
+
+    def generate(self, step: Step | None) -> torch.Tensor:
+        if self.on_device:
+            out = torch.empty(tuple(self.shape), dtype=self.dtype, device=self.seed.device)
+            self._generate_device(out)
+            return out
+        component = self._static_pyramid if self.props.static and self._static_pyramid is not None else None
+        noise = self._randn() + (component if component is not None else self.pyramid())
+        return noise / noise.std()
+
+
+@dataclass(frozen=True)
+class BrownianProps(TensorNoiseProps):
+    max_steps: int = 10_000
+
+
+@dataclass
+class Brownian(TensorNoiseCommon[BrownianProps]):
+    "torchsde.BrownianInterval pass-through (third-party tree; not accelerated). reference: noise.py:210-252"
+
+    def __post_init__(self) -> None:
+        import torchsde
+
+        self._tree = torchsde.BrownianInterval(
+            t0=0,
+            t1=1,
+            size=self.shape,
+            entropy=self.seed.initial_seed(),
+            dtype=self.dtype,
+            device=self.seed.device,
+            halfway_tree=True,
+            tol=1 / (self.props.max_steps * 10),
+            pool_size=2**6,
+            cache_size=round(math.log2(self.props.max_steps * 10) * 1.3),
+        )
+
+    def generate(self, step: Step | None) -> torch.Tensor:
+        if not step:
+            return self._randn()
+        step = step.normal().clamp()
+        return self._tree(*step) / math.sqrt(step.distance())
+
+    @classmethod
+    def from_inputs(
+        cls, shape: tuple[int, ...], seed: torch.Generator, props: BrownianProps = BrownianProps(), dtype: torch.dtype = torch.float32
+    ) -> Self:
+        return cls(shape=shape, seed=seed, dtype=dtype, props=props)
+
+
+@dataclass(frozen=True)
+class ColoredProps(TensorNoiseProps):
+    energy: float | None = None
+    "Target standard deviation; None keeps the white noise's own"
+    color_start: float = 1 / 4
+    "Power-law exponent at the start of sampling (step None); > 0 is redder"
+    color_end: float = -2
+    "Exponent at the end of sampling"
+    color_curve: float = 2
+    "Curvature of the exponent ramp (like FlowShift)"
+
+
+@dataclass
+class Colored(TensorNoiseCommon[ColoredProps]):
+    "Power-law coloured noise whose exponent follows the step. reference: noise.py:274-436"
+
+    @staticmethod
+    def _radial_freq_grid(shape: torch.Size, device: torch.device) -> torch.Tensor:
+        "Normalised radial frequency of every rfftn bin (host/torch form, used for CPU tensors). reference: noise.py:285-335"
+        rank = len(shape)
+        axes = []
+        for i, dim in enumerate(shape):
+            if i == rank - 1:
+                axes.append(torch.arange(dim // 2 + 1, device=device) / dim)
+            else:
+                axes.append(torch.fft.fftfreq(dim, d=1.0, device=device).abs())
+        radius = torch.stack(torch.meshgrid(*axes, indexing="ij"), dim=-1).norm(p=2, dim=-1)
+        top = radius.max()
+        return radius / top if top > 0 else radius
+
+    @staticmethod
+    def colorize_noise(white: torch.Tensor, exponent: float = 0.0, energy: float | None = None) -> torch.Tensor:
+        """Shape ``white`` to a ``f^-exponent`` power spectrum and restore its deviation (or ``energy``).
+
+        reference: noise.py:338-405.  CUDA tensors: moments, spectral shaping and the final rescale are custom
+        kernels around cuFFT, with no host synchronisation; CPU tensors use torch ops.
+        """
+        if white.is_cuda:
+            return Colored._colorize_device(white, exponent, energy, None)
+        wstd = white.std()
+        if exponent == 0.0:
+            return white if energy is None or wstd < 1e-8 else white * (energy / wstd)
+        w = white.squeeze()
+        if w.dtype not in (torch.float32, torch.float64):
+            w = w.to(torch.float32)
+        spectrum = torch.fft.rfftn(w)
+        radius = Colored._radial_freq_grid(w.shape, w.device)
+        mean_extent = sum(w.shape) / len(w.shape) if w.shape else 1.0
+        floor = 0.5 / max(mean_extent, 4.0)
+        shaped = spectrum * (torch.clamp(radius, min=floor) ** (-exponent / 2.0))
+        colored = torch.fft.irfftn(shaped, s=w.shape)
+        cstd = colored.std()
+        if cstd > 1e-8:
+            colored *= wstd / cstd if energy is None else energy / cstd
+        return colored.view(white.shape).to(dtype=white.dtype)
+
+    @staticmethod
+    def _colorize_device(
+        white: torch.Tensor, exponent: float, energy: float | None, white_moments: torch.Tensor | None, out_dtype: torch.dtype | None = None
+    ) -> torch.Tensor:
+        lib = _lib()
+        native = _native()
+        n = white.numel()
+        out_dtype = out_dtype or white.dtype
+        with _DeviceGuard(white.device):
+            stream = _stream()
+            if white_moments is None:
+                white_moments = torch.zeros(2, dtype=torch.float64, device=white.device)
+                native.check(lib.skr_noise_moments(white.data_ptr(), _code(white.dtype), n, white_moments.data_ptr(), stream), "skr_noise_moments")
+            if exponent == 0.0:
+                if energy is None:
+                    return white if white.dtype == out_dtype else white.to(out_dtype)
+                out = torch.empty(white.shape, dtype=out_dtype, device=white.device)
+                native.check(
+                    lib.skr_noise_scale(white.data_ptr(), _code(white.dtype), out.data_ptr(), _code(out.dtype), n, float(energy), None, 0, white_moments.data_ptr(), n, 1e-8, stream),
+                    "skr_noise_scale",
+                )
+                return out
+            w = white.squeeze()
+            if w.dtype not in (torch.float32, torch.float64):
+                w = w.to(torch.float32)
+            spectrum = torch.fft.rfftn(w).contiguous()
+            dims = (ctypes.c_int64 * max(1, w.dim()))(*(w.shape if w.dim() else (1,)))
+            native.check(
+                lib.skr_colored_shape(spectrum.data_ptr(), _code(w.dtype), dims, max(1, w.dim()), float(exponent), stream),
+                "skr_colored_shape",
+            )
+            colored = torch.fft.irfftn(spectrum, s=w.shape).contiguous()
+            colored_moments = torch.zeros(2, dtype=torch.float64, device=white.device)
+            native.check(lib.skr_noise_moments(colored.data_ptr(), _code(colored.dtype), n, colored_moments.data_ptr(), stream), "skr_noise_moments")
+            out = torch.empty(white.shape, dtype=out_dtype, device=white.device)
+            native.check(
+                lib.skr_noise_scale(
+                    colored.data_ptr(),
+                    _code(colored.dtype),
+                    out.data_ptr(),
+                    _code(out.dtype),
+                    n,
+                    1.0 if energy is None else float(energy),
+                    white_moments.data_ptr() if energy is None else None,
+                    n,
+                    colored_moments.data_ptr(),
+                    n,
+                    1e-8,
+                    stream,
+                ),
+                "skr_noise_scale",
+            )
+        return out
+
+    def exponent(self, step: Step | None) -> float:
+        "Power-law exponent for this step. reference: noise.py:410-420"
+        if step is None:
+            return self.props.color_start
+        if self.props.color_curve == math.inf:
+            return self.props.color_end
+        t = step.normal().clamp().time_to
+        shift = rescale_positive(-self.props.color_curve)  # negative: steps ascend like alpha, not sigma
+        t = shift / (shift + (divf(1, t) - 1))
+        return (1 - t) * self.props.color_start + t * self.props.color_end
+
+    def generate(self, step: Step | None) -> torch.Tensor:
+        exponent = self.exponent(step)
+        if self.on_device:
+            work_dtype = self.dtype if self.dtype in (torch.float32, torch.float64) else torch.float32
+            white = torch.empty(tuple(self.shape), dtype=work_dtype, device=self.seed.device)
+            moments = torch.zeros(2, dtype=torch.float64, device=white.device)
+            self._fill(white, self._tick(), moments=moments)
+            return self._colorize_device(white, exponent, self.props.energy, moments, self.dtype)
+        return self.colorize_noise(self._randn(), exponent=exponent, energy=self.props.energy)
+
+    @classmethod
+    def from_inputs(
+        cls, shape: tuple[int, ...], seed: torch.Generator, props: ColoredProps = ColoredProps(), dtype: torch.dtype = torch.float32
+    ) -> Self:
+        return cls(shape=shape, seed=seed, dtype=dtype, props=props)
+
+
+@dataclass
+class BatchTensorNoise[T: TensorNoiseProps | None](SkrampleTensorNoise):
+    """One generator per batch item so every item keeps its own seed. reference: noise.py:438-466
+
+    Items write straight into their slice of one ``[batch, *unit]`` tensor (no ``torch.stack`` copy) when all
+    generators live on the same CUDA device."""
+
+    generators: list[TensorNoiseCommon[T]]
+
+    def generate(self, step: Step | None) -> torch.Tensor:
+        first = self.generators[0]
+        same_place = all(g.on_device and g.seed.device == first.seed.device and g.dtype == first.dtype and g.shape == first.shape for g in self.generators)
+        if same_place:
+            out = torch.empty((len(self.generators), *first.shape), dtype=first.dtype, device=first.seed.device)
+            for row, generator in zip(out, self.generators, strict=True):
+                generator.generate_into(row, step)
+            return out
+        return torch.stack([g.generate(step) for g in self.generators])
+
+    @classmethod
+    def from_batch_inputs[U: TensorNoiseProps | None](
+        cls,
+        subclass: type[TensorNoiseCommon[U]],
+        unit_shape: tuple[int, ...],
+        seeds: list[torch.Generator],
+        props: U | None = None,
+        dtype: torch.dtype = torch.float32,
+    ) -> "BatchTensorNoise[U]":
+        "Batched ``from_inputs``: the result of ``generate`` is ``[len(seeds), *unit_shape]``."
+        build = (lambda seed: subclass.from_inputs(unit_shape, seed, props, dtype)) if props is not None else (
+            lambda seed: subclass.from_inputs(unit_shape, seed, dtype=dtype)
+        )
+        return cls([build(seed) for seed in seeds])  # type: ignore[arg-type]

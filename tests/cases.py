@@ -110,3 +110,77 @@ def trajectory_inputs(case: dict) -> tuple[np.ndarray, list[np.ndarray], list[np
     outs = [draw(0.5) for _ in range(case["steps"])]
     noises = [draw() for _ in range(case["steps"])]
     return x0, outs, noises
+
+
+# ---------------------------------------------------------------------------------------------------------
+# functional (Runge-Kutta) cases: whole generate_model trajectories with a closed-form "network"
+
+
+def _functional_cases() -> list[dict]:
+    out: list[dict] = []
+    seed = 5000
+    table = [
+        ("RKUltra", {"order": 1}),
+        ("RKUltra", {"order": 2, "stochasticity": 1}),
+        ("RKUltra", {"order": 4}),
+        ("RKUltra", {"order": 4, "stochasticity": 0.5, "derivative_transform": "FlowModel"}),
+        ("RKUltra", {"order": 6, "derivative_transform": None}),
+        ("RKUltra", {"order": 15}),
+        ("RKUltra", {"order": 2, "providers": "heun"}),
+        ("DynasauRK", {"order": 2}),
+        ("DynasauRK", {"order": 3, "stochasticity": 1}),
+        ("DynasauRK", {"order": 4}),
+        ("RKMoire", {"order": 4}),
+        ("Adapter", {"sampler": ["DPM", {"order": 3, "stochasticity": 1}]}),
+    ]
+    for (sampler, kw), (schedule, model) in itertools.product(table, [("scaled", "NoiseModel"), ("flow", "FlowModel"), ("sinner_linear", "VelocityModel")]):
+        for dtype in ("f32", "f64"):
+            seed += 1
+            kw_id = ",".join(f"{k}={v}" for k, v in sorted(kw.items()))
+            out.append(
+                {
+                    "id": f"{sampler}({kw_id})|{schedule}|{model}|{dtype}",
+                    "sampler": sampler,
+                    "kw": kw,
+                    "schedule": schedule,
+                    "model": model,
+                    "dtype": dtype,
+                    "steps": 6,
+                    "seed": seed,
+                    "numel": N_GOLDEN,
+                }
+            )
+    return out
+
+
+FUNCTIONAL_CASES = _functional_cases()
+
+
+def make_functional(mod_functional: Any, mod_interface: Any, mod_structured: Any, mod_models: Any, mod_tableaux: Any, case: dict) -> Any:
+    kw = dict(case["kw"])
+    if "derivative_transform" in kw:
+        kw["derivative_transform"] = make_model(mod_models, kw["derivative_transform"])
+    if kw.get("providers") == "heun":
+        kw["providers"] = {2: mod_tableaux.RKE2.Heun}
+    if case["sampler"] == "Adapter":
+        name, sub = kw["sampler"]
+        return mod_interface.StructuredFunctionalAdapter(getattr(mod_structured, name)(**sub))
+    return getattr(mod_functional, case["sampler"])(**kw)
+
+
+def network(x: Any, t: float, s: float, a: float) -> Any:
+    "Stand-in denoiser: two individually rounded elementwise ops, identical on CPU and CUDA."
+    import math
+
+    return x * 0.3 + math.sin(t) * 0.1
+
+
+def functional_rng(case: dict) -> Any:
+    "Deterministic noise source: call k returns the k-th float32-exact normal draw."
+    rng = np.random.default_rng(case["seed"])
+    n = case["numel"]
+
+    def draw(_step: Any = None) -> np.ndarray:
+        return rng.standard_normal(n).astype(np.float32).astype(np.float64)
+
+    return draw

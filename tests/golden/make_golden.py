@@ -71,5 +71,73 @@ def build_structured() -> None:
     print("structured:", len(index), "cases,", (HERE / "structured.npz").stat().st_size // 1024, "KiB")
 
 
+def build_functional() -> None:
+    import skrample.sampling.functional as ref_functional
+    import skrample.sampling.interface as ref_interface
+    import skrample.sampling.tableaux as ref_tableaux
+
+    arrays: dict[str, np.ndarray] = {}
+    index: list[dict] = []
+    for case in cases.FUNCTIONAL_CASES:
+        sampler = cases.make_functional(ref_functional, ref_interface, ref_structured, ref_models, ref_tableaux, case)
+        schedule = cases.make_schedule(ref_scheduling, case["schedule"])
+        model = cases.make_model(ref_models, case["model"])
+        dtype = {"f32": torch.float32, "f64": torch.float64}[case["dtype"]]
+        draw = cases.functional_rng(case)
+        result = sampler.generate_model(
+            cases.network, model, schedule, lambda step: torch.from_numpy(draw(step)).to(dtype), case["steps"]
+        )
+        arrays[f"{case['id']}/final"] = result.numpy()
+        index.append(case)
+    np.savez_compressed(HERE / "functional.npz", **arrays)
+    (HERE / "functional.json").write_text(json.dumps(index, indent=1))
+    print("functional:", len(index), "cases,", (HERE / "functional.npz").stat().st_size // 1024, "KiB")
+
+
+NOISE_PYRAMID_CASES = [((4, 64, 64), (-1, -2), 99), ((3, 40, 56), (-1, -2), 1), ((5, 96), (-1,), 99)]
+NOISE_COLORED_CASES = [((4, 32, 32), 1.5, None), ((2, 1, 40, 31), -2.0, 3.0), ((4096,), 0.7, None)]
+
+
+def build_noise() -> None:
+    "Reference Pyramid / Colored outputs together with every random draw they consumed (recorded by patching torch)."
+    import skrample.pytorch.noise as ref_noise
+
+    arrays: dict[str, np.ndarray] = {}
+    for n, (shape, dims, depth) in enumerate(NOISE_PYRAMID_CASES):
+        drawn: list[tuple[str, np.ndarray]] = []
+        real_randn, real_rand = torch.randn, torch.rand
+
+        def randn(*a, **k):
+            out = real_randn(*a, **k)
+            drawn.append(("randn", out.numpy().copy()))
+            return out
+
+        def rand(*a, **k):
+            out = real_rand(*a, **k)
+            drawn.append(("rand", out.numpy().copy()))
+            return out
+
+        torch.randn, torch.rand = randn, rand
+        try:
+            gen = ref_noise.Pyramid.from_inputs(shape, torch.Generator().manual_seed(40 + n), ref_noise.PyramidProps(dims=dims, depth=depth))
+            out = gen.generate(None)
+        finally:
+            torch.randn, torch.rand = real_randn, real_rand
+        normals = [v for kind, v in drawn if kind == "randn"]
+        arrays[f"pyramid{n}/out"] = out.numpy()
+        arrays[f"pyramid{n}/base"] = normals[0]
+        arrays[f"pyramid{n}/ratios"] = np.asarray([float(v[0]) * 2 + 2 for kind, v in drawn if kind == "rand"])
+        for l, level in enumerate(normals[1:]):
+            arrays[f"pyramid{n}/level{l}"] = level
+    for n, (shape, exponent, energy) in enumerate(NOISE_COLORED_CASES):
+        white = torch.randn(shape, generator=torch.Generator().manual_seed(60 + n))
+        arrays[f"colored{n}/white"] = white.numpy()
+        arrays[f"colored{n}/out"] = ref_noise.Colored.colorize_noise(white, exponent, energy).numpy()
+    np.savez_compressed(HERE / "noise.npz", **arrays)
+    print("noise:", len(arrays), "arrays,", (HERE / "noise.npz").stat().st_size // 1024, "KiB")
+
+
 if __name__ == "__main__":
     build_structured()
+    build_functional()
+    build_noise()

@@ -1,0 +1,132 @@
+"""Functional (Runge-Kutta) samplers: host layer, oracle and CUDA kernels against the reference's golden tensors."""
+
+from __future__ import annotations
+
+import ctypes
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import oracle_run
+from oracle import skrample_oracle as O
+from skrample_b200 import scheduling
+from skrample_b200.sampling import functional, interface, models, structured, tableaux
+from skrample_b200.sampling import program as pg
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+FUNCTIONAL = np.load(GOLDEN / "functional.npz")
+INDEX = json.loads((GOLDEN / "functional.json").read_text())
+
+
+def run_product(case: dict, device: str = "cpu") -> torch.Tensor:
+    sampler = cases.make_functional(functional, interface, structured, models, tableaux, case)
+    schedule = cases.make_schedule(scheduling, case["schedule"])
+    model = cases.make_model(models, case["model"])
+    dtype = {"f32": torch.float32, "f64": torch.float64}[case["dtype"]]
+    draw = cases.functional_rng(case)
+    return sampler.generate_model(
+        cases.network, model, schedule, lambda step: torch.from_numpy(draw(step)).to(device=device, dtype=dtype), case["steps"]
+    )
+
+
+def test_fixture_table_is_current() -> None:
+    assert [c["id"] for c in INDEX] == [c["id"] for c in cases.FUNCTIONAL_CASES]
+
+
+@pytest.mark.parametrize("case", INDEX, ids=lambda c: c["id"])
+def test_cpu_tensors_match_reference(case: dict) -> None:
+    got = run_product(case).numpy()
+    want = FUNCTIONAL[f"{case['id']}/final"]
+    assert got.dtype == want.dtype
+    assert np.array_equal(got, want, equal_nan=True)
+
+
+def _oracle_supported(case: dict) -> bool:
+    return case["sampler"] in ("RKUltra", "DynasauRK") and case["kw"].get("order") in (1, 2, 3, 4) and not (
+        case["sampler"] == "RKUltra" and case["kw"].get("order") == 3
+    )
+
+
+def _oracle_tableau(case: dict, step: O.St) -> O.Tableau:
+    kw = case["kw"]
+    if case["sampler"] == "DynasauRK":
+        return O.dynasaurk_tableau(step, kw["order"])
+    if kw.get("providers") == "heun":
+        return O.HEUN
+    order = kw["order"]
+    if order == 1:
+        return O.Tableau(((0.0, ()),), ((1.0,),))
+    if order == 2:
+        return O.rk2_tableau(1 / 2)  # RK2.Mid, reference: functional.py:20
+    return O.ees27_tableau(1 / 14 * (5 - 3 * 2**0.5))  # RK2.EES7_MIN, reference: functional.py:22
+
+
+@pytest.mark.parametrize("case", [c for c in INDEX if _oracle_supported(c)], ids=lambda c: c["id"])
+def test_oracle_matches_reference_functional(case: dict) -> None:
+    "Pins oracle.step_tableau / tableaux generators against the reference (bit-exact fp32/fp64)."
+    np_dtype = {"f32": np.float32, "f64": np.float64}[case["dtype"]]
+    sch = oracle_run.schedule(case["schedule"])
+    model = oracle_run.MODELS[case["model"]]
+    kw = case["kw"]
+    deriv = O.DATA
+    if "derivative_transform" in kw:
+        deriv = None if kw["derivative_transform"] is None else O.Model(oracle_run.MODELS[kw["derivative_transform"]].kind)
+    draw = cases.functional_rng(case)
+    sample = draw(None).astype(np_dtype)
+    steps = case["steps"]
+    for n in range(steps):
+        step = O.St.from_int(n, steps)
+        noise = draw(step).astype(np_dtype)
+        sample = O.step_tableau(_oracle_tableau(case, step), sample, cases.network, model, sch, step, deriv, noise, kw.get("stochasticity", 0))[0]
+    want = FUNCTIONAL[f"{case['id']}/final"]
+    assert np.array_equal(np.asarray(sample), want, equal_nan=True)
+
+
+def test_rk_programs_are_block_shaped(monkeypatch: pytest.MonkeyPatch) -> None:
+    "Every launch of a 4-stage flow-matching RK step takes the structured kernel (host-side classification)."
+    from skrample_b200 import native
+
+    kinds: list[int] = []
+    real = pg.execute
+
+    def spy(program: pg.Program):
+        if all(isinstance(v, torch.Tensor) for v in program.inputs):
+            outs = [torch.empty_like(program.inputs[0]) for _ in program.outputs]
+            kinds.append(native.load().skr_program_classify(ctypes.byref(native.pack_program(program, list(program.inputs), outs))))
+        return real(program)
+
+    monkeypatch.setattr(pg, "execute", spy)
+    case = next(c for c in INDEX if c["sampler"] == "RKUltra" and c["kw"] == {"order": 4} and c["schedule"] == "flow" and c["dtype"] == "f32")
+    run_product(case)
+    assert kinds and all(k == 0 for k in kinds), kinds
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", INDEX, ids=lambda c: c["id"])
+def test_cuda_matches_reference_golden(case: dict) -> None:
+    from skrample_b200 import native
+
+    before = native.launch_count()
+    got = run_product(case, device="cuda").cpu().numpy()
+    assert native.launch_count() > before
+    want = FUNCTIONAL[f"{case['id']}/final"]
+    assert got.dtype == want.dtype
+    assert np.array_equal(got, want, equal_nan=True), f"max abs diff {np.nanmax(np.abs(got - want))}"
+
+
+@pytest.mark.gpu
+def test_rkultra4_launch_count() -> None:
+    "A 4-stage RK step is 4 fused launches (one per model-call boundary)."
+    from skrample_b200 import native
+    from skrample_b200.common import Step
+
+    x = torch.randn(4, 16, 32, 32, device="cuda")
+    sampler = functional.RKUltra(order=4)
+    assert len(sampler.tableau().stages) == 4
+    before = native.launch_count()
+    sampler.step(x, cases.network, models.FlowModel(), scheduling.FlowShift(scheduling.Linear()), Step.from_int(3, 10))
+    assert native.launch_count() - before == 4

@@ -1,0 +1,297 @@
+"""Noise generators: CPU-generator stream parity with the reference recipe, oracle pinning, CUDA kernels."""
+
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import skrample_oracle as O
+from skrample_b200.common import Step
+from skrample_b200.pytorch import noise
+
+# ------------------------------------------------------------------------------------------- CPU (no GPU needed)
+
+
+def test_random_cpu_generator_is_torch_randn() -> None:
+    "reference: noise.py:36-42,73-74 - a CPU generator keeps its own stream, so seeds reproduce the reference."
+    g = torch.Generator().manual_seed(3)
+    want = torch.randn((2, 8, 8), generator=torch.Generator().manual_seed(3))
+    assert torch.equal(noise.Random.from_inputs((2, 8, 8), g).generate(None), want)
+
+
+def test_offset_cpu_draw_order() -> None:
+    "reference: noise.py:104-113 - offset first (reduced shape), then the full draw."
+    g = torch.Generator().manual_seed(5)
+    ref = torch.Generator().manual_seed(5)
+    off = torch.randn((4, 1, 1), generator=ref) * 0.2**2
+    want = torch.randn((4, 8, 8), generator=ref) + off
+    assert torch.equal(noise.Offset.from_inputs((4, 8, 8), g).generate(None), want)
+
+
+def _record_pyramid(shape: tuple[int, ...], props: noise.PyramidProps, seed: int) -> tuple[torch.Tensor, np.ndarray, list[np.ndarray], list[float]]:
+    "Run the CPU-generator pyramid while recording every draw it makes (the reference's draw order)."
+    g = torch.Generator().manual_seed(seed)
+    replay = torch.Generator().manual_seed(seed)
+    out = noise.Pyramid.from_inputs(shape, g, props).generate(None)
+    base = torch.randn(shape, generator=replay)
+    mask = [n in [len(shape) + d if d < 0 else d for d in props.dims] for n in range(len(shape))]
+    running = list(shape)
+    levels, ratios = [], []
+    for level in range(99):
+        r = torch.rand([1], generator=replay).item() * 2 + 2
+        ratios.append(r)
+        running = [max(1, int(s / (r**level))) if m else s for m, s in zip(mask, running)]
+        levels.append(torch.randn(running, generator=replay).numpy())
+        if any(s <= 1 for m, s in zip(mask, running) if m):
+            break
+    return out, base.numpy(), levels, ratios
+
+
+GOLDEN_NOISE = np.load(__import__("pathlib").Path(__file__).resolve().parent / "golden" / "noise.npz")
+GOLDEN_PYRAMID = [((4, 64, 64), (-1, -2), 99), ((3, 40, 56), (-1, -2), 1), ((5, 96), (-1,), 99)]  # make_golden.NOISE_PYRAMID_CASES
+GOLDEN_COLORED = [((4, 32, 32), 1.5, None), ((2, 1, 40, 31), -2.0, 3.0), ((4096,), 0.7, None)]  # make_golden.NOISE_COLORED_CASES
+
+
+def _golden_pyramid(n: int) -> tuple[np.ndarray, np.ndarray, list[np.ndarray], list[float]]:
+    levels = []
+    while f"pyramid{n}/level{len(levels)}" in GOLDEN_NOISE:
+        levels.append(GOLDEN_NOISE[f"pyramid{n}/level{len(levels)}"])
+    return GOLDEN_NOISE[f"pyramid{n}/out"], GOLDEN_NOISE[f"pyramid{n}/base"], levels, GOLDEN_NOISE[f"pyramid{n}/ratios"].tolist()
+
+
+@pytest.mark.parametrize("n", range(len(GOLDEN_PYRAMID)))
+def test_oracle_pyramid_matches_reference_golden(n: int) -> None:
+    "Pins oracle.pyramid_compose / level shapes to the reference's own output for the draws it consumed."
+    shape, dims, depth = GOLDEN_PYRAMID[n]
+    out, base, levels, ratios = _golden_pyramid(n)
+    mask = [i in [len(shape) + d if d < 0 else d for d in dims] for i in range(len(shape))]
+    assert [lv.shape for lv in levels] == O.pyramid_level_shapes(shape, mask, ratios)
+    np.testing.assert_allclose(O.pyramid_compose(base, levels, mask, 0.3, depth), out, rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("n", range(len(GOLDEN_PYRAMID)))
+def test_pyramid_cpu_generator_matches_reference_golden(n: int) -> None:
+    "The product's CPU-generator path reproduces the reference bit for bit (same seed, same draw order)."
+    shape, dims, depth = GOLDEN_PYRAMID[n]
+    got = noise.Pyramid.from_inputs(shape, torch.Generator().manual_seed(40 + n), noise.PyramidProps(dims=dims, depth=depth)).generate(None)
+    assert np.array_equal(got.numpy(), GOLDEN_NOISE[f"pyramid{n}/out"])
+
+
+@pytest.mark.parametrize("n", range(len(GOLDEN_COLORED)))
+def test_colorize_matches_reference_golden(n: int) -> None:
+    shape, exponent, energy = GOLDEN_COLORED[n]
+    white = GOLDEN_NOISE[f"colored{n}/white"]
+    want = GOLDEN_NOISE[f"colored{n}/out"]
+    assert np.array_equal(noise.Colored.colorize_noise(torch.from_numpy(white), exponent, energy).numpy(), want)
+    np.testing.assert_allclose(O.colorize(white, exponent, energy), want, rtol=1e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize(("shape", "dims"), [((4, 64, 64), (-1, -2)), ((3, 40, 56), (-1, -2)), ((5, 96), (-1,)), ((48, 4, 48), (0, 2))])
+def test_oracle_pyramid_matches_reference_recipe(shape: tuple[int, ...], dims: tuple[int, ...]) -> None:
+    "Pins oracle.pyramid_compose (the checker of the CUDA kernel) to the torch recipe of noise.py:146-207."
+    props = noise.PyramidProps(dims=dims)
+    out, base, levels, ratios = _record_pyramid(shape, props, 11)
+    mask = [n in [len(shape) + d if d < 0 else d for d in dims] for n in range(len(shape))]
+    assert [lv.shape for lv in levels] == O.pyramid_level_shapes(shape, mask, ratios)
+    want = O.pyramid_compose(base, levels, mask, props.strength, props.depth)
+    np.testing.assert_allclose(out.numpy(), want, rtol=2e-5, atol=2e-6)
+    assert abs(float(out.std()) - 1) < 1e-5
+
+
+@pytest.mark.parametrize(("shape", "exponent", "energy"), [((4, 32, 32), 1.5, None), ((2, 1, 40, 31), -2.0, 3.0), ((4096,), 0.7, None)])
+def test_oracle_colorize_matches_torch_recipe(shape: tuple[int, ...], exponent: float, energy: float | None) -> None:
+    "Pins oracle.colorize to noise.py:338-405 (FFT libraries differ, hence a tolerance)."
+    white = torch.randn(shape, generator=torch.Generator().manual_seed(2))
+    got = noise.Colored.colorize_noise(white, exponent, energy).numpy()
+    want = O.colorize(white.numpy(), exponent, energy)
+    np.testing.assert_allclose(got, want, rtol=1e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize("n", [0, 3, 6, 9])
+def test_colored_exponent_schedule(n: int) -> None:
+    "reference: noise.py:410-420 (defaults give 0.17, -0.16, -0.73, -2.0 over 10 steps, SURVEY appendix A.12)"
+    gen = noise.Colored.from_inputs((8,), torch.Generator())
+    got = gen.exponent(Step.from_int(n, 10))
+    assert got == pytest.approx(O.colored_exponent(O.St.from_int(n, 10)), abs=0)
+    assert got == pytest.approx({0: 0.17, 3: -0.16, 6: -0.73, 9: -2.0}[n], abs=6e-3)
+
+
+def test_brownian_needs_torchsde() -> None:
+    try:
+        import torchsde  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            noise.Brownian.from_inputs((4,), torch.Generator())
+
+
+# ------------------------------------------------------------------------------------------- CUDA kernels
+
+gpu = pytest.mark.gpu
+
+
+def _gen(seed: int = 1234) -> torch.Generator:
+    return torch.Generator(device="cuda").manual_seed(seed)
+
+
+@gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16, torch.float64])
+def test_random_determinism_and_moments(dtype: torch.dtype) -> None:
+    from skrample_b200 import native
+
+    shape = (4, 16, 128, 128)
+    before = native.launch_count_kind(2)
+    a = noise.Random.from_inputs(shape, _gen(), dtype=dtype)
+    b = noise.Random.from_inputs(shape, _gen(), dtype=dtype)
+    a0, a1 = a.generate(None), a.generate(Step.from_int(0, 10))
+    b0, b1 = b.generate(None), b.generate(Step.from_int(0, 10))
+    assert native.launch_count_kind(2) - before == 4
+    assert a0.dtype == dtype and a0.is_cuda and a0.shape == shape
+    assert torch.equal(a0, b0) and torch.equal(a1, b1), "same seed must give identical bits"
+    assert not torch.equal(a0, a1), "successive draws must differ"
+    x = a0.double().flatten()
+    n = x.numel()
+    assert abs(x.mean().item()) < 5 / math.sqrt(n)
+    assert abs(x.var().item() - 1) < (2e-2 if dtype in (torch.bfloat16, torch.float16) else 6e-3)
+    assert abs((x**3).mean().item()) < 2e-2  # skewness
+    assert abs((x**4).mean().item() - 3) < 6e-2  # kurtosis
+    assert abs((x[:-1] * x[1:]).mean().item()) < 5 / math.sqrt(n)  # lag-1 autocorrelation
+    assert (x.abs() > 4).float().mean().item() < 2e-4  # tails present but sane
+    assert x.abs().max().item() > 4
+
+
+@gpu
+def test_random_values_do_not_depend_on_sharding() -> None:
+    "Per-item generators: generating items together or one by one gives the same bits (BatchTensorNoise)."
+    unit = (16, 64, 64)
+    seeds = [_gen(100 + i) for i in range(4)]
+    batch = noise.BatchTensorNoise.from_batch_inputs(noise.Random, unit, seeds).generate(None)
+    assert batch.shape == (4, *unit)
+    for i in range(4):
+        alone = noise.Random.from_inputs(unit, _gen(100 + i)).generate(None)
+        assert torch.equal(batch[i], alone)
+
+
+@gpu
+def test_ragged_and_unaligned_fill() -> None:
+    big = torch.empty(1031 + 3, device="cuda")
+    a = noise.Random.from_inputs((1031,), _gen(9))
+    b = noise.Random.from_inputs((1031,), _gen(9))
+    x = a.generate(None)
+    b.generate_into(big[3:], None)  # misaligned view falls back to a copy
+    assert torch.equal(x, big[3:])
+
+
+@gpu
+def test_offset_structure() -> None:
+    "out - plain draw is constant along the non-kept axes and ~N(0, strength^4) along the kept one."
+    shape = (64, 32, 32)
+    props = noise.OffsetProps(dims=(0,), strength=0.5)
+    off = noise.Offset.from_inputs(shape, _gen(7), props).generate(None)
+    plain = noise.Random.from_inputs(shape, _gen(7)).generate(None)  # same seed, same main stream
+    delta = off - plain
+    per_slice = delta.reshape(64, -1)
+    assert (per_slice.std(dim=1) < 1e-6).all(), "offset must be constant within a slice"
+    assert abs(per_slice[:, 0].std().item() - 0.25) < 0.08
+    static = noise.Offset.from_inputs(shape, _gen(7), noise.OffsetProps(static=True))
+    d0 = static.generate(None)
+    d1 = static.generate(None)
+    assert not torch.equal(d0, d1)
+
+
+def _pyramid_supplied(base: np.ndarray, levels: list[np.ndarray], mask: list[bool], strength: float, depth: int) -> torch.Tensor:
+    "Drive skr_noise_pyramid with supplied draws (test hook of the C ABI)."
+    from skrample_b200 import native
+
+    lib = noise._lib()
+    dev = [torch.from_numpy(np.ascontiguousarray(lv, dtype=np.float32)).cuda() for lv in levels]
+    base_dev = torch.from_numpy(np.ascontiguousarray(base, dtype=np.float32)).cuda()
+    desc = noise._SkrPyramid()
+    desc.ndim = base.ndim
+    desc.n_levels = len(levels)
+    desc.base_buffer = base_dev.data_ptr()
+    top = len(levels) - 1
+    skip = min(top, max(0, top - depth))
+    for n, d in enumerate(base.shape):
+        desc.shape[n] = d
+        desc.masked[n] = int(mask[n])
+    for l, lv in enumerate(levels):
+        ext = [s for m, s in zip(mask, lv.shape) if m]
+        desc.levels[l].buffer = dev[l].data_ptr()
+        desc.levels[l].extent[0] = ext[0]
+        desc.levels[l].extent[1] = ext[1] if len(ext) > 1 else 1
+        desc.levels[l].weight = strength**l if l >= skip else 0.0
+    out = torch.empty(base.shape, device="cuda")
+    moments = torch.zeros(2, dtype=torch.float64, device="cuda")
+    native.check(lib.skr_noise_pyramid(out.data_ptr(), 0, ctypes.byref(desc), moments.data_ptr(), torch.cuda.current_stream().cuda_stream), "pyramid")
+    return out
+
+
+@gpu
+@pytest.mark.parametrize(("shape", "dims", "depth"), [((4, 64, 64), (-1, -2), 99), ((3, 40, 56), (-1, -2), 1), ((5, 96), (-1,), 99), ((48, 4, 48), (0, 2), 99)])
+def test_pyramid_kernel_vs_oracle_on_supplied_draws(shape: tuple[int, ...], dims: tuple[int, ...], depth: int) -> None:
+    "Identical supplied draws -> the kernel's upsample / weights / std equal the oracle's (fp32 rounding only)."
+    props = noise.PyramidProps(dims=dims, depth=depth)
+    _out, base, levels, _ratios = _record_pyramid(shape, props, 21)
+    mask = [n in [len(shape) + d if d < 0 else d for d in dims] for n in range(len(shape))]
+    got = _pyramid_supplied(base, levels, mask, props.strength, depth).cpu().numpy()
+    want = O.pyramid_compose(base, levels, mask, props.strength, depth)
+    np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-6)
+
+
+@gpu
+@pytest.mark.parametrize("shape", [(4, 128, 128), (16, 21, 90, 160), (336, 90, 160)])
+def test_pyramid_philox_statistics(shape: tuple[int, ...]) -> None:
+    "In-kernel pyramid: unit std (1e-3), deterministic, low-frequency energy above white noise."
+    a = noise.Pyramid.from_inputs(shape, _gen(5)).generate(None)
+    b = noise.Pyramid.from_inputs(shape, _gen(5)).generate(None)
+    assert torch.equal(a, b)
+    assert abs(a.double().std().item() - 1) < 1e-3
+    assert abs(a.double().mean().item()) < 0.05
+    # coarse levels add spatially correlated energy: neighbouring pixels correlate positively
+    corr = (a[..., :-1] * a[..., 1:]).double().mean().item()
+    assert 0.01 < corr < 0.5
+
+
+@gpu
+@pytest.mark.parametrize(("shape", "exponent", "energy"), [((4, 32, 32), 1.5, None), ((2, 1, 40, 31), -2.0, 3.0), ((4096,), 0.7, None), ((16, 8, 30, 40), 0.25, None)])
+def test_colorize_kernel_vs_oracle(shape: tuple[int, ...], exponent: float, energy: float | None) -> None:
+    white = torch.randn(shape, generator=torch.Generator().manual_seed(2))
+    got = noise.Colored.colorize_noise(white.cuda(), exponent, energy).cpu().numpy()
+    want = O.colorize(white.numpy(), exponent, energy)
+    np.testing.assert_allclose(got, want, rtol=2e-3, atol=5e-4)
+
+
+def _spectral_slope(data: np.ndarray) -> float:
+    "Radially binned log-log PSD slope (same estimator idea as reference tests/self_noise.py:13-60)."
+    spec = np.abs(np.fft.fftshift(np.fft.fftn(data))) ** 2
+    freqs = [np.fft.fftshift(np.fft.fftfreq(s)) for s in data.shape]
+    radius = np.sqrt(sum(m**2 for m in np.meshgrid(*freqs, indexing="ij")))
+    keep = radius > 0
+    r, p = radius[keep], spec[keep]
+    bins = min(data.shape) // 2
+    edges = np.linspace(r.min(), r.max(), bins + 1)
+    which = np.digitize(r, edges) - 1
+    centers = 0.5 * (edges[:-1] + edges[1:])
+    power = np.array([p[which == i].mean() if (which == i).any() else 0 for i in range(bins)])
+    ok = (power > 0) & (centers > 0)
+    slope = np.polyfit(np.log(centers[ok]), np.log(power[ok]), 1)[0]
+    return float(-slope)
+
+
+@gpu
+@pytest.mark.parametrize("exponent", [-3, -1.5, 0, 1.5, 3])
+@pytest.mark.parametrize("shape", [(65536,), (512, 512), (64, 64, 64)])
+def test_colored_generator_color_and_energy(exponent: float, shape: tuple[int, ...]) -> None:
+    "Mirrors reference tests/self_noise.py:63-103 on the CUDA path: PSD slope within 0.1, std 1 (+-1e-2) or |energy|."
+    gen = noise.Colored(shape, _gen(3), torch.float32, noise.ColoredProps(color_curve=0, color_start=exponent, color_end=-exponent))
+    n0 = gen.generate(None)
+    assert abs(exponent - _spectral_slope(n0.cpu().numpy())) < 0.1
+    n1 = gen.generate(Step(0, 1))
+    assert abs(-exponent - _spectral_slope(n1.cpu().numpy())) < 0.1
+    assert abs(n0.std().item() - 1) < 1e-2
+    fixed = noise.Colored(shape, _gen(3), torch.float32, noise.ColoredProps(energy=-1.5, color_start=exponent))
+    assert abs(fixed.generate(None).std().item() - 1.5) < 1e-4

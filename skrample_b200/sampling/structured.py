@@ -21,9 +21,11 @@ converting on demand.  Inputs are aliased, not deep-copied.
 
 from __future__ import annotations
 
+import contextlib
 import math
+import threading
 from abc import ABC, abstractmethod
-from collections.abc import Sequence
+from collections.abc import Iterator, Sequence
 from dataclasses import dataclass, replace
 from typing import Any
 
@@ -92,21 +94,69 @@ class _View:
     noise: Any
 
 
+class _StepOptions(threading.local):
+    "Per-thread overrides the diffusers wrapper sets around ``sample_packed``."
+
+    final_dtype: Any = None  # dtype of `final` (default: dtype of the step's sample)
+
+
+_OPTIONS = _StepOptions()
+
+
+@contextlib.contextmanager
+def step_options(final_dtype: Any = None) -> Iterator[None]:
+    "Write `final` (and a copy of x-hat for predictor-corrector samplers) directly in ``final_dtype``."
+    saved = _OPTIONS.final_dtype
+    _OPTIONS.final_dtype = final_dtype
+    try:
+        yield
+    finally:
+        _OPTIONS.final_dtype = saved
+
+
+def low_precision_prediction(result: "SKSamples") -> Any:
+    "The x-hat copy in the wrapper's dtype that a fused UniPC/SPC step wrote next to its fp32 state (or None)."
+    return getattr(result, "_skr_pred_lowp", None)
+
+
 class _Ctx:
     "One program under construction plus the outputs the caller wants back."
 
-    __slots__ = ("depth", "out_dtype", "preserve_p", "prog", "xhat_key", "xhat_slot")
+    __slots__ = ("depth", "lowp_slot", "out_dtype", "preserve_p", "prog", "xhat_key", "xhat_slot")
 
     def __init__(self, like: Any = None) -> None:
         self.prog = Program()
         self.depth = 0
         self.out_dtype = getattr(like, "dtype", None) if pg.is_cuda_tensor(like) else None  # results follow the sample
+        if self.out_dtype is not None and _OPTIONS.final_dtype is not None:
+            self.out_dtype = _OPTIONS.final_dtype
         self.preserve_p = False  # a later block of the same program still needs P as it is
+        self.lowp_slot: int | None = None
         self.xhat_slot: int | None = None
         self.xhat_key: Any = None
 
 
 _XHAT_ATTR = "_skr_xhat"
+
+
+def _HALF_DTYPES() -> tuple[Any, ...]:
+    import torch
+
+    return (torch.bfloat16, torch.float16)
+
+
+def _finish_pc(ctx: "_Ctx", packed: SampleInput, outs: list[Any], sample_slot: int | None, xhat_slot: int | None, final_slot: int) -> "SKSamples":
+    "Assemble the SKSamples of a fused predictor-corrector step."
+    result = SKSamples(
+        packed.sample if sample_slot is None else outs[sample_slot],
+        packed.prediction if xhat_slot is None else outs[xhat_slot],
+        packed.step,
+        packed.noise,
+        outs[final_slot],
+    )
+    if ctx.lowp_slot is not None:
+        object.__setattr__(result, "_skr_pred_lowp", outs[ctx.lowp_slot])
+    return result
 
 
 def _remember_xhat(entry: SKSamples, key: Any, value: Any) -> None:
@@ -553,7 +603,12 @@ def _converted_current(
     prog.conv(live[0] if live else None, packed.prediction)
     for spec in live[1:]:
         prog.conv(spec)
-    return prog.store(P, COMPUTE) if live else None
+    if not live:
+        return None
+    slot = prog.store(P, COMPUTE)
+    if ctx.out_dtype is not None and ctx.out_dtype in _HALF_DTYPES():
+        ctx.lowp_slot = prog.store(P, ctx.out_dtype)  # what the pipeline gets back as pred_original_sample
+    return slot
 
 
 @dataclass(frozen=True)
@@ -608,13 +663,7 @@ class UniPC(UniP):
                 self.predictor._emit(ctx, view, inner_model, schedule, previous)
             final_slot = prog.store(R, ctx.out_dtype)
             outs = prog.run()
-            return SKSamples(
-                packed.sample if sample_slot is None else outs[sample_slot],
-                packed.prediction if xhat_slot is None else outs[xhat_slot],
-                packed.step,
-                packed.noise,
-                outs[final_slot],
-            )
+            return _finish_pc(ctx, packed, outs, sample_slot, xhat_slot, final_slot)
         except CannotFuse:
             pass
 
@@ -685,13 +734,7 @@ class SPC(traits.DerivativeTransform, StructuredSampler):
             self.predictor._emit(ctx, _View(IN_X, IN_P, packed.step, packed.noise), inner_model, schedule, previous)
             final_slot = prog.store(R, ctx.out_dtype)
             outs = prog.run()
-            return SKSamples(
-                packed.sample if sample_slot is None else outs[sample_slot],
-                packed.prediction if xhat_slot is None else outs[xhat_slot],
-                packed.step,
-                packed.noise,
-                outs[final_slot],
-            )
+            return _finish_pc(ctx, packed, outs, sample_slot, xhat_slot, final_slot)
         except CannotFuse:
             pass
 

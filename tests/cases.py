@@ -184,3 +184,104 @@ def functional_rng(case: dict) -> Any:
         return rng.standard_normal(n).astype(np.float32).astype(np.float64)
 
     return draw
+
+
+# ---------------------------------------------------------------------------------------------------------
+# diffusers-wrapper cases: a pipeline-style loop over wrapper.timesteps with a closed-form "network"
+
+FLOW_CONFIG = {
+    "base_image_seq_len": 256,
+    "base_shift": 0.5,
+    "flow_shift": 3.0,
+    "max_image_seq_len": 4096,
+    "max_shift": 1.15,
+    "num_train_timesteps": 1000,
+    "prediction_type": "flow_prediction",
+    "shift": 3.0,
+    "use_dynamic_shifting": True,
+}
+SCALED_CONFIG = {
+    "beta_end": 0.012,
+    "beta_schedule": "scaled_linear",
+    "beta_start": 0.00085,
+    "num_train_timesteps": 1000,
+    "prediction_type": "epsilon",
+    "steps_offset": 1,
+    "timestep_spacing": "trailing",
+    "use_karras_sigmas": False,
+}
+
+
+def _wrapper_cases() -> list[dict]:
+    table = [
+        ("struct", "scaled", {"_class_name": "UniPCMultistepScheduler", "solver_order": 3}, {}, "Random"),
+        ("struct", "scaled", {"_class_name": "DPMSolverSDEScheduler"}, {}, "Random"),
+        ("struct", "scaled", {"_class_name": "EulerAncestralDiscreteScheduler", "use_karras_sigmas": True}, {}, "Pyramid"),
+        ("struct", "flow", {"_class_name": "FlowMatchEulerDiscreteScheduler"}, {}, "Random"),
+        ("struct", "flow", {"_class_name": "IPNDMScheduler"}, {}, "Random"),
+        ("struct", "flow", {"_class_name": "MiniMaxH3Scheduler"}, {}, "Random"),
+        ("rku", "flow", {}, {"sampler_order": 4}, "Random"),
+        ("rku", "scaled", {}, {"sampler_order": 2, "stochasticity": 1}, "Random"),
+        ("dyna", "flow", {}, {"sampler_order": 3, "stochasticity": 0.5}, "Random"),
+    ]
+    out = []
+    for n, (kind, base, extra, kw, noise) in enumerate(table):
+        for dtype in ("f32", "bf16"):
+            out.append({"id": f"{kind}|{base}|{extra.get('_class_name', '')}|{kw}|{noise}|{dtype}", "kind": kind, "base": base, "extra": extra, "kw": kw, "noise": noise, "dtype": dtype, "steps": 8, "mu": 0.8 if base == "flow" else None, "seed": 7000 + n})
+    return out
+
+
+WRAPPER_CASES = _wrapper_cases()
+
+
+def run_wrapper(mod_diffusers: Any, mod_noise: Any, case: dict, device: str = "cpu") -> Any:
+    "A pipeline-style denoising loop; returns (final latents, last pred_original_sample)."
+    import torch
+
+    config = (FLOW_CONFIG if case["base"] == "flow" else SCALED_CONFIG) | case["extra"]
+    cls = {"struct": "SkrampleWrapperScheduler", "rku": "RKUltraWrapperScheduler", "dyna": "DynasauRKWrapperScheduler"}[case["kind"]]
+    wrapper = getattr(mod_diffusers, cls).from_diffusers_config(config, noise_type=getattr(mod_noise, case["noise"]), **case["kw"])
+    wrapper.set_timesteps(case["steps"], device=device, mu=case["mu"])
+    dtype = {"f32": torch.float32, "bf16": torch.bfloat16}[case["dtype"]]
+    x = torch.randn((2, 4, 24, 24), generator=torch.Generator().manual_seed(case["seed"])).to(device=device, dtype=dtype)
+    generators = [torch.Generator().manual_seed(case["seed"] + 1), torch.Generator().manual_seed(case["seed"] + 2)]
+    pred = x
+    for t in wrapper.timesteps:
+        out = (x * 0.31 + x.roll(1, -1) * (0.05 * float(t) / 1000)).to(dtype)  # individually rounded ops, same on CPU and CUDA
+        x, pred = wrapper.step(out, t, x, generator=generators, return_dict=False)
+    return x, pred
+
+
+# ---------------------------------------------------------------------------------------------------------
+# schedule stacks: (base, base kwargs, sub, sub kwargs, [modifiers...])
+
+SCHEDULE_CASES = [
+    ("Linear", {}, None, {}, []),
+    ("Linear", {"sigma_start": 14.6}, None, {}, []),
+    ("Linear", {"base_timesteps": -1}, None, {}, [("FlowShift", {"shift": 12})]),
+    ("Scaled", {}, None, {}, []),
+    ("Scaled", {"beta_scale": 1}, None, {}, []),
+    ("Scaled", {"base_timesteps": -1000}, None, {}, [("Hyper", {})]),
+    ("ZSNR", {}, None, {}, []),
+    ("Scaled", {}, "Karras", {}, []),
+    ("Scaled", {}, "Exponential", {"rho": 2.0}, []),
+    ("Scaled", {}, "Beta", {}, []),
+    ("Scaled", {}, "Probit", {}, [("Sinner", {})]),
+    ("Linear", {}, "Karras", {"steps": 30}, [("FlowShift", {})]),
+    ("Linear", {}, None, {}, [("FlowShift", {"shift": 0.7}), ("Hyper", {"scale": -1.5, "tail": False})]),
+    ("Linear", {}, None, {}, [("Sinner", {"count": 3, "scale": -2}), ("NoMod", {})]),
+    ("Linear", {}, "NoSub", {}, [("Hyper", {}), ("Hyper", {})]),
+]
+
+
+def make_schedule_stack(mod: Any, case: tuple) -> Any:
+    base, base_kw, sub, sub_kw, mods = case
+    built = getattr(mod, base)(**base_kw)
+    if sub:
+        built = getattr(mod, sub)(built, **sub_kw)
+    for name, kw in mods:
+        built = getattr(mod, name)(built, **kw)
+    return built
+
+
+SCHEDULE_TIMES = [0.0, 1.0, 0.5, 0.04, 0.96, 1 / 3, 0.123456789, 0.75, 2 / 7]

@@ -137,7 +137,39 @@ def build_noise() -> None:
     print("noise:", len(arrays), "arrays,", (HERE / "noise.npz").stat().st_size // 1024, "KiB")
 
 
+def build_wrappers() -> None:
+    import skrample.diffusers as ref_diffusers
+    import skrample.pytorch.noise as ref_noise
+
+    arrays: dict[str, np.ndarray] = {}
+    for case in cases.WRAPPER_CASES:
+        final, pred = cases.run_wrapper(ref_diffusers, ref_noise, case)
+        arrays[f"{case['id']}/final"] = final.float().numpy()
+        arrays[f"{case['id']}/pred"] = pred.float().numpy()
+    np.savez_compressed(HERE / "wrappers.npz", **arrays)
+    (HERE / "wrappers.json").write_text(json.dumps(cases.WRAPPER_CASES, indent=1))
+    print("wrappers:", len(cases.WRAPPER_CASES), "cases,", (HERE / "wrappers.npz").stat().st_size // 1024, "KiB")
+
+
+def build_schedules() -> None:
+    "Exact float64 points of schedule stacks (hex floats): sigma / alpha / timestep must be bit-identical."
+    table = {}
+    with np.errstate(all="ignore"):
+        for n, case in enumerate(cases.SCHEDULE_CASES):
+            sch = cases.make_schedule_stack(ref_scheduling, case)
+            table[str(n)] = {
+                "points": [[float(v).hex() for v in row] for row in sch.points_np(cases.SCHEDULE_TIMES).tolist()],
+                "ipoints": [[float(v).hex() for v in row] for row in sch.ipoints_np(cases.SCHEDULE_TIMES).tolist()],
+                "schedule7": [[float(v).hex() for v in row] for row in sch.schedule_np(7).tolist()],
+                "schedule25": [[float(v).hex() for v in row] for row in sch.schedule_np(25).tolist()],
+            }
+    (HERE / "schedules.json").write_text(json.dumps(table))
+    print("schedules:", len(table), "stacks")
+
+
 if __name__ == "__main__":
+    build_schedules()
     build_structured()
     build_functional()
     build_noise()
+    build_wrappers()

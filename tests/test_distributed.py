@@ -1,0 +1,67 @@
+"""Batch sharding across ranks: no collective on the step path, an all_gather only to validate (gloo, world size 2)."""
+
+from __future__ import annotations
+
+import os
+import socket
+import sys
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _trajectory(x: torch.Tensor, outs: list[torch.Tensor], noises: list[torch.Tensor]) -> torch.Tensor:
+    from skrample_b200 import scheduling
+    from skrample_b200.common import Step
+    from skrample_b200.sampling import models, structured
+
+    sampler = structured.UniPC(order=3, stochasticity=1)
+    schedule, model = scheduling.Scaled(), models.NoiseModel()
+    previous: list = []
+    for n, (out, noise) in enumerate(zip(outs, noises, strict=True)):
+        res = sampler.sample(x, out, Step.from_int(n, len(outs)), model, schedule, noise, previous)
+        previous = (previous + [res])[-sampler.require_previous :]
+        x = res.final
+    return x
+
+
+def _inputs() -> tuple[torch.Tensor, list[torch.Tensor], list[torch.Tensor]]:
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((4, 4, 16, 16), generator=g)
+    outs = [torch.randn((4, 4, 16, 16), generator=g) * 0.5 for _ in range(6)]
+    noises = [torch.randn((4, 4, 16, 16), generator=g) for _ in range(6)]
+    return x, outs, noises
+
+
+def _worker(rank: int, world: int, port: int, result_path: str) -> None:
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    x, outs, noises = _inputs()
+    per = x.shape[0] // world
+    mine = slice(rank * per, (rank + 1) * per)
+    local = _trajectory(x[mine], [o[mine] for o in outs], [z[mine] for z in noises])  # the step path: no communication
+    gathered = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)  # validation only
+    if rank == 0:
+        torch.save(torch.cat(gathered), result_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_batch_shards_reproduce_the_unsharded_run(tmp_path: Path) -> None:
+    path = str(tmp_path / "gathered.pt")
+    mp.spawn(_worker, args=(2, _free_port(), path), nprocs=2, join=True)
+    sharded = torch.load(path)
+    x, outs, noises = _inputs()
+    assert torch.equal(sharded, _trajectory(x, outs, noises))

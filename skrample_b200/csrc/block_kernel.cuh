@@ -56,7 +56,7 @@ template <typename CT>
 struct BHead {
     int32_t x_in, y_in, store_p, n_conv, neg;
     int32_t conv_flags[2];
-    int32_t pad;
+    int32_t store_p2;  // optional second copy of P (e.g. fp32 solver state + 16-bit copy for the caller)
     CT conv_c[2][3];
 };
 
@@ -232,6 +232,7 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
         }
     }
     if (h.store_p >= 0) io.store(h.store_p, P);
+    if (h.store_p2 >= 0) io.store(h.store_p2, P);
 
     // ---- blocks -------------------------------------------------------------------------------
 #pragma unroll
@@ -598,7 +599,7 @@ static bool parse_block_program(const skr_program* p, BProgram<CT>& out) {
     OpCursor cur{p, 0};
     BHead<CT>& h = out.head;
     memset(&h, 0, sizeof(h));
-    h.x_in = h.y_in = h.store_p = -1;
+    h.x_in = h.y_in = h.store_p = h.store_p2 = -1;
 
     if (cur.is_load(SKR_X)) {
         const skr_op* o = cur.take();
@@ -626,6 +627,7 @@ static bool parse_block_program(const skr_program* p, BProgram<CT>& out) {
     for (int c = 0; c < h.n_conv; ++c)
         if ((h.conv_flags[c] & SKR_CONV_USE_X) && h.x_in < 0) return false;
     if (cur.is_store(SKR_P)) h.store_p = cur.take()->dst;
+    if (cur.is_store(SKR_P)) h.store_p2 = cur.take()->dst;
 
     if (!parse_block<CT>(cur, out.blk[0])) return false;
     if (!parse_block<CT>(cur, out.blk[1])) return false;

@@ -41,6 +41,8 @@ extern "C" {
 #define SKR_MAX_INPUTS 32
 #define SKR_MAX_OUTPUTS 8
 #define SKR_MAX_DIMS 8
+#define SKR_MAX_PHILOX 2
+#define SKR_MAX_PHILOX_ITEMS 32
 #define SKR_MAX_LEVELS 16
 
 /* element types */
@@ -82,7 +84,8 @@ enum {
     SKR_OP_DPM3A = 12, /* T = in; U = c0*(B - in)                    structured.py:243          */
     SKR_OP_DPM3B = 13, /* d11 = c0*(T - in); d = U - d11; T = U + c1*d; U = c2*d   :254-256     */
     SKR_OP_DPM3C = 14, /* A = (B + c0*T) + c1*U                      structured.py:268          */
-    SKR_OP_FWD = 15,   /* R = ((0 + X*c0) + reg[a]*c1) [+ in*c2 if b&1]    models.py:53-67      */
+    SKR_OP_FWD = 15,   /* R = ((0 + X*c0) + reg[a]*c1) [+ n*c2]; n = in (b&1) or a normal drawn in the
+                          kernel from philox[src] (b&2)                     models.py:53-67      */
     SKR_OP_BACK = 16,  /* P = ((R - X*c0) [- in*c2 if b&1]) / c1           models.py:69-83      */
     SKR_OP_BLEND = 17, /* a==0: X = S*c0 + R*c1; a==1: signed-power blend, c2 = pw, c3 = 1/pw
                                                                       structured.py:568-575     */
@@ -108,14 +111,28 @@ typedef struct skr_tensor {
     int32_t reserved;
 } skr_tensor;
 
+/*
+ * A noise tensor that is never materialised: element e of batch item i is the standard normal of Philox
+ * stream (seed[i], stream[i]) at counter e / 4 - bit-identical to what skr_noise_fill writes for that item
+ * (noise.py:36-42 + BatchTensorNoise noise.py:438-466: one generator per batch item).
+ */
+typedef struct skr_philox {
+    uint64_t seed[SKR_MAX_PHILOX_ITEMS];
+    uint64_t stream[SKR_MAX_PHILOX_ITEMS];
+    int64_t item_numel; /* elements per batch item; numel == n_items * item_numel */
+    int32_t n_items;    /* 1..SKR_MAX_PHILOX_ITEMS */
+    int32_t reserved;
+} skr_philox;
+
 typedef struct skr_program {
     int32_t n_ops;
     int32_t n_inputs;
     int32_t n_outputs;
-    int32_t reserved;
+    int32_t n_philox;
     skr_op ops[SKR_MAX_OPS];
     skr_tensor inputs[SKR_MAX_INPUTS];
     skr_tensor outputs[SKR_MAX_OUTPUTS];
+    skr_philox philox[SKR_MAX_PHILOX];
 } skr_program;
 
 /* Library identification / diagnostics. */

@@ -73,6 +73,7 @@ struct BProgram {
     int32_t out_dtype[SKR_MAX_OUTPUTS];
     BHead<CT> head;
     BBlock<CT> blk[2];
+    KPhilox philox[SKR_MAX_PHILOX];
 };
 
 // ---- staged operand fetch, V elements per thread ---------------------------------------------------
@@ -338,7 +339,8 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
             for (int j = 0; j < V; ++j) R[j] = Ar::add(Ar::add((CT)0, Ar::mul(X[j], gamma)), Ar::mul(A[j], delta));
         }
         if (k.has_noise) {
-            io.load(k.noise_in, in);
+            if (k.has_noise == 2) draw_normals<CT, V>(prog.philox[k.noise_in], first, prog.numel, in);
+            else io.load(k.noise_in, in);
             const CT zeta = k.zeta;
 #pragma unroll
             for (int j = 0; j < V; ++j) R[j] = Ar::add(R[j], Ar::mul(in[j], zeta));
@@ -566,6 +568,7 @@ static bool parse_block(OpCursor& cur, BBlock<CT>& k) {
         k.gamma = (CT)t->c[0];
         k.delta = (CT)t->c[1];
         if (t->b & 1) { k.has_noise = 1; k.noise_in = t->src; k.zeta = (CT)t->c[2]; }
+        else if (t->b & 2) { k.has_noise = 2; k.noise_in = t->src; k.zeta = (CT)t->c[2]; }
     }
     if (cur.is_store(SKR_R)) k.store_r = cur.take()->dst;
 

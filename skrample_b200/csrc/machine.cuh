@@ -5,6 +5,7 @@
 #include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace skr {
 
@@ -153,6 +154,57 @@ __device__ __forceinline__ void store_vec(void* ptr, int dtype, int64_t first, i
                 }
             }
         }
+    }
+}
+
+
+// Device copy of skr_philox (kernel-parameter constant bank).
+struct KPhilox {
+    uint64_t seed[SKR_MAX_PHILOX_ITEMS];
+    uint64_t stream[SKR_MAX_PHILOX_ITEMS];
+    int64_t item_numel;
+    int32_t n_items;
+    int32_t aligned;  // item_numel % 4 == 0: four consecutive elements share one Philox block
+};
+
+// V consecutive elements starting at global element `first` (a multiple of 4) of the virtual noise tensor.
+template <typename CT, int V>
+__device__ __forceinline__ void draw_normals(const KPhilox& d, int64_t first, int64_t numel, CT (&v)[V]) {
+    if (d.aligned) {
+#pragma unroll
+        for (int g = 0; g < V / 4; ++g) {
+            const int64_t e = first + 4 * g;
+            float z[4] = {0.f, 0.f, 0.f, 0.f};
+            if (e < numel) {
+                const int64_t item = e / d.item_numel;
+                const int64_t local = e - item * d.item_numel;
+                const Philox ph(d.seed[item]);
+                normal4(ph((uint64_t)local >> 2, d.stream[item]), z);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[4 * g + j] = (CT)z[j];
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const int64_t e = first + j;
+            float z = 0.f;
+            if (e < numel) {
+                const int64_t item = e / d.item_numel;
+                const int64_t local = e - item * d.item_numel;
+                z = normal_at(Philox(d.seed[item]), (uint64_t)local, d.stream[item]);
+            }
+            v[j] = (CT)z;
+        }
+    }
+}
+
+static inline void fill_kphilox(KPhilox* out, const skr_philox* in, int count) {
+    for (int i = 0; i < count; ++i) {
+        for (int j = 0; j < SKR_MAX_PHILOX_ITEMS; ++j) { out[i].seed[j] = in[i].seed[j]; out[i].stream[j] = in[i].stream[j]; }
+        out[i].item_numel = in[i].item_numel;
+        out[i].n_items = in[i].n_items;
+        out[i].aligned = (in[i].item_numel % 4) == 0;
     }
 }
 

@@ -51,6 +51,7 @@ struct KProgram {
     uint32_t in_off[SKR_MAX_INPUTS];  // byte offset of input i inside a stage
     uint8_t in_dtype[SKR_MAX_INPUTS];
     uint8_t out_dtype[SKR_MAX_OUTPUTS];
+    KPhilox philox[SKR_MAX_PHILOX];
 };
 
 // ------------------------------------------------------------------------------------------
@@ -90,7 +91,9 @@ __device__ __forceinline__ void run_tile(const KProgram<CT>& prog, int64_t tile,
         const CT c0 = op.c[0], c1 = op.c[1], c2 = op.c[2], c3 = op.c[3];
 
         CT in[kVec];
-        if (src >= 0) {
+        if (code == SKR_OP_FWD && (b & 2)) {
+            draw_normals<CT, kVec>(prog.philox[src], first, numel, in);
+        } else if (src >= 0) {
             if constexpr (DIRECT) fetch_direct<CT>(prog.in_ptr[src], prog.in_dtype[src], first, numel, in);
             else fetch_staged<CT>(stage, prog.in_off[src], prog.in_dtype[src], tid, in);
         } else {
@@ -198,7 +201,7 @@ __device__ __forceinline__ void run_tile(const KProgram<CT>& prog, int64_t tile,
                 for (int j = 0; j < kVec; ++j) {
                     CT v = Ar::add((CT)0, Ar::mul(rX[j], c0));
                     v = Ar::add(v, Ar::mul(p[j], c1));
-                    if (b & 1) v = Ar::add(v, Ar::mul(in[j], c2));
+                    if (b & 3) v = Ar::add(v, Ar::mul(in[j], c2));
                     rR[j] = v;
                 }
             } break;
@@ -366,6 +369,7 @@ static int launch_typed(const skr_program* p, int64_t numel, cudaStream_t stream
         k.out_dtype[i] = (uint8_t)p->outputs[i].dtype;
     }
     k.stage_bytes = off;
+    fill_kphilox(k.philox, p->philox, p->n_philox);
 
     int err = 0;
     DeviceInfo* dev = device_info(&err);
@@ -472,6 +476,7 @@ static int launch_block_inst(const skr_program* p, BProgram<CT>& k, int64_t nume
         k.out_dtype[i] = p->outputs[i].dtype;
     }
     k.stage_bytes = off;
+    fill_kphilox(k.philox, p->philox, p->n_philox);
 
     int err = 0;
     DeviceInfo* dev = device_info(&err);
@@ -555,7 +560,7 @@ int skr_program_classify(const skr_program* p) {
     using namespace skr;
     if (!p) return fail(SKR_E_NULL, "null program");
     if (p->n_ops < 0 || p->n_ops > SKR_MAX_OPS) return fail(SKR_E_RANGE, "n_ops %d out of range", p->n_ops);
-    BProgram<double> b;
+    static BProgram<double> b;
     memset(&b, 0, sizeof(b));
     return parse_block_program<double>(p, b) ? 0 : 1;
 }
@@ -567,6 +572,12 @@ int skr_program_launch(const skr_program* p, int64_t numel, void* stream) {
     if (p->n_ops < 0 || p->n_ops > SKR_MAX_OPS) return fail(SKR_E_RANGE, "n_ops %d out of range", p->n_ops);
     if (p->n_inputs < 0 || p->n_inputs > SKR_MAX_INPUTS) return fail(SKR_E_RANGE, "n_inputs %d out of range", p->n_inputs);
     if (p->n_outputs < 0 || p->n_outputs > SKR_MAX_OUTPUTS) return fail(SKR_E_RANGE, "n_outputs %d out of range", p->n_outputs);
+    if (p->n_philox < 0 || p->n_philox > SKR_MAX_PHILOX) return fail(SKR_E_RANGE, "n_philox %d out of range", p->n_philox);
+    for (int i = 0; i < p->n_philox; ++i) {
+        const skr_philox& d = p->philox[i];
+        if (d.n_items < 1 || d.n_items > SKR_MAX_PHILOX_ITEMS) return fail(SKR_E_RANGE, "philox %d: n_items %d out of range", i, d.n_items);
+        if (d.item_numel < 1 || d.item_numel * d.n_items != numel) return fail(SKR_E_SHAPE, "philox %d: n_items * item_numel != numel", i);
+    }
     bool any64 = false, aligned = true;
     for (int i = 0; i < p->n_inputs; ++i) {
         const skr_tensor& t = p->inputs[i];
@@ -585,7 +596,10 @@ int skr_program_launch(const skr_program* p, int64_t numel, void* stream) {
     for (int i = 0; i < p->n_ops; ++i) {
         const skr_op& o = p->ops[i];
         if (o.code >= SKR_OP__COUNT) return fail(SKR_E_OPCODE, "op %d: unknown code %d", i, (int)o.code);
-        if (o.src >= p->n_inputs) return fail(SKR_E_RANGE, "op %d: input index %d out of range", i, (int)o.src);
+        const bool draws = o.code == SKR_OP_FWD && (o.b & 2);
+        if (draws && (o.b & 1)) return fail(SKR_E_RANGE, "op %d: noise is either a tensor or a Philox draw", i);
+        if (draws ? (o.src < 0 || o.src >= p->n_philox) : o.src >= p->n_inputs)
+            return fail(SKR_E_RANGE, "op %d: input index %d out of range", i, (int)o.src);
         if (o.dst >= p->n_outputs) return fail(SKR_E_RANGE, "op %d: output index %d out of range", i, (int)o.dst);
         if (o.code == SKR_OP_STORE && o.dst < 0) return fail(SKR_E_RANGE, "op %d: STORE without an output", i);
         const bool reads = o.code == SKR_OP_LOAD || o.code == SKR_OP_UNI || o.code == SKR_OP_DPM2 || o.code == SKR_OP_DPM3A ||

@@ -282,6 +282,9 @@ def _cast_inputs(compute_scale: torch.dtype | None, *tensors: Tensor) -> tuple[T
 class SkrampleWrapperCore(abc.ABC):
     "Common scheduler facade. reference: diffusers.py:233-387"
 
+    fused_noise = True
+    "Let the step kernel draw plain Random noise itself when the generators live on the sample's CUDA device"
+
     def __post_init__(self) -> None:
         self._steps: int = 50
         self._index: int = 0
@@ -379,7 +382,14 @@ class SkrampleWrapperCore(abc.ABC):
                 props=noise_props,
                 dtype=torch.float32 if any(s.device.type == "cpu" for s in seeds) else sample.dtype,
             )
-        noise = self._noise_generator.generate(step)
+        if sample.is_cuda and self.fused_noise:
+            noise = self._noise_generator.lazy(step)
+            if pg.is_lazy_noise(noise):
+                if noise.device == sample.device:
+                    return noise  # drawn inside the step kernel, never written to memory
+                noise = noise.materialize()
+        else:
+            noise = self._noise_generator.generate(step)
         if noise.device != sample.device:
             noise = noise.to(device=sample.device, non_blocking=True)
         want = dtype or sample.dtype

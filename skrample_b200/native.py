@@ -49,16 +49,44 @@ class SkrTensor(ctypes.Structure):
     _fields_ = [("ptr", ctypes.c_void_p), ("dtype", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
+MAX_PHILOX = 2
+MAX_PHILOX_ITEMS = 32
+
+
+class SkrPhilox(ctypes.Structure):
+    _fields_ = [
+        ("seed", ctypes.c_uint64 * MAX_PHILOX_ITEMS),
+        ("stream", ctypes.c_uint64 * MAX_PHILOX_ITEMS),
+        ("item_numel", ctypes.c_int64),
+        ("n_items", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
 class SkrProgram(ctypes.Structure):
     _fields_ = [
         ("n_ops", ctypes.c_int32),
         ("n_inputs", ctypes.c_int32),
         ("n_outputs", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("n_philox", ctypes.c_int32),
         ("ops", SkrOp * MAX_OPS),
         ("inputs", SkrTensor * MAX_INPUTS),
         ("outputs", SkrTensor * MAX_OUTPUTS),
+        ("philox", SkrPhilox * MAX_PHILOX),
     ]
+
+
+def _pack_draws(packed: SkrProgram, draws: list[Any]) -> None:
+    "Copy lazy Philox noise descriptors (skrample_b200.pytorch.noise.PhiloxDraw) into the program."
+    if len(draws) > MAX_PHILOX:
+        raise RuntimeError("skrample_b200: at most two in-kernel noise draws per step program")
+    packed.n_philox = len(draws)
+    for slot, draw in zip(packed.philox, draws, strict=False):
+        slot.n_items = len(draw.seeds)
+        slot.item_numel = draw.item_numel
+        for j, (seed, stream) in enumerate(zip(draw.seeds, draw.streams, strict=True)):
+            slot.seed[j] = seed
+            slot.stream[j] = stream
 
 
 EXPORTS = (
@@ -165,6 +193,7 @@ def pack_program(program: "Program", inputs: list[torch.Tensor], outputs: list[t
     for slot, tensor in zip(packed.outputs, outputs, strict=False):
         slot.ptr = tensor.data_ptr()
         slot.dtype = DTYPE_CODE[tensor.dtype]
+    _pack_draws(packed, getattr(program, "philox", []))
     return packed
 
 
@@ -189,6 +218,83 @@ def launch_program(program: "Program") -> list[Any]:
         ACCOUNT["bytes"] += sum(t.numel() * t.element_size() for t in inputs) + sum(t.numel() * t.element_size() for t in outputs)
     packed = pack_program(program, inputs, outputs)
     device = first.device
+    if torch.cuda.current_device() != device.index:
+        with torch.cuda.device(device):
+            status = lib.skr_program_launch(ctypes.byref(packed), first.numel(), torch.cuda.current_stream().cuda_stream)
+    else:
+        status = lib.skr_program_launch(ctypes.byref(packed), first.numel(), torch.cuda.current_stream().cuda_stream)
+    check(status, "skr_program_launch")
+    return outputs
+
+
+class CompiledProgram:
+    "A packed program whose op table is final; only tensor pointers / dtypes change between launches."
+
+    __slots__ = ("n_inputs", "out_specs", "packed")
+
+    def __init__(self, program: "Program") -> None:
+        if len(program.ops) > MAX_OPS or len(program.inputs) > MAX_INPUTS or len(program.outputs) > MAX_OUTPUTS:
+            raise RuntimeError("skrample_b200: step program too large")
+        packed = SkrProgram()
+        packed.n_ops = len(program.ops)
+        packed.n_inputs = len(program.inputs)
+        packed.n_outputs = len(program.outputs)
+        for slot, op in zip(packed.ops, program.ops, strict=False):
+            slot.code, slot.a, slot.b, slot.src, slot.dst = op.code, op.a, op.b, op.src, op.dst
+            for j, value in enumerate(op.c):
+                slot.c[j] = value
+        self.packed = packed
+        self.n_inputs = len(program.inputs)
+        self.out_specs = tuple(program.outputs)
+
+
+_ALLOWED = frozenset(DTYPE_CODE)
+
+
+def _on_device(t: Any) -> bool:
+    return t.is_cuda
+
+
+def launch_compiled(compiled: CompiledProgram, inputs: list[Any], draws: list[Any] | None = None) -> list[Any] | None:
+    "Bind tensors (and lazy noise draws) to a compiled program and launch it.  None when they do not qualify."
+    first = inputs[0]
+    shape, device = first.shape, first.device
+    any64 = False
+    all_half = True
+    kinds = set()
+    for t in inputs:
+        if not (_on_device(t) and t.shape == shape and t.device == device and t.dtype in _ALLOWED and t.is_contiguous()):
+            return None
+        kinds.add(t.dtype)
+        any64 |= t.dtype == torch.float64
+    if any64:
+        default = torch.float64
+    elif torch.float32 in kinds or len(kinds) > 1:
+        default = torch.float32
+    else:
+        default = first.dtype
+    compute = torch.float64 if any64 else torch.float32
+    del all_half
+    packed = compiled.packed
+    for slot, t in zip(packed.inputs, inputs, strict=False):
+        slot.ptr = t.data_ptr()
+        slot.dtype = DTYPE_CODE[t.dtype]
+    outputs = []
+    for slot, want in zip(packed.outputs, compiled.out_specs, strict=False):
+        dtype = default if want is None else (compute if isinstance(want, str) else want)
+        out = torch.empty(shape, dtype=dtype, device=device)
+        slot.ptr = out.data_ptr()
+        slot.dtype = DTYPE_CODE[dtype]
+        outputs.append(out)
+    if draws:
+        numel = first.numel()
+        if any(d.numel != numel or d.device != device for d in draws):
+            return None
+        _pack_draws(packed, draws)
+    if ACCOUNT["on"]:
+        ACCOUNT["launches"] += 1
+        ACCOUNT["bytes"] += sum(t.numel() * t.element_size() for t in inputs) + sum(t.numel() * t.element_size() for t in outputs)
+    lib = _lib if _lib is not None else load()
     if torch.cuda.current_device() != device.index:
         with torch.cuda.device(device):
             status = lib.skr_program_launch(ctypes.byref(packed), first.numel(), torch.cuda.current_stream().cuda_stream)

@@ -146,6 +146,51 @@ def _host_uniform(seed: int, stream: int, index: int) -> float:
     return (z >> 11) / float(1 << 53)
 
 
+class PhiloxDraw:
+    """A normal noise tensor that exists only as Philox keys: the fused step kernel draws it while it runs.
+
+    Passing this as ``noise`` to a sampler removes the noise tensor's write (generation) and every read of it
+    (the step itself and, for UniPC, the corrector of the next step, which re-draws it).  ``materialize()``
+    produces the bit-identical tensor through ``skr_noise_fill``.  One (seed, stream) pair per batch item.
+    """
+
+    is_lazy_noise = True
+    __slots__ = ("device", "dtype", "seeds", "shape", "streams", "_tensor")
+
+    def __init__(self, shape: tuple[int, ...], seeds: tuple[int, ...], streams: tuple[int, ...], dtype: torch.dtype, device: torch.device) -> None:
+        self.shape = tuple(shape)
+        self.seeds = seeds
+        self.streams = streams
+        self.dtype = dtype
+        self.device = device
+        self._tensor: torch.Tensor | None = None
+
+    @property
+    def numel(self) -> int:
+        return math.prod(self.shape)
+
+    @property
+    def item_numel(self) -> int:
+        return self.numel // len(self.seeds)
+
+    def materialize(self) -> torch.Tensor:
+        if self._tensor is None:
+            out = torch.empty(self.shape, dtype=self.dtype, device=self.device)
+            rows = out.reshape(len(self.seeds), -1)
+            with _DeviceGuard(self.device):
+                for row, seed, stream in zip(rows, self.seeds, self.streams, strict=True):
+                    status = _lib().skr_noise_fill(row.data_ptr(), _code(out.dtype), row.numel(), seed, stream, None, None, _stream())
+                    _native().check(status, "skr_noise_fill")
+            self._tensor = out
+        return self._tensor
+
+    def to(self, *args: Any, **kwargs: Any) -> torch.Tensor:
+        return self.materialize().to(*args, **kwargs)
+
+    def __repr__(self) -> str:
+        return f"PhiloxDraw(shape={self.shape}, items={len(self.seeds)}, dtype={self.dtype}, device={self.device})"
+
+
 @dataclass
 class TensorNoiseCommon[T: TensorNoiseProps | None](SkrampleTensorNoise):
     "Shape / seed / dtype / props shared by the base generators. reference: noise.py:27-55"
@@ -228,6 +273,12 @@ class Random(TensorNoiseCommon[None]):
             self._fill(out, self._tick())
         else:
             out.copy_(self.generate(step))
+
+    def lazy(self, step: Step | None) -> "PhiloxDraw | torch.Tensor":
+        "The next draw as Philox keys for in-kernel generation (CUDA generators); a tensor otherwise."
+        if not self.on_device:
+            return self.generate(step)
+        return PhiloxDraw(tuple(self.shape), (self._key(),), (self._tick(),), self.dtype, self.seed.device)
 
 
 @dataclass(frozen=True)
@@ -617,6 +668,24 @@ class BatchTensorNoise[T: TensorNoiseProps | None](SkrampleTensorNoise):
                 generator.generate_into(row, step)
             return out
         return torch.stack([g.generate(step) for g in self.generators])
+
+    def lazy(self, step: Step | None) -> "PhiloxDraw | torch.Tensor":
+        """The next batch of noise as Philox keys when every item is a plain ``Random`` on one CUDA device (and the
+        batch fits the kernel's key table); otherwise the materialised tensor."""
+        first = self.generators[0]
+        eligible = len(self.generators) <= 32 and all(
+            type(g) is Random and g.on_device and g.seed.device == first.seed.device and g.dtype == first.dtype and g.shape == first.shape
+            for g in self.generators
+        )
+        if not eligible:
+            return self.generate(step)
+        return PhiloxDraw(
+            (len(self.generators), *first.shape),
+            tuple(g._key() for g in self.generators),
+            tuple(g._tick() for g in self.generators),
+            first.dtype,
+            first.seed.device,
+        )
 
     @classmethod
     def from_batch_inputs[U: TensorNoiseProps | None](

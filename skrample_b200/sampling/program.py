@@ -104,12 +104,20 @@ class ConvSpec:
 class Program:
     "Builder for one fused step; inputs are de-duplicated by object identity."
 
-    __slots__ = ("inputs", "ops", "outputs")
+    __slots__ = ("inputs", "ops", "outputs", "philox")
 
     def __init__(self) -> None:
         self.ops: list[Op] = []
         self.inputs: list[Any] = []
         self.outputs: list[Any] = []  # per output: requested dtype (or None = dtype of first input)
+        self.philox: list[Any] = []  # lazy noise draws generated inside the kernel (PhiloxDraw)
+
+    def draw(self, value: Any) -> int:
+        for index, known in enumerate(self.philox):
+            if known is value:
+                return index
+        self.philox.append(value)
+        return len(self.philox) - 1
 
     # -- operands
     def input(self, value: Any) -> int:
@@ -179,6 +187,12 @@ class Program:
         self.ops.append(Op(OP_DPM3C, c=(c1, c2)))
 
     def fwd(self, gamma: float, delta: float, pred: int = A, noise: Any = None, zeta: float = 0.0) -> None:
+        if noise is not None and is_lazy_noise(noise):
+            if len(self.philox) >= 2 and not any(known is noise for known in self.philox):
+                noise = noise.materialize()  # the kernel draws at most two noise tensors itself
+            else:
+                self.ops.append(Op(OP_FWD, pred, 2, src=self.draw(noise), c=(gamma, delta, zeta)))
+                return
         if noise is not None:
             self.ops.append(Op(OP_FWD, pred, 1, src=self.input(noise), c=(gamma, delta, zeta)))
         else:
@@ -215,6 +229,11 @@ def _torch() -> Any:
     return sys.modules.get("torch")
 
 
+def is_lazy_noise(value: Any) -> bool:
+    "A noise tensor that only exists as (seeds, streams): skrample_b200.pytorch.noise.PhiloxDraw."
+    return getattr(value, "is_lazy_noise", False)
+
+
 def is_cuda_tensor(value: Any) -> bool:
     torch = _torch()
     return torch is not None and isinstance(value, torch.Tensor) and value.is_cuda
@@ -246,7 +265,7 @@ def execute(program: Program) -> list[Any]:
     if not program.inputs:
         raise ValueError("step program has no inputs")
     if any_cuda(program.inputs):
-        if _fusable(program.inputs):
+        if _fusable(program.inputs) and all(d.numel == program.inputs[0].numel() for d in program.philox):
             from skrample_b200 import native
 
             return native.launch_program(program)
@@ -350,7 +369,10 @@ def execute_generic(program: Program) -> list[Any]:
         elif code == OP_DPM3C:
             reg[A] = reg[B] + c[0] * reg[T] + c[1] * reg[U]
         elif code == OP_FWD:
-            if op.b & 1:
+            if op.b & 2:
+                drawn = program.philox[op.src].materialize()
+                reg[R] = math.sumprod((reg[X], reg[op.a], drawn), (c[0], c[1], c[2]))
+            elif op.b & 1:
                 reg[R] = math.sumprod((reg[X], reg[op.a], values[op.src]), (c[0], c[1], c[2]))
             else:
                 reg[R] = math.sumprod((reg[X], reg[op.a]), (c[0], c[1]))

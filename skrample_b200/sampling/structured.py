@@ -35,7 +35,7 @@ from skrample_b200 import common
 from skrample_b200.common import DeltaPoint, Point, Sample, Step, divf, ln, softmax
 from skrample_b200.scheduling import SkrampleSchedule
 
-from . import models, traits
+from . import models, plan, traits
 from . import program as pg
 from .program import A, B, P, R, S, X, Program
 
@@ -145,18 +145,51 @@ def _HALF_DTYPES() -> tuple[Any, ...]:
     return (torch.bfloat16, torch.float16)
 
 
-def _finish_pc(ctx: "_Ctx", packed: SampleInput, outs: list[Any], sample_slot: int | None, xhat_slot: int | None, final_slot: int) -> "SKSamples":
-    "Assemble the SKSamples of a fused predictor-corrector step."
+def _assemble(packed: SampleInput, outs: list[Any], spec: tuple) -> "SKSamples":
+    "SKSamples of a fused step from its outputs; spec = (final, sample, prediction, xhat cache, xhat key, low-precision x-hat)."
+    final_slot, sample_slot, pred_slot, cache_slot, cache_key, lowp_slot = spec
     result = SKSamples(
         packed.sample if sample_slot is None else outs[sample_slot],
-        packed.prediction if xhat_slot is None else outs[xhat_slot],
+        packed.prediction if pred_slot is None else outs[pred_slot],
         packed.step,
         packed.noise,
         outs[final_slot],
     )
-    if ctx.lowp_slot is not None:
-        object.__setattr__(result, "_skr_pred_lowp", outs[ctx.lowp_slot])
+    if cache_slot is not None:
+        object.__setattr__(result, _XHAT_ATTR, (cache_key, outs[cache_slot]))
+    if lowp_slot is not None:
+        object.__setattr__(result, "_skr_pred_lowp", outs[lowp_slot])
     return result
+
+
+def _drive(sampler: Any, packed: SampleInput, model_transform: Any, schedule: Any, previous: Any, build: Any) -> "SKSamples":
+    """Run one fused step: replay a cached plan when this exact step was taken before (device tensors only),
+    otherwise emit the program with ``build(ctx) -> spec``, run it, and remember the plan."""
+    on_device = pg.is_cuda_tensor(packed.sample)
+    key = None
+    if on_device:
+        out_dtype = _OPTIONS.final_dtype if _OPTIONS.final_dtype is not None else packed.sample.dtype
+        key = plan.key_for(sampler, packed, model_transform, schedule, previous, out_dtype)
+        hit = plan.lookup(key, sampler, model_transform, schedule)
+        if hit is not None:
+            bound = plan.bind(hit, packed, previous)
+            if bound is not None:
+                from skrample_b200 import native
+
+                count = hit.compiled.n_inputs
+                outs = native.launch_compiled(hit.compiled, bound[:count], bound[count:])
+                if outs is not None:
+                    return _assemble(packed, outs, hit.result)
+    ctx = _Ctx(packed.sample)
+    spec = build(ctx)
+    outs = ctx.prog.run()
+    if key is not None and pg._fusable(ctx.prog.inputs):
+        roles = plan.roles_of([*ctx.prog.inputs, *ctx.prog.philox], packed, previous)
+        if roles is not None:
+            from skrample_b200 import native
+
+            plan.store(key, (sampler, model_transform, schedule), native.CompiledProgram(ctx.prog), roles, spec)
+    return _assemble(packed, outs, spec)
 
 
 def _remember_xhat(entry: SKSamples, key: Any, value: Any) -> None:
@@ -258,20 +291,18 @@ class StatedSampler(StructuredSampler):
         schedule: SkrampleSchedule,
         previous: Sequence[SKSamples[T]] = (),
     ) -> SKSamples[T]:
-        ctx = _Ctx(packed.sample)
-        try:
+        def build(ctx: _Ctx) -> tuple:
             self._emit(ctx, _View(packed.sample, packed.prediction, packed.step, packed.noise), model_transform, schedule, previous)
+            final_slot = ctx.prog.store(R, ctx.out_dtype)
+            return (final_slot, None, None, ctx.xhat_slot, ctx.xhat_key, None)
+
+        try:
+            return _drive(self, packed, model_transform, schedule, previous, build)
         except CannotFuse:
             if type(self)._sample_packed is StatedSampler._sample_packed:
                 raise
             final = self._sample_packed(packed, model_transform, schedule, previous)
             return SKSamples(packed.sample, packed.prediction, packed.step, packed.noise, final)
-        final_slot = ctx.prog.store(R, ctx.out_dtype)
-        outs = ctx.prog.run()
-        result = SKSamples(packed.sample, packed.prediction, packed.step, packed.noise, outs[final_slot])
-        if ctx.xhat_slot is not None:
-            _remember_xhat(result, ctx.xhat_key, outs[ctx.xhat_slot])
-        return result
 
 
 @dataclass(frozen=True)
@@ -642,8 +673,7 @@ class UniPC(UniP):
     ) -> SKSamples[T]:
         convert = models.ModelConvert(model_transform, self.derivative_transform) if self.derivative_transform else None
         inner_model = convert.transform_to if convert is not None else model_transform
-        try:
-            ctx = _Ctx(packed.sample)
+        def build(ctx: _Ctx) -> tuple:
             ctx.depth = 1
             prog = ctx.prog
             origin = _point_from(packed.step, schedule)
@@ -662,8 +692,10 @@ class UniPC(UniP):
             else:
                 self.predictor._emit(ctx, view, inner_model, schedule, previous)
             final_slot = prog.store(R, ctx.out_dtype)
-            outs = prog.run()
-            return _finish_pc(ctx, packed, outs, sample_slot, xhat_slot, final_slot)
+            return (final_slot, sample_slot, xhat_slot, None, None, ctx.lowp_slot)
+
+        try:
+            return _drive(self, packed, model_transform, schedule, previous, build)
         except CannotFuse:
             pass
 
@@ -716,8 +748,7 @@ class SPC(traits.DerivativeTransform, StructuredSampler):
         convert = models.ModelConvert(model_transform, self.derivative_transform) if self.derivative_transform else None
         inner_model = convert.transform_to if convert is not None else model_transform
         origin = _point_from(packed.step, schedule)
-        try:
-            ctx = _Ctx(packed.sample)
+        def build(ctx: _Ctx) -> tuple:
             ctx.depth = 1
             prog = ctx.prog
             xhat_slot = _converted_current(ctx, packed, convert, origin)
@@ -733,8 +764,10 @@ class SPC(traits.DerivativeTransform, StructuredSampler):
                 sample_slot = prog.store(X, COMPUTE)  # solver state stays in compute precision
             self.predictor._emit(ctx, _View(IN_X, IN_P, packed.step, packed.noise), inner_model, schedule, previous)
             final_slot = prog.store(R, ctx.out_dtype)
-            outs = prog.run()
-            return _finish_pc(ctx, packed, outs, sample_slot, xhat_slot, final_slot)
+            return (final_slot, sample_slot, xhat_slot, None, None, ctx.lowp_slot)
+
+        try:
+            return _drive(self, packed, model_transform, schedule, previous, build)
         except CannotFuse:
             pass
 

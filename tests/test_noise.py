@@ -295,3 +295,58 @@ def test_colored_generator_color_and_energy(exponent: float, shape: tuple[int, .
     assert abs(n0.std().item() - 1) < 1e-2
     fixed = noise.Colored(shape, _gen(3), torch.float32, noise.ColoredProps(energy=-1.5, color_start=exponent))
     assert abs(fixed.generate(None).std().item() - 1.5) < 1e-4
+
+
+@gpu
+@pytest.mark.parametrize("kernel", ["block", "interpreter"])
+@pytest.mark.parametrize(("sampler_name", "kw"), [("Euler", {"stochasticity": 1}), ("UniPC", {"order": 3, "stochasticity": 1}), ("Adams", {"order": 4, "stochasticity": 1})])
+def test_in_kernel_noise_equals_materialised_noise(sampler_name: str, kw: dict, kernel: str, monkeypatch: pytest.MonkeyPatch) -> None:
+    """The noise term drawn inside the step kernel (PhiloxDraw) is bit-identical to supplying the tensor that
+    skr_noise_fill writes for the same keys - for a batch of per-item generators, a ragged size, both kernels."""
+    from skrample_b200 import native, scheduling
+    from skrample_b200.sampling import models, structured
+
+    if kernel == "interpreter":
+        monkeypatch.setenv("SKR_FORCE_INTERP", "1")
+    sampler = getattr(structured, sampler_name)(**kw)
+    unit = (4, 33, 31)  # item_numel = 4092: multiple of 4 but not of the tile
+    batch = 3
+    schedule, model = scheduling.Scaled(), models.NoiseModel()
+    results = []
+    for lazy in (True, False):
+        gens = [_gen(50 + i) for i in range(batch)]
+        source = noise.BatchTensorNoise.from_batch_inputs(noise.Random, unit, gens)
+        g = torch.Generator(device="cuda").manual_seed(1)
+        x = torch.randn((batch, *unit), device="cuda", generator=g)
+        previous: list = []
+        fills_before = native.launch_count_kind(2)
+        for n in range(5):
+            out = torch.randn((batch, *unit), device="cuda", generator=g) * 0.5
+            step = Step.from_int(n, 5)
+            drawn = source.lazy(step)
+            assert isinstance(drawn, noise.PhiloxDraw)
+            res = sampler.sample(x, out, step, model, schedule, drawn if lazy else drawn.materialize(), previous)
+            previous = (previous + [res])[-sampler.require_previous :] if sampler.require_previous else []
+            x = res.final
+        if lazy:
+            assert native.launch_count_kind(2) == fills_before, "lazy noise must not launch a fill kernel"
+        results.append(x)
+    assert torch.equal(results[0], results[1])
+
+
+@gpu
+def test_in_kernel_noise_unaligned_items() -> None:
+    "item_numel not a multiple of 4: per-element Philox indexing still matches the materialised tensor."
+    from skrample_b200 import scheduling
+    from skrample_b200.sampling import models, structured
+
+    unit = (3, 7, 5)
+    gens = [_gen(9), _gen(10)]
+    source = noise.BatchTensorNoise.from_batch_inputs(noise.Random, unit, gens)
+    drawn = source.lazy(None)
+    x = torch.randn((2, *unit), device="cuda")
+    o = torch.randn((2, *unit), device="cuda")
+    sampler = structured.Euler(stochasticity=1)
+    a = sampler.sample(x, o, Step.from_int(2, 9), models.FlowModel(), scheduling.Linear(), drawn)
+    b = sampler.sample(x, o, Step.from_int(2, 9), models.FlowModel(), scheduling.Linear(), drawn.materialize())
+    assert torch.equal(a.final, b.final)

@@ -4,11 +4,12 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--sweep]
 
 A "step" is ONE solver step of the workload's sampler over one latent batch = one fused kernel launch.
-The default workload is BASELINE.json configs[1]: UniPC order 3, stochastic, supplied Random noise, Scaled
+The default workload is BASELINE.json configs[1]: UniPC order 3, stochastic, Random noise (in-kernel Philox), Scaled
 schedule, epsilon model, SDXL latent 8x4x128x128, bf16 storage / fp32 compute, on one B200.
 
-  value      whole-job algorithmic GB/s of the sampler steps, inputs resident in HBM, launches replayed from a
-             CUDA graph (device-side time between two events; max over ranks).  Trajectories of several latent
+  value      whole-job latent-steps/s (batch items x solver steps per second; ``sampler_step_GBps`` is the same run
+             as algorithmic GB/s), inputs resident in HBM, launches replayed from a CUDA graph (device-side time
+             between two events; max over ranks).  Trajectories of several latent
              batches are interleaved so consecutive launches never touch the same buffers and the working set
              (> 2x L2) comes from HBM.
   e2e        the same steps through the public API (``sampler.sample``) with HOST buffers: per step the model
@@ -84,7 +85,7 @@ def measured_peak() -> tuple[float, str]:
 class Trajectory:
     """One latent batch walking a 25-step schedule with the analytic Gaussian denoiser's predictions pre-recorded."""
 
-    def __init__(self, spec: dict, device: torch.device, seed: int, predictions: int | None = None) -> None:
+    def __init__(self, spec: dict, device: torch.device, seed: int, predictions: int | None = None, supplied_noise: bool = False) -> None:
         import cases
         from skrample_b200 import scheduling
         from skrample_b200.sampling import models, structured
@@ -101,9 +102,21 @@ class Trajectory:
         sigma_max = self.points[0].sigma
         self.x0 = (torch.randn(shape, device=device, generator=g) * sigma_max).to(self.dtype)
         count = predictions or STEPS_PER_TRAJECTORY
-        self.noises = [torch.randn(shape, device=device, generator=g).to(self.dtype) for _ in range(count)]
-        self.predictions: list[torch.Tensor] = []
         self.count = count
+        self.predictions: list[torch.Tensor] = []
+        # "Random noise" of the workload: one CUDA generator per batch item (what the diffusers wrapper builds).
+        # The draws are Philox keys; the step kernel generates the normals itself, nothing is written to memory.
+        from skrample_b200.pytorch import noise as sk_noise
+
+        self.noise_source = sk_noise.BatchTensorNoise.from_batch_inputs(
+            sk_noise.Random,
+            tuple(shape[1:]),
+            [torch.Generator(device=device).manual_seed(seed * 1000 + i) for i in range(shape[0])],
+            dtype=torch.float32,
+        )
+        self.noises = [self.noise_source.lazy(None) for _ in range(count)] if self.sampler.require_noise else [None] * count
+        if supplied_noise and self.sampler.require_noise:
+            self.noises = [z.materialize().to(self.dtype) if hasattr(z, "materialize") else z for z in self.noises]
         self.reset()
 
     def reset(self) -> None:
@@ -289,14 +302,12 @@ def e2e_throughput(spec: dict, device: torch.device, steps: int, warmup: int) ->
     traj.record()
     per_step = step_bytes(spec, device)
     host_pred = [p.cpu().pin_memory() for p in traj.predictions]
-    host_noise = [z.cpu().pin_memory() for z in traj.noises]
     result_host = torch.empty(spec["shape"], dtype=traj.dtype).pin_memory()
-    needs_noise = traj.sampler.require_noise
 
     def one(k: int) -> None:
         n = traj.n
         pred = host_pred[n].to(device, non_blocking=True)
-        noise = host_noise[n].to(device, non_blocking=True) if needs_noise else None
+        noise = traj.noise_source.lazy(None) if traj.sampler.require_noise else None  # fresh Philox keys, drawn in-kernel
         final = traj.step(pred, noise)
         result_host.copy_(final, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller consumes the result before the next step
@@ -318,7 +329,7 @@ def e2e_throughput(spec: dict, device: torch.device, steps: int, warmup: int) ->
     return {
         "elapsed_s": elapsed,
         "bytes": total_bytes,
-        "h2d": n * esize * (2 if needs_noise else 1),
+        "h2d": n * esize,
         "d2h": n * esize,
     }
 
@@ -437,7 +448,7 @@ def main() -> None:
     spec = WORKLOADS[args.workload]
     n = numel_of(spec["shape"])
     config = {
-        "workload": f"{spec['sampler']}({', '.join(f'{k}={v}' for k, v in spec['kw'].items())}) {spec['schedule']} {spec['model']} latent {'x'.join(map(str, spec['shape']))} {spec['dtype']} storage / fp32 compute, {STEPS_PER_TRAJECTORY}-step trajectories, supplied Random noise, analytic Gaussian denoiser (pre-recorded)",
+        "workload": f"{spec['sampler']}({', '.join(f'{k}={v}' for k, v in spec['kw'].items())}) {spec['schedule']} {spec['model']} latent {'x'.join(map(str, spec['shape']))} {spec['dtype']} storage / fp32 compute, {STEPS_PER_TRAJECTORY}-step trajectories, Random noise drawn in-kernel (Philox, one generator per item), analytic Gaussian denoiser (pre-recorded)",
         "name": args.workload,
         "per_gpu_batch": spec["shape"][0],
         "global_batch": spec["shape"][0] * world,
@@ -450,11 +461,12 @@ def main() -> None:
         budget = 120.0
         res = cpu_oracle_steps(spec, args.steps, min(args.warmup, 25), budget)
         gbs = res["bytes"] / res["seconds"] / 1e9
+        lsps = res["steps"] * spec["shape"][0] / res["seconds"]
         line = {
             "impl": "reference",
-            "metric": "sampler_step_throughput",
-            "value": gbs,
-            "unit": "GB/s",
+            "metric": "sampler latent-steps/s (one batch item advanced one solver step)",
+            "value": lsps,
+            "unit": "latent-steps/s",
             "n_gpus": args.gpus,
             "steps": res["steps"],
             "warmup": min(args.warmup, 25),
@@ -465,15 +477,15 @@ def main() -> None:
             "dtype": "f32",
             "data": "synthetic",
             "config": config,
-            "latent_steps_per_s": res["steps"] * spec["shape"][0] / res["seconds"],
+            "sampler_step_GBps": gbs,
             "cpu_baseline": {
-                "value": gbs,
-                "unit": "GB/s",
+                "value": lsps,
+                "unit": "latent-steps/s",
                 "cores": res["threads"],
                 "kind": "port",
                 "sample": f"{res['steps']} sampler steps of the workload in fp32 on torch-CPU tensors (oracle/skrample_oracle.py), sampler time only",
             },
-            "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "e2e": {"value": lsps, "unit": "latent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
         print(json.dumps(line))
         return
@@ -506,9 +518,9 @@ def main() -> None:
     e2e_gbs = e2e["bytes"] * world / e2e_elapsed / 1e9
 
     line = {
-        "metric": "sampler_step_throughput",
-        "value": gbs,
-        "unit": "GB/s",
+        "metric": "sampler latent-steps/s (one batch item advanced one solver step)",
+        "value": latent_steps,
+        "unit": "latent-steps/s",
         "n_gpus": world,
         "steps": dev["steps"],
         "warmup": args.warmup,
@@ -524,16 +536,16 @@ def main() -> None:
             "l2": f"{dev['replicas']} interleaved latent batches, working set per round > 2x L2 (inputs come from HBM)",
             "storage_dtype": spec["dtype"],
         },
-        "latent_steps_per_s": latent_steps,
+        "sampler_step_GBps": gbs,
         "pct_of_hbm_peak": {"measured": gbs / world / peak, "nominal_8TBs": gbs / world / 8000.0},
         "gpu_launches": timed_launches,
         "clocks": dev["clocks"],
         "e2e": {
-            "value": e2e_gbs,
-            "unit": "GB/s",
+            "value": e2e_steps * spec["shape"][0] * world / e2e_elapsed,
+            "unit": "latent-steps/s",
             "h2d_bytes_per_step": e2e["h2d"],
             "d2h_bytes_per_step": e2e["d2h"],
-            "latent_steps_per_s": e2e_steps * spec["shape"][0] * world / e2e_elapsed,
+            "sampler_step_GBps": e2e_gbs,
             "ms_per_step": e2e_elapsed / e2e_steps * 1e3,
             "steps": e2e_steps,
         },
@@ -566,12 +578,12 @@ def main() -> None:
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         res = cpu_oracle_steps(spec, 10_000, 25, 15.0)
         line["cpu_baseline"] = {
-            "value": res["bytes"] / res["seconds"] / 1e9,
-            "unit": "GB/s",
+            "value": res["steps"] * spec["shape"][0] / res["seconds"],
+            "unit": "latent-steps/s",
             "cores": res["threads"],
             "kind": "port",
             "sample": f"{res['steps']} sampler steps of the workload in fp32 on torch-CPU tensors (oracle/skrample_oracle.py), sampler time only",
-            "latent_steps_per_s": res["steps"] * spec["shape"][0] / res["seconds"],
+            "sampler_step_GBps": res["bytes"] / res["seconds"] / 1e9,
             "ms_per_step": res["seconds"] / res["steps"] * 1e3,
         }
 

@@ -166,11 +166,14 @@ class Trajectory:
         return res.final
 
 
+SUPPLIED_NOISE = False
+
+
 def step_bytes(traj_spec: dict, device: torch.device) -> list[int]:
     "Algorithmic bytes (sum of distinct tensor reads + writes) of each of the 25 steps, counted from the launches."
     from skrample_b200 import native
 
-    t = Trajectory(traj_spec, device, seed=99, predictions=1)
+    t = Trajectory(traj_spec, device, seed=99, predictions=1, supplied_noise=SUPPLIED_NOISE)
     t.record()
     out: list[int] = []
     for _ in range(STEPS_PER_TRAJECTORY):
@@ -246,7 +249,7 @@ def graph_throughput(spec: dict, device: torch.device, steps: int, warmup: int, 
     replicas = max(2, min(64, -(-min_ring_bytes // replica_touch)))
     big = n * esize > 64 * 1024 * 1024
     keep = 2 if big else STEPS_PER_TRAJECTORY  # recorded predictions/noises per replica (memory bound for huge latents)
-    trajs = [Trajectory(spec, device, seed=1234 + i, predictions=keep) for i in range(replicas)]
+    trajs = [Trajectory(spec, device, seed=1234 + i, predictions=keep, supplied_noise=SUPPLIED_NOISE) for i in range(replicas)]
     for t in trajs:
         t.record()
 
@@ -439,8 +442,11 @@ def main() -> None:
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--sweep", action="store_true", help="also time the larger BASELINE shapes (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--supplied-noise", action="store_true", help="read the noise from a tensor instead of drawing it in the step kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    global SUPPLIED_NOISE
+    SUPPLIED_NOISE = args.supplied_noise
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

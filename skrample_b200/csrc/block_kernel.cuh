@@ -37,8 +37,8 @@ enum InMode : int { IN_MIXED = 0, IN_F32 = 1, IN_BF16 = 2, IN_F16 = 3 };
 template <typename CT>
 struct BTerm {
     CT c0, c1;
+    CT r0;       // correctly rounded 1/c0 when c0 is a divisor (UNI terms), else 0
     int32_t in;  // input index
-    int32_t pad;
 };
 
 template <typename CT>
@@ -49,6 +49,7 @@ struct BBlock {
     int32_t sample_in, base_in, noise_in, store_r, store_link;  // -1 = not used
     int32_t pad;
     CT p_coef, div, gamma, delta, zeta, l0, l1, e0, e1, e2;
+    CT div_r, l1_r;  // reciprocals of div / l1 for the uniform-divisor fast path (0 = use IEEE division)
     BTerm<CT> terms[kMaxTerms];
 };
 
@@ -58,6 +59,7 @@ struct BHead {
     int32_t conv_flags[2];
     int32_t store_p2;  // optional second copy of P (e.g. fp32 solver state + 16-bit copy for the caller)
     CT conv_c[2][3];
+    CT conv_r[2];      // reciprocal of conv_c[.][2] (0 = use IEEE division)
 };
 
 template <typename CT>
@@ -103,9 +105,41 @@ __device__ __forceinline__ void fetch_tile(const unsigned char* stage, uint32_t 
             v[2 * i] = (CT)f.x;
             v[2 * i + 1] = (CT)f.y;
         }
-    } else {
-        static_assert(V == 4, "mixed tiles use 4 elements per thread");
+    } else if constexpr (V == 4) {
         fetch_staged<CT>(stage, off, dtype, tid, v);
+    } else {
+        static_assert(V == 8, "mixed tiles use 4 or 8 elements per thread");
+        switch (dtype) {
+            case SKR_F32: {
+                const float4 q0 = *reinterpret_cast<const float4*>(base + tid * 32);
+                const float4 q1 = *reinterpret_cast<const float4*>(base + tid * 32 + 16);
+                v[0] = (CT)q0.x; v[1] = (CT)q0.y; v[2] = (CT)q0.z; v[3] = (CT)q0.w;
+                v[4] = (CT)q1.x; v[5] = (CT)q1.y; v[6] = (CT)q1.z; v[7] = (CT)q1.w;
+            } break;
+            case SKR_BF16: {
+                const uint4 q = *reinterpret_cast<const uint4*>(base + tid * 16);
+                v[0] = (CT)bf16_lo(q.x); v[1] = (CT)bf16_hi(q.x); v[2] = (CT)bf16_lo(q.y); v[3] = (CT)bf16_hi(q.y);
+                v[4] = (CT)bf16_lo(q.z); v[5] = (CT)bf16_hi(q.z); v[6] = (CT)bf16_lo(q.w); v[7] = (CT)bf16_hi(q.w);
+            } break;
+            case SKR_F16: {
+                const uint4 q = *reinterpret_cast<const uint4*>(base + tid * 16);
+                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+                    v[2 * i] = (CT)f.x;
+                    v[2 * i + 1] = (CT)f.y;
+                }
+            } break;
+            default: {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const double2 q = *reinterpret_cast<const double2*>(base + tid * 64 + 16 * i);
+                    v[2 * i] = (CT)q.x;
+                    v[2 * i + 1] = (CT)q.y;
+                }
+            } break;
+        }
     }
 }
 
@@ -216,7 +250,7 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
         for (int c = 0; c < 2; ++c) {
             if (c < h.n_conv) {
                 const int f = h.conv_flags[c];
-                const CT c0 = h.conv_c[c][0], c1 = h.conv_c[c][1], c2 = h.conv_c[c][2];
+                const CT c0 = h.conv_c[c][0], c1 = h.conv_c[c][1], c2 = h.conv_c[c][2], r2 = h.conv_r[c];
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
                     CT v;
@@ -227,7 +261,7 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
                     } else {
                         v = (f & SKR_CONV_MUL_Y) ? Ar::mul(P[j], c1) : P[j];
                     }
-                    P[j] = (f & SKR_CONV_DIV) ? Ar::div(v, c2) : v;
+                    P[j] = (f & SKR_CONV_DIV) ? Ar::divu(v, c2, r2) : v;
                 }
             }
         }
@@ -282,17 +316,17 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
                     for (int j = 0; j < V; ++j) A[j] = Ar::add(A[j], Ar::mul(P[j], c));
                 }
                 if (k.has_div) {
-                    const CT d = k.div;
+                    const CT d = k.div, dr = k.div_r;
 #pragma unroll
-                    for (int j = 0; j < V; ++j) A[j] = Ar::div(A[j], d);
+                    for (int j = 0; j < V; ++j) A[j] = Ar::divu(A[j], d, dr);
                 }
             } else if (kind == BK_UNI) {
                 for (int t = 0; t < n_terms; ++t) {
                     io.load(k.terms[t].in, in);
-                    const CT rk = k.terms[t].c0, rho = k.terms[t].c1;
+                    const CT rk = k.terms[t].c0, rho = k.terms[t].c1, rkr = k.terms[t].r0;
 #pragma unroll
                     for (int j = 0; j < V; ++j) {
-                        const CT term = Ar::mul(Ar::div(Ar::sub(in[j], B[j]), rk), rho);
+                        const CT term = Ar::mul(Ar::divu(Ar::sub(in[j], B[j]), rk, rkr), rho);
                         A[j] = Ar::add(t == 0 ? (CT)0 : A[j], term);
                     }
                 }
@@ -358,9 +392,9 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
                 for (int j = 0; j < V; ++j) X[j] = Ar::add(Ar::mul(S[j], l0), Ar::mul(R[j], l1));
                 if (k.store_link >= 0) io.store(k.store_link, X);
             } else {  // BL_BACK
-                const CT l0 = k.l0, l1 = k.l1;
+                const CT l0 = k.l0, l1 = k.l1, l1r = k.l1_r;
 #pragma unroll
-                for (int j = 0; j < V; ++j) P[j] = Ar::div(Ar::sub(R[j], Ar::mul(X[j], l0)), l1);
+                for (int j = 0; j < V; ++j) P[j] = Ar::divu(Ar::sub(R[j], Ar::mul(X[j], l0)), l1, l1r);
                 if (k.store_link >= 0) io.store(k.store_link, P);
             }
         }
@@ -512,6 +546,7 @@ static bool parse_block(OpCursor& cur, BBlock<CT>& k) {
             k.terms[k.n_terms].in = t->src;
             k.terms[k.n_terms].c0 = (CT)t->c[0];
             k.terms[k.n_terms].c1 = (CT)t->c[1];
+            k.terms[k.n_terms].r0 = reciprocal_for<CT>((CT)t->c[0]);
             ++k.n_terms;
             ++seen;
         }
@@ -558,6 +593,7 @@ static bool parse_block(OpCursor& cur, BBlock<CT>& k) {
         const skr_op* t = cur.take();
         k.has_div = 1;
         k.div = (CT)t->c[0];
+        k.div_r = reciprocal_for<CT>(k.div);
     }
     if (!cur.is(SKR_OP_FWD)) return false;
     {
@@ -586,6 +622,7 @@ static bool parse_block(OpCursor& cur, BBlock<CT>& k) {
         k.link = BL_BACK;
         k.l0 = (CT)t->c[0];
         k.l1 = (CT)t->c[1];
+        k.l1_r = reciprocal_for<CT>(k.l1);
         if (cur.is_store(SKR_P)) k.store_link = cur.take()->dst;
     }
     return true;
@@ -618,6 +655,7 @@ static bool parse_block_program(const skr_program* p, BProgram<CT>& out) {
         h.y_in = o->src;
         h.conv_flags[0] = o->a;
         for (int j = 0; j < 3; ++j) h.conv_c[0][j] = (CT)o->c[j];
+        h.conv_r[0] = reciprocal_for<CT>(h.conv_c[0][2]);
         h.n_conv = 1;
     }
     while (cur.is(SKR_OP_CONV) && cur.peek()->b == 1) {
@@ -625,6 +663,7 @@ static bool parse_block_program(const skr_program* p, BProgram<CT>& out) {
         const skr_op* o = cur.take();
         h.conv_flags[h.n_conv] = o->a;
         for (int j = 0; j < 3; ++j) h.conv_c[h.n_conv][j] = (CT)o->c[j];
+        h.conv_r[h.n_conv] = reciprocal_for<CT>(h.conv_c[h.n_conv][2]);
         ++h.n_conv;
     }
     for (int c = 0; c < h.n_conv; ++c)

@@ -528,11 +528,14 @@ static int launch_block(const skr_program* p, BProgram<CT>& k, int64_t numel, cu
             all_bf16 &= p->inputs[i].dtype == SKR_BF16;
             all_f16 &= p->inputs[i].dtype == SKR_F16;
         }
-        const int force = env_int("SKR_IN_MODE", -1);  // development switch: 0 forces the mixed instantiation
+        const int force = env_int("SKR_IN_MODE", -1);  // development switch: 0 / 8 force a mixed instantiation
         if (force == 0) return launch_block_inst<float, IN_MIXED, 4>(p, k, numel, stream, aligned, 3);
+        if (force == 8) return launch_block_inst<float, IN_MIXED, 8>(p, k, numel, stream, aligned, 7);
         if (all_f32) return launch_block_inst<float, IN_F32, 4>(p, k, numel, stream, aligned, 4);
         if (all_bf16) return launch_block_inst<float, IN_BF16, 8>(p, k, numel, stream, aligned, 5);
         if (all_f16) return launch_block_inst<float, IN_F16, 8>(p, k, numel, stream, aligned, 6);
+        // mixed storage: 8 elements per thread halve the per-tile control overhead once there are enough tiles
+        if (numel >= (int64_t)kThreads * 8 * 296) return launch_block_inst<float, IN_MIXED, 8>(p, k, numel, stream, aligned, 7);
         return launch_block_inst<float, IN_MIXED, 4>(p, k, numel, stream, aligned, 3);
     }
 }

@@ -4,7 +4,7 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--sweep]
 
 A "step" is ONE solver step of the workload's sampler over one latent batch = one fused kernel launch.
-The default workload is BASELINE.json configs[1]: UniPC order 3, stochastic, Random noise (in-kernel Philox), Scaled
+The default workload is BASELINE.json configs[1]: UniPC order 3, stochastic, Random noise (device Philox), Scaled
 schedule, epsilon model, SDXL latent 8x4x128x128, bf16 storage / fp32 compute, on one B200.
 
   value      whole-job latent-steps/s (batch items x solver steps per second; ``sampler_step_GBps`` is the same run
@@ -166,7 +166,7 @@ class Trajectory:
         return res.final
 
 
-SUPPLIED_NOISE = False
+SUPPLIED_NOISE = True
 
 
 def step_bytes(traj_spec: dict, device: torch.device) -> list[int]:
@@ -310,7 +310,9 @@ def e2e_throughput(spec: dict, device: torch.device, steps: int, warmup: int) ->
     def one(k: int) -> None:
         n = traj.n
         pred = host_pred[n].to(device, non_blocking=True)
-        noise = traj.noise_source.lazy(None) if traj.sampler.require_noise else None  # fresh Philox keys, drawn in-kernel
+        noise = None
+        if traj.sampler.require_noise:  # fresh noise every step, generated on the device (fill kernel or in-step draw)
+            noise = traj.noise_source.generate(None) if SUPPLIED_NOISE else traj.noise_source.lazy(None)
         final = traj.step(pred, noise)
         result_host.copy_(final, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller consumes the result before the next step
@@ -442,11 +444,11 @@ def main() -> None:
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--sweep", action="store_true", help="also time the larger BASELINE shapes (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--supplied-noise", action="store_true", help="read the noise from a tensor instead of drawing it in the step kernel")
+    ap.add_argument("--fused-noise", action="store_true", help="draw the noise inside the step kernel (PhiloxDraw) instead of reading the tensor skr_noise_fill wrote")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     global SUPPLIED_NOISE
-    SUPPLIED_NOISE = args.supplied_noise
+    SUPPLIED_NOISE = not args.fused_noise
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -454,7 +456,7 @@ def main() -> None:
     spec = WORKLOADS[args.workload]
     n = numel_of(spec["shape"])
     config = {
-        "workload": f"{spec['sampler']}({', '.join(f'{k}={v}' for k, v in spec['kw'].items())}) {spec['schedule']} {spec['model']} latent {'x'.join(map(str, spec['shape']))} {spec['dtype']} storage / fp32 compute, {STEPS_PER_TRAJECTORY}-step trajectories, Random noise drawn in-kernel (Philox, one generator per item), analytic Gaussian denoiser (pre-recorded)",
+        "workload": f"{spec['sampler']}({', '.join(f'{k}={v}' for k, v in spec['kw'].items())}) {spec['schedule']} {spec['model']} latent {'x'.join(map(str, spec['shape']))} {spec['dtype']} storage / fp32 compute, {STEPS_PER_TRAJECTORY}-step trajectories, Random noise (Philox, one generator per item; {'drawn inside the step kernel' if args.fused_noise else 'written by skr_noise_fill before the timed region, like the CPU arm'}), analytic Gaussian denoiser (pre-recorded)",
         "name": args.workload,
         "per_gpu_batch": spec["shape"][0],
         "global_batch": spec["shape"][0] * world,

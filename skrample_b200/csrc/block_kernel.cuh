@@ -14,6 +14,10 @@
 // (one lane per input tensor) and runs ahead of the eight consumer warps through a full/empty
 // mbarrier ring; consumers never synchronise with each other.
 //
+// The noise term can be drawn inside the kernel (PHILOX instantiations: Philox4x32-10 + Box-Muller per element,
+// bit-identical to skr_noise_fill); programs that read their noise from a tensor use instantiations without
+// that code, which measurably matters for the instruction footprint of the hot loop.
+//
 // Instantiations: storage mode of the inputs (all fp32 / all bf16 / all fp16 / mixed, chosen per
 // launch) x elements per thread (4, or 8 for 16-bit storage so every shared-memory read is
 // 128-bit) x compute type (fp32, fp64).  The descriptor is plain int32/float fields in the
@@ -37,8 +41,8 @@ enum InMode : int { IN_MIXED = 0, IN_F32 = 1, IN_BF16 = 2, IN_F16 = 3 };
 template <typename CT>
 struct BTerm {
     CT c0, c1;
-    CT r0;       // correctly rounded 1/c0 when c0 is a divisor (UNI terms), else 0
     int32_t in;  // input index
+    int32_t pad;
 };
 
 template <typename CT>
@@ -49,7 +53,6 @@ struct BBlock {
     int32_t sample_in, base_in, noise_in, store_r, store_link;  // -1 = not used
     int32_t pad;
     CT p_coef, div, gamma, delta, zeta, l0, l1, e0, e1, e2;
-    CT div_r, l1_r;  // reciprocals of div / l1 for the uniform-divisor fast path (0 = use IEEE division)
     BTerm<CT> terms[kMaxTerms];
 };
 
@@ -59,7 +62,6 @@ struct BHead {
     int32_t conv_flags[2];
     int32_t store_p2;  // optional second copy of P (e.g. fp32 solver state + 16-bit copy for the caller)
     CT conv_c[2][3];
-    CT conv_r[2];      // reciprocal of conv_c[.][2] (0 = use IEEE division)
 };
 
 template <typename CT>
@@ -226,7 +228,7 @@ struct TileIO {
     }
 };
 
-template <typename CT, int MODE, int V, bool GUARDED>
+template <typename CT, int MODE, int V, bool GUARDED, bool PHILOX>
 __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t first, const unsigned char* stage, int tid) {
     using Ar = Arith<CT>;
     const TileIO<CT, MODE, V, GUARDED> io{prog, stage, tid, first};
@@ -250,7 +252,7 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
         for (int c = 0; c < 2; ++c) {
             if (c < h.n_conv) {
                 const int f = h.conv_flags[c];
-                const CT c0 = h.conv_c[c][0], c1 = h.conv_c[c][1], c2 = h.conv_c[c][2], r2 = h.conv_r[c];
+                const CT c0 = h.conv_c[c][0], c1 = h.conv_c[c][1], c2 = h.conv_c[c][2];
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
                     CT v;
@@ -261,7 +263,7 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
                     } else {
                         v = (f & SKR_CONV_MUL_Y) ? Ar::mul(P[j], c1) : P[j];
                     }
-                    P[j] = (f & SKR_CONV_DIV) ? Ar::divu(v, c2, r2) : v;
+                    P[j] = (f & SKR_CONV_DIV) ? Ar::div(v, c2) : v;
                 }
             }
         }
@@ -269,7 +271,7 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
     if (h.store_p >= 0) io.store(h.store_p, P);
     if (h.store_p2 >= 0) io.store(h.store_p2, P);
 
-    // ---- blocks -------------------------------------------------------------------------------
+    // ---- blocks (one copy of the block code: the instruction footprint matters more than the loop) ----
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
         const BBlock<CT>& k = prog.blk[b];
@@ -316,17 +318,17 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
                     for (int j = 0; j < V; ++j) A[j] = Ar::add(A[j], Ar::mul(P[j], c));
                 }
                 if (k.has_div) {
-                    const CT d = k.div, dr = k.div_r;
+                    const CT d = k.div;
 #pragma unroll
-                    for (int j = 0; j < V; ++j) A[j] = Ar::divu(A[j], d, dr);
+                    for (int j = 0; j < V; ++j) A[j] = Ar::div(A[j], d);
                 }
             } else if (kind == BK_UNI) {
                 for (int t = 0; t < n_terms; ++t) {
                     io.load(k.terms[t].in, in);
-                    const CT rk = k.terms[t].c0, rho = k.terms[t].c1, rkr = k.terms[t].r0;
+                    const CT rk = k.terms[t].c0, rho = k.terms[t].c1;
 #pragma unroll
                     for (int j = 0; j < V; ++j) {
-                        const CT term = Ar::mul(Ar::divu(Ar::sub(in[j], B[j]), rk, rkr), rho);
+                        const CT term = Ar::mul(Ar::div(Ar::sub(in[j], B[j]), rk), rho);
                         A[j] = Ar::add(t == 0 ? (CT)0 : A[j], term);
                     }
                 }
@@ -373,7 +375,7 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
             for (int j = 0; j < V; ++j) R[j] = Ar::add(Ar::add((CT)0, Ar::mul(X[j], gamma)), Ar::mul(A[j], delta));
         }
         if (k.has_noise) {
-            if (k.has_noise == 2) draw_normals<CT, V>(prog.philox[k.noise_in], first, prog.numel, in);
+            if (PHILOX && k.has_noise == 2) draw_normals<CT, V>(prog.philox[k.noise_in], first, prog.numel, in);
             else io.load(k.noise_in, in);
             const CT zeta = k.zeta;
 #pragma unroll
@@ -392,9 +394,9 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
                 for (int j = 0; j < V; ++j) X[j] = Ar::add(Ar::mul(S[j], l0), Ar::mul(R[j], l1));
                 if (k.store_link >= 0) io.store(k.store_link, X);
             } else {  // BL_BACK
-                const CT l0 = k.l0, l1 = k.l1, l1r = k.l1_r;
+                const CT l0 = k.l0, l1 = k.l1;
 #pragma unroll
-                for (int j = 0; j < V; ++j) P[j] = Ar::divu(Ar::sub(R[j], Ar::mul(X[j], l0)), l1, l1r);
+                for (int j = 0; j < V; ++j) P[j] = Ar::div(Ar::sub(R[j], Ar::mul(X[j], l0)), l1);
                 if (k.store_link >= 0) io.store(k.store_link, P);
             }
         }
@@ -402,14 +404,14 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
 }
 
 // The ragged tail (and unaligned launches) run out of line so the pipelined loop stays compact.
-template <typename CT, int MODE, int V>
+template <typename CT, int MODE, int V, bool PHILOX>
 __device__ __noinline__ void run_guarded_tiles(const BProgram<CT>& prog, int64_t first_tile, int64_t n_tiles, int tid) {
     for (int64_t tile = first_tile + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        run_block_tile<CT, MODE, V, true>(prog, tile * (kThreads * V) + (int64_t)tid * V, nullptr, tid);
+        run_block_tile<CT, MODE, V, true, PHILOX>(prog, tile * (kThreads * V) + (int64_t)tid * V, nullptr, tid);
     }
 }
 
-template <typename CT, int MODE, int V>
+template <typename CT, int MODE, int V, bool PHILOX>
 __global__ void __launch_bounds__(kThreads + kProducerThreads) block_kernel(const __grid_constant__ BProgram<CT> prog) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
@@ -461,7 +463,7 @@ __global__ void __launch_bounds__(kThreads + kProducerThreads) block_kernel(cons
             const int64_t stride = (int64_t)grid * TILE;
             for (int k = 0; k < mine; ++k) {
                 mbar_wait(&full_bar[s], phase);
-                run_block_tile<CT, MODE, V, false>(prog, first, smem + (size_t)s * stage_bytes, tid);
+                run_block_tile<CT, MODE, V, false, PHILOX>(prog, first, smem + (size_t)s * stage_bytes, tid);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[s]);
                 first += stride;
@@ -471,7 +473,7 @@ __global__ void __launch_bounds__(kThreads + kProducerThreads) block_kernel(cons
     }
     if (!producer) {
         const int64_t n_tiles = (prog.numel + TILE - 1) / TILE;
-        if ((int64_t)n_full < n_tiles) run_guarded_tiles<CT, MODE, V>(prog, n_full, n_tiles, tid);
+        if ((int64_t)n_full < n_tiles) run_guarded_tiles<CT, MODE, V, PHILOX>(prog, n_full, n_tiles, tid);
     }
 }
 
@@ -546,7 +548,6 @@ static bool parse_block(OpCursor& cur, BBlock<CT>& k) {
             k.terms[k.n_terms].in = t->src;
             k.terms[k.n_terms].c0 = (CT)t->c[0];
             k.terms[k.n_terms].c1 = (CT)t->c[1];
-            k.terms[k.n_terms].r0 = reciprocal_for<CT>((CT)t->c[0]);
             ++k.n_terms;
             ++seen;
         }
@@ -593,7 +594,6 @@ static bool parse_block(OpCursor& cur, BBlock<CT>& k) {
         const skr_op* t = cur.take();
         k.has_div = 1;
         k.div = (CT)t->c[0];
-        k.div_r = reciprocal_for<CT>(k.div);
     }
     if (!cur.is(SKR_OP_FWD)) return false;
     {
@@ -622,7 +622,6 @@ static bool parse_block(OpCursor& cur, BBlock<CT>& k) {
         k.link = BL_BACK;
         k.l0 = (CT)t->c[0];
         k.l1 = (CT)t->c[1];
-        k.l1_r = reciprocal_for<CT>(k.l1);
         if (cur.is_store(SKR_P)) k.store_link = cur.take()->dst;
     }
     return true;
@@ -655,7 +654,6 @@ static bool parse_block_program(const skr_program* p, BProgram<CT>& out) {
         h.y_in = o->src;
         h.conv_flags[0] = o->a;
         for (int j = 0; j < 3; ++j) h.conv_c[0][j] = (CT)o->c[j];
-        h.conv_r[0] = reciprocal_for<CT>(h.conv_c[0][2]);
         h.n_conv = 1;
     }
     while (cur.is(SKR_OP_CONV) && cur.peek()->b == 1) {
@@ -663,7 +661,6 @@ static bool parse_block_program(const skr_program* p, BProgram<CT>& out) {
         const skr_op* o = cur.take();
         h.conv_flags[h.n_conv] = o->a;
         for (int j = 0; j < 3; ++j) h.conv_c[h.n_conv][j] = (CT)o->c[j];
-        h.conv_r[h.n_conv] = reciprocal_for<CT>(h.conv_c[h.n_conv][2]);
         ++h.n_conv;
     }
     for (int c = 0; c < h.n_conv; ++c)

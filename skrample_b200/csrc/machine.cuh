@@ -7,7 +7,6 @@
 #include "common.cuh"
 #include "philox.cuh"
 
-#include <cmath>
 
 namespace skr {
 
@@ -20,27 +19,12 @@ constexpr int kMaxStages = 8;
 // individually rounded arithmetic
 
 template <typename CT> struct Arith;
+// IEEE division out of line: the uniform-divisor fast path below keeps it off the hot instruction stream.
 template <> struct Arith<float> {
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
     static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
     static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
-    // a / c for a grid-uniform divisor c whose correctly rounded reciprocal rc was computed on the host
-    // (rc == 0: not available).  Markstein's sequence: two residual corrections with exact FMA residuals give the
-    // correctly rounded quotient when no intermediate over/underflows, which the magnitude guard ensures; anything
-    // else (zeros, infinities, NaN, extreme magnitudes) takes the IEEE division.  Bit-identical to __fdiv_rn
-    // (tests/test_gpu_structured.py::test_uniform_division_is_ieee).
-    static __device__ __forceinline__ float divu(float a, float c, float rc) {
-        const float m = fabsf(a);
-        if (rc != 0.0f && m > 0x1p-60f && m < 0x1p60f) {
-            float q = __fmul_rn(a, rc);
-            float r = __fmaf_rn(-c, q, a);
-            q = __fmaf_rn(r, rc, q);
-            r = __fmaf_rn(-c, q, a);
-            return __fmaf_rn(r, rc, q);
-        }
-        return __fdiv_rn(a, c);
-    }
     static __device__ __forceinline__ float spow(float x, float f) {
         // |x|^f * sign(x); torch's tensor-scalar pow has exact special cases (reference: common.py:187-190)
         const float m = fabsf(x);
@@ -60,7 +44,6 @@ template <> struct Arith<double> {
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
     static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
     static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
-    static __device__ __forceinline__ double divu(double a, double c, double) { return __ddiv_rn(a, c); }
     static __device__ __forceinline__ double spow(double x, double f) {
         const double m = fabs(x);
         double r;
@@ -187,6 +170,28 @@ struct KPhilox {
                       // bit 1: numel < 2^31 (32-bit index arithmetic)
 };
 
+// Four normals of the virtual noise tensor starting at element e (e % 4 == 0, item_numel % 4 == 0).
+__device__ __forceinline__ float4 draw_group(const KPhilox& d, int64_t e) {
+    int64_t item, local;
+    if (d.aligned & 2) {
+        const uint32_t i32 = (uint32_t)e / (uint32_t)d.item_numel;
+        item = i32;
+        local = (uint32_t)e - i32 * (uint32_t)d.item_numel;
+    } else {
+        item = e / d.item_numel;
+        local = e - item * d.item_numel;
+    }
+    float z[4];
+    normal4(Philox(d.seed[item])((uint64_t)local >> 2, d.stream[item]), z);
+    return make_float4(z[0], z[1], z[2], z[3]);
+}
+
+__device__ __forceinline__ float draw_single(const KPhilox& d, int64_t e) {
+    const int64_t item = e / d.item_numel;
+    const int64_t local = e - item * d.item_numel;
+    return normal_at(Philox(d.seed[item]), (uint64_t)local, d.stream[item]);
+}
+
 // V consecutive elements starting at global element `first` (a multiple of 4) of the virtual noise tensor.
 template <typename CT, int V>
 __device__ __forceinline__ void draw_normals(const KPhilox& d, int64_t first, int64_t numel, CT (&v)[V]) {
@@ -194,56 +199,18 @@ __device__ __forceinline__ void draw_normals(const KPhilox& d, int64_t first, in
 #pragma unroll
         for (int g = 0; g < V / 4; ++g) {
             const int64_t e = first + 4 * g;
-            float z[4] = {0.f, 0.f, 0.f, 0.f};
-            if (e < numel) {
-                int64_t item, local;
-                if (d.aligned & 2) {
-                    const uint32_t i32 = (uint32_t)e / (uint32_t)d.item_numel;
-                    item = i32;
-                    local = (uint32_t)e - i32 * (uint32_t)d.item_numel;
-                } else {
-                    item = e / d.item_numel;
-                    local = e - item * d.item_numel;
-                }
-                const Philox ph(d.seed[item]);
-                normal4(ph((uint64_t)local >> 2, d.stream[item]), z);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[4 * g + j] = (CT)z[j];
+            float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (e < numel) z = draw_group(d, e);
+            v[4 * g] = (CT)z.x; v[4 * g + 1] = (CT)z.y; v[4 * g + 2] = (CT)z.z; v[4 * g + 3] = (CT)z.w;
         }
     } else {
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             const int64_t e = first + j;
-            float z = 0.f;
-            if (e < numel) {
-                const int64_t item = e / d.item_numel;
-                const int64_t local = e - item * d.item_numel;
-                z = normal_at(Philox(d.seed[item]), (uint64_t)local, d.stream[item]);
-            }
-            v[j] = (CT)z;
+            v[j] = (CT)(e < numel ? draw_single(d, e) : 0.f);
         }
     }
 }
-
-// Correctly rounded fp32 reciprocal of a divisor, or 0 when the fast division must not be used.
-static inline float exact_reciprocal(float c) {
-    const float m = c < 0 ? -c : c;
-    if (!(m >= 0x1p-20f && m <= 0x1p20f)) return 0.0f;  // also rejects NaN / inf / 0 / subnormals
-    const double cd = (double)c;
-    float best = (float)(1.0 / cd);
-    // c * y is exact in double (24 x 24 bits), and 1 - c*y is exact by Sterbenz: pick the neighbour closest to 1/c
-    const float cand[3] = {nextafterf(best, -INFINITY), best, nextafterf(best, INFINITY)};
-    double err = 2.0;
-    for (int i = 0; i < 3; ++i) {
-        const double e = fabs(1.0 - cd * (double)cand[i]);
-        if (e < err) { err = e; best = cand[i]; }
-    }
-    return best;
-}
-template <typename CT> static inline CT reciprocal_for(CT c);
-template <> inline float reciprocal_for<float>(float c) { return exact_reciprocal(c); }
-template <> inline double reciprocal_for<double>(double) { return 0.0; }
 
 static inline void fill_kphilox(KPhilox* out, const skr_philox* in, int count) {
     for (int i = 0; i < count; ++i) {

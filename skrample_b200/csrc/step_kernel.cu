@@ -310,7 +310,7 @@ int fail(int code, const char* fmt, ...) {
 struct DeviceInfo {
     int sm_count = 0;
     int max_smem = 0;
-    bool attr_set[8] = {false, false, false, false, false, false, false, false};
+    bool attr_set[16] = {};
 };
 
 static int env_int(const char* name, int fallback) {
@@ -459,8 +459,8 @@ static Shape pick_shape(uint32_t stage_bytes, int max_smem, int max_ctas) {
     return sh;
 }
 
-template <typename CT, int MODE, int V>
-static int launch_block_inst(const skr_program* p, BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned, int slot) {
+template <typename CT, int MODE, int V, bool PHILOX>
+static int launch_block_one(const skr_program* p, BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned, int slot) {
     constexpr int TILE = kThreads * V;
     k.numel = numel;
     k.n_inputs = p->n_inputs;
@@ -502,19 +502,25 @@ static int launch_block_inst(const skr_program* p, BProgram<CT>& k, int64_t nume
 
     if (!dev->attr_set[slot]) {
         cudaFuncAttributes fa;
-        cudaError_t e = cudaFuncGetAttributes(&fa, block_kernel<CT, MODE, V>);
+        cudaError_t e = cudaFuncGetAttributes(&fa, block_kernel<CT, MODE, V, PHILOX>);
         if (e != cudaSuccess) return fail((int)e, "cudaFuncGetAttributes: %s", cudaGetErrorString(e));
-        e = cudaFuncSetAttribute(block_kernel<CT, MODE, V>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        e = cudaFuncSetAttribute(block_kernel<CT, MODE, V, PHILOX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  dev->max_smem - (int)fa.sharedSizeBytes);
         if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         dev->attr_set[slot] = true;
     }
-    block_kernel<CT, MODE, V><<<(unsigned)grid, kThreads + kProducerThreads, smem, stream>>>(k);
+    block_kernel<CT, MODE, V, PHILOX><<<(unsigned)grid, kThreads + kProducerThreads, smem, stream>>>(k);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, "block kernel launch: %s", cudaGetErrorString(e));
     ++g_launches;
     ++g_launches_kind[0];
     return 0;
+}
+
+template <typename CT, int MODE, int V>
+static int launch_block_inst(const skr_program* p, BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned, int slot) {
+    if (p->n_philox > 0) return launch_block_one<CT, MODE, V, true>(p, k, numel, stream, aligned, slot + 8);
+    return launch_block_one<CT, MODE, V, false>(p, k, numel, stream, aligned, slot);
 }
 
 template <typename CT>
@@ -534,8 +540,9 @@ static int launch_block(const skr_program* p, BProgram<CT>& k, int64_t numel, cu
         if (all_f32) return launch_block_inst<float, IN_F32, 4>(p, k, numel, stream, aligned, 4);
         if (all_bf16) return launch_block_inst<float, IN_BF16, 8>(p, k, numel, stream, aligned, 5);
         if (all_f16) return launch_block_inst<float, IN_F16, 8>(p, k, numel, stream, aligned, 6);
-        // mixed storage: 8 elements per thread halve the per-tile control overhead once there are enough tiles
-        if (numel >= (int64_t)kThreads * 8 * 296) return launch_block_inst<float, IN_MIXED, 8>(p, k, numel, stream, aligned, 7);
+        // Mixed storage stays at 4 elements per thread: measured on B200 the 8-wide variant loses more to halved
+        // occupancy / doubled stage size than it gains from amortised control (Adams-9 bf16 59 vs 31 us,
+        // UniPC-3 bf16 46 vs 37 us per step); SKR_IN_MODE=8 keeps it reachable for experiments.
         return launch_block_inst<float, IN_MIXED, 4>(p, k, numel, stream, aligned, 3);
     }
 }

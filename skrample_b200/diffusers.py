@@ -282,8 +282,11 @@ def _cast_inputs(compute_scale: torch.dtype | None, *tensors: Tensor) -> tuple[T
 class SkrampleWrapperCore(abc.ABC):
     "Common scheduler facade. reference: diffusers.py:233-387"
 
-    fused_noise = True
-    "Let the step kernel draw plain Random noise itself when the generators live on the sample's CUDA device"
+    fused_noise = False
+    """Let the step kernel draw plain ``Random`` noise itself (CUDA generators on the sample's device) instead of reading
+    the tensor the fill kernel wrote.  Same values either way.  It removes a launch, one write and up to two reads of
+    the noise, but adds Philox + Box-Muller work to the step kernel: a win for fp32 latents that are HBM-bound
+    (measured free on B200), a loss for small or 16-bit latents where the step kernel is issue-bound."""
 
     def __post_init__(self) -> None:
         self._steps: int = 50

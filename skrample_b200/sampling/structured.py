@@ -637,7 +637,7 @@ def _converted_current(
     if not live:
         return None
     slot = prog.store(P, COMPUTE)
-    if ctx.out_dtype is not None and ctx.out_dtype in _HALF_DTYPES():
+    if _OPTIONS.final_dtype is not None and ctx.out_dtype in _HALF_DTYPES():
         ctx.lowp_slot = prog.store(P, ctx.out_dtype)  # what the pipeline gets back as pred_original_sample
     return slot
 

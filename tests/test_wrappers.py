@@ -133,10 +133,12 @@ def test_cuda_wrapper_matches_reference(case: dict) -> None:
 
 @pytest.mark.gpu
 def test_cuda_wrapper_device_generators() -> None:
-    "CUDA generators: noise is drawn by the Philox kernels, the trajectory is deterministic and finite."
+    """CUDA generators: noise is drawn by the Philox kernels, the trajectory is deterministic and finite, and drawing
+    the noise inside the step kernel (fused_noise) gives the same latents as reading the filled tensor."""
     outs = []
-    for _ in range(2):
-        w = diffusers.SkrampleWrapperScheduler.from_diffusers_config(cases.SCALED_CONFIG | {"_class_name": "UniPCMultistepScheduler"}, sampler_props={"stochasticity": 1})
+    for fused in (False, False, True):
+        w = diffusers.SkrampleWrapperScheduler.from_diffusers_config(cases.SCALED_CONFIG | {"_class_name": "UniPCMultistepScheduler"}, sampler_props={"stochasticity": 1}, compute_scale=torch.float32)
+        w.fused_noise = fused
         w.set_timesteps(10, device="cuda")
         x = torch.randn((2, 4, 32, 32), generator=torch.Generator().manual_seed(1)).cuda().bfloat16()
         gens = [torch.Generator(device="cuda").manual_seed(5), torch.Generator(device="cuda").manual_seed(6)]
@@ -145,3 +147,5 @@ def test_cuda_wrapper_device_generators() -> None:
         assert x.dtype == torch.bfloat16 and torch.isfinite(x).all()
         outs.append(x)
     assert torch.equal(outs[0], outs[1])
+    # the filled tensor is bf16 (the wrapper generates in the sample's dtype), the in-kernel draw is unrounded fp32
+    assert (outs[0].float() - outs[2].float()).abs().max().item() < 0.25

@@ -188,6 +188,13 @@ typedef struct skr_offset {
 int skr_noise_fill(void* out, int32_t dtype, int64_t numel, uint64_t seed, uint64_t stream, const skr_offset* offset,
                    double* moments, void* cuda_stream);
 
+/*
+ * The same for a whole batch in one launch: item i (keys->item_numel elements) is the normal stream
+ * (keys->seed[i], keys->stream[i]) - BatchTensorNoise.generate without the per-item launches and the stack copy
+ * (noise.py:445-446).  numel = keys->n_items * keys->item_numel.
+ */
+int skr_noise_fill_batch(void* out, int32_t dtype, const skr_philox* keys, void* cuda_stream);
+
 /* sum / sum^2 of a tensor into device double[2] (pre-zeroed), for Tensor.std() (noise.py:207,365,401). */
 int skr_noise_moments(const void* in, int32_t dtype, int64_t numel, double* moments, void* cuda_stream);
 

@@ -23,7 +23,7 @@
 
 #include "../../include/skrample_b200.h"
 #include "common.cuh"
-#include "philox.cuh"
+#include "machine.cuh"
 
 namespace skr {
 
@@ -148,6 +148,26 @@ __global__ void __launch_bounds__(256) fill_kernel(const __grid_constant__ FillP
     if (p.moments) {
         block_sum2(s1, s2);
         if (threadIdx.x == 0) { atomicAdd(&p.moments[0], s1); atomicAdd(&p.moments[1], s2); }
+    }
+}
+
+// Batched Random fill: one launch for every batch item, each with its own (seed, stream) - the same values
+// skr_noise_fill writes item by item (reference: BatchTensorNoise.generate, noise.py:445-446).
+struct BatchFillParams {
+    void* out;
+    int64_t numel;
+    int32_t dtype, aligned;
+    KPhilox keys;
+};
+
+__global__ void __launch_bounds__(256) batch_fill_kernel(const __grid_constant__ BatchFillParams p) {
+    const int64_t groups = (p.numel + 3) >> 2;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t first = g << 2;
+        float z[4];
+        draw_normals<float, 4>(p.keys, first, p.numel, z);
+        if (p.aligned && first + 4 <= p.numel) store4(p.out, p.dtype, first, z);
+        else for (int j = 0; j < 4 && first + j < p.numel; ++j) store1(p.out, p.dtype, first + j, z[j]);
     }
 }
 
@@ -404,6 +424,24 @@ int skr_noise_fill(void* out, int32_t dtype, int64_t numel, uint64_t seed, uint6
     }
     fill_kernel<<<grid_for((numel + 3) / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
     return check_launch("noise fill");
+}
+
+int skr_noise_fill_batch(void* out, int32_t dtype, const skr_philox* keys, void* cuda_stream) {
+    using namespace skr;
+    if (!keys) return fail(SKR_E_NULL, "null keys");
+    if (dtype < 0 || dtype > SKR_F16) return fail(SKR_E_DTYPE, "unknown dtype %d", dtype);
+    if (keys->n_items < 1 || keys->n_items > SKR_MAX_PHILOX_ITEMS) return fail(SKR_E_RANGE, "n_items %d out of range", keys->n_items);
+    if (keys->item_numel < 0) return fail(SKR_E_RANGE, "negative item_numel");
+    const int64_t numel = keys->item_numel * keys->n_items;
+    if (numel == 0) return 0;
+    if (!out) return fail(SKR_E_NULL, "null output");
+    BatchFillParams p;
+    memset(&p, 0, sizeof(p));
+    p.out = out; p.numel = numel; p.dtype = dtype;
+    p.aligned = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+    fill_kphilox(&p.keys, keys, 1);
+    batch_fill_kernel<<<grid_for((numel + 3) / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
+    return check_launch("noise batch fill");
 }
 
 int skr_noise_moments(const void* in, int32_t dtype, int64_t numel, double* moments, void* cuda_stream) {

@@ -99,6 +99,8 @@ def _lib() -> Any:
         vp, i32, i64, u64, dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double
         lib.skr_noise_fill.restype = ctypes.c_int
         lib.skr_noise_fill.argtypes = [vp, i32, i64, u64, u64, ctypes.POINTER(_SkrOffset), vp, vp]
+        lib.skr_noise_fill_batch.restype = ctypes.c_int
+        lib.skr_noise_fill_batch.argtypes = [vp, i32, ctypes.POINTER(native.SkrPhilox), vp]
         lib.skr_noise_moments.restype = ctypes.c_int
         lib.skr_noise_moments.argtypes = [vp, i32, i64, vp, vp]
         lib.skr_noise_scale.restype = ctypes.c_int
@@ -176,11 +178,15 @@ class PhiloxDraw:
     def materialize(self) -> torch.Tensor:
         if self._tensor is None:
             out = torch.empty(self.shape, dtype=self.dtype, device=self.device)
-            rows = out.reshape(len(self.seeds), -1)
+            keys = _native().SkrPhilox()
+            keys.n_items = len(self.seeds)
+            keys.item_numel = self.item_numel
+            for j, (seed, stream) in enumerate(zip(self.seeds, self.streams, strict=True)):
+                keys.seed[j] = seed
+                keys.stream[j] = stream
             with _DeviceGuard(self.device):
-                for row, seed, stream in zip(rows, self.seeds, self.streams, strict=True):
-                    status = _lib().skr_noise_fill(row.data_ptr(), _code(out.dtype), row.numel(), seed, stream, None, None, _stream())
-                    _native().check(status, "skr_noise_fill")
+                status = _lib().skr_noise_fill_batch(out.data_ptr(), _code(out.dtype), ctypes.byref(keys), _stream())
+            _native().check(status, "skr_noise_fill_batch")
             self._tensor = out
         return self._tensor
 
@@ -660,6 +666,9 @@ class BatchTensorNoise[T: TensorNoiseProps | None](SkrampleTensorNoise):
     generators: list[TensorNoiseCommon[T]]
 
     def generate(self, step: Step | None) -> torch.Tensor:
+        drawn = self.lazy(step, _fallback=False)
+        if drawn is not None:
+            return drawn.materialize()  # plain Random on one CUDA device: one launch for the whole batch
         first = self.generators[0]
         same_place = all(g.on_device and g.seed.device == first.seed.device and g.dtype == first.dtype and g.shape == first.shape for g in self.generators)
         if same_place:
@@ -669,7 +678,7 @@ class BatchTensorNoise[T: TensorNoiseProps | None](SkrampleTensorNoise):
             return out
         return torch.stack([g.generate(step) for g in self.generators])
 
-    def lazy(self, step: Step | None) -> "PhiloxDraw | torch.Tensor":
+    def lazy(self, step: Step | None, _fallback: bool = True) -> "PhiloxDraw | torch.Tensor | None":
         """The next batch of noise as Philox keys when every item is a plain ``Random`` on one CUDA device (and the
         batch fits the kernel's key table); otherwise the materialised tensor."""
         first = self.generators[0]
@@ -678,7 +687,7 @@ class BatchTensorNoise[T: TensorNoiseProps | None](SkrampleTensorNoise):
             for g in self.generators
         )
         if not eligible:
-            return self.generate(step)
+            return self.generate(step) if _fallback else None
         return PhiloxDraw(
             (len(self.generators), *first.shape),
             tuple(g._key() for g in self.generators),

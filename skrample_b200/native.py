@@ -82,11 +82,11 @@ def _pack_draws(packed: SkrProgram, draws: list[Any]) -> None:
         raise RuntimeError("skrample_b200: at most two in-kernel noise draws per step program")
     packed.n_philox = len(draws)
     for slot, draw in zip(packed.philox, draws, strict=False):
-        slot.n_items = len(draw.seeds)
+        count = len(draw.seeds)
+        slot.n_items = count
         slot.item_numel = draw.item_numel
-        for j, (seed, stream) in enumerate(zip(draw.seeds, draw.streams, strict=True)):
-            slot.seed[j] = seed
-            slot.stream[j] = stream
+        slot.seed[:count] = draw.seeds
+        slot.stream[:count] = draw.streams
 
 
 EXPORTS = (
@@ -139,6 +139,13 @@ def load() -> ctypes.CDLL:
     ]
     _lib = lib
     return lib
+
+
+def raw_stream(device_index: int | None = None) -> int:
+    "cudaStream_t of torch's current stream as an integer (no Stream object construction on the hot path)."
+    if device_index is None:
+        device_index = torch._C._cuda_getDevice()
+    return torch._C._cuda_getCurrentRawStream(device_index)
 
 
 def check(status: int, what: str) -> None:
@@ -218,11 +225,11 @@ def launch_program(program: "Program") -> list[Any]:
         ACCOUNT["bytes"] += sum(t.numel() * t.element_size() for t in inputs) + sum(t.numel() * t.element_size() for t in outputs)
     packed = pack_program(program, inputs, outputs)
     device = first.device
-    if torch.cuda.current_device() != device.index:
+    if torch._C._cuda_getDevice() != device.index:
         with torch.cuda.device(device):
-            status = lib.skr_program_launch(ctypes.byref(packed), first.numel(), torch.cuda.current_stream().cuda_stream)
+            status = lib.skr_program_launch(ctypes.byref(packed), first.numel(), raw_stream(device.index))
     else:
-        status = lib.skr_program_launch(ctypes.byref(packed), first.numel(), torch.cuda.current_stream().cuda_stream)
+        status = lib.skr_program_launch(ctypes.byref(packed), first.numel(), raw_stream(device.index))
     check(status, "skr_program_launch")
     return outputs
 
@@ -259,46 +266,52 @@ def launch_compiled(compiled: CompiledProgram, inputs: list[Any], draws: list[An
     "Bind tensors (and lazy noise draws) to a compiled program and launch it.  None when they do not qualify."
     first = inputs[0]
     shape, device = first.shape, first.device
-    any64 = False
-    all_half = True
-    kinds = set()
-    for t in inputs:
-        if not (_on_device(t) and t.shape == shape and t.device == device and t.dtype in _ALLOWED and t.is_contiguous()):
-            return None
-        kinds.add(t.dtype)
-        any64 |= t.dtype == torch.float64
-    if any64:
-        default = torch.float64
-    elif torch.float32 in kinds or len(kinds) > 1:
-        default = torch.float32
-    else:
-        default = first.dtype
-    compute = torch.float64 if any64 else torch.float32
-    del all_half
     packed = compiled.packed
-    for slot, t in zip(packed.inputs, inputs, strict=False):
+    slots = packed.inputs
+    any64 = any32 = False
+    kind = first.dtype
+    mixed = False
+    for i, t in enumerate(inputs):
+        dtype = t.dtype
+        code = DTYPE_CODE.get(dtype)
+        if code is None or not _on_device(t) or t.shape != shape or t.device != device or not t.is_contiguous():
+            return None
+        if code == F64:
+            any64 = True
+        elif code == F32:
+            any32 = True
+        if dtype != kind:
+            mixed = True
+        slot = slots[i]
         slot.ptr = t.data_ptr()
-        slot.dtype = DTYPE_CODE[t.dtype]
+        slot.dtype = code
+    default = torch.float64 if any64 else (torch.float32 if any32 or mixed else kind)
+    compute = torch.float64 if any64 else torch.float32
     outputs = []
-    for slot, want in zip(packed.outputs, compiled.out_specs, strict=False):
-        dtype = default if want is None else (compute if isinstance(want, str) else want)
+    slots = packed.outputs
+    for i, want in enumerate(compiled.out_specs):
+        dtype = default if want is None else (compute if want.__class__ is str else want)
         out = torch.empty(shape, dtype=dtype, device=device)
+        slot = slots[i]
         slot.ptr = out.data_ptr()
         slot.dtype = DTYPE_CODE[dtype]
         outputs.append(out)
     if draws:
         numel = first.numel()
-        if any(d.numel != numel or d.device != device for d in draws):
-            return None
+        for d in draws:
+            if d.numel != numel or d.device != device:
+                return None
         _pack_draws(packed, draws)
     if ACCOUNT["on"]:
         ACCOUNT["launches"] += 1
         ACCOUNT["bytes"] += sum(t.numel() * t.element_size() for t in inputs) + sum(t.numel() * t.element_size() for t in outputs)
     lib = _lib if _lib is not None else load()
-    if torch.cuda.current_device() != device.index:
+    index = device.index
+    if torch._C._cuda_getDevice() != index:
         with torch.cuda.device(device):
-            status = lib.skr_program_launch(ctypes.byref(packed), first.numel(), torch.cuda.current_stream().cuda_stream)
+            status = lib.skr_program_launch(ctypes.byref(packed), first.numel(), torch._C._cuda_getCurrentRawStream(index))
     else:
-        status = lib.skr_program_launch(ctypes.byref(packed), first.numel(), torch.cuda.current_stream().cuda_stream)
-    check(status, "skr_program_launch")
+        status = lib.skr_program_launch(ctypes.byref(packed), first.numel(), torch._C._cuda_getCurrentRawStream(index))
+    if status:
+        check(status, "skr_program_launch")
     return outputs

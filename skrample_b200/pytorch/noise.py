@@ -114,7 +114,7 @@ def _lib() -> Any:
 
 
 def _stream() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    return _native().raw_stream()
 
 
 def _code(dtype: torch.dtype) -> int:
@@ -128,7 +128,7 @@ class _DeviceGuard:
     "Make ``device`` current for the launches inside (no-op when it already is)."
 
     def __init__(self, device: torch.device) -> None:
-        self.ctx = torch.cuda.device(device) if torch.cuda.current_device() != device.index else None
+        self.ctx = torch.cuda.device(device) if torch._C._cuda_getDevice() != device.index else None
 
     def __enter__(self) -> None:
         if self.ctx is not None:
@@ -179,11 +179,11 @@ class PhiloxDraw:
         if self._tensor is None:
             out = torch.empty(self.shape, dtype=self.dtype, device=self.device)
             keys = _native().SkrPhilox()
-            keys.n_items = len(self.seeds)
+            count = len(self.seeds)
+            keys.n_items = count
             keys.item_numel = self.item_numel
-            for j, (seed, stream) in enumerate(zip(self.seeds, self.streams, strict=True)):
-                keys.seed[j] = seed
-                keys.stream[j] = stream
+            keys.seed[:count] = self.seeds
+            keys.stream[:count] = self.streams
             with _DeviceGuard(self.device):
                 status = _lib().skr_noise_fill_batch(out.data_ptr(), _code(out.dtype), ctypes.byref(keys), _stream())
             _native().check(status, "skr_noise_fill_batch")

@@ -68,13 +68,38 @@ DEFAULT_EMBEDDED_PROVIDERS: Mapping[int, tableaux.TableauProvider[tableaux.Embed
 # the fused explicit RK step
 
 
+_CHUNK = 24
+"Most tensor terms one launch accumulates (the kernel binds at most 32 tensors and 64 ops per program)."
+
+
 def _emit_combination(prog: Program, derivatives: list[Any], coefficients: tuple[float, ...], in_register: int | None) -> None:
     """A = sum_i k_i * c_i in tableau order, skipping exact-zero coefficients.  ``derivatives[in_register]``
-    (if any) is the one still sitting in register P of this program."""
+    (if any) is the one still sitting in register P of this program.
+
+    Tableaux with more stages than one launch can bind (Feagin's 25/35-stage methods) accumulate a leading run of
+    terms in extra launches; the partial sum round-trips through memory in compute precision, which is exact."""
+    terms = [(index, k, c) for index, (k, c) in enumerate(zip(derivatives, coefficients, strict=True)) if c != 0]
     first = True
-    for index, (k, c) in enumerate(zip(derivatives, coefficients, strict=True)):
-        if c == 0:
-            continue
+    tensors = [t for t in terms if t[0] != in_register]
+    if len(tensors) > _CHUNK and all(pg.is_cuda_tensor(t[1]) for t in tensors):
+        partial = None
+        while sum(1 for t in terms if t[0] != in_register) > _CHUNK:
+            head = []
+            while terms and terms[0][0] != in_register and len(head) < _CHUNK:
+                head.append(terms.pop(0))
+            if not head:
+                break
+            sub = Program()
+            if partial is not None:
+                sub.load(A, partial)
+            for n, (_, k, c) in enumerate(head):
+                sub.acc(c, k, first=partial is None and n == 0)
+            slot = sub.store(A, "compute")
+            partial = sub.run()[slot]
+        if partial is not None:
+            prog.load(A, partial)
+            first = False
+    for index, k, c in terms:
         if index == in_register:
             prog.acc(c, reg=P, first=first)
         else:

@@ -306,10 +306,17 @@ def execute_generic(program: Program) -> list[Any]:
     # is extended-precision and whose generic path is the plain left-to-right ((0 + a*b) + c*d)...
     pend_p: list[Any] = []
     pend_q: list[Any] = []
+    carry: list[Any] = []  # [A] when a dot product continues an accumulator loaded from memory
 
     def flush() -> None:
         if pend_p:
-            reg[A] = math.sumprod(pend_p, pend_q)
+            if carry:
+                total = carry.pop()
+                for p_, q_ in zip(pend_p, pend_q, strict=True):
+                    total = total + p_ * q_
+                reg[A] = total
+            else:
+                reg[A] = math.sumprod(pend_p, pend_q)
             pend_p.clear()
             pend_q.clear()
 
@@ -320,6 +327,9 @@ def execute_generic(program: Program) -> list[Any]:
             if code == OP_ACC0:
                 pend_p.clear()
                 pend_q.clear()
+                carry.clear()
+            elif not pend_p and not carry:
+                carry.append(reg[A])
             pend_p.append(values[op.src] if op.a == 0 else reg[op.a - 1])
             pend_q.append(c[0])
             continue

@@ -130,3 +130,19 @@ def test_rkultra4_launch_count() -> None:
     before = native.launch_count()
     sampler.step(x, cases.network, models.FlowModel(), scheduling.FlowShift(scheduling.Linear()), Step.from_int(3, 10))
     assert native.launch_count() - before == 4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["Feagin14", "Feagin12", "Stepanov10"])
+def test_many_stage_tableaux_chunk_across_launches(name: str) -> None:
+    "35/25/15-stage tableaux exceed one launch's 32 tensors: partial sums continue across launches, bit-exact vs CPU."
+    from skrample_b200.common import Step
+
+    tab = getattr(tableaux.RKZ, name).tableau()
+    schedule, model = scheduling.FlowShift(scheduling.Linear()), models.FlowModel()
+    x = torch.randn(3000, generator=torch.Generator().manual_seed(4))
+    noise = torch.randn(3000, generator=torch.Generator().manual_seed(5))
+    step = Step.from_int(2, 6)
+    want = functional.step_tableau(tab, x, cases.network, model, schedule, step, models.DataModel(), noise, 1.0)[0]
+    got = functional.step_tableau(tab, x.cuda(), cases.network, model, schedule, step, models.DataModel(), noise.cuda(), 1.0)[0]
+    assert torch.equal(got.cpu(), want)

@@ -134,11 +134,13 @@ __device__ __forceinline__ void fetch_tile(const unsigned char* stage, uint32_t 
                 }
             } break;
             default: {
+                if constexpr (sizeof(CT) == 8) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const double2 q = *reinterpret_cast<const double2*>(base + tid * 64 + 16 * i);
-                    v[2 * i] = (CT)q.x;
-                    v[2 * i + 1] = (CT)q.y;
+                    for (int i = 0; i < 4; ++i) {
+                        const double2 q = *reinterpret_cast<const double2*>(base + tid * 64 + 16 * i);
+                        v[2 * i] = (CT)q.x;
+                        v[2 * i + 1] = (CT)q.y;
+                    }
                 }
             } break;
         }
@@ -167,10 +169,12 @@ __device__ __forceinline__ void store_tile(void* ptr, int dtype, int64_t first, 
             if constexpr (V == 8) *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(ptr) + first) = make_uint4(w[0], w[1], w[2], w[3]);
             else *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(ptr) + first) = make_uint2(w[0], w[1]);
         } break;
-        default: {
-            double2* p = reinterpret_cast<double2*>(reinterpret_cast<double*>(ptr) + first);
+        default: {  // SKR_F64 - only reachable in the fp64-compute instantiation
+            if constexpr (sizeof(CT) == 8) {
+                double2* p = reinterpret_cast<double2*>(reinterpret_cast<double*>(ptr) + first);
 #pragma unroll
-            for (int i = 0; i < V / 2; ++i) p[i] = make_double2((double)v[2 * i], (double)v[2 * i + 1]);
+                for (int i = 0; i < V / 2; ++i) p[i] = make_double2((double)v[2 * i], (double)v[2 * i + 1]);
+            }
         } break;
     }
 }
@@ -242,10 +246,9 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
     if (h.x_in >= 0) io.load(h.x_in, X);
     if (h.y_in >= 0) {
         io.load(h.y_in, P);
-        if (h.neg) {
+        const bool neg = h.neg != 0;
 #pragma unroll
-            for (int j = 0; j < V; ++j) P[j] = -P[j];
-        }
+        for (int j = 0; j < V; ++j) P[j] = neg ? -P[j] : P[j];
     }
     if (h.n_conv > 0) {
 #pragma unroll
@@ -276,10 +279,8 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
     for (int b = 0; b < 2; ++b) {
         const BBlock<CT>& k = prog.blk[b];
         if (!k.enabled) continue;
-        if (k.save_s) {
 #pragma unroll
-            for (int j = 0; j < V; ++j) S[j] = X[j];
-        }
+        for (int j = 0; j < V; ++j) S[j] = X[j];  // only the SPC blend reads S; an unconditional copy beats a branch
         if (k.sample_in >= 0) io.load(k.sample_in, X);
 
         CT in[V];
@@ -367,12 +368,11 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
         }
 
         const CT gamma = k.gamma, delta = k.delta;
-        if (k.pred_is_p) {
+        const bool from_p = k.pred_is_p != 0;
 #pragma unroll
-            for (int j = 0; j < V; ++j) R[j] = Ar::add(Ar::add((CT)0, Ar::mul(X[j], gamma)), Ar::mul(P[j], delta));
-        } else {
-#pragma unroll
-            for (int j = 0; j < V; ++j) R[j] = Ar::add(Ar::add((CT)0, Ar::mul(X[j], gamma)), Ar::mul(A[j], delta));
+        for (int j = 0; j < V; ++j) {
+            const CT pred = from_p ? P[j] : A[j];
+            R[j] = Ar::add(Ar::add((CT)0, Ar::mul(X[j], gamma)), Ar::mul(pred, delta));
         }
         if (k.has_noise) {
             if (PHILOX && k.has_noise == 2) draw_normals<CT, V>(prog.philox[k.noise_in], first, prog.numel, in);

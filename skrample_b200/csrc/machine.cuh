@@ -82,10 +82,12 @@ __device__ __forceinline__ void fetch_staged(const unsigned char* stage, uint32_
             const float2 a = __half22float2(lo), b = __half22float2(hi);
             v[0] = (CT)a.x; v[1] = (CT)a.y; v[2] = (CT)b.x; v[3] = (CT)b.y;
         } break;
-        default: {  // SKR_F64
-            const double2 q0 = *reinterpret_cast<const double2*>(base + tid * 32);
-            const double2 q1 = *reinterpret_cast<const double2*>(base + tid * 32 + 16);
-            v[0] = (CT)q0.x; v[1] = (CT)q0.y; v[2] = (CT)q1.x; v[3] = (CT)q1.y;
+        default: {  // SKR_F64 - only reachable in the fp64-compute instantiation
+            if constexpr (sizeof(CT) == 8) {
+                const double2 q0 = *reinterpret_cast<const double2*>(base + tid * 32);
+                const double2 q1 = *reinterpret_cast<const double2*>(base + tid * 32 + 16);
+                v[0] = (CT)q0.x; v[1] = (CT)q0.y; v[2] = (CT)q1.x; v[3] = (CT)q1.y;
+            }
         } break;
     }
 }

@@ -41,8 +41,8 @@ enum InMode : int { IN_MIXED = 0, IN_F32 = 1, IN_BF16 = 2, IN_F16 = 3 };
 template <typename CT>
 struct BTerm {
     CT c0, c1;
+    CT r0;       // RN(1/c0) where c0 is a divisor (UNI terms)
     int32_t in;  // input index
-    int32_t pad;
 };
 
 template <typename CT>
@@ -53,6 +53,7 @@ struct BBlock {
     int32_t sample_in, base_in, noise_in, store_r, store_link;  // -1 = not used
     int32_t pad;
     CT p_coef, div, gamma, delta, zeta, l0, l1, e0, e1, e2;
+    CT div_r, l1_r;  // reciprocals of the divisors `div` and `l1`
     BTerm<CT> terms[kMaxTerms];
 };
 
@@ -62,6 +63,7 @@ struct BHead {
     int32_t conv_flags[2];
     int32_t store_p2;  // optional second copy of P (e.g. fp32 solver state + 16-bit copy for the caller)
     CT conv_c[2][3];
+    CT conv_r[2];  // reciprocals of the conversion divisors conv_c[.][2]
 };
 
 template <typename CT>
@@ -69,7 +71,8 @@ struct BProgram {
     int64_t numel;
     int32_t n_inputs, stages;
     uint32_t stage_bytes, use_tma;
-    int32_t n_full_tiles, pad;
+    int32_t n_full_tiles;
+    int32_t fast_div;  // every divisor has a host-side reciprocal (machine.cuh, div_uniform)
     const void* in_ptr[SKR_MAX_INPUTS];
     void* out_ptr[SKR_MAX_OUTPUTS];
     uint32_t in_off[SKR_MAX_INPUTS];
@@ -214,6 +217,90 @@ __device__ __forceinline__ void store_guarded(void* ptr, int dtype, int64_t firs
     }
 }
 
+// ---- compile-time shapes -------------------------------------------------------------------------------
+//
+// The descriptor fields that only steer control flow (which operands exist, block kind, storage types) can be
+// pinned at compile time: a shape type carries them as constants, -1 meaning "read the descriptor".  ShAny pins
+// nothing and runs every program the parser accepts; the pinned shapes cover the steady-state step of the common
+// samplers, where the uniform branches and dtype switches otherwise make up ~40% of the instruction stream.
+
+template <int PIN>
+__device__ __forceinline__ int pinned(int runtime) {
+    if constexpr (PIN >= 0) return PIN;
+    else return runtime;
+}
+
+struct BlkAny {
+    static constexpr int enabled = -1, kind = -1, sample = -1, base = -1, p_mode = -1, has_div = -1, pred_p = -1;
+    static constexpr int noise = -1, store = -1, link = -1, slink = -1;
+    static constexpr int dt_state = -1, dt_noise = -1, dt_store = -1, dt_slink = -1;
+};
+struct BlkOff : BlkAny {
+    static constexpr int enabled = 0;
+};
+struct ShAny {
+    static constexpr int x = -1, y = -1, neg = -1, n_conv = -1, sp = -1, sp2 = -1;
+    static constexpr int dt_x = -1, dt_y = -1, dt_sp = -1, dt_sp2 = -1;
+    using B0 = BlkAny;
+    using B1 = BlkAny;
+};
+
+// UniP / UniPC steady state on 16-bit latents (LP): sample, network output and noise in 16-bit storage, solver
+// state (previous sample, x-hat history) in fp32.  Block 0 is the corrector of the previous step, block 1 the
+// predictor of this one.
+template <int LP>
+struct ShUniPC : ShAny {
+    static constexpr int x = 1, y = 1, neg = 0, n_conv = 1, sp = 1, sp2 = 0;
+    static constexpr int dt_x = LP, dt_y = LP, dt_sp = SKR_F32;
+    struct B0 : BlkAny {
+        static constexpr int enabled = 1, kind = BK_UNI, sample = 1, base = 1, p_mode = 1, has_div = 0, pred_p = 0;
+        static constexpr int store = 1, link = BL_X_FROM_R, slink = 0;
+        static constexpr int dt_state = SKR_F32, dt_noise = LP, dt_store = SKR_F32;
+    };
+    struct B1 : BlkAny {
+        static constexpr int enabled = 1, kind = BK_UNI, sample = 0, base = 0, p_mode = 0, has_div = 0, pred_p = 0;
+        static constexpr int store = 1, link = BL_NONE, slink = 0;
+        static constexpr int dt_state = SKR_F32, dt_noise = LP, dt_store = LP;
+    };
+};
+
+template <typename BS, typename CT>
+static bool block_matches(const BBlock<CT>& k, const int32_t* in_dt, const int32_t* out_dt) {
+    auto eq = [](int pin, int v) { return pin < 0 || pin == v; };
+    if (!eq(BS::enabled, k.enabled)) return false;
+    if (!k.enabled) return true;
+    bool ok = eq(BS::kind, k.kind) && eq(BS::sample, k.sample_in >= 0) && eq(BS::base, k.base_in >= 0) &&
+              eq(BS::p_mode, k.p_mode) && eq(BS::has_div, k.has_div) && eq(BS::pred_p, k.pred_is_p) &&
+              eq(BS::noise, k.has_noise) && eq(BS::store, k.store_r >= 0) && eq(BS::link, k.link) &&
+              eq(BS::slink, k.store_link >= 0);
+    if (!ok) return false;
+    if (BS::dt_state >= 0) {
+        if (k.sample_in >= 0 && in_dt[k.sample_in] != BS::dt_state) return false;
+        if (k.base_in >= 0 && in_dt[k.base_in] != BS::dt_state) return false;
+        for (int t = 0; t < k.n_terms; ++t)
+            if (in_dt[k.terms[t].in] != BS::dt_state) return false;
+    }
+    if (BS::dt_noise >= 0 && k.has_noise == 1 && in_dt[k.noise_in] != BS::dt_noise) return false;
+    if (BS::dt_store >= 0 && k.store_r >= 0 && out_dt[k.store_r] != BS::dt_store) return false;
+    if (BS::dt_slink >= 0 && k.store_link >= 0 && out_dt[k.store_link] != BS::dt_slink) return false;
+    return true;
+}
+
+template <typename Sh, typename CT>
+static bool shape_matches(const BProgram<CT>& p) {
+    auto eq = [](int pin, int v) { return pin < 0 || pin == v; };
+    const BHead<CT>& h = p.head;
+    if (!(eq(Sh::x, h.x_in >= 0) && eq(Sh::y, h.y_in >= 0) && eq(Sh::neg, h.neg) && eq(Sh::n_conv, h.n_conv) &&
+          eq(Sh::sp, h.store_p >= 0) && eq(Sh::sp2, h.store_p2 >= 0)))
+        return false;
+    if (Sh::dt_x >= 0 && h.x_in >= 0 && p.in_dtype[h.x_in] != Sh::dt_x) return false;
+    if (Sh::dt_y >= 0 && h.y_in >= 0 && p.in_dtype[h.y_in] != Sh::dt_y) return false;
+    if (Sh::dt_sp >= 0 && h.store_p >= 0 && p.out_dtype[h.store_p] != Sh::dt_sp) return false;
+    if (Sh::dt_sp2 >= 0 && h.store_p2 >= 0 && p.out_dtype[h.store_p2] != Sh::dt_sp2) return false;
+    return block_matches<typename Sh::B0>(p.blk[0], p.in_dtype, p.out_dtype) &&
+           block_matches<typename Sh::B1>(p.blk[1], p.in_dtype, p.out_dtype);
+}
+
 // ---- one tile of the skeleton -------------------------------------------------------------------------
 
 template <typename CT, int MODE, int V, bool GUARDED>
@@ -222,17 +309,152 @@ struct TileIO {
     const unsigned char* stage;
     int tid;
     int64_t first;
+    template <int DT = -1>
     __device__ __forceinline__ void load(int in, CT (&v)[V]) const {
         if constexpr (GUARDED) fetch_guarded<CT, V>(prog.in_ptr[in], prog.in_dtype[in], first, prog.numel, v);
-        else fetch_tile<CT, MODE, V>(stage, prog.in_off[in], prog.in_dtype[in], tid, v);
+        else fetch_tile<CT, MODE, V>(stage, prog.in_off[in], pinned<DT>(prog.in_dtype[in]), tid, v);
     }
+    template <int DT = -1>
     __device__ __forceinline__ void store(int out, const CT (&v)[V]) const {
         if constexpr (GUARDED) store_guarded<CT, V>(prog.out_ptr[out], prog.out_dtype[out], first, prog.numel, v);
-        else store_tile<CT, V>(prog.out_ptr[out], prog.out_dtype[out], first, v);
+        else store_tile<CT, V>(prog.out_ptr[out], pinned<DT>(prog.out_dtype[out]), first, v);
     }
 };
 
-template <typename CT, int MODE, int V, bool GUARDED, bool PHILOX>
+template <typename CT, int MODE, int V, bool GUARDED, bool PHILOX, typename BS>
+__device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BBlock<CT>& k,
+                                              const TileIO<CT, MODE, V, GUARDED>& io, CT (&X)[V], CT (&P)[V],
+                                              CT (&B)[V], CT (&A)[V], CT (&S)[V], CT (&R)[V]) {
+    using Ar = Arith<CT>;
+    if (!pinned<BS::enabled>(k.enabled)) return;
+    const bool fast_div = prog.fast_div != 0;
+    const int link = pinned<BS::link>(k.link);
+    if (link == BL_BLEND) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) S[j] = X[j];
+    }
+    if (pinned<BS::sample>(k.sample_in >= 0)) io.template load<BS::dt_state>(k.sample_in, X);
+
+    CT in[V];
+    const int kind = pinned<BS::kind>(k.kind);
+    if (kind != BK_NONE) {
+        const int n_terms = k.n_terms;
+        const int p_mode = pinned<BS::p_mode>(k.p_mode);
+        if (kind != BK_ACC) {
+            if (pinned<BS::base>(k.base_in >= 0)) io.template load<BS::dt_state>(k.base_in, B);
+            else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) B[j] = P[j];
+            }
+        }
+        if (kind == BK_ACC) {
+            int t = 0;
+            if (p_mode == 1 || n_terms == 0) {
+                const CT c = k.p_coef;
+#pragma unroll
+                for (int j = 0; j < V; ++j) A[j] = Ar::add((CT)0, Ar::mul(P[j], c));
+            } else {
+                io.template load<BS::dt_state>(k.terms[0].in, in);
+                const CT c = k.terms[0].c0;
+#pragma unroll
+                for (int j = 0; j < V; ++j) A[j] = Ar::add((CT)0, Ar::mul(in[j], c));
+                t = 1;
+            }
+            for (; t < n_terms; ++t) {
+                io.template load<BS::dt_state>(k.terms[t].in, in);
+                const CT c = k.terms[t].c0;
+#pragma unroll
+                for (int j = 0; j < V; ++j) A[j] = Ar::add(A[j], Ar::mul(in[j], c));
+            }
+            if (p_mode == 2 && n_terms > 0) {
+                const CT c = k.p_coef;
+#pragma unroll
+                for (int j = 0; j < V; ++j) A[j] = Ar::add(A[j], Ar::mul(P[j], c));
+            }
+            if (pinned<BS::has_div>(k.has_div)) {
+                div_uniform<V>(A, k.div, k.div_r, fast_div);
+            }
+        } else if (kind == BK_UNI) {
+            for (int t = 0; t < n_terms; ++t) {
+                io.template load<BS::dt_state>(k.terms[t].in, in);
+                const CT rho = k.terms[t].c1;
+#pragma unroll
+                for (int j = 0; j < V; ++j) in[j] = Ar::sub(in[j], B[j]);
+                div_uniform<V>(in, k.terms[t].c0, k.terms[t].r0, fast_div);
+#pragma unroll
+                for (int j = 0; j < V; ++j) A[j] = Ar::add(t == 0 ? (CT)0 : A[j], Ar::mul(in[j], rho));
+            }
+            if (p_mode == 1) {
+                const CT rho = k.p_coef;
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const CT term = Ar::mul(Ar::sub(P[j], B[j]), rho);
+                    A[j] = Ar::add(n_terms == 0 ? (CT)0 : A[j], term);
+                }
+            }
+            const bool empty = k.empty_sum != 0;
+#pragma unroll
+            for (int j = 0; j < V; ++j) A[j] = Ar::add(B[j], empty ? (CT)0 : A[j]);
+        } else if (kind == BK_DPM2) {
+            io.template load<BS::dt_state>(k.terms[0].in, in);
+            const CT inv_r = k.terms[0].c0, half = k.terms[0].c1;
+#pragma unroll
+            for (int j = 0; j < V; ++j) A[j] = Ar::add(B[j], Ar::mul(half, Ar::mul(inv_r, Ar::sub(B[j], in[j]))));
+        } else {  // BK_DPM3
+            CT in2[V];
+            io.template load<BS::dt_state>(k.terms[0].in, in);
+            io.template load<BS::dt_state>(k.terms[1].in, in2);
+            const CT inv_r = k.terms[0].c0, inv_r2 = k.terms[1].c0, mix = k.terms[1].c1;
+            const CT inv_sum = k.e0, w1 = k.e1, w2 = k.e2;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const CT d10 = Ar::mul(inv_r, Ar::sub(B[j], in[j]));
+                const CT d11 = Ar::mul(inv_r2, Ar::sub(in[j], in2[j]));
+                const CT d = Ar::sub(d10, d11);
+                const CT d1 = Ar::add(d10, Ar::mul(mix, d));
+                const CT d2 = Ar::mul(inv_sum, d);
+                A[j] = Ar::add(Ar::add(B[j], Ar::mul(w1, d1)), Ar::mul(w2, d2));
+            }
+        }
+    }
+
+    const CT gamma = k.gamma, delta = k.delta;
+    const bool from_p = pinned<BS::pred_p>(k.pred_is_p) != 0;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const CT pred = from_p ? P[j] : A[j];
+        R[j] = Ar::add(Ar::add((CT)0, Ar::mul(X[j], gamma)), Ar::mul(pred, delta));
+    }
+    const int has_noise = pinned<BS::noise>(k.has_noise);
+    if (has_noise) {
+        if (PHILOX && has_noise == 2) draw_normals<CT, V>(prog.philox[k.noise_in], io.first, prog.numel, in);
+        else io.template load<BS::dt_noise>(k.noise_in, in);
+        const CT zeta = k.zeta;
+#pragma unroll
+        for (int j = 0; j < V; ++j) R[j] = Ar::add(R[j], Ar::mul(in[j], zeta));
+    }
+    if (pinned<BS::store>(k.store_r >= 0)) io.template store<BS::dt_store>(k.store_r, R);
+
+    if (link != BL_NONE) {
+        if (link == BL_X_FROM_R) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) X[j] = R[j];
+        } else if (link == BL_BLEND) {
+            const CT l0 = k.l0, l1 = k.l1;
+#pragma unroll
+            for (int j = 0; j < V; ++j) X[j] = Ar::add(Ar::mul(S[j], l0), Ar::mul(R[j], l1));
+            if (pinned<BS::slink>(k.store_link >= 0)) io.template store<BS::dt_slink>(k.store_link, X);
+        } else {  // BL_BACK
+            const CT l0 = k.l0;
+#pragma unroll
+            for (int j = 0; j < V; ++j) P[j] = Ar::sub(R[j], Ar::mul(X[j], l0));
+            div_uniform<V>(P, k.l1, k.l1_r, fast_div);
+            if (pinned<BS::slink>(k.store_link >= 0)) io.template store<BS::dt_slink>(k.store_link, P);
+        }
+    }
+}
+
+template <typename CT, int MODE, int V, bool GUARDED, bool PHILOX, typename Sh>
 __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t first, const unsigned char* stage, int tid) {
     using Ar = Arith<CT>;
     const TileIO<CT, MODE, V, GUARDED> io{prog, stage, tid, first};
@@ -243,176 +465,52 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
 
     // ---- head ---------------------------------------------------------------------------------
     const BHead<CT>& h = prog.head;
-    if (h.x_in >= 0) io.load(h.x_in, X);
-    if (h.y_in >= 0) {
-        io.load(h.y_in, P);
-        const bool neg = h.neg != 0;
+    const bool fast_div = prog.fast_div != 0;
+    if (pinned<Sh::x>(h.x_in >= 0)) io.template load<Sh::dt_x>(h.x_in, X);
+    if (pinned<Sh::y>(h.y_in >= 0)) {
+        io.template load<Sh::dt_y>(h.y_in, P);
+        const bool neg = pinned<Sh::neg>(h.neg) != 0;
 #pragma unroll
         for (int j = 0; j < V; ++j) P[j] = neg ? -P[j] : P[j];
     }
-    if (h.n_conv > 0) {
+    const int n_conv = pinned<Sh::n_conv>(h.n_conv);
+    if (n_conv > 0) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-            if (c < h.n_conv) {
+            if (c < n_conv) {
                 const int f = h.conv_flags[c];
                 const CT c0 = h.conv_c[c][0], c1 = h.conv_c[c][1], c2 = h.conv_c[c][2];
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
-                    CT v;
                     if (f & SKR_CONV_USE_X) {
                         const CT lhs = (f & SKR_CONV_MUL_X) ? Ar::mul(c0, X[j]) : X[j];
                         const CT rhs = (f & SKR_CONV_MUL_Y) ? Ar::mul(c1, P[j]) : P[j];
-                        v = Ar::sub(lhs, rhs);
+                        P[j] = Ar::sub(lhs, rhs);
                     } else {
-                        v = (f & SKR_CONV_MUL_Y) ? Ar::mul(P[j], c1) : P[j];
+                        P[j] = (f & SKR_CONV_MUL_Y) ? Ar::mul(P[j], c1) : P[j];
                     }
-                    P[j] = (f & SKR_CONV_DIV) ? Ar::div(v, c2) : v;
                 }
+                if (f & SKR_CONV_DIV) div_uniform<V>(P, c2, h.conv_r[c], fast_div);
             }
         }
     }
-    if (h.store_p >= 0) io.store(h.store_p, P);
-    if (h.store_p2 >= 0) io.store(h.store_p2, P);
+    if (pinned<Sh::sp>(h.store_p >= 0)) io.template store<Sh::dt_sp>(h.store_p, P);
+    if (pinned<Sh::sp2>(h.store_p2 >= 0)) io.template store<Sh::dt_sp2>(h.store_p2, P);
 
-    // ---- blocks (one copy of the block code: the instruction footprint matters more than the loop) ----
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-        const BBlock<CT>& k = prog.blk[b];
-        if (!k.enabled) continue;
-#pragma unroll
-        for (int j = 0; j < V; ++j) S[j] = X[j];  // only the SPC blend reads S; an unconditional copy beats a branch
-        if (k.sample_in >= 0) io.load(k.sample_in, X);
-
-        CT in[V];
-        const int kind = k.kind;
-        if (kind != BK_NONE) {
-            const int n_terms = k.n_terms;
-            if (kind != BK_ACC) {
-                if (k.base_in >= 0) io.load(k.base_in, B);
-                else {
-#pragma unroll
-                    for (int j = 0; j < V; ++j) B[j] = P[j];
-                }
-            }
-            if (kind == BK_ACC) {
-                int t = 0;
-                if (k.p_mode == 1 || n_terms == 0) {
-                    const CT c = k.p_coef;
-#pragma unroll
-                    for (int j = 0; j < V; ++j) A[j] = Ar::add((CT)0, Ar::mul(P[j], c));
-                } else {
-                    io.load(k.terms[0].in, in);
-                    const CT c = k.terms[0].c0;
-#pragma unroll
-                    for (int j = 0; j < V; ++j) A[j] = Ar::add((CT)0, Ar::mul(in[j], c));
-                    t = 1;
-                }
-                for (; t < n_terms; ++t) {
-                    io.load(k.terms[t].in, in);
-                    const CT c = k.terms[t].c0;
-#pragma unroll
-                    for (int j = 0; j < V; ++j) A[j] = Ar::add(A[j], Ar::mul(in[j], c));
-                }
-                if (k.p_mode == 2 && n_terms > 0) {
-                    const CT c = k.p_coef;
-#pragma unroll
-                    for (int j = 0; j < V; ++j) A[j] = Ar::add(A[j], Ar::mul(P[j], c));
-                }
-                if (k.has_div) {
-                    const CT d = k.div;
-#pragma unroll
-                    for (int j = 0; j < V; ++j) A[j] = Ar::div(A[j], d);
-                }
-            } else if (kind == BK_UNI) {
-                for (int t = 0; t < n_terms; ++t) {
-                    io.load(k.terms[t].in, in);
-                    const CT rk = k.terms[t].c0, rho = k.terms[t].c1;
-#pragma unroll
-                    for (int j = 0; j < V; ++j) {
-                        const CT term = Ar::mul(Ar::div(Ar::sub(in[j], B[j]), rk), rho);
-                        A[j] = Ar::add(t == 0 ? (CT)0 : A[j], term);
-                    }
-                }
-                if (k.p_mode == 1) {
-                    const CT rho = k.p_coef;
-#pragma unroll
-                    for (int j = 0; j < V; ++j) {
-                        const CT term = Ar::mul(Ar::sub(P[j], B[j]), rho);
-                        A[j] = Ar::add(n_terms == 0 ? (CT)0 : A[j], term);
-                    }
-                }
-                const bool empty = k.empty_sum != 0;
-#pragma unroll
-                for (int j = 0; j < V; ++j) A[j] = Ar::add(B[j], empty ? (CT)0 : A[j]);
-            } else if (kind == BK_DPM2) {
-                io.load(k.terms[0].in, in);
-                const CT inv_r = k.terms[0].c0, half = k.terms[0].c1;
-#pragma unroll
-                for (int j = 0; j < V; ++j) A[j] = Ar::add(B[j], Ar::mul(half, Ar::mul(inv_r, Ar::sub(B[j], in[j]))));
-            } else {  // BK_DPM3
-                CT in2[V];
-                io.load(k.terms[0].in, in);
-                io.load(k.terms[1].in, in2);
-                const CT inv_r = k.terms[0].c0, inv_r2 = k.terms[1].c0, mix = k.terms[1].c1;
-                const CT inv_sum = k.e0, w1 = k.e1, w2 = k.e2;
-#pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    const CT d10 = Ar::mul(inv_r, Ar::sub(B[j], in[j]));
-                    const CT d11 = Ar::mul(inv_r2, Ar::sub(in[j], in2[j]));
-                    const CT d = Ar::sub(d10, d11);
-                    const CT d1 = Ar::add(d10, Ar::mul(mix, d));
-                    const CT d2 = Ar::mul(inv_sum, d);
-                    A[j] = Ar::add(Ar::add(B[j], Ar::mul(w1, d1)), Ar::mul(w2, d2));
-                }
-            }
-        }
-
-        const CT gamma = k.gamma, delta = k.delta;
-        const bool from_p = k.pred_is_p != 0;
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-            const CT pred = from_p ? P[j] : A[j];
-            R[j] = Ar::add(Ar::add((CT)0, Ar::mul(X[j], gamma)), Ar::mul(pred, delta));
-        }
-        if (k.has_noise) {
-            if (PHILOX && k.has_noise == 2) draw_normals<CT, V>(prog.philox[k.noise_in], first, prog.numel, in);
-            else io.load(k.noise_in, in);
-            const CT zeta = k.zeta;
-#pragma unroll
-            for (int j = 0; j < V; ++j) R[j] = Ar::add(R[j], Ar::mul(in[j], zeta));
-        }
-        if (k.store_r >= 0) io.store(k.store_r, R);
-
-        const int link = k.link;
-        if (link != BL_NONE) {
-            if (link == BL_X_FROM_R) {
-#pragma unroll
-                for (int j = 0; j < V; ++j) X[j] = R[j];
-            } else if (link == BL_BLEND) {
-                const CT l0 = k.l0, l1 = k.l1;
-#pragma unroll
-                for (int j = 0; j < V; ++j) X[j] = Ar::add(Ar::mul(S[j], l0), Ar::mul(R[j], l1));
-                if (k.store_link >= 0) io.store(k.store_link, X);
-            } else {  // BL_BACK
-                const CT l0 = k.l0, l1 = k.l1;
-#pragma unroll
-                for (int j = 0; j < V; ++j) P[j] = Ar::div(Ar::sub(R[j], Ar::mul(X[j], l0)), l1);
-                if (k.store_link >= 0) io.store(k.store_link, P);
-            }
-        }
-    }
+    run_one_block<CT, MODE, V, GUARDED, PHILOX, typename Sh::B0>(prog, prog.blk[0], io, X, P, B, A, S, R);
+    run_one_block<CT, MODE, V, GUARDED, PHILOX, typename Sh::B1>(prog, prog.blk[1], io, X, P, B, A, S, R);
 }
 
 // The ragged tail (and unaligned launches) run out of line so the pipelined loop stays compact.
 template <typename CT, int MODE, int V, bool PHILOX>
 __device__ __noinline__ void run_guarded_tiles(const BProgram<CT>& prog, int64_t first_tile, int64_t n_tiles, int tid) {
     for (int64_t tile = first_tile + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        run_block_tile<CT, MODE, V, true, PHILOX>(prog, tile * (kThreads * V) + (int64_t)tid * V, nullptr, tid);
+        run_block_tile<CT, MODE, V, true, PHILOX, ShAny>(prog, tile * (kThreads * V) + (int64_t)tid * V, nullptr, tid);
     }
 }
 
-template <typename CT, int MODE, int V, bool PHILOX>
-__global__ void __launch_bounds__(kThreads + kProducerThreads) block_kernel(const __grid_constant__ BProgram<CT> prog) {
+template <typename CT, int MODE, int V, bool PHILOX, typename Sh>
+__global__ void __launch_bounds__(kThreads + kProducerThreads, (V == 8 || sizeof(CT) == 8) ? 2 : 4) block_kernel(const __grid_constant__ BProgram<CT> prog) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -463,7 +561,7 @@ __global__ void __launch_bounds__(kThreads + kProducerThreads) block_kernel(cons
             const int64_t stride = (int64_t)grid * TILE;
             for (int k = 0; k < mine; ++k) {
                 mbar_wait(&full_bar[s], phase);
-                run_block_tile<CT, MODE, V, false, PHILOX>(prog, first, smem + (size_t)s * stage_bytes, tid);
+                run_block_tile<CT, MODE, V, false, PHILOX, Sh>(prog, first, smem + (size_t)s * stage_bytes, tid);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[s]);
                 first += stride;
@@ -632,6 +730,24 @@ static bool block_reads_p(const BBlock<CT>& k) {
     return k.enabled && (k.pred_is_p || k.p_mode != 0 || (k.kind != BK_NONE && k.kind != BK_ACC && k.base_in < 0));
 }
 
+// Host-side reciprocals of every divisor in the descriptor (machine.cuh, div_uniform).
+template <typename CT>
+static void fill_reciprocals(BProgram<CT>& out) {
+    bool fast = true;
+    BHead<CT>& h = out.head;
+    for (int c = 0; c < h.n_conv; ++c)
+        if (h.conv_flags[c] & SKR_CONV_DIV) h.conv_r[c] = uniform_reciprocal(h.conv_c[c][2], &fast);
+    for (int b = 0; b < 2; ++b) {
+        BBlock<CT>& k = out.blk[b];
+        if (!k.enabled) continue;
+        if (k.has_div) k.div_r = uniform_reciprocal(k.div, &fast);
+        if (k.link == BL_BACK) k.l1_r = uniform_reciprocal(k.l1, &fast);
+        if (k.kind == BK_UNI)
+            for (int t = 0; t < k.n_terms; ++t) k.terms[t].r0 = uniform_reciprocal(k.terms[t].c0, &fast);
+    }
+    out.fast_div = (fast && sizeof(CT) == 4) ? 1 : 0;
+}
+
 // Returns true when `p` matches the skeleton; fills head/blk of `out`.
 template <typename CT>
 static bool parse_block_program(const skr_program* p, BProgram<CT>& out) {
@@ -671,6 +787,7 @@ static bool parse_block_program(const skr_program* p, BProgram<CT>& out) {
     if (!parse_block<CT>(cur, out.blk[0])) return false;
     if (!parse_block<CT>(cur, out.blk[1])) return false;
     if (cur.peek()) return false;  // trailing ops the skeleton cannot express
+    fill_reciprocals<CT>(out);
     if (out.blk[0].enabled && h.x_in < 0 && out.blk[0].sample_in < 0) return false;  // X must come from somewhere
     if ((block_reads_p(out.blk[0]) || block_reads_p(out.blk[1]) || h.store_p >= 0) && h.y_in < 0) return false;
     return out.blk[0].enabled || h.store_p >= 0;

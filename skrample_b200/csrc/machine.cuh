@@ -59,6 +59,70 @@ template <> struct Arith<double> {
 };
 
 // ------------------------------------------------------------------------------------------
+// division by a grid-uniform scalar
+//
+// Every division of a solver step has a scalar divisor (alpha, r_k, the RK normaliser ...).  IEEE division costs
+// ~12 instructions per element including a subroutine guard; with r = RN(1/d) from the host,
+//
+//     q0 = RN(a*r);  e = fma(-q0, d, a);  q = fma(e, r, q0)
+//
+// is the correctly rounded quotient whenever nothing under- or overflows (Markstein's correction step).  That is
+// not taken on faith: tools/verify_divr.cu compares it with IEEE division for all 2^23 x 2^23 significand pairs on
+// the GPU (result recorded in DESIGN.md).  The exponent range is guarded per group of elements: |d| in
+// [2^-20, 2^20] is checked by the host (else `fast` is false), |a| in [2^-60, 2^60] here; zeros, subnormals,
+// infinities and NaNs take the IEEE path out of line.
+
+// Out of line and by value: the hot loop must not carry the IEEE sequence nor spill the operands to the stack.
+static __device__ __noinline__ float4 div_ieee4(float4 a, float d) {
+    return make_float4(__fdiv_rn(a.x, d), __fdiv_rn(a.y, d), __fdiv_rn(a.z, d), __fdiv_rn(a.w, d));
+}
+
+template <int V>
+__device__ __forceinline__ void div_uniform(float (&a)[V], float d, float r, bool fast) {
+#ifdef SKR_IEEE_DIV
+    (void)r; (void)fast;
+#pragma unroll
+    for (int j = 0; j < V; ++j) a[j] = __fdiv_rn(a[j], d);
+#else
+    bool ok = fast;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const float m = fabsf(a[j]);
+        ok = ok && (m >= 0x1p-60f) && (m <= 0x1p60f);  // false for NaN
+    }
+    if (ok) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float q0 = __fmul_rn(a[j], r);
+            const float e = __fmaf_rn(-q0, d, a[j]);
+            a[j] = __fmaf_rn(e, r, q0);
+        }
+    } else {
+        static_assert(V % 4 == 0, "elements per thread come in groups of four");
+#pragma unroll
+        for (int g = 0; g < V / 4; ++g) {
+            const float4 q = div_ieee4(make_float4(a[4 * g], a[4 * g + 1], a[4 * g + 2], a[4 * g + 3]), d);
+            a[4 * g] = q.x; a[4 * g + 1] = q.y; a[4 * g + 2] = q.z; a[4 * g + 3] = q.w;
+        }
+    }
+#endif
+}
+
+template <int V>
+__device__ __forceinline__ void div_uniform(double (&a)[V], double d, double, bool) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) a[j] = __ddiv_rn(a[j], d);
+}
+
+// Host side: r = RN(1/d) in the compute type, or 0 (and *fast = false) when d is outside the guarded range.
+static inline float uniform_reciprocal(float d, bool* fast) {
+    const float m = d < 0 ? -d : d;
+    if (!(m >= 0x1p-20f && m <= 0x1p20f)) { *fast = false; return 0.0f; }
+    return 1.0f / d;  // IEEE division on the host: correctly rounded
+}
+static inline double uniform_reciprocal(double, bool*) { return 0.0; }
+
+// ------------------------------------------------------------------------------------------
 // operand fetch / result store
 
 // Staged path: this thread's 4 consecutive elements of input `i` from the shared-memory tile.

@@ -459,8 +459,8 @@ static Shape pick_shape(uint32_t stage_bytes, int max_smem, int max_ctas) {
     return sh;
 }
 
-template <typename CT, int MODE, int V, bool PHILOX>
-static int launch_block_one(const skr_program* p, BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned, int slot) {
+template <typename CT, int MODE, int V, bool PHILOX, typename Sh>
+static int launch_block_one(const skr_program* p, BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned) {
     constexpr int TILE = kThreads * V;
     k.numel = numel;
     k.n_inputs = p->n_inputs;
@@ -500,16 +500,18 @@ static int launch_block_one(const skr_program* p, BProgram<CT>& k, int64_t numel
     }
     if (grid < 1) grid = 1;
 
-    if (!dev->attr_set[slot]) {
+    static bool attr_set[64] = {};  // per instantiation, per device
+    const int ordinal = (int)(dev - g_devices);
+    if (!attr_set[ordinal]) {
         cudaFuncAttributes fa;
-        cudaError_t e = cudaFuncGetAttributes(&fa, block_kernel<CT, MODE, V, PHILOX>);
+        cudaError_t e = cudaFuncGetAttributes(&fa, block_kernel<CT, MODE, V, PHILOX, Sh>);
         if (e != cudaSuccess) return fail((int)e, "cudaFuncGetAttributes: %s", cudaGetErrorString(e));
-        e = cudaFuncSetAttribute(block_kernel<CT, MODE, V, PHILOX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        e = cudaFuncSetAttribute(block_kernel<CT, MODE, V, PHILOX, Sh>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  dev->max_smem - (int)fa.sharedSizeBytes);
         if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        dev->attr_set[slot] = true;
+        attr_set[ordinal] = true;
     }
-    block_kernel<CT, MODE, V, PHILOX><<<(unsigned)grid, kThreads + kProducerThreads, smem, stream>>>(k);
+    block_kernel<CT, MODE, V, PHILOX, Sh><<<(unsigned)grid, kThreads + kProducerThreads, smem, stream>>>(k);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, "block kernel launch: %s", cudaGetErrorString(e));
     ++g_launches;
@@ -518,15 +520,25 @@ static int launch_block_one(const skr_program* p, BProgram<CT>& k, int64_t numel
 }
 
 template <typename CT, int MODE, int V>
-static int launch_block_inst(const skr_program* p, BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned, int slot) {
-    if (p->n_philox > 0) return launch_block_one<CT, MODE, V, true>(p, k, numel, stream, aligned, slot + 8);
-    return launch_block_one<CT, MODE, V, false>(p, k, numel, stream, aligned, slot);
+static int launch_block_inst(const skr_program* p, BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned) {
+    if (p->n_philox > 0) return launch_block_one<CT, MODE, V, true, ShAny>(p, k, numel, stream, aligned);
+    return launch_block_one<CT, MODE, V, false, ShAny>(p, k, numel, stream, aligned);
+}
+
+// Pinned shapes (block_kernel.cuh) first, the generic shape otherwise.
+template <int MODE, int V, typename Sh>
+static bool try_shape(const skr_program* p, BProgram<float>& k, int64_t numel, cudaStream_t stream, bool aligned, int* rc) {
+    if (!shape_matches<Sh>(k)) return false;
+    *rc = launch_block_one<float, MODE, V, false, Sh>(p, k, numel, stream, aligned);
+    return true;
 }
 
 template <typename CT>
 static int launch_block(const skr_program* p, BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned) {
+    for (int i = 0; i < p->n_inputs; ++i) k.in_dtype[i] = p->inputs[i].dtype;
+    for (int i = 0; i < p->n_outputs; ++i) k.out_dtype[i] = p->outputs[i].dtype;
     if constexpr (sizeof(CT) == 8) {
-        return launch_block_inst<double, IN_MIXED, 4>(p, k, numel, stream, aligned, 2);
+        return launch_block_inst<double, IN_MIXED, 4>(p, k, numel, stream, aligned);
     } else {
         bool all_f32 = true, all_bf16 = true, all_f16 = true;
         for (int i = 0; i < p->n_inputs; ++i) {
@@ -535,15 +547,19 @@ static int launch_block(const skr_program* p, BProgram<CT>& k, int64_t numel, cu
             all_f16 &= p->inputs[i].dtype == SKR_F16;
         }
         const int force = env_int("SKR_IN_MODE", -1);  // development switch: 0 / 8 force a mixed instantiation
-        if (force == 0) return launch_block_inst<float, IN_MIXED, 4>(p, k, numel, stream, aligned, 3);
-        if (force == 8) return launch_block_inst<float, IN_MIXED, 8>(p, k, numel, stream, aligned, 7);
-        if (all_f32) return launch_block_inst<float, IN_F32, 4>(p, k, numel, stream, aligned, 4);
-        if (all_bf16) return launch_block_inst<float, IN_BF16, 8>(p, k, numel, stream, aligned, 5);
-        if (all_f16) return launch_block_inst<float, IN_F16, 8>(p, k, numel, stream, aligned, 6);
+        if (force == 0) return launch_block_inst<float, IN_MIXED, 4>(p, k, numel, stream, aligned);
+        if (force == 8) return launch_block_inst<float, IN_MIXED, 8>(p, k, numel, stream, aligned);
+        if (all_f32) return launch_block_inst<float, IN_F32, 4>(p, k, numel, stream, aligned);
+        if (all_bf16) return launch_block_inst<float, IN_BF16, 8>(p, k, numel, stream, aligned);
+        if (all_f16) return launch_block_inst<float, IN_F16, 8>(p, k, numel, stream, aligned);
         // Mixed storage stays at 4 elements per thread: measured on B200 the 8-wide variant loses more to halved
         // occupancy / doubled stage size than it gains from amortised control (Adams-9 bf16 59 vs 31 us,
         // UniPC-3 bf16 46 vs 37 us per step); SKR_IN_MODE=8 keeps it reachable for experiments.
-        return launch_block_inst<float, IN_MIXED, 4>(p, k, numel, stream, aligned, 3);
+        if (p->n_philox == 0 && !env_int("SKR_NO_PINNED", 0)) {
+            int rc = 0;
+            if (try_shape<IN_MIXED, 4, ShUniPC<SKR_BF16>>(p, k, numel, stream, aligned, &rc)) return rc;
+        }
+        return launch_block_inst<float, IN_MIXED, 4>(p, k, numel, stream, aligned);
     }
 }
 

@@ -11,7 +11,11 @@ dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 out = []
 for name in names:
+    if name not in bench.WORKLOADS:
+        print(f"unknown workload {name}; known: {sorted(bench.WORKLOADS)}", file=sys.stderr)
+        continue
     r = bench.graph_throughput(bench.WORKLOADS[name], dev, 200, 50, 2 * bench.L2_BYTES)
     us = r["elapsed_ms"] * 1e3 / r["launches"]
-    out.append(f"{name.replace('_sde','')}={us:.1f}us")
-print(" ".join(out))
+    gbs = r["bytes"] / (r["elapsed_ms"] * 1e-3) / 1e9
+    out.append(f"{name.replace('_sde','')}={us:.1f}us/{gbs:.0f}GB/s")
+    print(out[-1], flush=True)

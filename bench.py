@@ -116,7 +116,9 @@ class Trajectory:
         )
         self.noises = [self.noise_source.lazy(None) for _ in range(count)] if self.sampler.require_noise else [None] * count
         if supplied_noise and self.sampler.require_noise:
-            self.noises = [z.materialize().to(self.dtype) if hasattr(z, "materialize") else z for z in self.noises]
+            # batches beyond the kernel's Philox table come back as tensors already; either way the workload's noise
+            # is stored in the latent dtype, as a pipeline would hand it over
+            self.noises = [(z.materialize() if hasattr(z, "materialize") else z).to(self.dtype) for z in self.noises]
         self.reset()
 
     def reset(self) -> None:

@@ -159,6 +159,14 @@ int skr_program_launch(const skr_program* program, int64_t numel, void* stream);
 int skr_program_classify(const skr_program* program);
 
 /*
+ * Like skr_program_classify, and writes a one-line description of the parsed step into `text`
+ * (NUL-terminated, at most `capacity` bytes): compute type, the compiled kernel shape the step
+ * would run with ("any" = generic instantiation) and the control fields of head and blocks.
+ * Uses only the dtypes of the tensors, never the pointers.  Pure host logic; tests and tooling.
+ */
+int skr_program_describe(const skr_program* program, char* text, int32_t capacity);
+
+/*
  * Point.add_noise / remove_noise (common.py:32-40):
  *   remove == 0: out = sample*alpha + noise*sigma
  *   remove != 0: out = (sample - noise*sigma) / alpha

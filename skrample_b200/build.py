@@ -8,15 +8,24 @@ nvcc cross-compiles without a GPU.  The shared library stays in the source tree
 
 from __future__ import annotations
 
+import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
 ROOT = CSRC.parent.parent
 LIB = CSRC / "libskrample_b200.so"
-SOURCES = ["step_kernel.cu", "noise_kernels.cu"]
+# (source, extra defines, object name): pinned_shapes.cu is compiled once per latent storage type
+UNITS = [
+    ("step_kernel.cu", (), "step_kernel.o"),
+    ("noise_kernels.cu", (), "noise_kernels.o"),
+    ("pinned_shapes.cu", ("SKR_LP=0",), "pinned_f32.o"),
+    ("pinned_shapes.cu", ("SKR_LP=2",), "pinned_bf16.o"),
+    ("pinned_shapes.cu", ("SKR_LP=3",), "pinned_f16.o"),
+]
 NVCC_FLAGS = [
     "-gencode",
     "arch=compute_100a,code=sm_100a",
@@ -24,7 +33,6 @@ NVCC_FLAGS = [
     "-std=c++17",
     "-lineinfo",
     "-fmad=false",  # every product and sum is individually rounded, like the reference's separate ATen ops
-    "--shared",
     "-Xcompiler",
     "-fPIC",
 ]
@@ -39,21 +47,38 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, defines: tuple[str, ...] = (), out: Path | None = None) -> Path:
-    """Compile the library.  ``defines`` / ``out`` build an experiment variant next to the product library
-    (load it with ``SKRAMPLE_B200_LIB=<path>``); the default call builds the product."""
+    """Compile the library: the translation units in parallel, then one link.  ``defines`` / ``out`` build an
+    experiment variant next to the product library (load it with ``SKRAMPLE_B200_LIB=<path>``); the default call
+    builds the product."""
     target = out if out is not None else LIB
     if out is None and not force and not _stale():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    sources = [str(CSRC / s) for s in SOURCES if (CSRC / s).exists()]
-    flags = [*NVCC_FLAGS, *(f"-D{d}" for d in defines), *(["-Xptxas", "-v"] if verbose else [])]
-    cmd = [nvcc, *flags, "-o", str(target), *sources]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        sys.stderr.write(proc.stdout + proc.stderr)
-        raise RuntimeError("nvcc failed building libskrample_b200.so")
+    objdir = CSRC / "build" / (target.stem if out is not None else "product")
+    objdir.mkdir(parents=True, exist_ok=True)
+    common = [*NVCC_FLAGS, *(f"-D{d}" for d in defines), *(["-Xptxas", "-v"] if verbose else [])]
+
+    def compile_unit(unit: tuple[str, tuple[str, ...], str]) -> subprocess.CompletedProcess[str]:
+        source, unit_defines, obj = unit
+        cmd = [nvcc, *common, *(f"-D{d}" for d in unit_defines), "-c", str(CSRC / source), "-o", str(objdir / obj)]
+        return subprocess.run(cmd, capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_unit, UNITS))
+    log = "".join(r.stdout + r.stderr for r in results)
+    if any(r.returncode != 0 for r in results):
+        sys.stderr.write(log)
+        raise RuntimeError("nvcc failed compiling libskrample_b200.so")
+    link = subprocess.run(
+        [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", str(target), *(str(objdir / u[2]) for u in UNITS)],
+        capture_output=True,
+        text=True,
+    )
+    if link.returncode != 0:
+        sys.stderr.write(log + link.stdout + link.stderr)
+        raise RuntimeError("nvcc failed linking libskrample_b200.so")
     if verbose:
-        sys.stderr.write(proc.stderr)
+        sys.stderr.write(log)
     return target
 
 

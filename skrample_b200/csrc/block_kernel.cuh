@@ -239,30 +239,67 @@ struct BlkOff : BlkAny {
     static constexpr int enabled = 0;
 };
 struct ShAny {
+    static constexpr int ctas8 = 2;  // CTAs per SM the 8-elements-per-thread instantiation is compiled for
     static constexpr int x = -1, y = -1, neg = -1, n_conv = -1, sp = -1, sp2 = -1;
     static constexpr int dt_x = -1, dt_y = -1, dt_sp = -1, dt_sp2 = -1;
     using B0 = BlkAny;
     using B1 = BlkAny;
 };
 
-// UniP / UniPC steady state on 16-bit latents (LP): sample, network output and noise in 16-bit storage, solver
-// state (previous sample, x-hat history) in fp32.  Block 0 is the corrector of the previous step, block 1 the
-// predictor of this one.
-template <int LP>
-struct ShUniPC : ShAny {
-    static constexpr int x = 1, y = 1, neg = 0, n_conv = 1, sp = 1, sp2 = 0;
-    static constexpr int dt_x = LP, dt_y = LP, dt_sp = SKR_F32;
-    struct B0 : BlkAny {
-        static constexpr int enabled = 1, kind = BK_UNI, sample = 1, base = 1, p_mode = 1, has_div = 0, pred_p = 0;
-        static constexpr int store = 1, link = BL_X_FROM_R, slink = 0;
-        static constexpr int dt_state = SKR_F32, dt_noise = LP, dt_store = SKR_F32;
-    };
-    struct B1 : BlkAny {
-        static constexpr int enabled = 1, kind = BK_UNI, sample = 0, base = 0, p_mode = 0, has_div = 0, pred_p = 0;
-        static constexpr int store = 1, link = BL_NONE, slink = 0;
-        static constexpr int dt_state = SKR_F32, dt_noise = LP, dt_store = LP;
-    };
+// Pinned shapes.  LP is the storage type of the latents the caller hands in and gets back (sample, network
+// output, noise, `final`); ST that of the solver state a block reads (x-hat history, previous samples: fp32; the
+// raw derivatives of an unconverted RK step: LP).  Whether a block adds noise and whether x-hat is stored a second
+// time stay run-time flags: one uniform branch each.
+template <int KIND, int SAMPLE, int BASE, int PMODE, int DIV, int PREDP, int STORE, int LINK, int SLINK, int OUT, int ST, int LP>
+struct BlkPin : BlkAny {
+    static constexpr int enabled = 1, kind = KIND, sample = SAMPLE, base = BASE, p_mode = PMODE, has_div = DIV;
+    static constexpr int pred_p = PREDP, store = STORE, link = LINK, slink = SLINK;
+    static constexpr int dt_state = ST, dt_noise = LP, dt_store = OUT, dt_slink = SKR_F32;
 };
+// head of a structured sampler step: X = sample, P = x-hat = convert(X, network output), stored as fp32 state
+template <int LP, typename BLK0, typename BLK1>
+struct ShStep : ShAny {
+    static constexpr int x = 1, y = 1, neg = 0, n_conv = 1, sp = 1;
+    static constexpr int dt_x = LP, dt_y = LP, dt_sp = SKR_F32;
+    using B0 = BLK0;
+    using B1 = BLK1;
+};
+// head without a conversion: X = sample, optionally P = raw network output (Euler; RK combinations)
+template <int LP, int Y, typename BLK0>
+struct ShRaw : ShAny {
+    static constexpr int ctas8 = 4;  // few live values: the 8-wide instantiation still fits 56 registers
+    static constexpr int x = 1, y = Y, neg = 0, n_conv = 0, sp = 0, sp2 = 0;
+    static constexpr int dt_x = LP, dt_y = LP;
+    using B0 = BLK0;
+    using B1 = BlkOff;
+};
+
+// Euler: R = X*G + y*D (+ noise*Z), the conversion folded into the scalars
+template <int LP>
+using ShEuler = ShRaw<LP, 1, BlkPin<BK_NONE, 0, 0, 0, 0, 1, 1, BL_NONE, 0, LP, SKR_F32, LP>>;
+// Adams / DPM-1 and every "weighted sum of the x-hat history, x-hat first" predictor
+template <int LP>
+using ShAcc = ShStep<LP, BlkPin<BK_ACC, 0, 0, 1, 0, 0, 1, BL_NONE, 0, LP, SKR_F32, LP>, BlkOff>;
+template <int LP>
+using ShDpm2 = ShStep<LP, BlkPin<BK_DPM2, 0, 0, 0, 0, 0, 1, BL_NONE, 0, LP, SKR_F32, LP>, BlkOff>;
+template <int LP>
+using ShDpm3 = ShStep<LP, BlkPin<BK_DPM3, 0, 0, 0, 0, 0, 1, BL_NONE, 0, LP, SKR_F32, LP>, BlkOff>;
+// UniP: predictor only
+template <int LP>
+using ShUniP = ShStep<LP, BlkPin<BK_UNI, 0, 0, 0, 0, 0, 1, BL_NONE, 0, LP, SKR_F32, LP>, BlkOff>;
+// UniPC steady state: block 0 corrects the previous step (UniC term, fp32 state out, X = R), block 1 predicts
+template <int LP>
+using ShUniPC = ShStep<LP, BlkPin<BK_UNI, 1, 1, 1, 0, 0, 1, BL_X_FROM_R, 0, SKR_F32, SKR_F32, LP>,
+                       BlkPin<BK_UNI, 0, 0, 0, 0, 0, 1, BL_NONE, 0, LP, SKR_F32, LP>>;
+// SPC steady state: block 0 = Adams corrector blended into the previous sample (fp32 state out), block 1 = Euler
+template <int LP>
+using ShSPC = ShStep<LP, BlkPin<BK_ACC, 1, 0, 1, 0, 0, 0, BL_BLEND, 1, SKR_F32, SKR_F32, LP>,
+                     BlkPin<BK_NONE, 0, 0, 0, 0, 1, 1, BL_NONE, 0, LP, SKR_F32, LP>>;
+// explicit RK on raw derivatives: stage input = X*G + (sum k_i c_i / sum c_i)*D, final = X*G + (sum k_i b_i)*D
+template <int LP>
+using ShRKStage = ShRaw<LP, 0, BlkPin<BK_ACC, 0, 0, 0, 1, 0, 1, BL_NONE, 0, LP, LP, LP>>;
+template <int LP>
+using ShRKFinal = ShRaw<LP, 0, BlkPin<BK_ACC, 0, 0, 0, 0, 0, 1, BL_NONE, 0, LP, LP, LP>>;
 
 template <typename BS, typename CT>
 static bool block_matches(const BBlock<CT>& k, const int32_t* in_dt, const int32_t* out_dt) {
@@ -509,8 +546,14 @@ __device__ __noinline__ void run_guarded_tiles(const BProgram<CT>& prog, int64_t
     }
 }
 
+// Occupancy each instantiation is compiled for (register cap) and launched with (pipeline shape).
+template <typename CT, int V, typename Sh>
+constexpr int block_ctas_per_sm() {
+    return sizeof(CT) == 8 ? 2 : V == 8 ? Sh::ctas8 : 4;
+}
+
 template <typename CT, int MODE, int V, bool PHILOX, typename Sh>
-__global__ void __launch_bounds__(kThreads + kProducerThreads, (V == 8 || sizeof(CT) == 8) ? 2 : 4) block_kernel(const __grid_constant__ BProgram<CT> prog) {
+__global__ void __launch_bounds__(kThreads + kProducerThreads, block_ctas_per_sm<CT, V, Sh>()) block_kernel(const __grid_constant__ BProgram<CT> prog) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];

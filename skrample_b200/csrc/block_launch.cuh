@@ -1,0 +1,108 @@
+// skrample_b200 - host launcher of one block-kernel instantiation, shared by step_kernel.cu (generic shapes)
+// and pinned_shapes.cu (one translation unit per latent storage type, so the instantiations compile in parallel).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "../../include/skrample_b200.h"
+#include "block_kernel.cuh"
+#include "host.cuh"
+
+namespace skr {
+
+template <typename CT, int MODE, int V, bool PHILOX, typename Sh>
+static int launch_block_one(const skr_program* p, BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned) {
+    constexpr int TILE = kThreads * V;
+    k.numel = numel;
+    k.n_inputs = p->n_inputs;
+    uint32_t off = 0;
+    for (int i = 0; i < p->n_inputs; ++i) {
+        k.in_ptr[i] = p->inputs[i].ptr;
+        k.in_dtype[i] = p->inputs[i].dtype;
+        k.in_off[i] = off;
+        off += TILE * dtype_size_host(p->inputs[i].dtype);
+    }
+    for (int i = 0; i < p->n_outputs; ++i) {
+        k.out_ptr[i] = p->outputs[i].ptr;
+        k.out_dtype[i] = p->outputs[i].dtype;
+    }
+    k.stage_bytes = off;
+    fill_kphilox(k.philox, p->philox, p->n_philox);
+
+    int err = 0;
+    DeviceInfo* dev = device_info(&err);
+    if (!dev) return fail(err, "cudaGetDevice failed");
+
+    const int64_t n_tiles = (numel + TILE - 1) / TILE;
+    const int64_t n_full = numel / TILE;
+    if (n_full > 0x7fffffff) return fail(SKR_E_RANGE, "numel too large");
+    PipeShape sh = pick_shape(off, dev->max_smem, block_ctas_per_sm<CT, V, Sh>());
+    k.use_tma = (aligned && n_full > 0 && sh.ok) ? 1u : 0u;
+    k.n_full_tiles = (int32_t)n_full;
+    k.stages = sh.stages;
+    size_t smem = k.use_tma ? (size_t)sh.stages * off : 0;
+
+    int64_t grid;
+    if (k.use_tma) {
+        grid = (int64_t)dev->sm_count * sh.ctas_per_sm;
+        if (grid > n_full) grid = n_full;
+    } else {
+        grid = n_tiles < (int64_t)dev->sm_count * 8 ? n_tiles : (int64_t)dev->sm_count * 8;
+    }
+    if (grid < 1) grid = 1;
+
+    static bool attr_set[64] = {};  // per instantiation, per device
+    const int ordinal = dev->ordinal;
+    if (!attr_set[ordinal]) {
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, block_kernel<CT, MODE, V, PHILOX, Sh>);
+        if (e != cudaSuccess) return fail((int)e, "cudaFuncGetAttributes: %s", cudaGetErrorString(e));
+        e = cudaFuncSetAttribute(block_kernel<CT, MODE, V, PHILOX, Sh>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 dev->max_smem - (int)fa.sharedSizeBytes);
+        if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set[ordinal] = true;
+    }
+    block_kernel<CT, MODE, V, PHILOX, Sh><<<(unsigned)grid, kThreads + kProducerThreads, smem, stream>>>(k);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail((int)e, "block kernel launch: %s", cudaGetErrorString(e));
+    count_launch(0);
+    return 0;
+}
+
+template <typename Sh, int MODE, int V>
+struct ShapeEntry {
+    using shape = Sh;
+    static constexpr int mode = MODE, v = V;
+    const char* name;
+};
+
+struct StorageClass {
+    bool all_f32 = true, all_bf16 = true, all_f16 = true;
+    template <typename CT>
+    explicit StorageClass(const BProgram<CT>& k) {
+        for (int i = 0; i < k.n_inputs; ++i) {
+            all_f32 &= k.in_dtype[i] == SKR_F32;
+            all_bf16 &= k.in_dtype[i] == SKR_BF16;
+            all_f16 &= k.in_dtype[i] == SKR_F16;
+        }
+    }
+    bool allows(int mode) const {
+        return mode == IN_MIXED || (mode == IN_F32 && all_f32) || (mode == IN_BF16 && all_bf16) || (mode == IN_F16 && all_f16);
+    }
+};
+
+template <typename CT>
+static void fill_dtypes(const skr_program* p, BProgram<CT>& k) {
+    k.n_inputs = p->n_inputs;
+    for (int i = 0; i < p->n_inputs; ++i) k.in_dtype[i] = p->inputs[i].dtype;
+    for (int i = 0; i < p->n_outputs; ++i) k.out_dtype[i] = p->outputs[i].dtype;
+}
+
+
+// Pinned shapes of one latent storage type (pinned_shapes.cu).  Returns true when a shape matches; with `launch`
+// the kernel has been launched (status in *rc), otherwise only *name is set.
+bool pinned_f32(const skr_program* p, BProgram<float>& k, int64_t numel, cudaStream_t stream, bool aligned, bool launch, int* rc, const char** name);
+bool pinned_bf16(const skr_program* p, BProgram<float>& k, int64_t numel, cudaStream_t stream, bool aligned, bool launch, int* rc, const char** name);
+bool pinned_f16(const skr_program* p, BProgram<float>& k, int64_t numel, cudaStream_t stream, bool aligned, bool launch, int* rc, const char** name);
+
+}  // namespace skr

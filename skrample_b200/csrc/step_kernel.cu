@@ -29,6 +29,8 @@
 #include "common.cuh"
 #include "machine.cuh"
 #include "block_kernel.cuh"
+#include "block_launch.cuh"
+#include "host.cuh"
 
 namespace skr {
 
@@ -307,24 +309,19 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
-struct DeviceInfo {
-    int sm_count = 0;
-    int max_smem = 0;
-    bool attr_set[16] = {};
-};
-
-static int env_int(const char* name, int fallback) {
+int env_int(const char* name, int fallback) {
     const char* v = getenv(name);
     return v && *v ? atoi(v) : fallback;
 }
 static DeviceInfo g_devices[64];
 
-static DeviceInfo* device_info(int* err) {
+DeviceInfo* device_info(int* err) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess || dev < 0 || dev >= 64) { *err = e ? (int)e : 1; return nullptr; }
     DeviceInfo& d = g_devices[dev];
     if (d.sm_count == 0) {
+        d.ordinal = dev;
         cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev);
         cudaDeviceGetAttribute(&d.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     }
@@ -431,16 +428,9 @@ static int launch_typed(const skr_program* p, int64_t numel, cudaStream_t stream
     return 0;
 }
 
-// Pipeline shape for the block kernel: stages per CTA and CTAs per SM from the size of one staged tile.
-struct Shape {
-    int stages;
-    int ctas_per_sm;
-    bool ok;
-};
-
-static Shape pick_shape(uint32_t stage_bytes, int max_smem, int max_ctas) {
+PipeShape pick_shape(uint32_t stage_bytes, int max_smem, int max_ctas) {
     // keep roughly 64-96 KB of bulk loads in flight per SM; more CTAs per SM when a stage is small
-    Shape sh{2, 1, true};
+    PipeShape sh{2, 1, true};
     const uint32_t usable = (uint32_t)max_smem - 4096u;
     if (stage_bytes == 0 || 2u * stage_bytes > usable) { sh.ok = false; return sh; }
     int ctas = max_ctas;
@@ -459,106 +449,47 @@ static Shape pick_shape(uint32_t stage_bytes, int max_smem, int max_ctas) {
     return sh;
 }
 
-template <typename CT, int MODE, int V, bool PHILOX, typename Sh>
-static int launch_block_one(const skr_program* p, BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned) {
-    constexpr int TILE = kThreads * V;
-    k.numel = numel;
-    k.n_inputs = p->n_inputs;
-    uint32_t off = 0;
-    for (int i = 0; i < p->n_inputs; ++i) {
-        k.in_ptr[i] = p->inputs[i].ptr;
-        k.in_dtype[i] = p->inputs[i].dtype;
-        k.in_off[i] = off;
-        off += TILE * dtype_size_host(p->inputs[i].dtype);
-    }
-    for (int i = 0; i < p->n_outputs; ++i) {
-        k.out_ptr[i] = p->outputs[i].ptr;
-        k.out_dtype[i] = p->outputs[i].dtype;
-    }
-    k.stage_bytes = off;
-    fill_kphilox(k.philox, p->philox, p->n_philox);
-
-    int err = 0;
-    DeviceInfo* dev = device_info(&err);
-    if (!dev) return fail(err, "cudaGetDevice failed");
-
-    const int64_t n_tiles = (numel + TILE - 1) / TILE;
-    const int64_t n_full = numel / TILE;
-    if (n_full > 0x7fffffff) return fail(SKR_E_RANGE, "numel too large");
-    Shape sh = pick_shape(off, dev->max_smem, V == 8 || sizeof(CT) == 8 ? 2 : 4);
-    k.use_tma = (aligned && n_full > 0 && sh.ok) ? 1u : 0u;
-    k.n_full_tiles = (int32_t)n_full;
-    k.stages = sh.stages;
-    size_t smem = k.use_tma ? (size_t)sh.stages * off : 0;
-
-    int64_t grid;
-    if (k.use_tma) {
-        grid = (int64_t)dev->sm_count * sh.ctas_per_sm;
-        if (grid > n_full) grid = n_full;
-    } else {
-        grid = n_tiles < (int64_t)dev->sm_count * 8 ? n_tiles : (int64_t)dev->sm_count * 8;
-    }
-    if (grid < 1) grid = 1;
-
-    static bool attr_set[64] = {};  // per instantiation, per device
-    const int ordinal = (int)(dev - g_devices);
-    if (!attr_set[ordinal]) {
-        cudaFuncAttributes fa;
-        cudaError_t e = cudaFuncGetAttributes(&fa, block_kernel<CT, MODE, V, PHILOX, Sh>);
-        if (e != cudaSuccess) return fail((int)e, "cudaFuncGetAttributes: %s", cudaGetErrorString(e));
-        e = cudaFuncSetAttribute(block_kernel<CT, MODE, V, PHILOX, Sh>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 dev->max_smem - (int)fa.sharedSizeBytes);
-        if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set[ordinal] = true;
-    }
-    block_kernel<CT, MODE, V, PHILOX, Sh><<<(unsigned)grid, kThreads + kProducerThreads, smem, stream>>>(k);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail((int)e, "block kernel launch: %s", cudaGetErrorString(e));
-    ++g_launches;
-    ++g_launches_kind[0];
-    return 0;
-}
-
 template <typename CT, int MODE, int V>
 static int launch_block_inst(const skr_program* p, BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned) {
     if (p->n_philox > 0) return launch_block_one<CT, MODE, V, true, ShAny>(p, k, numel, stream, aligned);
     return launch_block_one<CT, MODE, V, false, ShAny>(p, k, numel, stream, aligned);
 }
 
-// Pinned shapes (block_kernel.cuh) first, the generic shape otherwise.
-template <int MODE, int V, typename Sh>
-static bool try_shape(const skr_program* p, BProgram<float>& k, int64_t numel, cudaStream_t stream, bool aligned, int* rc) {
-    if (!shape_matches<Sh>(k)) return false;
-    *rc = launch_block_one<float, MODE, V, false, Sh>(p, k, numel, stream, aligned);
-    return true;
+// ---- pinned shapes (pinned_shapes.cu), tried before the generic instantiations ------------------------------
+
+static bool pinned_any(const skr_program* p, BProgram<float>& k, int64_t numel, cudaStream_t stream, bool aligned, bool launch,
+                       int* rc, const char** name) {
+    if (p->n_philox > 0 || env_int("SKR_NO_PINNED", 0)) return false;
+    // the latent storage type is that of the network output (head.y) or, for RK combinations, of the sample
+    const int probe = k.head.y_in >= 0 ? k.head.y_in : k.head.x_in;
+    if (probe < 0) return false;
+    switch (k.in_dtype[probe]) {
+        case SKR_F32: return pinned_f32(p, k, numel, stream, aligned, launch, rc, name);
+        case SKR_BF16: return pinned_bf16(p, k, numel, stream, aligned, launch, rc, name);
+        case SKR_F16: return pinned_f16(p, k, numel, stream, aligned, launch, rc, name);
+        default: return false;
+    }
 }
 
 template <typename CT>
 static int launch_block(const skr_program* p, BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned) {
-    for (int i = 0; i < p->n_inputs; ++i) k.in_dtype[i] = p->inputs[i].dtype;
-    for (int i = 0; i < p->n_outputs; ++i) k.out_dtype[i] = p->outputs[i].dtype;
+    fill_dtypes(p, k);
     if constexpr (sizeof(CT) == 8) {
         return launch_block_inst<double, IN_MIXED, 4>(p, k, numel, stream, aligned);
     } else {
-        bool all_f32 = true, all_bf16 = true, all_f16 = true;
-        for (int i = 0; i < p->n_inputs; ++i) {
-            all_f32 &= p->inputs[i].dtype == SKR_F32;
-            all_bf16 &= p->inputs[i].dtype == SKR_BF16;
-            all_f16 &= p->inputs[i].dtype == SKR_F16;
-        }
+        const StorageClass storage(k);
         const int force = env_int("SKR_IN_MODE", -1);  // development switch: 0 / 8 force a mixed instantiation
         if (force == 0) return launch_block_inst<float, IN_MIXED, 4>(p, k, numel, stream, aligned);
         if (force == 8) return launch_block_inst<float, IN_MIXED, 8>(p, k, numel, stream, aligned);
-        if (all_f32) return launch_block_inst<float, IN_F32, 4>(p, k, numel, stream, aligned);
-        if (all_bf16) return launch_block_inst<float, IN_BF16, 8>(p, k, numel, stream, aligned);
-        if (all_f16) return launch_block_inst<float, IN_F16, 8>(p, k, numel, stream, aligned);
+        int rc = 0;
+        const char* name = nullptr;
+        if (pinned_any(p, k, numel, stream, aligned, true, &rc, &name)) return rc;
+        if (storage.all_f32) return launch_block_inst<float, IN_F32, 4>(p, k, numel, stream, aligned);
+        if (storage.all_bf16) return launch_block_inst<float, IN_BF16, 8>(p, k, numel, stream, aligned);
+        if (storage.all_f16) return launch_block_inst<float, IN_F16, 8>(p, k, numel, stream, aligned);
         // Mixed storage stays at 4 elements per thread: measured on B200 the 8-wide variant loses more to halved
         // occupancy / doubled stage size than it gains from amortised control (Adams-9 bf16 59 vs 31 us,
         // UniPC-3 bf16 46 vs 37 us per step); SKR_IN_MODE=8 keeps it reachable for experiments.
-        if (p->n_philox == 0 && !env_int("SKR_NO_PINNED", 0)) {
-            int rc = 0;
-            if (try_shape<IN_MIXED, 4, ShUniPC<SKR_BF16>>(p, k, numel, stream, aligned, &rc)) return rc;
-        }
         return launch_block_inst<float, IN_MIXED, 4>(p, k, numel, stream, aligned);
     }
 }
@@ -589,6 +520,40 @@ int skr_program_classify(const skr_program* p) {
     static BProgram<double> b;
     memset(&b, 0, sizeof(b));
     return parse_block_program<double>(p, b) ? 0 : 1;
+}
+
+int skr_program_describe(const skr_program* p, char* text, int32_t capacity) {
+    using namespace skr;
+    if (!p || !text || capacity < 1) return fail(SKR_E_NULL, "null argument");
+    if (p->n_ops < 0 || p->n_ops > SKR_MAX_OPS) return fail(SKR_E_RANGE, "n_ops %d out of range", p->n_ops);
+    if (p->n_inputs < 0 || p->n_inputs > SKR_MAX_INPUTS) return fail(SKR_E_RANGE, "n_inputs %d out of range", p->n_inputs);
+    if (p->n_outputs < 0 || p->n_outputs > SKR_MAX_OUTPUTS) return fail(SKR_E_RANGE, "n_outputs %d out of range", p->n_outputs);
+    bool any64 = false;
+    for (int i = 0; i < p->n_inputs; ++i) any64 |= p->inputs[i].dtype == SKR_F64;
+    for (int i = 0; i < p->n_outputs; ++i) any64 |= p->outputs[i].dtype == SKR_F64;
+    static BProgram<float> b;  // host-only scratch; the descriptor is too large for the stack of small threads
+    memset(&b, 0, sizeof(b));
+    if (!parse_block_program<float>(p, b)) {
+        snprintf(text, (size_t)capacity, "interpreter");
+        return 1;
+    }
+    fill_dtypes(p, b);
+    const char* shape_name = "any";
+    int unused = 0;
+    if (!any64) pinned_any(p, b, 0, nullptr, true, false, &unused, &shape_name);
+    const BHead<float>& h = b.head;
+    int n = snprintf(text, (size_t)capacity, "block compute=%s shape=%s fast_div=%d head[x=%d y=%d neg=%d conv=%d sp=%d sp2=%d]",
+                     any64 ? "f64" : "f32", any64 ? "any" : shape_name, any64 ? 0 : b.fast_div,
+                     h.x_in >= 0, h.y_in >= 0, h.neg, h.n_conv, h.store_p >= 0, h.store_p2 >= 0);
+    for (int i = 0; i < 2 && n > 0 && n < capacity; ++i) {
+        const BBlock<float>& k = b.blk[i];
+        if (!k.enabled) continue;
+        n += snprintf(text + n, (size_t)(capacity - n),
+                      " blk%d[kind=%d sample=%d base=%d p_mode=%d div=%d pred_p=%d noise=%d terms=%d store=%d link=%d slink=%d]", i,
+                      k.kind, k.sample_in >= 0, k.base_in >= 0, k.p_mode, k.has_div, k.pred_is_p, k.has_noise, k.n_terms,
+                      k.store_r >= 0, k.link, k.store_link >= 0);
+    }
+    return 0;
 }
 
 int skr_program_launch(const skr_program* p, int64_t numel, void* stream) {

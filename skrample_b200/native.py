@@ -96,6 +96,7 @@ EXPORTS = (
     "skr_launch_count_kind",
     "skr_program_launch",
     "skr_program_classify",
+    "skr_program_describe",
     "skr_axpby",
 )
 
@@ -125,6 +126,8 @@ def load() -> ctypes.CDLL:
     lib.skr_program_launch.argtypes = [ctypes.POINTER(SkrProgram), ctypes.c_int64, ctypes.c_void_p]
     lib.skr_program_classify.restype = ctypes.c_int
     lib.skr_program_classify.argtypes = [ctypes.POINTER(SkrProgram)]
+    lib.skr_program_describe.restype = ctypes.c_int
+    lib.skr_program_describe.argtypes = [ctypes.POINTER(SkrProgram), ctypes.c_char_p, ctypes.c_int32]
     lib.skr_axpby.restype = ctypes.c_int
     lib.skr_axpby.argtypes = [
         ctypes.c_void_p,

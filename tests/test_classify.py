@@ -61,3 +61,65 @@ def test_bf16_unipc_program_with_two_xhat_stores_is_block_shaped(monkeypatch: py
             previous = (previous + [res])[-sampler.require_previous :]
             x = res.final.bfloat16()
     assert len(seen) == 4 and all(kind == 0 and stores == 2 for kind, stores in seen), seen
+
+
+def describe(program: pg.Program, state_dtype: torch.dtype = torch.float32) -> str:
+    "skr_program_describe with outputs typed the way the device path allocates them (solver state in fp32)."
+    tensors = list(program.inputs)
+    first = tensors[0].dtype
+    dtypes = [d if isinstance(d, torch.dtype) else (state_dtype if d == "compute" else first) for d in program.outputs]
+    packed = native.pack_program(program, tensors, [torch.empty(0, dtype=d) for d in dtypes])
+    text = ctypes.create_string_buffer(1024)
+    assert native.load().skr_program_describe(ctypes.byref(packed), text, len(text)) in (0, 1)
+    return text.value.decode()
+
+
+PINNED = [
+    ("Euler", {}, "euler"),
+    ("Euler", {"stochasticity": 1}, "euler"),
+    ("DPM", {"order": 2}, "dpm2"),
+    ("DPM", {"order": 3, "stochasticity": 1}, "dpm3"),
+    ("Adams", {"order": 4}, "acc"),
+    ("UniP", {"order": 3}, "unip"),
+    ("UniPC", {"order": 3, "stochasticity": 1}, "unipc"),
+    ("SPC", {}, "spc"),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16], ids=["f32", "bf16", "f16"])
+@pytest.mark.parametrize(("sampler", "kw", "shape"), PINNED, ids=[f"{s}-{n}" for n, (s, _, _) in enumerate(PINNED)])
+def test_steady_state_steps_take_a_pinned_kernel_shape(sampler: str, kw: dict, shape: str, dtype: torch.dtype, monkeypatch: pytest.MonkeyPatch) -> None:
+    "Past the warm-up steps every standard sampler runs a block-kernel instantiation compiled for exactly its step."
+    from skrample_b200 import scheduling
+    from skrample_b200.common import Step
+    from skrample_b200.sampling import models, structured
+
+    seen: list[str] = []
+
+    def spy(program: pg.Program):
+        seen.append(describe(program))
+        first = program.inputs[0].dtype
+        dtypes = [d if isinstance(d, torch.dtype) else (torch.float32 if d == "compute" else first) for d in program.outputs]
+        return [out.to(d) for out, d in zip(pg.execute_generic(program), dtypes)]
+
+    monkeypatch.setattr(pg, "execute", spy)
+    monkeypatch.setattr(pg, "is_cuda_tensor", lambda v: isinstance(v, torch.Tensor))  # emit what a device run would emit
+    instance = getattr(structured, sampler)(**kw)
+    x = torch.randn(64).to(dtype)
+    previous: list = []
+    for n in range(6):
+        res = instance.sample(x, torch.randn(64).to(dtype), Step.from_int(n, 8), models.NoiseModel(), scheduling.Scaled(), torch.randn(64).to(dtype), previous)
+        previous = (previous + [res])[-instance.require_previous :] if instance.require_previous else []
+        x = res.final.to(dtype)
+    name = {torch.float32: "f32", torch.bfloat16: "bf16", torch.float16: "f16"}[dtype]
+    assert len(seen) == 6
+    assert f"shape={shape}/{name} " in seen[-1], seen[-1]
+
+
+def test_describe_reports_interpreter_for_unstructured_programs() -> None:
+    program = pg.Program()
+    x = torch.randn(8)
+    program.load(pg.X, x)
+    program.axpby(torch.randn(8), 0.5, 0.25)
+    program.store(pg.R)
+    assert describe(program) == "interpreter"

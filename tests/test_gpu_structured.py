@@ -34,13 +34,17 @@ def test_native_library_is_the_path() -> None:
     assert np.array_equal(got.cpu().numpy(), want)
 
 
-@pytest.fixture(params=["block", "interpreter"])
+@pytest.fixture(params=["block", "block-generic", "interpreter"])
 def kernel_kind(request: pytest.FixtureRequest, monkeypatch: pytest.MonkeyPatch) -> int:
-    "Run a test once per kernel: the structured block kernel (default) and the general interpreter."
+    """Run a test once per kernel: the structured block kernel with its pinned-shape instantiations (default), the
+    generic block-kernel instantiations only, and the general interpreter."""
+    monkeypatch.delenv("SKR_FORCE_INTERP", raising=False)
+    monkeypatch.delenv("SKR_NO_PINNED", raising=False)
     if request.param == "interpreter":
         monkeypatch.setenv("SKR_FORCE_INTERP", "1")
         return 1
-    monkeypatch.delenv("SKR_FORCE_INTERP", raising=False)
+    if request.param == "block-generic":
+        monkeypatch.setenv("SKR_NO_PINNED", "1")
     return 0
 
 

@@ -29,6 +29,13 @@
 
 #include "machine.cuh"
 
+// History-term loops: left to the compiler's unroller by default; -DSKR_TERM_ROLLED keeps them rolled (experiment).
+#ifdef SKR_TERM_ROLLED
+#define SKR_TERM_LOOP _Pragma("unroll 1")
+#else
+#define SKR_TERM_LOOP
+#endif
+
 namespace skr {
 
 constexpr int kMaxTerms = 36;
@@ -88,64 +95,78 @@ struct BProgram {
 __device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
-template <typename CT, int MODE, int V>
-__device__ __forceinline__ void fetch_tile(const unsigned char* stage, uint32_t off, int dtype, int tid, CT (&v)[V]) {
-    const unsigned char* base = stage + off;
-    if constexpr (MODE == IN_F32) {
-        static_assert(V == 4, "fp32 tiles use 4 elements per thread");
-        const float4 q = *reinterpret_cast<const float4*>(base + tid * 16);
-        v[0] = (CT)q.x; v[1] = (CT)q.y; v[2] = (CT)q.z; v[3] = (CT)q.w;
-    } else if constexpr (MODE == IN_BF16) {
-        static_assert(V == 8, "16-bit tiles use 8 elements per thread");
-        const uint4 q = *reinterpret_cast<const uint4*>(base + tid * 16);
-        v[0] = (CT)bf16_lo(q.x); v[1] = (CT)bf16_hi(q.x); v[2] = (CT)bf16_lo(q.y); v[3] = (CT)bf16_hi(q.y);
-        v[4] = (CT)bf16_lo(q.z); v[5] = (CT)bf16_hi(q.z); v[6] = (CT)bf16_lo(q.w); v[7] = (CT)bf16_hi(q.w);
-    } else if constexpr (MODE == IN_F16) {
-        static_assert(V == 8, "16-bit tiles use 8 elements per thread");
-        const uint4 q = *reinterpret_cast<const uint4*>(base + tid * 16);
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+// Shared-memory reads by 32-bit shared address: the generic-pointer window arithmetic stays out of the hot loop.
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 q;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
+    return q;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 q;
+    asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(q.x), "=r"(q.y) : "r"(addr));
+    return q;
+}
+
+template <typename CT, int N>
+__device__ __forceinline__ void unpack_f32(uint32_t addr, CT* v) {  // N floats, 16 bytes per read
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
-            v[2 * i] = (CT)f.x;
-            v[2 * i + 1] = (CT)f.y;
-        }
-    } else if constexpr (V == 4) {
-        fetch_staged<CT>(stage, off, dtype, tid, v);
+    for (int i = 0; i < N / 4; ++i) {
+        const uint4 q = lds128(addr + 16 * i);
+        v[4 * i] = (CT)__uint_as_float(q.x); v[4 * i + 1] = (CT)__uint_as_float(q.y);
+        v[4 * i + 2] = (CT)__uint_as_float(q.z); v[4 * i + 3] = (CT)__uint_as_float(q.w);
+    }
+}
+template <typename CT, bool BF16>
+__device__ __forceinline__ void unpack_half2(uint32_t w, CT& lo, CT& hi) {
+    if constexpr (BF16) {
+        lo = (CT)bf16_lo(w);
+        hi = (CT)bf16_hi(w);
     } else {
-        static_assert(V == 8, "mixed tiles use 4 or 8 elements per thread");
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+        lo = (CT)f.x;
+        hi = (CT)f.y;
+    }
+}
+template <typename CT, int N, bool BF16>
+__device__ __forceinline__ void unpack_16(uint32_t addr, CT* v) {  // N 16-bit values
+    if constexpr (N == 8) {
+        const uint4 q = lds128(addr);
+        unpack_half2<CT, BF16>(q.x, v[0], v[1]); unpack_half2<CT, BF16>(q.y, v[2], v[3]);
+        unpack_half2<CT, BF16>(q.z, v[4], v[5]); unpack_half2<CT, BF16>(q.w, v[6], v[7]);
+    } else {
+        const uint2 q = lds64(addr);
+        unpack_half2<CT, BF16>(q.x, v[0], v[1]); unpack_half2<CT, BF16>(q.y, v[2], v[3]);
+    }
+}
+template <typename CT, int N>
+__device__ __forceinline__ void unpack_f64(uint32_t addr, CT* v) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+        const uint4 q = lds128(addr + 16 * i);
+        v[2 * i] = (CT)__hiloint2double((int)q.y, (int)q.x);
+        v[2 * i + 1] = (CT)__hiloint2double((int)q.w, (int)q.z);
+    }
+}
+
+// This thread's V consecutive elements of one staged input.  `stage` is the shared address of the stage, `off`
+// the input's byte offset inside it, `first_elem` = tid * V.
+template <typename CT, int MODE, int V>
+__device__ __forceinline__ void fetch_tile(uint32_t stage, uint32_t off, int dtype, uint32_t first_elem, CT (&v)[V]) {
+    const uint32_t base = stage + off;
+    if constexpr (MODE == IN_F32) {
+        unpack_f32<CT, V>(base + first_elem * 4u, v);
+    } else if constexpr (MODE == IN_BF16) {
+        unpack_16<CT, V, true>(base + first_elem * 2u, v);
+    } else if constexpr (MODE == IN_F16) {
+        unpack_16<CT, V, false>(base + first_elem * 2u, v);
+    } else {
         switch (dtype) {
-            case SKR_F32: {
-                const float4 q0 = *reinterpret_cast<const float4*>(base + tid * 32);
-                const float4 q1 = *reinterpret_cast<const float4*>(base + tid * 32 + 16);
-                v[0] = (CT)q0.x; v[1] = (CT)q0.y; v[2] = (CT)q0.z; v[3] = (CT)q0.w;
-                v[4] = (CT)q1.x; v[5] = (CT)q1.y; v[6] = (CT)q1.z; v[7] = (CT)q1.w;
-            } break;
-            case SKR_BF16: {
-                const uint4 q = *reinterpret_cast<const uint4*>(base + tid * 16);
-                v[0] = (CT)bf16_lo(q.x); v[1] = (CT)bf16_hi(q.x); v[2] = (CT)bf16_lo(q.y); v[3] = (CT)bf16_hi(q.y);
-                v[4] = (CT)bf16_lo(q.z); v[5] = (CT)bf16_hi(q.z); v[6] = (CT)bf16_lo(q.w); v[7] = (CT)bf16_hi(q.w);
-            } break;
-            case SKR_F16: {
-                const uint4 q = *reinterpret_cast<const uint4*>(base + tid * 16);
-                const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
-                    v[2 * i] = (CT)f.x;
-                    v[2 * i + 1] = (CT)f.y;
-                }
-            } break;
-            default: {
-                if constexpr (sizeof(CT) == 8) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const double2 q = *reinterpret_cast<const double2*>(base + tid * 64 + 16 * i);
-                        v[2 * i] = (CT)q.x;
-                        v[2 * i + 1] = (CT)q.y;
-                    }
-                }
-            } break;
+            case SKR_F32: unpack_f32<CT, V>(base + first_elem * 4u, v); break;
+            case SKR_BF16: unpack_16<CT, V, true>(base + first_elem * 2u, v); break;
+            case SKR_F16: unpack_16<CT, V, false>(base + first_elem * 2u, v); break;
+            default:  // SKR_F64 - only reachable in the fp64-compute instantiation
+                if constexpr (sizeof(CT) == 8) unpack_f64<CT, V>(base + first_elem * 8u, v);
+                break;
         }
     }
 }
@@ -343,13 +364,13 @@ static bool shape_matches(const BProgram<CT>& p) {
 template <typename CT, int MODE, int V, bool GUARDED>
 struct TileIO {
     const BProgram<CT>& prog;
-    const unsigned char* stage;
-    int tid;
+    uint32_t stage;       // shared address of the staged tile
+    uint32_t first_elem;  // tid * V
     int64_t first;
     template <int DT = -1>
     __device__ __forceinline__ void load(int in, CT (&v)[V]) const {
         if constexpr (GUARDED) fetch_guarded<CT, V>(prog.in_ptr[in], prog.in_dtype[in], first, prog.numel, v);
-        else fetch_tile<CT, MODE, V>(stage, prog.in_off[in], pinned<DT>(prog.in_dtype[in]), tid, v);
+        else fetch_tile<CT, MODE, V>(stage, prog.in_off[in], pinned<DT>(prog.in_dtype[in]), first_elem, v);
     }
     template <int DT = -1>
     __device__ __forceinline__ void store(int out, const CT (&v)[V]) const {
@@ -397,6 +418,7 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BB
                 for (int j = 0; j < V; ++j) A[j] = Ar::add((CT)0, Ar::mul(in[j], c));
                 t = 1;
             }
+            SKR_TERM_LOOP
             for (; t < n_terms; ++t) {
                 io.template load<BS::dt_state>(k.terms[t].in, in);
                 const CT c = k.terms[t].c0;
@@ -412,6 +434,9 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BB
                 div_uniform<V>(A, k.div, k.div_r, fast_div);
             }
         } else if (kind == BK_UNI) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) A[j] = (CT)0;  // 0 + first term, like the reference's running sum
+            SKR_TERM_LOOP
             for (int t = 0; t < n_terms; ++t) {
                 io.template load<BS::dt_state>(k.terms[t].in, in);
                 const CT rho = k.terms[t].c1;
@@ -419,14 +444,14 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BB
                 for (int j = 0; j < V; ++j) in[j] = Ar::sub(in[j], B[j]);
                 div_uniform<V>(in, k.terms[t].c0, k.terms[t].r0, fast_div);
 #pragma unroll
-                for (int j = 0; j < V; ++j) A[j] = Ar::add(t == 0 ? (CT)0 : A[j], Ar::mul(in[j], rho));
+                for (int j = 0; j < V; ++j) A[j] = Ar::add(A[j], Ar::mul(in[j], rho));
             }
             if (p_mode == 1) {
                 const CT rho = k.p_coef;
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
                     const CT term = Ar::mul(Ar::sub(P[j], B[j]), rho);
-                    A[j] = Ar::add(n_terms == 0 ? (CT)0 : A[j], term);
+                    A[j] = Ar::add(A[j], term);
                 }
             }
             const bool empty = k.empty_sum != 0;
@@ -492,9 +517,9 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BB
 }
 
 template <typename CT, int MODE, int V, bool GUARDED, bool PHILOX, typename Sh>
-__device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t first, const unsigned char* stage, int tid) {
+__device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t first, uint32_t stage, int tid) {
     using Ar = Arith<CT>;
-    const TileIO<CT, MODE, V, GUARDED> io{prog, stage, tid, first};
+    const TileIO<CT, MODE, V, GUARDED> io{prog, stage, (uint32_t)tid * V, first};
 
     CT X[V], P[V], B[V], A[V], S[V], R[V];
 #pragma unroll
@@ -542,7 +567,7 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
 template <typename CT, int MODE, int V, bool PHILOX>
 __device__ __noinline__ void run_guarded_tiles(const BProgram<CT>& prog, int64_t first_tile, int64_t n_tiles, int tid) {
     for (int64_t tile = first_tile + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        run_block_tile<CT, MODE, V, true, PHILOX, ShAny>(prog, tile * (kThreads * V) + (int64_t)tid * V, nullptr, tid);
+        run_block_tile<CT, MODE, V, true, PHILOX, ShAny>(prog, tile * (kThreads * V) + (int64_t)tid * V, 0u, tid);
     }
 }
 
@@ -568,6 +593,9 @@ __global__ void __launch_bounds__(kThreads + kProducerThreads, block_ctas_per_sm
     const int mine = n_full > cta ? (n_full - cta + grid - 1) / grid : 0;
     const bool producer = warp == kThreads / 32;
 
+    // PDL: the next step's grid may start its prologue now; this grid touches global memory only after every
+    // predecessor has completed (the step reads what the previous step wrote).
+    griddep_launch_dependents();
     if (mine > 0) {
         if (tid == 0) {
             for (int s = 0; s < stages; ++s) {
@@ -577,6 +605,9 @@ __global__ void __launch_bounds__(kThreads + kProducerThreads, block_ctas_per_sm
             fence_barrier_init();
         }
         __syncthreads();
+    }
+    griddep_wait();
+    if (mine > 0) {
 
         if (producer) {
             // one lane per input tensor; lanes beyond n_inputs idle (SKR_MAX_INPUTS == 32 == warp size)
@@ -602,13 +633,16 @@ __global__ void __launch_bounds__(kThreads + kProducerThreads, block_ctas_per_sm
             uint32_t phase = 0;
             int64_t first = (int64_t)cta * TILE + (int64_t)tid * V;
             const int64_t stride = (int64_t)grid * TILE;
+            const uint32_t smem_addr = (uint32_t)__cvta_generic_to_shared(smem);
+            uint32_t stage_addr = smem_addr;
             for (int k = 0; k < mine; ++k) {
                 mbar_wait(&full_bar[s], phase);
-                run_block_tile<CT, MODE, V, false, PHILOX, Sh>(prog, first, smem + (size_t)s * stage_bytes, tid);
+                run_block_tile<CT, MODE, V, false, PHILOX, Sh>(prog, first, stage_addr, tid);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[s]);
                 first += stride;
-                if (++s == stages) { s = 0; phase ^= 1u; }
+                stage_addr += stage_bytes;
+                if (++s == stages) { s = 0; phase ^= 1u; stage_addr = smem_addr; }
             }
         }
     }

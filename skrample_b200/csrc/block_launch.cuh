@@ -62,8 +62,20 @@ static int launch_block_one(const skr_program* p, BProgram<CT>& k, int64_t numel
         if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set[ordinal] = true;
     }
-    block_kernel<CT, MODE, V, PHILOX, Sh><<<(unsigned)grid, kThreads + kProducerThreads, smem, stream>>>(k);
-    cudaError_t e = cudaGetLastError();
+    // Programmatic dependent launch: consecutive steps overlap launch latency and prologue (SKR_PDL=0 disables).
+    static const bool pdl = env_int("SKR_PDL", 1) != 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads + kProducerThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, block_kernel<CT, MODE, V, PHILOX, Sh>, k);
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, "block kernel launch: %s", cudaGetErrorString(e));
     count_launch(0);
     return 0;

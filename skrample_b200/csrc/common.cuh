@@ -61,4 +61,12 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
                  : "memory");
 }
 
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// become resident while its predecessor in the stream is still running.  launch_dependents lets the successor of
+// THIS grid start its prologue; wait blocks until every predecessor grid has completed and its memory is visible.
+// Both are no-ops for a kernel that was launched without the attribute.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 }  // namespace skr

@@ -46,10 +46,10 @@ enum BlockLink : int32_t { BL_NONE = 0, BL_X_FROM_R = 1, BL_BLEND = 2, BL_BACK =
 enum InMode : int { IN_MIXED = 0, IN_F32 = 1, IN_BF16 = 2, IN_F16 = 3 };
 
 template <typename CT>
-struct BTerm {
+struct BTerm {  // 16 bytes for fp32 compute: one 128-bit constant load per history term
     CT c0, c1;
-    CT r0;       // RN(1/c0) where c0 is a divisor (UNI terms)
-    int32_t in;  // input index
+    CT r0;         // RN(1/c0) where c0 is a divisor (UNI terms)
+    uint32_t off;  // byte offset of the term's tensor inside a staged tile (filled at launch)
 };
 
 template <typename CT>
@@ -61,7 +61,9 @@ struct BBlock {
     int32_t pad;
     CT p_coef, div, gamma, delta, zeta, l0, l1, e0, e1, e2;
     CT div_r, l1_r;  // reciprocals of the divisors `div` and `l1`
+    uint32_t sample_off, base_off, noise_off, pad_off;  // staged byte offsets of sample_in / base_in / noise_in
     BTerm<CT> terms[kMaxTerms];
+    int32_t term_in[kMaxTerms];  // input index of each term (guarded path, host matching)
 };
 
 template <typename CT>
@@ -71,6 +73,7 @@ struct BHead {
     int32_t store_p2;  // optional second copy of P (e.g. fp32 solver state + 16-bit copy for the caller)
     CT conv_c[2][3];
     CT conv_r[2];  // reciprocals of the conversion divisors conv_c[.][2]
+    uint32_t x_off, y_off;  // staged byte offsets of x_in / y_in
 };
 
 template <typename CT>
@@ -336,7 +339,7 @@ static bool block_matches(const BBlock<CT>& k, const int32_t* in_dt, const int32
         if (k.sample_in >= 0 && in_dt[k.sample_in] != BS::dt_state) return false;
         if (k.base_in >= 0 && in_dt[k.base_in] != BS::dt_state) return false;
         for (int t = 0; t < k.n_terms; ++t)
-            if (in_dt[k.terms[t].in] != BS::dt_state) return false;
+            if (in_dt[k.term_in[t]] != BS::dt_state) return false;
     }
     if (BS::dt_noise >= 0 && k.has_noise == 1 && in_dt[k.noise_in] != BS::dt_noise) return false;
     if (BS::dt_store >= 0 && k.store_r >= 0 && out_dt[k.store_r] != BS::dt_store) return false;
@@ -367,10 +370,11 @@ struct TileIO {
     uint32_t stage;       // shared address of the staged tile
     uint32_t first_elem;  // tid * V
     int64_t first;
+    // `in` = input index (pointer / dtype tables), `off` = its byte offset inside the staged tile
     template <int DT = -1>
-    __device__ __forceinline__ void load(int in, CT (&v)[V]) const {
+    __device__ __forceinline__ void load(int in, uint32_t off, CT (&v)[V]) const {
         if constexpr (GUARDED) fetch_guarded<CT, V>(prog.in_ptr[in], prog.in_dtype[in], first, prog.numel, v);
-        else fetch_tile<CT, MODE, V>(stage, prog.in_off[in], pinned<DT>(prog.in_dtype[in]), first_elem, v);
+        else fetch_tile<CT, MODE, V>(stage, off, pinned<DT>(prog.in_dtype[in]), first_elem, v);
     }
     template <int DT = -1>
     __device__ __forceinline__ void store(int out, const CT (&v)[V]) const {
@@ -391,7 +395,7 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BB
 #pragma unroll
         for (int j = 0; j < V; ++j) S[j] = X[j];
     }
-    if (pinned<BS::sample>(k.sample_in >= 0)) io.template load<BS::dt_state>(k.sample_in, X);
+    if (pinned<BS::sample>(k.sample_in >= 0)) io.template load<BS::dt_state>(k.sample_in, k.sample_off, X);
 
     CT in[V];
     const int kind = pinned<BS::kind>(k.kind);
@@ -399,7 +403,7 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BB
         const int n_terms = k.n_terms;
         const int p_mode = pinned<BS::p_mode>(k.p_mode);
         if (kind != BK_ACC) {
-            if (pinned<BS::base>(k.base_in >= 0)) io.template load<BS::dt_state>(k.base_in, B);
+            if (pinned<BS::base>(k.base_in >= 0)) io.template load<BS::dt_state>(k.base_in, k.base_off, B);
             else {
 #pragma unroll
                 for (int j = 0; j < V; ++j) B[j] = P[j];
@@ -412,7 +416,7 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BB
 #pragma unroll
                 for (int j = 0; j < V; ++j) A[j] = Ar::add((CT)0, Ar::mul(P[j], c));
             } else {
-                io.template load<BS::dt_state>(k.terms[0].in, in);
+                io.template load<BS::dt_state>(k.term_in[0], k.terms[0].off, in);
                 const CT c = k.terms[0].c0;
 #pragma unroll
                 for (int j = 0; j < V; ++j) A[j] = Ar::add((CT)0, Ar::mul(in[j], c));
@@ -420,7 +424,7 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BB
             }
             SKR_TERM_LOOP
             for (; t < n_terms; ++t) {
-                io.template load<BS::dt_state>(k.terms[t].in, in);
+                io.template load<BS::dt_state>(k.term_in[t], k.terms[t].off, in);
                 const CT c = k.terms[t].c0;
 #pragma unroll
                 for (int j = 0; j < V; ++j) A[j] = Ar::add(A[j], Ar::mul(in[j], c));
@@ -438,7 +442,7 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BB
             for (int j = 0; j < V; ++j) A[j] = (CT)0;  // 0 + first term, like the reference's running sum
             SKR_TERM_LOOP
             for (int t = 0; t < n_terms; ++t) {
-                io.template load<BS::dt_state>(k.terms[t].in, in);
+                io.template load<BS::dt_state>(k.term_in[t], k.terms[t].off, in);
                 const CT rho = k.terms[t].c1;
 #pragma unroll
                 for (int j = 0; j < V; ++j) in[j] = Ar::sub(in[j], B[j]);
@@ -458,14 +462,14 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BB
 #pragma unroll
             for (int j = 0; j < V; ++j) A[j] = Ar::add(B[j], empty ? (CT)0 : A[j]);
         } else if (kind == BK_DPM2) {
-            io.template load<BS::dt_state>(k.terms[0].in, in);
+            io.template load<BS::dt_state>(k.term_in[0], k.terms[0].off, in);
             const CT inv_r = k.terms[0].c0, half = k.terms[0].c1;
 #pragma unroll
             for (int j = 0; j < V; ++j) A[j] = Ar::add(B[j], Ar::mul(half, Ar::mul(inv_r, Ar::sub(B[j], in[j]))));
         } else {  // BK_DPM3
             CT in2[V];
-            io.template load<BS::dt_state>(k.terms[0].in, in);
-            io.template load<BS::dt_state>(k.terms[1].in, in2);
+            io.template load<BS::dt_state>(k.term_in[0], k.terms[0].off, in);
+            io.template load<BS::dt_state>(k.term_in[1], k.terms[1].off, in2);
             const CT inv_r = k.terms[0].c0, inv_r2 = k.terms[1].c0, mix = k.terms[1].c1;
             const CT inv_sum = k.e0, w1 = k.e1, w2 = k.e2;
 #pragma unroll
@@ -490,7 +494,7 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BB
     const int has_noise = pinned<BS::noise>(k.has_noise);
     if (has_noise) {
         if (PHILOX && has_noise == 2) draw_normals<CT, V>(prog.philox[k.noise_in], io.first, prog.numel, in);
-        else io.template load<BS::dt_noise>(k.noise_in, in);
+        else io.template load<BS::dt_noise>(k.noise_in, k.noise_off, in);
         const CT zeta = k.zeta;
 #pragma unroll
         for (int j = 0; j < V; ++j) R[j] = Ar::add(R[j], Ar::mul(in[j], zeta));
@@ -528,9 +532,9 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
     // ---- head ---------------------------------------------------------------------------------
     const BHead<CT>& h = prog.head;
     const bool fast_div = prog.fast_div != 0;
-    if (pinned<Sh::x>(h.x_in >= 0)) io.template load<Sh::dt_x>(h.x_in, X);
+    if (pinned<Sh::x>(h.x_in >= 0)) io.template load<Sh::dt_x>(h.x_in, h.x_off, X);
     if (pinned<Sh::y>(h.y_in >= 0)) {
-        io.template load<Sh::dt_y>(h.y_in, P);
+        io.template load<Sh::dt_y>(h.y_in, h.y_off, P);
         const bool neg = pinned<Sh::neg>(h.neg) != 0;
 #pragma unroll
         for (int j = 0; j < V; ++j) P[j] = neg ? -P[j] : P[j];
@@ -698,7 +702,7 @@ static bool parse_block(OpCursor& cur, BBlock<CT>& k) {
             if (t->a == 0) {
                 if (k.p_mode == 2) return false;  // tensor term after the trailing P term
                 if (k.n_terms >= kMaxTerms) return false;
-                k.terms[k.n_terms].in = t->src;
+                k.term_in[k.n_terms] = t->src;
                 k.terms[k.n_terms].c0 = (CT)t->c[0];
                 ++k.n_terms;
             } else if (t->a == SKR_P + 1) {
@@ -720,7 +724,7 @@ static bool parse_block(OpCursor& cur, BBlock<CT>& k) {
             const skr_op* t = cur.take();
             if ((t->a != 0) != (seen == 0)) return false;
             if (k.n_terms >= kMaxTerms) return false;
-            k.terms[k.n_terms].in = t->src;
+            k.term_in[k.n_terms] = t->src;
             k.terms[k.n_terms].c0 = (CT)t->c[0];
             k.terms[k.n_terms].c1 = (CT)t->c[1];
             ++k.n_terms;
@@ -742,7 +746,7 @@ static bool parse_block(OpCursor& cur, BBlock<CT>& k) {
         const skr_op* t = cur.take();
         k.kind = BK_DPM2;
         k.n_terms = 1;
-        k.terms[0].in = t->src;
+        k.term_in[0] = t->src;
         k.terms[0].c0 = (CT)t->c[0];
         k.terms[0].c1 = (CT)t->c[1];
         pred_from_a = true;
@@ -754,9 +758,9 @@ static bool parse_block(OpCursor& cur, BBlock<CT>& k) {
         const skr_op* c = cur.take();
         k.kind = BK_DPM3;
         k.n_terms = 2;
-        k.terms[0].in = a->src;
+        k.term_in[0] = a->src;
         k.terms[0].c0 = (CT)a->c[0];
-        k.terms[1].in = b->src;
+        k.term_in[1] = b->src;
         k.terms[1].c0 = (CT)b->c[0];
         k.terms[1].c1 = (CT)b->c[1];
         k.e0 = (CT)b->c[2];
@@ -823,6 +827,21 @@ static void fill_reciprocals(BProgram<CT>& out) {
             for (int t = 0; t < k.n_terms; ++t) k.terms[t].r0 = uniform_reciprocal(k.terms[t].c0, &fast);
     }
     out.fast_div = (fast && sizeof(CT) == 4) ? 1 : 0;
+}
+
+// Staged byte offsets of every operand (after in_off[] is known for the launch's tile size).
+template <typename CT>
+static void resolve_offsets(BProgram<CT>& k) {
+    auto at = [&](int in) { return in >= 0 ? k.in_off[in] : 0u; };
+    k.head.x_off = at(k.head.x_in);
+    k.head.y_off = at(k.head.y_in);
+    for (int b = 0; b < 2; ++b) {
+        BBlock<CT>& blk = k.blk[b];
+        blk.sample_off = at(blk.sample_in);
+        blk.base_off = at(blk.base_in);
+        blk.noise_off = blk.has_noise == 1 ? at(blk.noise_in) : 0u;
+        for (int t = 0; t < blk.n_terms; ++t) blk.terms[t].off = at(blk.term_in[t]);
+    }
 }
 
 // Returns true when `p` matches the skeleton; fills head/blk of `out`.

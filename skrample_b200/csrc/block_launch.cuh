@@ -27,6 +27,7 @@ static int launch_block_one(const skr_program* p, BProgram<CT>& k, int64_t numel
         k.out_dtype[i] = p->outputs[i].dtype;
     }
     k.stage_bytes = off;
+    resolve_offsets(k);
     fill_kphilox(k.philox, p->philox, p->n_philox);
 
     int err = 0;

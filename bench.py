@@ -341,6 +341,42 @@ def e2e_throughput(spec: dict, device: torch.device, steps: int, warmup: int) ->
     }
 
 
+def e2e_graphed_throughput(spec: dict, device: torch.device, steps: int, warmup: int) -> dict:
+    """The e2e step through skrample_b200.graphs.GraphedTrajectory: the same host buffers and copies, the sampler
+    launches replayed from CUDA graphs captured once."""
+    from skrample_b200.graphs import GraphedTrajectory
+
+    traj = Trajectory(spec, device, seed=4321)
+    traj.record()
+    host_pred = [p.cpu().pin_memory() for p in traj.predictions]
+    result_host = torch.empty(spec["shape"], dtype=traj.dtype).pin_memory()
+    graphed = GraphedTrajectory(traj.sampler, traj.model, traj.schedule, STEPS_PER_TRAJECTORY, like=traj.x0)
+
+    def one() -> None:
+        if graphed.position == len(graphed):
+            graphed.start(traj.x0)
+        graphed.prediction().copy_(host_pred[graphed.position], non_blocking=True)
+        if traj.sampler.require_noise:
+            traj.noise_source.generate_into(graphed.noise(), None)  # fresh noise every step, written in place
+        final = graphed.step()
+        result_host.copy_(final, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    graphed.start(traj.x0)
+    for _ in range(warmup):
+        one()
+    graphed.start(traj.x0)
+    torch.cuda.synchronize(device)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    torch.cuda.synchronize(device)
+    elapsed = time.perf_counter() - t0
+    barrier()
+    return {"elapsed_s": elapsed}
+
+
 def barrier() -> None:
     if torch.distributed.is_available() and torch.distributed.is_initialized():
         torch.distributed.barrier()
@@ -526,6 +562,7 @@ def main() -> None:
     e2e = e2e_throughput(spec, device, e2e_steps, min(args.warmup, 50))
     e2e_elapsed = max_over_ranks(e2e["elapsed_s"], device)
     e2e_gbs = e2e["bytes"] * world / e2e_elapsed / 1e9
+    graphed_elapsed = max_over_ranks(e2e_graphed_throughput(spec, device, e2e_steps, min(args.warmup, 50))["elapsed_s"], device)
 
     line = {
         "metric": "sampler latent-steps/s (one batch item advanced one solver step)",
@@ -558,6 +595,14 @@ def main() -> None:
             "sampler_step_GBps": e2e_gbs,
             "ms_per_step": e2e_elapsed / e2e_steps * 1e3,
             "steps": e2e_steps,
+            "api": "structured sampler .sample() per step (the reference's call), pinned-host prediction in, result out",
+        },
+        "e2e_graphed": {
+            "value": e2e_steps * spec["shape"][0] * world / graphed_elapsed,
+            "unit": "latent-steps/s",
+            "ms_per_step": graphed_elapsed / e2e_steps * 1e3,
+            "steps": e2e_steps,
+            "api": "skrample_b200.graphs.GraphedTrajectory.step(): same host buffers and copies, launches replayed from CUDA graphs",
         },
         "roofline": {
             "bound": "hbm",

@@ -20,6 +20,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import threading
 from abc import ABC, abstractmethod
 from dataclasses import dataclass
 from typing import Any, Self
@@ -148,6 +149,17 @@ def _host_uniform(seed: int, stream: int, index: int) -> float:
     return (z >> 11) / float(1 << 53)
 
 
+_scratch = threading.local()
+
+
+def _philox_scratch() -> Any:
+    "One reusable key table per thread (the C call copies it before returning)."
+    keys = getattr(_scratch, "keys", None)
+    if keys is None:
+        keys = _scratch.keys = _native().SkrPhilox()
+    return keys
+
+
 class PhiloxDraw:
     """A normal noise tensor that exists only as Philox keys: the fused step kernel draws it while it runs.
 
@@ -178,17 +190,21 @@ class PhiloxDraw:
     def materialize(self) -> torch.Tensor:
         if self._tensor is None:
             out = torch.empty(self.shape, dtype=self.dtype, device=self.device)
-            keys = _native().SkrPhilox()
-            count = len(self.seeds)
-            keys.n_items = count
-            keys.item_numel = self.item_numel
-            keys.seed[:count] = self.seeds
-            keys.stream[:count] = self.streams
-            with _DeviceGuard(self.device):
-                status = _lib().skr_noise_fill_batch(out.data_ptr(), _code(out.dtype), ctypes.byref(keys), _stream())
-            _native().check(status, "skr_noise_fill_batch")
+            self.materialize_into(out)
             self._tensor = out
         return self._tensor
+
+    def materialize_into(self, out: torch.Tensor) -> None:
+        "Write the draw into ``out`` (contiguous, on this draw's device; rounded once to ``out``'s dtype)."
+        keys = _philox_scratch()
+        count = len(self.seeds)
+        keys.n_items = count
+        keys.item_numel = self.item_numel
+        keys.seed[:count] = self.seeds
+        keys.stream[:count] = self.streams
+        with _DeviceGuard(self.device):
+            status = _lib().skr_noise_fill_batch(out.data_ptr(), _code(out.dtype), ctypes.byref(keys), _stream())
+        _native().check(status, "skr_noise_fill_batch")
 
     def to(self, *args: Any, **kwargs: Any) -> torch.Tensor:
         return self.materialize().to(*args, **kwargs)
@@ -678,16 +694,39 @@ class BatchTensorNoise[T: TensorNoiseProps | None](SkrampleTensorNoise):
             return out
         return torch.stack([g.generate(step) for g in self.generators])
 
+    def generate_into(self, out: torch.Tensor, step: Step | None) -> None:
+        """Write the next batch of noise into ``out`` (``[batch, *unit]``, any floating dtype): the values of
+        ``generate(step).to(out.dtype)`` without the intermediate tensor when the batch is plain ``Random`` on
+        ``out``'s device."""
+        if out.is_cuda and out.is_contiguous() and self._uniform_random() and out.device == self.generators[0].seed.device:
+            drawn = self.lazy(step, _fallback=False)
+            if drawn is not None and tuple(out.shape) == drawn.shape:
+                drawn.materialize_into(out)
+                return
+            out.copy_(drawn.materialize() if drawn is not None else self.generate(step))
+            return
+        out.copy_(self.generate(step))
+
+    def _uniform_random(self) -> bool:
+        "Every item is a plain ``Random`` with one shape / dtype on one CUDA device (checked once per generator list)."
+        stamp = tuple(id(g) for g in self.generators)
+        cached = self.__dict__.get("_skr_uniform")
+        if cached is None or cached[0] != stamp:
+            first = self.generators[0]
+            ok = len(self.generators) <= 32 and all(
+                type(g) is Random and g.on_device and g.seed.device == first.seed.device and g.dtype == first.dtype and g.shape == first.shape
+                for g in self.generators
+            )
+            cached = (stamp, ok)
+            self.__dict__["_skr_uniform"] = cached
+        return cached[1]
+
     def lazy(self, step: Step | None, _fallback: bool = True) -> "PhiloxDraw | torch.Tensor | None":
         """The next batch of noise as Philox keys when every item is a plain ``Random`` on one CUDA device (and the
         batch fits the kernel's key table); otherwise the materialised tensor."""
-        first = self.generators[0]
-        eligible = len(self.generators) <= 32 and all(
-            type(g) is Random and g.on_device and g.seed.device == first.seed.device and g.dtype == first.dtype and g.shape == first.shape
-            for g in self.generators
-        )
-        if not eligible:
+        if not self._uniform_random():
             return self.generate(step) if _fallback else None
+        first = self.generators[0]
         return PhiloxDraw(
             (len(self.generators), *first.shape),
             tuple(g._key() for g in self.generators),

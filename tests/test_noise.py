@@ -176,6 +176,24 @@ def test_random_values_do_not_depend_on_sharding() -> None:
 
 
 @gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_batch_generate_into_equals_generate_then_cast(dtype: torch.dtype) -> None:
+    "Writing the batch straight into a caller's buffer (graph-captured trajectories) gives generate().to(dtype)."
+    unit = (4, 33, 31)
+    a = noise.BatchTensorNoise.from_batch_inputs(noise.Random, unit, [_gen(40 + i) for i in range(3)])
+    b = noise.BatchTensorNoise.from_batch_inputs(noise.Random, unit, [_gen(40 + i) for i in range(3)])
+    for _ in range(3):  # consecutive draws stay in step
+        out = torch.empty((3, *unit), device="cuda", dtype=dtype)
+        b.generate_into(out, None)
+        assert torch.equal(out, a.generate(None).to(dtype))
+    mixed = noise.BatchTensorNoise([noise.Random.from_inputs(unit, _gen(1)), noise.Offset.from_inputs(unit, _gen(2))])
+    twin = noise.BatchTensorNoise([noise.Random.from_inputs(unit, _gen(1)), noise.Offset.from_inputs(unit, _gen(2))])
+    out = torch.empty((2, *unit), device="cuda", dtype=dtype)
+    mixed.generate_into(out, None)  # not a plain Random batch: generic path
+    assert torch.equal(out, twin.generate(None).to(dtype))
+
+
+@gpu
 def test_ragged_and_unaligned_fill() -> None:
     big = torch.empty(1031 + 3, device="cuda")
     a = noise.Random.from_inputs((1031,), _gen(9))

@@ -293,6 +293,7 @@ class SkrampleWrapperCore(abc.ABC):
         self._index: int = 0
         self._device: torch.device = torch.device("cpu")
         self._noise_generator: BatchTensorNoise | None = None
+        self._handed_out: list[tuple[Tensor, int, int, int, list[float]]] = []  # timesteps tensors given to the caller: (tensor, base address, byte pitch, version, values)
 
     @property
     @abc.abstractmethod
@@ -312,7 +313,27 @@ class SkrampleWrapperCore(abc.ABC):
 
     @property
     def timesteps(self) -> Tensor:
-        return torch.from_numpy(self.schedule_np[:, 0]).to(self._device)
+        values = self.schedule_np[:, 0]
+        tensor = torch.from_numpy(values).to(self._device)
+        # Remembered so that `for t in scheduler.timesteps: scheduler.step(out, t, x)` resolves `t` by its address
+        # inside this tensor instead of a device->host read (reference: diffusers.py:262-270 does `.item()`, a stream
+        # drain on every step).  Holding the tensor keeps its memory from being recycled while the entry lives.
+        pitch = 8 * (tensor.stride(0) if tensor.numel() > 1 else 1)  # bytes between consecutive timesteps
+        self._handed_out = [*self._handed_out[-3:], (tensor, tensor.data_ptr(), pitch, tensor._version, values.tolist())]
+        return tensor
+
+    def _index_without_sync(self, timestep: Tensor) -> int | None:
+        "Index of a one-element view of a timesteps tensor this wrapper handed out, or None."
+        if timestep.numel() != 1 or timestep.dtype != torch.float64:
+            return None
+        address = timestep.data_ptr()
+        for tensor, base, pitch, version, values in reversed(self._handed_out):
+            offset = address - base
+            if 0 <= offset < len(values) * pitch and offset % pitch == 0 and timestep.device == tensor.device and tensor._version == version:
+                if len(values) != len(self.schedule_np) or values != self.schedule_np[:, 0].tolist():
+                    return None  # the schedule changed since (set_timesteps): fall back to the value
+                return values.index(values[offset // pitch])  # first occurrence, like list.index on the value
+        return None
 
     @property
     def sigmas(self) -> Tensor:
@@ -443,6 +464,10 @@ class SkrampleWrapperCore(abc.ABC):
 
     def _index_of(self, timestep: float | Tensor) -> int:
         "Exact-match lookup of a timestep in the current schedule (bit-exact, like the reference's list.index)."
+        if isinstance(timestep, Tensor):
+            found = self._index_without_sync(timestep)
+            if found is not None:
+                return found
         return self.schedule_np[:, 0].tolist().index(_as_float(timestep))
 
     @staticmethod
@@ -576,7 +601,7 @@ class SkrampleWrapperScheduler[T: TensorNoiseProps | None](SkrampleWrapperCore):
         return_dict: bool = True,
     ) -> tuple[Tensor, Tensor] | OrderedDict[str, Tensor]:
         schedule_np = self.schedule_np
-        step = Step.from_int(schedule_np[:, 0].tolist().index(_as_float(timestep)), len(schedule_np))
+        step = Step.from_int(self._index_of(timestep), len(schedule_np))
 
         noise = None
         if self.sampler.require_noise:
@@ -772,9 +797,11 @@ class RKWrapperCore[T: TensorNoiseProps | None, U: functional.FunctionalUnified]
         return_dict: bool = True,
     ) -> tuple[Tensor, Tensor] | OrderedDict[str, Tensor]:
         all_points = self.all_points
-        assert timestep == all_points[self._index].timestep, (
-            f"Expected timestep {all_points[self._index].timestep} for step {self._index}, got {timestep=}!"
-        )
+        expected = all_points[self._index].timestep
+        known = self._index_without_sync(timestep) if isinstance(timestep, Tensor) else None
+        if known is not None:  # a view of our own timesteps tensor: compare on the host, no stream drain
+            timestep = float(self.schedule_np[known, 0])
+        assert timestep == expected, f"Expected timestep {expected} for step {self._index}, got {timestep=}!"
         points = [*all_points, Point(0, 0, 1)]
         if self.invert_prediction:
             model_output = -model_output

@@ -149,3 +149,44 @@ def test_cuda_wrapper_device_generators() -> None:
     assert torch.equal(outs[0], outs[1])
     # the filled tensor is bf16 (the wrapper generates in the sample's dtype), the in-kernel draw is unrounded fp32
     assert (outs[0].float() - outs[2].float()).abs().max().item() < 0.25
+
+
+@pytest.mark.parametrize("wrapper", [diffusers.SkrampleWrapperScheduler, diffusers.RKUltraWrapperScheduler])
+def test_timestep_views_resolve_without_a_host_read(wrapper: type, monkeypatch: pytest.MonkeyPatch) -> None:
+    """`for t in scheduler.timesteps: scheduler.step(out, t, x)`: `t` is a view of a tensor the wrapper handed out, so
+    its index comes from its address, not from `.item()` (on a GPU that read drains the stream every step;
+    reference: diffusers.py:262-270, 540-548)."""
+    sched = wrapper(schedule=scheduling.Scaled()) if wrapper is diffusers.RKUltraWrapperScheduler else wrapper(sampler=structured.DPM(order=2), schedule=scheduling.Scaled())
+    sched.set_timesteps(6)
+    timesteps = sched.timesteps
+    reads: list[int] = []
+    real_item = torch.Tensor.item
+    real_bool = torch.Tensor.__bool__
+    monkeypatch.setattr(torch.Tensor, "item", lambda self: (reads.append(1), real_item(self))[1])
+    monkeypatch.setattr(torch.Tensor, "__bool__", lambda self: (reads.append(1), real_bool(self))[1])  # `assert t == x`
+    x = torch.randn(2, 4, 8, 8, dtype=torch.float64)
+    g = torch.Generator().manual_seed(3)
+    twin = wrapper(schedule=scheduling.Scaled()) if wrapper is diffusers.RKUltraWrapperScheduler else wrapper(sampler=structured.DPM(order=2), schedule=scheduling.Scaled())
+    twin.set_timesteps(6)
+    y = x.clone()
+    for t in timesteps:
+        out = torch.randn(x.shape, generator=g, dtype=torch.float64)
+        before = len(reads)
+        x = sched.step(out, t, x, return_dict=False)[0]
+        assert len(reads) == before, "step() read the timestep back from the tensor"
+        y = twin.step(out, float(real_item(t)), y, return_dict=False)[0]  # the value path gives the same trajectory
+        assert torch.equal(x, y)
+    # a tensor that is not ours (a copy) still works, through the value
+    sched.set_timesteps(6)
+    copy = sched.timesteps.clone()
+    before = len(reads)
+    sched.step(torch.randn(x.shape, generator=g, dtype=torch.float64), copy[0], x, return_dict=False)
+    assert len(reads) > before
+    # in-place edits of the handed-out tensor invalidate the shortcut
+    sched = wrapper(schedule=scheduling.Scaled()) if wrapper is diffusers.RKUltraWrapperScheduler else wrapper(sampler=structured.DPM(order=2), schedule=scheduling.Scaled())
+    sched.set_timesteps(6)
+    edited = sched.timesteps
+    edited += 0
+    before = len(reads)
+    sched.step(torch.randn(x.shape, generator=g, dtype=torch.float64), edited[0], x, return_dict=False)
+    assert len(reads) > before

@@ -210,3 +210,40 @@ def test_full_size_flux_latent_subset_vs_oracle() -> None:
         prev_o = (prev_o + [rec])[-3:]
         assert np.array_equal(res.final.flatten()[pick].cpu().numpy(), rec.final), f"step {n}"
         x, x_o = res.final, rec.final
+
+
+def test_more_than_2_31_elements_subset_vs_oracle(kernel_kind: int) -> None:
+    """Maximum sizes: a latent batch of 2^31 + 3077 elements (64-bit element indices, > 2^21 tiles, ragged tail).  The
+    step is elementwise, so the oracle on elements around 0, around 2^31 and at the very end must match exactly."""
+    from skrample_b200 import scheduling
+    from skrample_b200.common import Step
+    from skrample_b200.sampling import models, structured
+
+    numel = 2**31 + 3 * 1024 + 5
+    if torch.cuda.mem_get_info()[0] < 70 * 2**30:
+        pytest.skip("needs ~60 GB of free device memory")
+    edges = [0, 2**31 - 2048, numel - 4096]
+    pick = torch.cat([torch.arange(e, e + 4096, device="cuda") for e in edges])
+    sampler = structured.Adams(order=2, stochasticity=1)
+    schedule, model = scheduling.Scaled(), models.NoiseModel()
+    case = {"sampler": "Adams", "kw": {"order": 2, "stochasticity": 1}}
+    x = torch.empty(numel, device="cuda", dtype=torch.bfloat16).normal_()
+    x_o = x[pick].float().cpu().numpy()
+    prev: list = []
+    prev_o: list[O.Rec] = []
+    for n in range(3):  # step 0: all-bf16 inputs (8 elements per thread); steps 1-2: fp32 history next to bf16 latents
+        out = torch.empty(numel, device="cuda", dtype=torch.bfloat16).normal_()
+        noise = torch.empty(numel, device="cuda", dtype=torch.bfloat16).normal_()
+        step = Step.from_int(n, 5)
+        res = sampler.sample(x, out, step, model, schedule, noise, prev)
+        assert res.final.dtype == torch.bfloat16 and res.final.numel() == numel
+        rec = oracle_run.one_step(
+            case, O.Rec(x_o, out[pick].float().cpu().numpy(), O.St(*step), noise[pick].float().cpu().numpy()), prev_o, O.Model("noise"), O.scaled()
+        )
+        want = O.round_bf16(rec.final)
+        got = res.final[pick].float().cpu().numpy()
+        assert np.array_equal(got, want), f"step {n}: {np.flatnonzero(got != want)[:8]}"
+        prev = (prev + [res])[-sampler.require_previous :]
+        prev_o = (prev_o + [rec])[-1:]
+        x, x_o = res.final, want
+        del out, noise

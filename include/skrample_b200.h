@@ -207,6 +207,14 @@ int skr_noise_fill_batch(void* out, int32_t dtype, const skr_philox* keys, void*
 int skr_noise_moments(const void* in, int32_t dtype, int64_t numel, double* moments, void* cuda_stream);
 
 /*
+ * Error norms of an embedded Runge-Kutta pair in one pass (FunctionalAdaptive.mae/.mse applied to (low, high) and
+ * (0, high), functional.py:197-214, used by RKMoire.sample_model functional.py:437-441):
+ *   sums[0] += sum |low - high|^power,  sums[1] += sum |high|^power      (power = 1 or 2; device double[2], pre-zeroed)
+ */
+int skr_error_norms(const void* low, const void* high, int32_t dtype, int64_t numel, int32_t power, double* sums,
+                    void* cuda_stream);
+
+/*
  * out = in * s, s = numerator [* std(num_moments, num_count)] [/ std(moments, count)], each factor applied when
  * its pointer is given (unbiased std from device double[2] accumulators); s stays 1 when the denominator std
  * is <= min_std.  In place allowed; casts in_dtype -> out_dtype.  (noise.py:207, 369, 402-405)

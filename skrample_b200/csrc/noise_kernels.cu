@@ -192,6 +192,36 @@ __global__ void __launch_bounds__(256) moments_kernel(const __grid_constant__ Mo
     if (threadIdx.x == 0) { atomicAdd(&p.moments[0], s1); atomicAdd(&p.moments[1], s2); }
 }
 
+// Error norms of an embedded Runge-Kutta pair in one pass: sums[0] += sum |low - high|^p, sums[1] += sum |high|^p
+// (p = 1 or 2).  Replaces `mean(abs(low - high) ** p)` and `mean(abs(0 - high) ** p)` - six elementwise passes, two
+// reductions and two host reads per adaptive step (reference: functional.py:197-214, 437-441).
+struct ErrorNormParams {
+    const void* low;
+    const void* high;
+    int64_t numel;
+    int32_t dtype, power;
+    double* sums;
+};
+
+__global__ void __launch_bounds__(256) error_norm_kernel(const __grid_constant__ ErrorNormParams p) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.numel; e += (int64_t)gridDim.x * blockDim.x) {
+        double lo, hi;
+        if (p.dtype == SKR_F64) {
+            lo = reinterpret_cast<const double*>(p.low)[e];
+            hi = reinterpret_cast<const double*>(p.high)[e];
+        } else {
+            lo = (double)load1(p.low, p.dtype, e);
+            hi = (double)load1(p.high, p.dtype, e);
+        }
+        const double d = fabs(lo - hi), h = fabs(hi);
+        s1 += p.power == 2 ? d * d : d;
+        s2 += p.power == 2 ? h * h : h;
+    }
+    block_sum2(s1, s2);
+    if (threadIdx.x == 0) { atomicAdd(&p.sums[0], s1); atomicAdd(&p.sums[1], s2); }
+}
+
 struct ScaleParams {
     const void* in;
     void* out;
@@ -454,6 +484,19 @@ int skr_noise_moments(const void* in, int32_t dtype, int64_t numel, double* mome
     MomentParams p{in, numel, dtype, moments};
     moments_kernel<<<grid_for(numel, 256 * 4), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
     return check_launch("noise moments");
+}
+
+int skr_error_norms(const void* low, const void* high, int32_t dtype, int64_t numel, int32_t power, double* sums, void* cuda_stream) {
+    using namespace skr;
+    if (numel < 0) return fail(SKR_E_RANGE, "negative numel");
+    if (dtype < 0 || dtype > SKR_F16) return fail(SKR_E_DTYPE, "unknown dtype %d", dtype);
+    if (power != 1 && power != 2) return fail(SKR_E_RANGE, "power must be 1 (mean absolute) or 2 (mean squared), got %d", power);
+    if (!sums) return fail(SKR_E_NULL, "null sums");
+    if (numel == 0) return 0;
+    if (!low || !high) return fail(SKR_E_NULL, "null input");
+    ErrorNormParams p{low, high, numel, dtype, power, sums};
+    error_norm_kernel<<<grid_for(numel, 256 * 4), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
+    return check_launch("error norms");
 }
 
 int skr_noise_scale(const void* in, int32_t in_dtype, void* out, int32_t out_dtype, int64_t numel, double numerator,

@@ -98,6 +98,7 @@ EXPORTS = (
     "skr_program_classify",
     "skr_program_describe",
     "skr_axpby",
+    "skr_error_norms",
 )
 
 _lib: ctypes.CDLL | None = None
@@ -140,6 +141,8 @@ def load() -> ctypes.CDLL:
         ctypes.c_int32,
         ctypes.c_void_p,
     ]
+    lib.skr_error_norms.restype = ctypes.c_int
+    lib.skr_error_norms.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
     _lib = lib
     return lib
 
@@ -318,3 +321,18 @@ def launch_compiled(compiled: CompiledProgram, inputs: list[Any], draws: list[An
     if status:
         check(status, "skr_program_launch")
     return outputs
+
+
+def error_norms(low: Any, high: Any, power: int) -> tuple[float, float]:
+    """(mean |low - high|^power, mean |high|^power) of two same-shaped CUDA tensors: one kernel, one host read
+    (reference: FunctionalAdaptive.mae/.mse applied twice, functional.py:197-214)."""
+    if low.shape != high.shape or low.dtype != high.dtype or low.device != high.device:
+        raise ValueError("error_norms needs two tensors of one shape, dtype and device")
+    low, high = low.contiguous(), high.contiguous()
+    sums = torch.zeros(2, dtype=torch.float64, device=high.device)
+    with torch.cuda.device(high.device):
+        status = load().skr_error_norms(low.data_ptr(), high.data_ptr(), DTYPE_CODE[high.dtype], high.numel(), power, sums.data_ptr(), raw_stream())
+    check(status, "skr_error_norms")
+    count = max(high.numel(), 1)
+    total = sums.tolist()  # the adaptive controller needs the value: the one synchronisation of the step
+    return total[0] / count, total[1] / count

@@ -457,6 +457,18 @@ class RKMoire(traits.DerivativeTransform, FunctionalAdaptive, FunctionalHigher):
         provider = _largest_provider(self.providers, self.order if order is None else order)
         return (provider or tableaux.RKE2.Heun).tableau()
 
+    def _relative_error[T: Sample](self, low: T, high: T, tiny: float) -> float:
+        "evaluator(low, high) / max(evaluator(0, high), tiny); one fused reduction for device tensors and stock norms."
+        stock = getattr(self.evaluator, "__func__", self.evaluator)
+        power = 2 if stock is FunctionalAdaptive.mse else 1 if stock is FunctionalAdaptive.mae else 0
+        if power and pg.is_cuda_tensor(low) and pg.is_cuda_tensor(high) and low.shape == high.shape and low.dtype == high.dtype:  # type: ignore[union-attr]
+            from skrample_b200 import native
+
+            if high.dtype in native.DTYPE_CODE:  # type: ignore[union-attr]
+                difference, magnitude = native.error_norms(low, high, power)
+                return difference / max(magnitude, tiny)
+        return self.evaluator(low, high) / max(self.evaluator(0, high), tiny)
+
     def sample_model[T: Sample](
         self,
         sample: T,
@@ -486,7 +498,7 @@ class RKMoire(traits.DerivativeTransform, FunctionalAdaptive, FunctionalHigher):
                 )
                 sigma0, sigma1, sigma2 = schedule.ipoints_np([at / steps, upto / steps, (upto + stride) / steps])[:, 1].tolist()
                 slope = abs(sigma0 - sigma1) / abs(sigma1 - sigma2)  # the next interval already differs by this much
-                error = self.evaluator(low, high) / max(self.evaluator(0, high), tiny)
+                error = self._relative_error(low, high, tiny)
                 adjustment: float = (self.threshold / max(error, tiny)) ** self.adaption / slope
                 stride = max(round(min(stride * adjustment, steps * longest)), 1)
                 if upto - at > stride and 1 / max(adjustment, tiny) > self.discard:

@@ -4,6 +4,7 @@ from __future__ import annotations
 
 import ctypes
 import json
+import math
 from pathlib import Path
 
 import numpy as np
@@ -146,3 +147,53 @@ def test_many_stage_tableaux_chunk_across_launches(name: str) -> None:
     want = functional.step_tableau(tab, x, cases.network, model, schedule, step, models.DataModel(), noise, 1.0)[0]
     got = functional.step_tableau(tab, x.cuda(), cases.network, model, schedule, step, models.DataModel(), noise.cuda(), 1.0)[0]
     assert torch.equal(got.cpu(), want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.bfloat16])
+@pytest.mark.parametrize("power", [1, 2])
+def test_fused_error_norms_match_the_evaluators(dtype: torch.dtype, power: int) -> None:
+    "skr_error_norms = FunctionalAdaptive.mae/.mse on (low, high) and (0, high) (reference: functional.py:197-214)."
+    from skrample_b200 import native
+    from skrample_b200.sampling.functional import FunctionalAdaptive
+
+    g = torch.Generator(device="cuda").manual_seed(8)
+    high = torch.randn(3, 4, 57, 61, device="cuda", generator=g).to(dtype)
+    low = (high.double() + 1e-2 * torch.randn(high.shape, device="cuda", generator=g).double()).to(dtype)
+    difference, magnitude = native.error_norms(low, high, power)
+    evaluator = FunctionalAdaptive.mse if power == 2 else FunctionalAdaptive.mae
+    want_difference, want_magnitude = evaluator(low.double(), high.double()), evaluator(0, high.double())
+    assert math.isclose(difference, want_difference, rel_tol=1e-12)
+    assert math.isclose(magnitude, want_magnitude, rel_tol=1e-12)
+    assert native.error_norms(low[:0], high[:0], power) == (0.0, 0.0)
+    with pytest.raises(ValueError):
+        native.error_norms(low, high[:1], power)
+
+
+@pytest.mark.gpu
+def test_rkmoire_takes_one_host_read_per_adaptive_step(monkeypatch: pytest.MonkeyPatch) -> None:
+    "The stock evaluators go through the fused reduction; a user evaluator is still called as in the reference."
+    from skrample_b200 import native, scheduling
+    from skrample_b200.sampling import functional, models
+
+    calls = {"fused": 0, "user": 0}
+    real = native.error_norms
+    monkeypatch.setattr(native, "error_norms", lambda *a: (calls.__setitem__("fused", calls["fused"] + 1), real(*a))[1])
+    x = torch.randn(2, 4, 16, 16, device="cuda")
+
+    def model(sample: torch.Tensor, t: float, sigma: float, alpha: float) -> torch.Tensor:
+        return sample * 0.25
+
+    stock = functional.RKMoire(order=4)
+    out = stock.sample_model(x, model, models.FlowModel(), scheduling.Linear(), 12)
+    assert calls["fused"] > 0 and torch.isfinite(out).all()
+
+    def evaluator(a, b) -> float:  # noqa: ANN001
+        calls["user"] += 1
+        return functional.FunctionalAdaptive.mse(a, b)
+
+    fused_before = calls["fused"]
+    custom = functional.RKMoire(order=4, evaluator=evaluator)
+    same = custom.sample_model(x, model, models.FlowModel(), scheduling.Linear(), 12)
+    assert calls["user"] > 0 and calls["fused"] == fused_before
+    assert torch.equal(out, same), "same strides, same kernels: the fused norm must not change the trajectory here"

@@ -20,21 +20,20 @@
 //
 // Instantiations: storage mode of the inputs (all fp32 / all bf16 / all fp16 / mixed, chosen per
 // launch) x elements per thread (4, or 8 for 16-bit storage so every shared-memory read is
-// 128-bit) x compute type (fp32, fp64).  The descriptor is plain int32/float fields in the
-// kernel-parameter constant bank so every test is a uniform-datapath compare.
+// 128-bit) x compute type (fp32, fp64) x shape.  The descriptor is plain int32/float fields in the
+// kernel-parameter constant bank so every test is a uniform-datapath compare; a *pinned shape*
+// (see "compile-time shapes" below, instantiated in pinned_shapes.cu) turns the fields that only
+// steer control flow into compile-time constants for the steady-state step of a standard sampler.
+//
+// Divisions are by grid-uniform scalars and use a host-side reciprocal with a residual correction
+// (machine.cuh, div_uniform: exactly the IEEE quotient, exhaustively verified).  Launches carry the
+// programmatic-dependent-launch attribute: the prologue of step n+1 overlaps the tail of step n.
 //
 // Arithmetic is identical to the interpreter (machine.cuh): individually rounded ops in the
 // reference's order.  A program that does not fit the skeleton is executed by the interpreter.
 #pragma once
 
 #include "machine.cuh"
-
-// History-term loops: left to the compiler's unroller by default; -DSKR_TERM_ROLLED keeps them rolled (experiment).
-#ifdef SKR_TERM_ROLLED
-#define SKR_TERM_LOOP _Pragma("unroll 1")
-#else
-#define SKR_TERM_LOOP
-#endif
 
 namespace skr {
 
@@ -61,7 +60,7 @@ struct BBlock {
     int32_t pad;
     CT p_coef, div, gamma, delta, zeta, l0, l1, e0, e1, e2;
     CT div_r, l1_r;  // reciprocals of the divisors `div` and `l1`
-    uint32_t sample_off, base_off, noise_off, pad_off;  // staged byte offsets of sample_in / base_in / noise_in
+    uint32_t sample_off, base_off, noise_off, reserved;  // staged byte offsets of sample_in / base_in / noise_in
     BTerm<CT> terms[kMaxTerms];
     int32_t term_in[kMaxTerms];  // input index of each term (guarded path, host matching)
 };
@@ -422,7 +421,6 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BB
                 for (int j = 0; j < V; ++j) A[j] = Ar::add((CT)0, Ar::mul(in[j], c));
                 t = 1;
             }
-            SKR_TERM_LOOP
             for (; t < n_terms; ++t) {
                 io.template load<BS::dt_state>(k.term_in[t], k.terms[t].off, in);
                 const CT c = k.terms[t].c0;
@@ -440,7 +438,6 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BB
         } else if (kind == BK_UNI) {
 #pragma unroll
             for (int j = 0; j < V; ++j) A[j] = (CT)0;  // 0 + first term, like the reference's running sum
-            SKR_TERM_LOOP
             for (int t = 0; t < n_terms; ++t) {
                 io.template load<BS::dt_state>(k.term_in[t], k.terms[t].off, in);
                 const CT rho = k.terms[t].c1;

@@ -19,7 +19,6 @@ constexpr int kMaxStages = 8;
 // individually rounded arithmetic
 
 template <typename CT> struct Arith;
-// IEEE division out of line: the uniform-divisor fast path below keeps it off the hot instruction stream.
 template <> struct Arith<float> {
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }

@@ -256,7 +256,7 @@ __device__ __forceinline__ int pinned(int runtime) {
 struct BlkAny {
     static constexpr int enabled = -1, kind = -1, sample = -1, base = -1, p_mode = -1, has_div = -1, pred_p = -1;
     static constexpr int noise = -1, store = -1, link = -1, slink = -1;
-    static constexpr int dt_state = -1, dt_noise = -1, dt_store = -1, dt_slink = -1;
+    static constexpr int dt_state = -1, dt_sample = -1, dt_noise = -1, dt_store = -1, dt_slink = -1;
 };
 struct BlkOff : BlkAny {
     static constexpr int enabled = 0;
@@ -277,7 +277,14 @@ template <int KIND, int SAMPLE, int BASE, int PMODE, int DIV, int PREDP, int STO
 struct BlkPin : BlkAny {
     static constexpr int enabled = 1, kind = KIND, sample = SAMPLE, base = BASE, p_mode = PMODE, has_div = DIV;
     static constexpr int pred_p = PREDP, store = STORE, link = LINK, slink = SLINK;
-    static constexpr int dt_state = ST, dt_noise = LP, dt_store = OUT, dt_slink = SKR_F32;
+    static constexpr int dt_state = ST, dt_sample = ST, dt_noise = LP, dt_store = OUT, dt_slink = SKR_F32;
+};
+// explicit RK on converted derivatives (the default: derivative_transform = DataModel): X = the step's sample (LP),
+// A = (sum k_i c_i [+ P c_s]) [/ sum c], derivatives k_i in fp32; covers stage inputs (has_div) and the final update
+template <int LP>
+struct BlkRK : BlkAny {
+    static constexpr int enabled = 1, kind = BK_ACC, sample = 1, base = 0, pred_p = 0, store = 1, link = BL_NONE, slink = 0;
+    static constexpr int dt_state = SKR_F32, dt_sample = LP, dt_noise = LP, dt_store = LP;
 };
 // head of a structured sampler step: X = sample, P = x-hat = convert(X, network output), stored as fp32 state
 template <int LP, typename BLK0, typename BLK1>
@@ -318,6 +325,8 @@ using ShUniPC = ShStep<LP, BlkPin<BK_UNI, 1, 1, 1, 0, 0, 1, BL_X_FROM_R, 0, SKR_
 template <int LP>
 using ShSPC = ShStep<LP, BlkPin<BK_ACC, 1, 0, 1, 0, 0, 0, BL_BLEND, 1, SKR_F32, SKR_F32, LP>,
                      BlkPin<BK_NONE, 0, 0, 0, 0, 1, 1, BL_NONE, 0, LP, SKR_F32, LP>>;
+template <int LP>
+using ShRK = ShStep<LP, BlkRK<LP>, BlkOff>;
 // explicit RK on raw derivatives: stage input = X*G + (sum k_i c_i / sum c_i)*D, final = X*G + (sum k_i b_i)*D
 template <int LP>
 using ShRKStage = ShRaw<LP, 0, BlkPin<BK_ACC, 0, 0, 0, 1, 0, 1, BL_NONE, 0, LP, LP, LP>>;
@@ -334,8 +343,8 @@ static bool block_matches(const BBlock<CT>& k, const int32_t* in_dt, const int32
               eq(BS::noise, k.has_noise) && eq(BS::store, k.store_r >= 0) && eq(BS::link, k.link) &&
               eq(BS::slink, k.store_link >= 0);
     if (!ok) return false;
+    if (BS::dt_sample >= 0 && k.sample_in >= 0 && in_dt[k.sample_in] != BS::dt_sample) return false;
     if (BS::dt_state >= 0) {
-        if (k.sample_in >= 0 && in_dt[k.sample_in] != BS::dt_state) return false;
         if (k.base_in >= 0 && in_dt[k.base_in] != BS::dt_state) return false;
         for (int t = 0; t < k.n_terms; ++t)
             if (in_dt[k.term_in[t]] != BS::dt_state) return false;
@@ -394,7 +403,7 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BB
 #pragma unroll
         for (int j = 0; j < V; ++j) S[j] = X[j];
     }
-    if (pinned<BS::sample>(k.sample_in >= 0)) io.template load<BS::dt_state>(k.sample_in, k.sample_off, X);
+    if (pinned<BS::sample>(k.sample_in >= 0)) io.template load<BS::dt_sample>(k.sample_in, k.sample_off, X);
 
     CT in[V];
     const int kind = pinned<BS::kind>(k.kind);

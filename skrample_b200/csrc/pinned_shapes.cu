@@ -45,6 +45,7 @@ static bool for_each_pinned_shape(F&& f) {
            f(ShapeEntry<ShDpm2<kLP>, IN_MIXED, 4>{"dpm2/" SKR_LP_NAME}) ||
            f(ShapeEntry<ShDpm3<kLP>, IN_MIXED, 4>{"dpm3/" SKR_LP_NAME}) ||
            f(ShapeEntry<ShSPC<kLP>, IN_MIXED, 4>{"spc/" SKR_LP_NAME}) ||
+           f(ShapeEntry<ShRK<kLP>, IN_MIXED, 4>{"rk/" SKR_LP_NAME}) ||
            f(ShapeEntry<ShEuler<kLP>, kModeLP, kVecLP>{"euler/" SKR_LP_NAME}) ||
            f(ShapeEntry<ShRKStage<kLP>, kModeLP, kVecLP>{"rk-stage/" SKR_LP_NAME}) ||
            f(ShapeEntry<ShRKFinal<kLP>, kModeLP, kVecLP>{"rk-final/" SKR_LP_NAME});

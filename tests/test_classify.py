@@ -123,3 +123,32 @@ def test_describe_reports_interpreter_for_unstructured_programs() -> None:
     program.axpby(torch.randn(8), 0.5, 0.25)
     program.store(pg.R)
     assert describe(program) == "interpreter"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16], ids=["f32", "bf16", "f16"])
+@pytest.mark.parametrize("derivative", ["default", None], ids=["converted", "raw"])
+def test_rk_stages_take_a_pinned_kernel_shape(dtype: torch.dtype, derivative, monkeypatch: pytest.MonkeyPatch) -> None:  # noqa: ANN001
+    "Every launch of an explicit RK step (stage inputs and the final update) runs a shape compiled for it."
+    from skrample_b200 import scheduling
+    from skrample_b200.common import Step
+    from skrample_b200.sampling import functional, models
+
+    seen: list[str] = []
+
+    def spy(program: pg.Program):
+        seen.append(describe(program))
+        first = program.inputs[0].dtype
+        dtypes = [d if isinstance(d, torch.dtype) else (torch.float32 if d == "compute" else first) for d in program.outputs]
+        return [out.to(d) for out, d in zip(pg.execute_generic(program), dtypes)]
+
+    monkeypatch.setattr(pg, "execute", spy)
+    monkeypatch.setattr(pg, "is_cuda_tensor", lambda v: isinstance(v, torch.Tensor))
+    sampler = functional.RKUltra(order=4) if derivative == "default" else functional.RKUltra(order=4, derivative_transform=None)
+    x = torch.randn(64).to(dtype)
+    sampler.step(x, lambda s, t, sigma, alpha: (s * 0.3).to(dtype), models.FlowModel(), scheduling.FlowShift(scheduling.Linear(), shift=3.0), Step.from_int(3, 25))
+    name = {torch.float32: "f32", torch.bfloat16: "bf16", torch.float16: "f16"}[dtype]
+    assert len(seen) == 4
+    if derivative == "default":
+        assert all(f"shape=rk/{name} " in line for line in seen), seen
+    else:  # the first stage of a raw-derivative step is "stage input = sample" with nothing to launch
+        assert all(f"shape=rk-stage/{name} " in line or f"shape=rk-final/{name} " in line for line in seen), seen

@@ -301,6 +301,61 @@ def graph_throughput(spec: dict, device: torch.device, steps: int, warmup: int, 
     }
 
 
+# BASELINE.json configs[2]: an explicit Runge-Kutta step (one launch per stage + the final update)
+RK_SWEEP = {
+    "rkultra4_flux_bf16": dict(order=4, shape=(16, 16, 128, 128), dtype="bf16"),
+    "rkultra4_flux_f32": dict(order=4, shape=(16, 16, 128, 128), dtype="f32"),
+}
+
+
+def rk_step_throughput(spec: dict, device: torch.device, replicas: int = 16, reps: int = 20) -> dict:
+    """RKUltra(order) / FlowShift(Linear(), 3) / FlowModel over `replicas` interleaved latents (inputs come from HBM).
+    The network is a table of pre-recorded outputs, so the captured graph holds only this library's launches."""
+    from skrample_b200 import native, scheduling
+    from skrample_b200.common import Step
+    from skrample_b200.sampling import functional, models
+
+    dtype = TORCH_DTYPE[spec["dtype"]]
+    sampler = functional.RKUltra(order=spec["order"])
+    schedule, model_transform = scheduling.FlowShift(scheduling.Linear(), shift=3.0), models.FlowModel()
+    g = torch.Generator(device=device).manual_seed(0)
+    latents = [torch.randn(spec["shape"], device=device, generator=g).to(dtype) for _ in range(replicas)]
+    outputs = [[torch.randn(spec["shape"], device=device, generator=g).to(dtype) * 0.3 for _ in range(8)] for _ in range(replicas)]
+    interior = (3, 12)  # two interior steps of a 25-step schedule per replica
+
+    def run() -> None:
+        for r in range(replicas):
+            calls, table, x = iter(range(1 << 30)), outputs[r], latents[r]
+            for n in interior:
+                x = sampler.step(x, lambda s, t, sigma, alpha: table[next(calls) % 8], model_transform, schedule, Step.from_int(n, STEPS_PER_TRAJECTORY))
+
+    stream = torch.cuda.Stream(device=device)
+    with torch.cuda.stream(stream):
+        run()
+        torch.cuda.synchronize(device)
+        before = native.launch_count()
+        native.ACCOUNT["bytes"] = 0
+        native.ACCOUNT["on"] = True
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream):
+            run()
+        native.ACCOUNT["on"] = False
+        launches = native.launch_count() - before
+    torch.cuda.synchronize(device)
+    for _ in range(5):
+        graph.replay()
+    torch.cuda.synchronize(device)
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(reps):
+        graph.replay()
+    stop.record()
+    torch.cuda.synchronize(device)
+    ms = start.elapsed_time(stop) / reps
+    rk_steps = replicas * len(interior)
+    return {"us_per_rk_step": ms * 1e3 / rk_steps, "launches_per_step": launches / rk_steps, "GBps": native.ACCOUNT["bytes"] / (ms * 1e-3) / 1e9, "bytes_per_step": native.ACCOUNT["bytes"] / rk_steps}
+
+
 def e2e_throughput(spec: dict, device: torch.device, steps: int, warmup: int) -> dict:
     "Public API with host buffers: H2D of the step's prediction + noise, sampler.sample, D2H of the result."
     traj = Trajectory(spec, device, seed=4321)
@@ -628,6 +683,10 @@ def main() -> None:
             us = r["elapsed_ms"] * 1e3 / r["launches"]
             ach = r["bytes"] / r["launches"] / (us * 1e-6) / 1e9
             sweep.append({"workload": name, "shape": list(s["shape"]), "dtype": s["dtype"], "us_per_step": us, "GBps": ach, "frac_of_measured_peak": ach / peak, "latent_steps_per_s": s["shape"][0] / (us * 1e-6), "bytes_per_step_avg": r["bytes_per_step_avg"]})
+        for name, s in RK_SWEEP.items():
+            torch.cuda.empty_cache()
+            r = rk_step_throughput(s, device)
+            sweep.append({"workload": name, "shape": list(s["shape"]), "dtype": s["dtype"], "us_per_step": r["us_per_rk_step"], "launches_per_step": r["launches_per_step"], "GBps": r["GBps"], "frac_of_measured_peak": r["GBps"] / peak, "latent_steps_per_s": s["shape"][0] / (r["us_per_rk_step"] * 1e-6), "bytes_per_step_avg": r["bytes_per_step"]})
         line["sweep"] = sweep
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

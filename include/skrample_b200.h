@@ -238,13 +238,19 @@ typedef struct skr_pyramid {
     uint64_t seed;
     uint64_t base_stream;         /* the plain randn(shape) term                                      */
     const float* base_buffer;     /* non-null: supplied base draw                                     */
+    float* scratch;               /* optional, numel floats (may alias base_buffer): see below        */
     skr_pyramid_level levels[SKR_MAX_LEVELS];
 } skr_pyramid;
 
 /*
  * Pyramid (noise.py:146-207): out = (base + sum_l weight_l * upsample(level_l)) / std, bilinear/linear
- * upsampling with align_corners=False semantics, unbiased std over the whole tensor.  Two kernels: moments,
- * then regenerate + normalise + write.  `moments` = device double[2], pre-zeroed.
+ * upsampling with align_corners=False semantics, unbiased std over the whole tensor.  `moments` = device
+ * double[2], pre-zeroed.  Two kernels either way:
+ *   - without `scratch`: moments pass, then a second pass that regenerates, normalises and writes (nothing
+ *     N-sized besides `out` exists; every interpolation corner is a Philox draw: compute-bound);
+ *   - with `scratch`: one composition pass writes the unnormalised field to scratch and accumulates the moments,
+ *     then a scale pass writes scratch / std to `out`.  Meant to be used with the base and the levels supplied
+ *     as buffers (skr_noise_fill with the level's stream gives the same values the in-kernel draw would).
  */
 int skr_noise_pyramid(void* out, int32_t dtype, const skr_pyramid* desc, double* moments, void* cuda_stream);
 

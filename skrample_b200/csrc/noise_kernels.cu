@@ -267,7 +267,8 @@ __global__ void __launch_bounds__(256) scale_kernel(const __grid_constant__ Scal
 struct PyramidParams {
     void* out;
     int64_t numel;
-    int32_t dtype, ndim, n_levels, mode;  // mode 0: accumulate moments only, 1: write out = value / std
+    int32_t dtype, ndim, n_levels, mode;  // mode 0: accumulate moments only, 1: write out = value / std,
+                                          // mode 2: write the unnormalised value to scratch and accumulate moments
     uint64_t seed;
     int64_t shape[SKR_MAX_DIMS];
     int32_t masked[SKR_MAX_DIMS];           // 1: axis is resized by the pyramid
@@ -278,7 +279,10 @@ struct PyramidParams {
     float weight[SKR_MAX_LEVELS];           // strength^l (0 for skipped levels)
     uint64_t base_stream;
     const float* base_buffer;
+    float* scratch;
     double* moments;
+    int32_t m_axis[2];                                  // the resized axes in order (-1: only one)
+    int64_t lstride[SKR_MAX_LEVELS][SKR_MAX_DIMS];      // row-major strides of each level grid
 };
 
 // F.interpolate(align_corners=False) source position along one axis (ATen area_pixel_compute_source_index)
@@ -296,40 +300,42 @@ __device__ __forceinline__ float level_value(const PyramidParams& p, const Philo
     return p.buffer[l] ? p.buffer[l][linear] : normal_at(ph, (uint64_t)linear, p.stream[l]);
 }
 
+// One element of base + sum_l weight_l * upsample(level_l).  I is the index type: 32-bit arithmetic when the
+// tensor has fewer than 2^31 elements (the integer divisions of the coordinate decomposition dominate otherwise).
+template <typename I>
 __device__ __forceinline__ float pyramid_value(const PyramidParams& p, const Philox& ph, int64_t e) {
-    int64_t idx[SKR_MAX_DIMS];
-    int64_t rem = e;
-    for (int d = p.ndim - 1; d >= 0; --d) { idx[d] = rem % p.shape[d]; rem /= p.shape[d]; }
-    int m_axis[2] = {-1, -1};
-    int n_masked = 0;
-    for (int d = 0; d < p.ndim; ++d) if (p.masked[d] && n_masked < 2) m_axis[n_masked++] = d;
+    I idx[SKR_MAX_DIMS];
+    I rem = (I)e;
+    for (int d = p.ndim - 1; d >= 0; --d) {
+        const I size = (I)p.shape[d];
+        const I q = rem / size;
+        idx[d] = rem - q * size;
+        rem = q;
+    }
+    const int m0 = p.m_axis[0], m1 = p.m_axis[1];
 
     float pyramid = 0.0f;  // the reference starts from a zero tensor and adds the kept levels in order
     for (int l = 0; l < p.n_levels; ++l) {
         const float wl = p.weight[l];
         if (wl == 0.0f) continue;
-        // linear index of a level element given coordinates along the masked axes
-        auto at = [&](int64_t a0, int64_t a1) {
-            int64_t lin = 0;
-            int seen = 0;
-            for (int d = 0; d < p.ndim; ++d) {
-                int64_t size = p.shape[d], coord = idx[d];
-                if (p.masked[d]) { size = p.extent[l][seen]; coord = seen == 0 ? a0 : a1; ++seen; }
-                lin = lin * size + coord;
-            }
-            return level_value(p, ph, l, lin);
-        };
+        I outer = 0;  // offset of this element's slice inside the level grid (all but the resized axes)
+        for (int d = 0; d < p.ndim; ++d)
+            if (!p.masked[d]) outer += idx[d] * (I)p.lstride[l][d];
         float v;
-        if (n_masked == 1) {
-            int64_t i0, i1; float w1;
-            source_index(idx[m_axis[0]], p.extent[l][0], p.shape[m_axis[0]], i0, i1, w1);
-            v = (1.0f - w1) * at(i0, 0) + w1 * at(i1, 0);
+        int64_t h0, h1;
+        float wh;
+        source_index((int64_t)idx[m0], p.extent[l][0], p.shape[m0], h0, h1, wh);
+        const I s0 = (I)p.lstride[l][m0];
+        if (m1 < 0) {
+            v = (1.0f - wh) * level_value(p, ph, l, outer + (I)h0 * s0) + wh * level_value(p, ph, l, outer + (I)h1 * s0);
         } else {
-            int64_t h0, h1, w0, w1i; float wh, ww;
-            source_index(idx[m_axis[0]], p.extent[l][0], p.shape[m_axis[0]], h0, h1, wh);
-            source_index(idx[m_axis[1]], p.extent[l][1], p.shape[m_axis[1]], w0, w1i, ww);
-            const float top = (1.0f - ww) * at(h0, w0) + ww * at(h0, w1i);
-            const float bot = (1.0f - ww) * at(h1, w0) + ww * at(h1, w1i);
+            int64_t w0, w1;
+            float ww;
+            source_index((int64_t)idx[m1], p.extent[l][1], p.shape[m1], w0, w1, ww);
+            const I s1 = (I)p.lstride[l][m1];
+            const I r0 = outer + (I)h0 * s0, r1 = outer + (I)h1 * s0;
+            const float top = (1.0f - ww) * level_value(p, ph, l, r0 + (I)w0 * s1) + ww * level_value(p, ph, l, r0 + (I)w1 * s1);
+            const float bot = (1.0f - ww) * level_value(p, ph, l, r1 + (I)w0 * s1) + ww * level_value(p, ph, l, r1 + (I)w1 * s1);
             v = (1.0f - wh) * top + wh * bot;
         }
         pyramid += v * wl;
@@ -338,17 +344,19 @@ __device__ __forceinline__ float pyramid_value(const PyramidParams& p, const Phi
     return base + pyramid;
 }
 
+template <typename I>
 __global__ void __launch_bounds__(256) pyramid_kernel(const __grid_constant__ PyramidParams p) {
     const Philox ph(p.seed);
     double s1 = 0.0, s2 = 0.0;
     float inv_std = 1.0f;
     if (p.mode == 1) inv_std = (float)(1.0 / std_from(p.moments, p.numel));
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.numel; e += (int64_t)gridDim.x * blockDim.x) {
-        const float v = pyramid_value(p, ph, e);
-        if (p.mode == 0) { s1 += v; s2 += (double)v * v; }
-        else store1(p.out, p.dtype, e, v * inv_std);
+        const float v = pyramid_value<I>(p, ph, e);
+        if (p.mode != 1) { s1 += v; s2 += (double)v * v; }
+        if (p.mode == 1) store1(p.out, p.dtype, e, v * inv_std);
+        else if (p.mode == 2) p.scratch[e] = v;  // may alias base_buffer: element e is read before it is written
     }
-    if (p.mode == 0) {
+    if (p.mode != 1) {
         block_sum2(s1, s2);
         if (threadIdx.x == 0) { atomicAdd(&p.moments[0], s1); atomicAdd(&p.moments[1], s2); }
     }
@@ -541,15 +549,35 @@ int skr_noise_pyramid(void* out, int32_t dtype, const skr_pyramid* desc, double*
     }
     p.base_stream = desc->base_stream;
     p.base_buffer = desc->base_buffer;
+    p.scratch = desc->scratch;
     p.moments = moments;
+    p.m_axis[0] = p.m_axis[1] = -1;
+    for (int d = 0, seen = 0; d < desc->ndim; ++d)
+        if (p.masked[d] && seen < 2) p.m_axis[seen++] = d;
+    bool narrow = numel < ((int64_t)1 << 31);
+    for (int l = 0; l < desc->n_levels; ++l) {
+        int64_t stride = 1;
+        for (int d = desc->ndim - 1, seen = masked; d >= 0; --d) {
+            p.lstride[l][d] = stride;
+            stride *= p.masked[d] ? p.extent[l][--seen] : p.shape[d];
+        }
+        narrow = narrow && stride < ((int64_t)1 << 31);
+    }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
-    p.mode = 0;
-    pyramid_kernel<<<grid_for(numel, 256), 256, 0, s>>>(p);
-    int rc = check_launch("pyramid moments");
+    auto pass = [&](int mode, const char* what) {
+        p.mode = mode;
+        if (narrow) pyramid_kernel<int32_t><<<grid_for(numel, 256), 256, 0, s>>>(p);
+        else pyramid_kernel<int64_t><<<grid_for(numel, 256), 256, 0, s>>>(p);
+        return check_launch(what);
+    };
+    if (p.scratch) {
+        int rc = pass(2, "pyramid compose");
+        if (rc) return rc;
+        return skr_noise_scale(p.scratch, SKR_F32, out, dtype, numel, 1.0, nullptr, 0, moments, numel, 0.0, cuda_stream);
+    }
+    int rc = pass(0, "pyramid moments");
     if (rc) return rc;
-    p.mode = 1;
-    pyramid_kernel<<<grid_for(numel, 256), 256, 0, s>>>(p);
-    return check_launch("pyramid write");
+    return pass(1, "pyramid write");
 }
 
 int skr_colored_shape(void* spectrum, int32_t complex_dtype, const int64_t* dims, int32_t ndim, double exponent, void* cuda_stream) {

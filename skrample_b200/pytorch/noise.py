@@ -85,6 +85,7 @@ class _SkrPyramid(ctypes.Structure):
         ("seed", ctypes.c_uint64),
         ("base_stream", ctypes.c_uint64),
         ("base_buffer", ctypes.c_void_p),
+        ("scratch", ctypes.c_void_p),
         ("levels", _SkrPyramidLevel * 16),
     ]
 
@@ -468,15 +469,31 @@ class Pyramid(TensorNoiseCommon[PyramidProps]):
         for n, d in enumerate(self.shape):
             desc.shape[n] = d
             desc.masked[n] = int(mask[n])
-        for level, shape in enumerate(shapes):
-            slot = desc.levels[level]
-            slot.stream = level_tick + 2 + level
-            extents = [s for m, s in zip(mask, shape) if m]
-            slot.extent[0] = extents[0]
-            slot.extent[1] = extents[1] if len(extents) > 1 else 1
-            slot.weight = self.props.strength**level if level >= first else 0.0
-        moments = torch.zeros(2, dtype=torch.float64, device=out.device)
+        # The base draw and every kept level are written once as fp32 grids (the levels are small: each is the unit
+        # shape shrunk by the level's ratio along the resized axes); the composition kernel then only interpolates.
+        # Drawing each interpolation corner inside the kernel instead costs ~32 Philox blocks per element.
+        numel = math.prod(self.shape)
+        align = lambda n: (n + 3) & ~3  # noqa: E731 - keep every grid 16-byte aligned for vector stores
+        sizes = [math.prod(shape) if level >= first else 0 for level, shape in enumerate(shapes)]
+        scratch = torch.empty(align(numel) + sum(align(n) for n in sizes), dtype=torch.float32, device=out.device)
         with _DeviceGuard(out.device):
+            self._fill(scratch[:numel], base)
+            cursor = align(numel)
+            for level, shape in enumerate(shapes):
+                slot = desc.levels[level]
+                slot.stream = level_tick + 2 + level
+                extents = [s for m, s in zip(mask, shape) if m]
+                slot.extent[0] = extents[0]
+                slot.extent[1] = extents[1] if len(extents) > 1 else 1
+                slot.weight = self.props.strength**level if level >= first else 0.0
+                if sizes[level]:
+                    grid = scratch[cursor : cursor + sizes[level]]
+                    self._fill(grid, slot.stream)
+                    slot.buffer = grid.data_ptr()
+                    cursor += align(sizes[level])
+            desc.base_buffer = scratch.data_ptr()
+            desc.scratch = scratch.data_ptr()  # composed in place over the base draw
+            moments = torch.zeros(2, dtype=torch.float64, device=out.device)
             status = _lib().skr_noise_pyramid(out.data_ptr(), _code(out.dtype), ctypes.byref(desc), moments.data_ptr(), _stream())
         _native().check(status, "skr_noise_pyramid")
 

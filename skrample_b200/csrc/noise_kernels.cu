@@ -108,6 +108,7 @@ struct FillParams {
     int64_t shape[SKR_MAX_DIMS];
     int32_t keep[SKR_MAX_DIMS];  // 1: axis indexes the offset tensor, 0: broadcast
     double* moments;             // optional [sum, sum^2] accumulators
+    int64_t inner;               // > 0: the kept axes are a leading prefix, offset index = element / inner
 };
 
 __device__ __forceinline__ int64_t reduced_index(const FillParams& p, int64_t e) {
@@ -128,9 +129,17 @@ __global__ void __launch_bounds__(256) fill_kernel(const __grid_constant__ FillP
         normal4(ph((uint64_t)g, p.stream), z);
         const int64_t first = g << 2;
         if (p.offset_scale != 0.0f) {
+            const int64_t row = p.inner > 0 ? first / p.inner : -1;
+            if (row >= 0 && first + 3 < (row + 1) * p.inner) {
+                // the usual case (offsets along leading axes): the four elements share one offset draw
+                const float shift = normal_at(ph, (uint64_t)row, p.offset_stream) * p.offset_scale;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (first + j < p.numel) z[j] = z[j] + normal_at(ph, (uint64_t)reduced_index(p, first + j), p.offset_stream) * p.offset_scale;
+                for (int j = 0; j < 4; ++j) z[j] = z[j] + shift;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (first + j < p.numel) z[j] = z[j] + normal_at(ph, (uint64_t)reduced_index(p, first + j), p.offset_stream) * p.offset_scale;
+                }
             }
         }
         if (p.aligned && first + 4 <= p.numel) {
@@ -282,6 +291,7 @@ struct PyramidParams {
     float* scratch;
     double* moments;
     int32_t m_axis[2];                                  // the resized axes in order (-1: only one)
+    int32_t same_size[SKR_MAX_LEVELS];                  // 1: the level has the unit shape (interpolation is the identity)
     int64_t lstride[SKR_MAX_LEVELS][SKR_MAX_DIMS];      // row-major strides of each level grid
 };
 
@@ -360,6 +370,100 @@ __global__ void __launch_bounds__(256) pyramid_kernel(const __grid_constant__ Py
         block_sum2(s1, s2);
         if (threadIdx.x == 0) { atomicAdd(&p.moments[0], s1); atomicAdd(&p.moments[1], s2); }
     }
+}
+
+// Composition pass over supplied grids, four consecutive elements of the last axis per thread (last extent % 4 == 0,
+// fewer than 2^31 elements): the coordinate decomposition, the slice offset and the source rows of the other resized
+// axis are shared by the four, base / same-size levels / result move as 128-bit accesses.  Same arithmetic, in the
+// same order, as pyramid_value.
+__global__ void __launch_bounds__(256) pyramid_compose4_kernel(const __grid_constant__ PyramidParams p) {
+    const int last = p.ndim - 1;
+    const int m0 = p.m_axis[0], m1 = p.m_axis[1];
+    const bool last_resized = p.masked[last] != 0;
+    const int other = last_resized ? (m1 >= 0 ? m0 : -1) : -1;  // the resized axis that is not the last one
+    const int32_t groups = (int32_t)(p.numel >> 2);
+    double s1 = 0.0, s2 = 0.0;
+    for (int32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
+        const int32_t e0 = g << 2;
+        int32_t idx[SKR_MAX_DIMS];
+        int32_t rem = e0;
+        for (int d = last; d >= 0; --d) {
+            const int32_t size = (int32_t)p.shape[d];
+            const int32_t q = rem / size;
+            idx[d] = rem - q * size;
+            rem = q;
+        }
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (int l = 0; l < p.n_levels; ++l) {
+            const float wl = p.weight[l];
+            if (wl == 0.0f) continue;
+            const float* grid = p.buffer[l];
+            if (p.same_size[l]) {
+                const float4 q = *reinterpret_cast<const float4*>(grid + e0);
+                acc[0] += q.x * wl; acc[1] += q.y * wl; acc[2] += q.z * wl; acc[3] += q.w * wl;
+                continue;
+            }
+            int32_t outer = 0;  // slice offset from the axes that are neither resized nor the last one
+            for (int d = 0; d < last; ++d)
+                if (!p.masked[d]) outer += idx[d] * (int32_t)p.lstride[l][d];
+            if (!last_resized) {
+                // the four elements sit in four consecutive slices: same interpolation footprint in each
+                int64_t h0, h1, w0 = 0, w1 = 0;
+                float wh, ww = 0.0f;
+                source_index((int64_t)idx[m0], p.extent[l][0], p.shape[m0], h0, h1, wh);
+                if (m1 >= 0) source_index((int64_t)idx[m1], p.extent[l][1], p.shape[m1], w0, w1, ww);
+                const int32_t sh = (int32_t)p.lstride[l][m0], sw = m1 >= 0 ? (int32_t)p.lstride[l][m1] : 0;
+                const int32_t sl = (int32_t)p.lstride[l][last];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int32_t o = outer + (idx[last] + j) * sl;
+                    float v;
+                    if (m1 < 0) {
+                        v = (1.0f - wh) * grid[o + (int32_t)h0 * sh] + wh * grid[o + (int32_t)h1 * sh];
+                    } else {
+                        const int32_t r0 = o + (int32_t)h0 * sh, r1 = o + (int32_t)h1 * sh;
+                        const float top = (1.0f - ww) * grid[r0 + (int32_t)w0 * sw] + ww * grid[r0 + (int32_t)w1 * sw];
+                        const float bot = (1.0f - ww) * grid[r1 + (int32_t)w0 * sw] + ww * grid[r1 + (int32_t)w1 * sw];
+                        v = (1.0f - wh) * top + wh * bot;
+                    }
+                    acc[j] += v * wl;
+                }
+            } else {
+                int64_t h0 = 0, h1 = 0;
+                float wh = 0.0f;
+                int32_t r0 = outer, r1 = outer;
+                if (other >= 0) {
+                    source_index((int64_t)idx[other], p.extent[l][0], p.shape[other], h0, h1, wh);
+                    const int32_t sh = (int32_t)p.lstride[l][other];
+                    r0 = outer + (int32_t)h0 * sh;
+                    r1 = outer + (int32_t)h1 * sh;
+                }
+                const int64_t extent_last = p.extent[l][other >= 0 ? 1 : 0];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    int64_t w0, w1;
+                    float ww;
+                    source_index((int64_t)(idx[last] + j), extent_last, p.shape[last], w0, w1, ww);
+                    float v;
+                    if (other < 0) {
+                        v = (1.0f - ww) * grid[outer + (int32_t)w0] + ww * grid[outer + (int32_t)w1];
+                    } else {
+                        const float top = (1.0f - ww) * grid[r0 + (int32_t)w0] + ww * grid[r0 + (int32_t)w1];
+                        const float bot = (1.0f - ww) * grid[r1 + (int32_t)w0] + ww * grid[r1 + (int32_t)w1];
+                        v = (1.0f - wh) * top + wh * bot;
+                    }
+                    acc[j] += v * wl;
+                }
+            }
+        }
+        const float4 b = *reinterpret_cast<const float4*>(p.base_buffer + e0);
+        const float4 v = make_float4(b.x + acc[0], b.y + acc[1], b.z + acc[2], b.w + acc[3]);
+        *reinterpret_cast<float4*>(p.scratch + e0) = v;
+        s1 += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
+        s2 += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    }
+    block_sum2(s1, s2);
+    if (threadIdx.x == 0) { atomicAdd(&p.moments[0], s1); atomicAdd(&p.moments[1], s2); }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -459,6 +563,16 @@ int skr_noise_fill(void* out, int32_t dtype, int64_t numel, uint64_t seed, uint6
         p.ndim = offset->ndim;
         p.offset_scale = (float)offset->scale;
         p.offset_stream = offset->stream;
+        // kept axes first, broadcast axes after: the offset index is the element index divided by the broadcast extent
+        int d = 0;
+        while (d < offset->ndim && p.keep[d]) ++d;
+        int64_t inner = 1;
+        bool prefix = true;
+        for (int k = d; k < offset->ndim; ++k) {
+            prefix = prefix && !p.keep[k];
+            inner *= p.shape[k];
+        }
+        p.inner = prefix ? inner : 0;
     }
     fill_kernel<<<grid_for((numel + 3) / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
     return check_launch("noise fill");
@@ -570,6 +684,19 @@ int skr_noise_pyramid(void* out, int32_t dtype, const skr_pyramid* desc, double*
         else pyramid_kernel<int64_t><<<grid_for(numel, 256), 256, 0, s>>>(p);
         return check_launch(what);
     };
+    bool grids = p.scratch && p.base_buffer && narrow && (p.shape[desc->ndim - 1] & 3) == 0 &&
+                 ((reinterpret_cast<uintptr_t>(p.scratch) | reinterpret_cast<uintptr_t>(p.base_buffer)) & 15u) == 0;
+    for (int l = 0; l < desc->n_levels; ++l) {
+        p.same_size[l] = p.extent[l][0] == p.shape[p.m_axis[0]] && (p.m_axis[1] < 0 || p.extent[l][1] == p.shape[p.m_axis[1]]);
+        if (p.weight[l] == 0.0f) continue;
+        grids = grids && p.buffer[l] && (!p.same_size[l] || (reinterpret_cast<uintptr_t>(p.buffer[l]) & 15u) == 0);
+    }
+    if (grids) {  // everything supplied as grids: four elements per thread
+        pyramid_compose4_kernel<<<grid_for(numel / 4, 256), 256, 0, s>>>(p);
+        int rc = check_launch("pyramid compose");
+        if (rc) return rc;
+        return skr_noise_scale(p.scratch, SKR_F32, out, dtype, numel, 1.0, nullptr, 0, moments, numel, 0.0, cuda_stream);
+    }
     if (p.scratch) {
         int rc = pass(2, "pyramid compose");
         if (rc) return rc;

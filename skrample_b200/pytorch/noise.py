@@ -444,6 +444,8 @@ class Pyramid(TensorNoiseCommon[PyramidProps]):
         return total + sum(levels[self._kept(len(levels)) :])
 
     # -- device path
+    _use_grids = True  # False: draw every interpolation corner inside the kernel (no scratch memory, ~20x slower)
+
     def _generate_device(self, out: torch.Tensor) -> None:
         rank = len(self.shape)
         if rank > 8:
@@ -474,10 +476,11 @@ class Pyramid(TensorNoiseCommon[PyramidProps]):
         # Drawing each interpolation corner inside the kernel instead costs ~32 Philox blocks per element.
         numel = math.prod(self.shape)
         align = lambda n: (n + 3) & ~3  # noqa: E731 - keep every grid 16-byte aligned for vector stores
-        sizes = [math.prod(shape) if level >= first else 0 for level, shape in enumerate(shapes)]
+        sizes = [math.prod(shape) if level >= first and self._use_grids else 0 for level, shape in enumerate(shapes)]
         scratch = torch.empty(align(numel) + sum(align(n) for n in sizes), dtype=torch.float32, device=out.device)
         with _DeviceGuard(out.device):
-            self._fill(scratch[:numel], base)
+            if self._use_grids:
+                self._fill(scratch[:numel], base)
             cursor = align(numel)
             for level, shape in enumerate(shapes):
                 slot = desc.levels[level]
@@ -491,8 +494,9 @@ class Pyramid(TensorNoiseCommon[PyramidProps]):
                     self._fill(grid, slot.stream)
                     slot.buffer = grid.data_ptr()
                     cursor += align(sizes[level])
-            desc.base_buffer = scratch.data_ptr()
-            desc.scratch = scratch.data_ptr()  # composed in place over the base draw
+            if self._use_grids:
+                desc.base_buffer = scratch.data_ptr()
+                desc.scratch = scratch.data_ptr()  # composed in place over the base draw
             moments = torch.zeros(2, dtype=torch.float64, device=out.device)
             status = _lib().skr_noise_pyramid(out.data_ptr(), _code(out.dtype), ctypes.byref(desc), moments.data_ptr(), _stream())
         _native().check(status, "skr_noise_pyramid")

@@ -12,6 +12,7 @@ from skrample_b200.pytorch import noise
 
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
+only = set(sys.argv[1:])  # e.g. `noise_bench.py Pyramid` times only that generator
 
 
 def timed(make, reps=30):
@@ -38,9 +39,13 @@ for label, unit in (("video 16x21x90x160", (16, 21, 90, 160)), ("flux item 16x12
             ("Colored", lambda: noise.Colored.from_inputs(unit, torch.Generator(device=dev).manual_seed(1), noise.ColoredProps(), dtype=dtype)),
         ]
         for name, make in rows:
+            if only and name not in only:
+                continue
             us, out = timed(make)
             nbytes = out.numel() * out.element_size()
             print(f"{label:22s} {str(dtype).replace('torch.', ''):9s} {name:8s} {us:9.1f} us  {nbytes / us / 1e3:8.1f} GB/s written  ({out.numel() / us:8.1f} Melem/s)")
+if only:
+    sys.exit(0)
 batch = noise.BatchTensorNoise.from_batch_inputs(noise.Random, (16, 128, 128), [torch.Generator(device=dev).manual_seed(i) for i in range(16)], dtype=torch.float32)
 us, out = timed(lambda: batch)
 print(f"{'flux batch 16x16x128x128':22s} float32   Random x16 {us:7.1f} us  {out.numel() * 4 / us / 1e3:8.1f} GB/s written")

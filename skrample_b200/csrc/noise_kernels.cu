@@ -480,24 +480,29 @@ struct ShapeParams {
     float r_max;
 };
 
+// I: index type (32-bit below 2^31 bins: the per-axis divisions dominate the kernel otherwise)
+template <typename I>
 __global__ void __launch_bounds__(256) colored_shape_kernel(const __grid_constant__ ShapeParams p) {
     const int last = p.ndim - 1;
-    const int64_t last_bins = p.dims[last] / 2 + 1;
-    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < p.bins; b += (int64_t)gridDim.x * blockDim.x) {
-        int64_t rem = b;
+    const I last_bins = (I)(p.dims[last] / 2 + 1);
+    const I bins = (I)p.bins;
+    for (I b = (I)(blockIdx.x * blockDim.x + threadIdx.x); b < bins; b += (I)(gridDim.x * blockDim.x)) {
+        I rem = b;
         float r2 = 0.0f;
         {
-            const int64_t k = rem % last_bins;
-            rem /= last_bins;
+            const I q = rem / last_bins;
+            const I k = rem - q * last_bins;
+            rem = q;
             const float f = (float)k / (float)p.dims[last];
             r2 = f * f;
         }
         for (int d = last - 1; d >= 0; --d) {
-            const int64_t n = p.dims[d];
-            const int64_t k = rem % n;
-            rem /= n;
+            const I n = (I)p.dims[d];
+            const I q = rem / n;
+            const I k = rem - q * n;
+            rem = q;
             // |fftfreq(n)|: k/n for k < ceil(n/2), else (n-k)/n
-            const int64_t kk = k < (n + 1) / 2 ? k : n - k;
+            const I kk = k < (n + 1) / 2 ? k : n - k;
             const float f = (float)kk / (float)n;
             r2 += f * f;
         }
@@ -732,7 +737,8 @@ int skr_colored_shape(void* spectrum, int32_t complex_dtype, const int64_t* dims
     p.eps_clip = (float)(0.5 / (n_eff > 4.0 ? n_eff : 4.0));
     p.r_max = sqrtf((float)rmax2);
     p.exponent_half_neg = (float)(-exponent / 2.0);
-    colored_shape_kernel<<<grid_for(bins, 256), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
+    if (bins < ((int64_t)1 << 31) - 256 * 148 * 8) colored_shape_kernel<int32_t><<<grid_for(bins, 256), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
+    else colored_shape_kernel<int64_t><<<grid_for(bins, 256), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
     return check_launch("colored shape");
 }
 

@@ -642,7 +642,9 @@ class Colored(TensorNoiseCommon[ColoredProps]):
                 lib.skr_colored_shape(spectrum.data_ptr(), _code(w.dtype), dims, max(1, w.dim()), float(exponent), stream),
                 "skr_colored_shape",
             )
-            colored = torch.fft.irfftn(spectrum, s=w.shape).contiguous()
+            # norm="forward": no 1/N pass on the inverse; the field is renormalised by its own std just below, so a
+            # constant factor only has to be carried into the degenerate-std threshold
+            colored = torch.fft.irfftn(spectrum, s=w.shape, norm="forward").contiguous()
             colored_moments = torch.zeros(2, dtype=torch.float64, device=white.device)
             native.check(lib.skr_noise_moments(colored.data_ptr(), _code(colored.dtype), n, colored_moments.data_ptr(), stream), "skr_noise_moments")
             out = torch.empty(white.shape, dtype=out_dtype, device=white.device)
@@ -658,7 +660,7 @@ class Colored(TensorNoiseCommon[ColoredProps]):
                     n,
                     colored_moments.data_ptr(),
                     n,
-                    1e-8,
+                    1e-8 * n,
                     stream,
                 ),
                 "skr_noise_scale",

@@ -18,7 +18,7 @@ only = set(sys.argv[1:])  # e.g. `noise_bench.py Pyramid` times only that genera
 def timed(make, reps=30):
     src = make()
     step = Step.from_int(5, 25)
-    for _ in range(5):
+    for _ in range(20):  # the first calls in a process pay for cuFFT plans, allocator growth and lazy module loading
         src.generate(step)
     torch.cuda.synchronize()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -432,6 +432,20 @@ def e2e_graphed_throughput(spec: dict, device: torch.device, steps: int, warmup:
     return {"elapsed_s": elapsed}
 
 
+def measured_traffic() -> float | None:
+    """DRAM bytes per launch of the dominant step kernel on the default workload, from the latest ncu launch list
+    summarised under profiles/ (tools/profile_round.sh + tools/summarize_profiles.py); None when not captured."""
+    if "--workload" in sys.argv:
+        return None
+    found = sorted((Path(__file__).resolve().parent / "profiles").glob("r*_traffic.json"))
+    if not found:
+        return None
+    try:
+        return float(json.loads(found[-1].read_text())["dram_bytes_per_launch"])
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def barrier() -> None:
     if torch.distributed.is_available() and torch.distributed.is_initialized():
         torch.distributed.barrier()
@@ -665,7 +679,7 @@ def main() -> None:
             "peak": peak,
             "unit": "GB/s",
             "frac": achieved / peak,
-            "traffic": None,
+            "traffic": measured_traffic(),
             "kernel": "skr::block_kernel",
             "bytes_per_launch": dev["bytes"] / dev["launches"],
             "us_per_launch": per_launch_us,

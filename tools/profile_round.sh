@@ -13,7 +13,7 @@ python bench.py --impl reference > $O/${R}_bench_reference.json 2>> $O/${R}_benc
 python bench.py --fused-noise --sweep --no-cpu-baseline > $O/${R}_bench_fused_noise.json 2>> $O/${R}_bench.err || echo "fused bench failed"
 
 BENCH="python bench.py --steps 400 --warmup 50 --no-cpu-baseline"
-$BENCH > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none \
+$BENCH > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
     -k regex:"block_kernel|step_kernel|fill_kernel" -c 3000 --csv --log-file $O/${R}_launches.csv $BENCH > $O/${R}_ncu_launch.log 2>&1
 
 capture() {  # name, kernel skip count, prof_one arguments...

@@ -51,7 +51,28 @@ def launches(round_name: str) -> None:
         if row["Metric Name"] == "gpu__time_duration.sum":
             name = re.sub(r"skr::", "", row["Kernel Name"])
             groups[(name, row["Grid Size"])].append(float(row["Metric Value"].replace(",", "")) / 1e3)
+    # DRAM traffic per launch of the dominant step kernel (the default workload's steady-state shape): bench.py
+    # reports it as roofline.traffic next to the algorithmic bytes
+    traffic: dict[tuple[str, str], list[float]] = collections.defaultdict(list)
+    per_id: dict[str, float] = collections.defaultdict(float)
+    kernel_of: dict[str, tuple[str, str]] = {}
+    for row in rows:
+        if row["Metric Name"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(row["Metric Unit"], 1.0)
+            per_id[row["ID"]] += float(row["Metric Value"].replace(",", "")) * scale
+            kernel_of[row["ID"]] = (re.sub(r"skr::", "", row["Kernel Name"]), row["Grid Size"])
+    for launch, nbytes in per_id.items():
+        traffic[kernel_of[launch]].append(nbytes)
     total = sum(sum(v) for v in groups.values())
+    if traffic:
+        top = max((k for k in groups if "block_kernel" in k[0]), key=lambda k: sum(groups[k]), default=None)
+        if top is not None and traffic.get(top):
+            import json
+
+            (PROFILES / f"{round_name}_traffic.json").write_text(
+                json.dumps({"kernel": top[0], "grid": top[1], "launches": len(traffic[top]), "dram_bytes_per_launch": sum(traffic[top]) / len(traffic[top]),
+                            "source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum over the launches of this kernel in `{round_name}_launches.csv` (bench command, 16 interleaved latent batches)"}, indent=1) + "\n"
+            )
     out = [
         f"# ncu launch list of `python bench.py --steps 400 --warmup 50 --no-cpu-baseline` (gpu__time_duration.sum, --clock-control none)",
         '# filter: -k regex:"block_kernel|step_kernel|fill_kernel" -c 3000; per-launch times are cold-cache and serialised: compare SHARES',

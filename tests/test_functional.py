@@ -197,3 +197,82 @@ def test_rkmoire_takes_one_host_read_per_adaptive_step(monkeypatch: pytest.Monke
     same = custom.sample_model(x, model, models.FlowModel(), scheduling.Linear(), 12)
     assert calls["user"] > 0 and calls["fused"] == fused_before
     assert torch.equal(out, same), "same strides, same kernels: the fused norm must not change the trajectory here"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize(
+    "make",
+    [
+        lambda f: f.RKUltra(order=2),
+        lambda f: f.RKUltra(order=4, stochasticity=1),
+        lambda f: f.RKUltra(order=7),
+        lambda f: f.RKUltra(order=4, derivative_transform=None),
+        lambda f: f.DynasauRK(order=4),
+    ],
+    ids=["rku2", "rku4-sde", "rku7", "rku4-raw", "dynasaurk4"],
+)
+def test_rk_step_replay_is_bit_identical(make, dtype: torch.dtype, monkeypatch: pytest.MonkeyPatch) -> None:  # noqa: ANN001
+    "The second time a step is taken its recorded launches are replayed: no program is emitted, same bits."
+    from skrample_b200 import scheduling
+    from skrample_b200.sampling import functional, models
+    from skrample_b200.sampling import program as pg
+
+    sampler = make(functional)
+    schedule, model_transform = scheduling.FlowShift(scheduling.Linear(), shift=3.0), models.FlowModel()
+    g = torch.Generator(device="cuda").manual_seed(21)
+    shape = (2, 4, 33, 31)
+    emitted = {"n": 0}
+    real = pg.execute
+    monkeypatch.setattr(pg, "execute", lambda program: (emitted.__setitem__("n", emitted["n"] + 1), real(program))[1])
+    functional._scripts.known.clear()
+
+    def trajectory(x0: torch.Tensor, weights: list[torch.Tensor], noises: list[torch.Tensor]) -> torch.Tensor:
+        calls = iter(range(1 << 20))
+
+        def model(sample: torch.Tensor, t: float, sigma: float, alpha: float) -> torch.Tensor:
+            return (sample.float() * weights[next(calls) % len(weights)].float()).to(sample.dtype)
+
+        draws = iter(noises)
+        return sampler.sample_model(x0, model, model_transform, schedule, 5, rng=lambda step=None: next(draws))
+
+    def inputs() -> tuple:
+        x0 = torch.randn(shape, device="cuda", generator=g).to(dtype)
+        weights = [torch.randn(shape, device="cuda", generator=g).to(dtype) * 0.2 for _ in range(5)]
+        noises = [torch.randn(shape, device="cuda", generator=g).to(dtype) for _ in range(8)]
+        return x0, weights, noises
+
+    first = inputs()
+    want_first = trajectory(*first)
+    recorded = emitted["n"]
+    assert recorded > 0 and functional._scripts.known
+    second = inputs()
+    got_second = trajectory(*second)  # replayed
+    assert emitted["n"] == recorded, "a cached step emitted programs again"
+    functional._scripts.known.clear()
+    want_second = trajectory(*second)  # emitted afresh on the same data
+    assert torch.equal(got_second, want_second)
+    assert torch.equal(trajectory(*first), want_first)
+
+
+@pytest.mark.gpu
+def test_rk_replay_is_not_used_when_roles_are_ambiguous() -> None:
+    "A model that hands back its input (or one tensor twice) cannot be recorded by tensor identity: steps stay correct."
+    from skrample_b200 import scheduling
+    from skrample_b200.common import Step
+    from skrample_b200.sampling import functional, models
+
+    functional._scripts.known.clear()
+    sampler = functional.RKUltra(order=4)
+    schedule, model_transform = scheduling.Linear(), models.FlowModel()
+    x = torch.randn(2, 4, 16, 16, device="cuda")
+    constant = torch.randn_like(x)
+    a = sampler.step(x, lambda s, t, sigma, alpha: constant, model_transform, schedule, Step.from_int(2, 10))
+    assert not functional._scripts.known
+    other = [torch.randn_like(x) for _ in range(4)]
+    calls = iter(range(100))
+    b = sampler.step(x, lambda s, t, sigma, alpha: other[next(calls)], model_transform, schedule, Step.from_int(2, 10))
+    assert functional._scripts.known and not torch.equal(a, b)
+    calls = iter(range(100))
+    c = sampler.step(x, lambda s, t, sigma, alpha: constant, model_transform, schedule, Step.from_int(2, 10))  # replayed with one tensor four times
+    assert torch.equal(a, c)

@@ -62,3 +62,20 @@ print(
     f"RKUltra({order}) {dtype}: {ms * 1e3 / rk_steps:.1f} us per RK step, {launches / rk_steps:.1f} launches/step, "
     f"{ms * 1e3 / launches:.1f} us/launch, {native.ACCOUNT['bytes'] / (ms * 1e-3) / 1e9:.0f} GB/s algorithmic"
 )
+
+# eager wall time of the same step (host emission + launches), to see how far the host is behind the device
+import time
+
+x = latents[0]
+table = outputs[0]
+calls = iter(range(1 << 30))
+model = lambda s, t, sig, alp: table[next(calls) % 8]  # noqa: E731
+for _ in range(20):
+    sampler.step(x, model, model_transform, schedule, Step.from_int(3, steps))
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+n = 200
+for _ in range(n):
+    sampler.step(x, model, model_transform, schedule, Step.from_int(3, steps))
+torch.cuda.synchronize()
+print(f"eager: {(time.perf_counter() - t0) / n * 1e6:.1f} us per RK step wall")

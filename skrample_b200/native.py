@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 from pathlib import Path
 from typing import TYPE_CHECKING, Any
 
@@ -210,10 +211,33 @@ def pack_program(program: "Program", inputs: list[torch.Tensor], outputs: list[t
     return packed
 
 
+class _Compiled(threading.local):
+    def __init__(self) -> None:
+        self.by_ops: dict[tuple, CompiledProgram] = {}
+
+
+_compiled = _Compiled()
+_MAX_COMPILED = 1024
+
+
 def launch_program(program: "Program") -> list[Any]:
-    "Run a step program on CUDA tensors: allocate outputs, one kernel launch, return outputs."
-    lib = load()
+    """Run a step program on CUDA tensors: allocate outputs, one kernel launch, return outputs.
+
+    The packed op table of a program is remembered by its ops (frozen, hashable): samplers that are driven step by
+    step without a step plan (RK wrappers, model conversions) re-emit equal programs, and filling the ctypes struct
+    field by field costs more than the launch."""
     inputs = [t if t.is_contiguous() else t.contiguous() for t in program.inputs]
+    if all(t.dtype in DTYPE_CODE for t in inputs):
+        key = (tuple(program.ops), tuple(program.outputs), len(inputs))
+        compiled = _compiled.by_ops.get(key)
+        if compiled is None:
+            if len(_compiled.by_ops) >= _MAX_COMPILED:
+                _compiled.by_ops.clear()
+            compiled = _compiled.by_ops[key] = CompiledProgram(program)
+        outs = launch_compiled(compiled, inputs, list(getattr(program, "philox", ())) or None)
+        if outs is not None:
+            return outs
+    lib = load()
     first = inputs[0]
     default_dtype = promoted_dtype(inputs)
     outputs: list[torch.Tensor] = []

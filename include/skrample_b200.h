@@ -9,8 +9,10 @@
  *   skrample/sampling/functional.py:55-105  (step_tableau)
  *   skrample/common.py:32-40               (Point.add_noise / remove_noise)
  *   skrample/pytorch/noise.py:36-425       (Random / Offset / Pyramid / Colored)
+ *   skrample/sampling/functional.py:197-214 (adaptive error norms)
  * Every entry point below replaces one of those call sites with ONE launch of a
- * hand-written sm_100a kernel.  Plain pointers and sizes only; no torch types.
+ * hand-written sm_100a kernel (the composite noise generators: a few).  Plain
+ * pointers and sizes only; no torch types.
  *
  * Conventions
  *   - every function returns int: 0 = ok, < 0 = bad argument (see SKR_E_*),

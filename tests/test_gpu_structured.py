@@ -247,3 +247,45 @@ def test_more_than_2_31_elements_subset_vs_oracle(kernel_kind: int) -> None:
         prev_o = (prev_o + [rec])[-1:]
         x, x_o = res.final, want
         del out, noise
+
+
+@pytest.mark.parametrize("generator", ["Pyramid", "Colored"])
+def test_full_size_video_latent_adams9_subset_vs_oracle(generator: str) -> None:
+    """BASELINE config 4, one GPU's shard (1x16x21x90x160, bf16 storage, Adams-9 SDE, Flow, Pyramid / Colored noise):
+    the oracle on a random subset of elements equals the kernel's output there, through the order ramp 1..9."""
+    from skrample_b200 import scheduling
+    from skrample_b200.common import Step
+    from skrample_b200.pytorch import noise as sk_noise
+    from skrample_b200.sampling import models, structured
+
+    shape = (1, 16, 21, 90, 160)
+    g = torch.Generator(device="cuda").manual_seed(17)
+    steps = 12
+    sampler = structured.Adams(order=9, stochasticity=1)
+    schedule, model = scheduling.FlowShift(scheduling.Linear()), models.FlowModel()
+    source = getattr(sk_noise, generator).from_inputs(shape[1:], torch.Generator(device="cuda").manual_seed(5), dtype=torch.float32)
+    x = torch.randn(shape, device="cuda", generator=g).bfloat16()
+    pick = torch.randint(0, x.numel(), (8192,), device="cuda", generator=g)
+    prev: list = []
+    prev_o: list[O.Rec] = []
+    x_o = x.flatten()[pick].float().cpu().numpy()
+    case = {"sampler": "Adams", "kw": {"order": 9, "stochasticity": 1}}
+    for n in range(steps):
+        out = (torch.randn(shape, device="cuda", generator=g) * 0.5).bfloat16()
+        noise = source.generate(Step.from_int(n, steps)).unsqueeze(0).bfloat16()
+        assert abs(noise.float().std().item() - 1.0) < 2e-2
+        step = Step.from_int(n, steps)
+        res = sampler.sample(x, out, step, model, schedule, noise, prev)
+        prev = (prev + [res])[-sampler.require_previous :]
+        rec = oracle_run.one_step(
+            case,
+            O.Rec(x_o, out.flatten()[pick].float().cpu().numpy(), O.St(*step), noise.flatten()[pick].float().cpu().numpy()),
+            prev_o,
+            O.Model("flow"),
+            O.flow_shift(O.linear()),
+        )
+        prev_o = (prev_o + [rec])[-8:]
+        want = O.round_bf16(rec.final)
+        got = res.final.flatten()[pick].float().cpu().numpy()
+        assert np.array_equal(got, want), f"step {n}: {int((got != want).sum())} of {got.size} differ"
+        x, x_o = res.final, want

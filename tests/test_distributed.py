@@ -7,6 +7,7 @@ import socket
 import sys
 from pathlib import Path
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -65,3 +66,48 @@ def test_batch_shards_reproduce_the_unsharded_run(tmp_path: Path) -> None:
     sharded = torch.load(path)
     x, outs, noises = _inputs()
     assert torch.equal(sharded, _trajectory(x, outs, noises))
+
+
+def _nccl_worker(rank: int, world: int, port: int, result_path: str) -> None:
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from skrample_b200.pytorch import noise as sk_noise
+
+    device = torch.device("cuda", rank)
+    x, outs, _ = _inputs()
+    per = x.shape[0] // world
+    mine = slice(rank * per, (rank + 1) * per)
+    # per-item generators keyed by the GLOBAL item index: any sharding draws the same noise for an item
+    source = sk_noise.BatchTensorNoise.from_batch_inputs(
+        sk_noise.Random, tuple(x.shape[1:]), [torch.Generator(device=device).manual_seed(1000 + i) for i in range(mine.start, mine.stop)]
+    )
+    noises = [source.generate(None) for _ in outs]
+    local = _trajectory(x[mine].to(device), [o[mine].to(device) for o in outs], noises)  # the step path: no communication
+    gathered = torch.empty((x.shape[0], *local.shape[1:]), device=device)
+    dist.all_gather_into_tensor(gathered, local)  # validation only (NCCL over NVLink)
+    if rank == 0:
+        torch.save(gathered.cpu(), result_path)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_nccl_batch_shards_reproduce_the_single_gpu_run(tmp_path: Path) -> None:
+    "Two ranks, one GPU each, batch-sharded with device-side noise: the gathered result is the one-GPU result bit for bit."
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from skrample_b200.pytorch import noise as sk_noise
+
+    path = str(tmp_path / "gathered.pt")
+    mp.spawn(_nccl_worker, args=(2, _free_port(), path), nprocs=2, join=True)
+    sharded = torch.load(path)
+    device = torch.device("cuda", 0)
+    x, outs, _ = _inputs()
+    source = sk_noise.BatchTensorNoise.from_batch_inputs(
+        sk_noise.Random, tuple(x.shape[1:]), [torch.Generator(device=device).manual_seed(1000 + i) for i in range(x.shape[0])]
+    )
+    noises = [source.generate(None) for _ in outs]
+    whole = _trajectory(x.to(device), [o.to(device) for o in outs], noises)
+    assert torch.equal(sharded, whole.cpu())

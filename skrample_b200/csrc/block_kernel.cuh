@@ -256,6 +256,7 @@ __device__ __forceinline__ int pinned(int runtime) {
 struct BlkAny {
     static constexpr int enabled = -1, kind = -1, sample = -1, base = -1, p_mode = -1, has_div = -1, pred_p = -1;
     static constexpr int noise = -1, store = -1, link = -1, slink = -1;
+    static constexpr int n_terms = -1;  // >= 0: the history loop is unrolled, its constants become immediates
     static constexpr int dt_state = -1, dt_sample = -1, dt_noise = -1, dt_store = -1, dt_slink = -1;
 };
 struct BlkOff : BlkAny {
@@ -273,10 +274,10 @@ struct ShAny {
 // output, noise, `final`); ST that of the solver state a block reads (x-hat history, previous samples: fp32; the
 // raw derivatives of an unconverted RK step: LP).  Whether a block adds noise and whether x-hat is stored a second
 // time stay run-time flags: one uniform branch each.
-template <int KIND, int SAMPLE, int BASE, int PMODE, int DIV, int PREDP, int STORE, int LINK, int SLINK, int OUT, int ST, int LP>
+template <int KIND, int SAMPLE, int BASE, int PMODE, int DIV, int PREDP, int STORE, int LINK, int SLINK, int OUT, int ST, int LP, int NT = -1>
 struct BlkPin : BlkAny {
     static constexpr int enabled = 1, kind = KIND, sample = SAMPLE, base = BASE, p_mode = PMODE, has_div = DIV;
-    static constexpr int pred_p = PREDP, store = STORE, link = LINK, slink = SLINK;
+    static constexpr int pred_p = PREDP, store = STORE, link = LINK, slink = SLINK, n_terms = NT;
     static constexpr int dt_state = ST, dt_sample = ST, dt_noise = LP, dt_store = OUT, dt_slink = SKR_F32;
 };
 // explicit RK on converted derivatives (the default: derivative_transform = DataModel): X = the step's sample (LP),
@@ -317,10 +318,11 @@ using ShDpm3 = ShStep<LP, BlkPin<BK_DPM3, 0, 0, 0, 0, 0, 1, BL_NONE, 0, LP, SKR_
 // UniP: predictor only
 template <int LP>
 using ShUniP = ShStep<LP, BlkPin<BK_UNI, 0, 0, 0, 0, 0, 1, BL_NONE, 0, LP, SKR_F32, LP>, BlkOff>;
-// UniPC steady state: block 0 corrects the previous step (UniC term, fp32 state out, X = R), block 1 predicts
-template <int LP>
-using ShUniPC = ShStep<LP, BlkPin<BK_UNI, 1, 1, 1, 0, 0, 1, BL_X_FROM_R, 0, SKR_F32, SKR_F32, LP>,
-                       BlkPin<BK_UNI, 0, 0, 0, 0, 0, 1, BL_NONE, 0, LP, SKR_F32, LP>>;
+// UniPC steady state: block 0 corrects the previous step (UniC term, fp32 state out, X = R), block 1 predicts.
+// NT = history terms of each block (order - 1 at steady state): pinned for orders 2 and 3, a loop otherwise.
+template <int LP, int NT = -1>
+using ShUniPC = ShStep<LP, BlkPin<BK_UNI, 1, 1, 1, 0, 0, 1, BL_X_FROM_R, 0, SKR_F32, SKR_F32, LP, NT>,
+                       BlkPin<BK_UNI, 0, 0, 0, 0, 0, 1, BL_NONE, 0, LP, SKR_F32, LP, NT>>;
 // SPC steady state: block 0 = Adams corrector blended into the previous sample (fp32 state out), block 1 = Euler
 template <int LP>
 using ShSPC = ShStep<LP, BlkPin<BK_ACC, 1, 0, 1, 0, 0, 0, BL_BLEND, 1, SKR_F32, SKR_F32, LP>,
@@ -341,7 +343,7 @@ static bool block_matches(const BBlock<CT>& k, const int32_t* in_dt, const int32
     bool ok = eq(BS::kind, k.kind) && eq(BS::sample, k.sample_in >= 0) && eq(BS::base, k.base_in >= 0) &&
               eq(BS::p_mode, k.p_mode) && eq(BS::has_div, k.has_div) && eq(BS::pred_p, k.pred_is_p) &&
               eq(BS::noise, k.has_noise) && eq(BS::store, k.store_r >= 0) && eq(BS::link, k.link) &&
-              eq(BS::slink, k.store_link >= 0);
+              eq(BS::slink, k.store_link >= 0) && eq(BS::n_terms, k.n_terms);
     if (!ok) return false;
     if (BS::dt_sample >= 0 && k.sample_in >= 0 && in_dt[k.sample_in] != BS::dt_sample) return false;
     if (BS::dt_state >= 0) {
@@ -408,7 +410,7 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BB
     CT in[V];
     const int kind = pinned<BS::kind>(k.kind);
     if (kind != BK_NONE) {
-        const int n_terms = k.n_terms;
+        const int n_terms = pinned<BS::n_terms>(k.n_terms);
         const int p_mode = pinned<BS::p_mode>(k.p_mode);
         if (kind != BK_ACC) {
             if (pinned<BS::base>(k.base_in >= 0)) io.template load<BS::dt_state>(k.base_in, k.base_off, B);
@@ -447,7 +449,7 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BB
         } else if (kind == BK_UNI) {
 #pragma unroll
             for (int j = 0; j < V; ++j) A[j] = (CT)0;  // 0 + first term, like the reference's running sum
-            for (int t = 0; t < n_terms; ++t) {
+            auto term = [&](int t) {
                 io.template load<BS::dt_state>(k.term_in[t], k.terms[t].off, in);
                 const CT rho = k.terms[t].c1;
 #pragma unroll
@@ -455,6 +457,12 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BB
                 div_uniform<V>(in, k.terms[t].c0, k.terms[t].r0, fast_div);
 #pragma unroll
                 for (int j = 0; j < V; ++j) A[j] = Ar::add(A[j], Ar::mul(in[j], rho));
+            };
+            if constexpr (BS::n_terms >= 0) {
+#pragma unroll
+                for (int t = 0; t < BS::n_terms; ++t) term(t);
+            } else {
+                for (int t = 0; t < n_terms; ++t) term(t);
             }
             if (p_mode == 1) {
                 const CT rho = k.p_coef;

@@ -39,7 +39,9 @@ constexpr int kLP = SKR_F16, kModeLP = IN_F16, kVecLP = 8;
 // latent type use 8 elements per thread for 16-bit storage (every shared-memory read 128-bit).
 template <typename F>
 static bool for_each_pinned_shape(F&& f) {
-    return f(ShapeEntry<ShUniPC<kLP>, IN_MIXED, 4>{"unipc/" SKR_LP_NAME}) ||
+    return f(ShapeEntry<ShUniPC<kLP, 2>, IN_MIXED, 4>{"unipc3/" SKR_LP_NAME}) ||
+           f(ShapeEntry<ShUniPC<kLP, 1>, IN_MIXED, 4>{"unipc2/" SKR_LP_NAME}) ||
+           f(ShapeEntry<ShUniPC<kLP>, IN_MIXED, 4>{"unipc/" SKR_LP_NAME}) ||
            f(ShapeEntry<ShUniP<kLP>, IN_MIXED, 4>{"unip/" SKR_LP_NAME}) ||
            f(ShapeEntry<ShAcc<kLP>, IN_MIXED, 4>{"acc/" SKR_LP_NAME}) ||
            f(ShapeEntry<ShDpm2<kLP>, IN_MIXED, 4>{"dpm2/" SKR_LP_NAME}) ||

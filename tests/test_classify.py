@@ -81,7 +81,9 @@ PINNED = [
     ("DPM", {"order": 3, "stochasticity": 1}, "dpm3"),
     ("Adams", {"order": 4}, "acc"),
     ("UniP", {"order": 3}, "unip"),
-    ("UniPC", {"order": 3, "stochasticity": 1}, "unipc"),
+    ("UniPC", {"order": 3, "stochasticity": 1}, "unipc3"),
+    ("UniPC", {"order": 2}, "unipc2"),
+    ("UniPC", {"order": 4}, "unipc"),
     ("SPC", {}, "spc"),
 ]
 

@@ -356,6 +356,32 @@ def rk_step_throughput(spec: dict, device: torch.device, replicas: int = 16, rep
     return {"us_per_rk_step": ms * 1e3 / rk_steps, "launches_per_step": launches / rk_steps, "GBps": native.ACCOUNT["bytes"] / (ms * 1e-3) / 1e9, "bytes_per_step": native.ACCOUNT["bytes"] / rk_steps}
 
 
+def noise_generator_times(device: torch.device, unit: tuple[int, ...] = (16, 21, 90, 160), reps: int = 30) -> list[dict]:
+    """Device time per draw of each noise generator on one BASELINE.json configs[3] unit (a 16x21x90x160 video latent,
+    fp32 generator dtype): CUDA events around `generate`, after warm-up (cuFFT plans, allocator)."""
+    from skrample_b200.common import Step
+    from skrample_b200.pytorch import noise
+
+    rows = []
+    step = Step.from_int(5, STEPS_PER_TRAJECTORY)
+    for name, props in (("Random", None), ("Offset", noise.OffsetProps()), ("Pyramid", noise.PyramidProps()), ("Colored", noise.ColoredProps())):
+        cls = getattr(noise, name)
+        generator = torch.Generator(device=device).manual_seed(1)
+        source = cls.from_inputs(unit, generator, dtype=torch.float32) if props is None else cls.from_inputs(unit, generator, props, dtype=torch.float32)
+        for _ in range(20):
+            out = source.generate(step)
+        torch.cuda.synchronize(device)
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(reps):
+            out = source.generate(step)
+        stop.record()
+        torch.cuda.synchronize(device)
+        us = start.elapsed_time(stop) / reps * 1e3
+        rows.append({"generator": name, "unit_shape": list(unit), "us_per_draw": us, "GBps_written": out.numel() * out.element_size() / us / 1e3})
+    return rows
+
+
 def e2e_throughput(spec: dict, device: torch.device, steps: int, warmup: int) -> dict:
     "Public API with host buffers: H2D of the step's prediction + noise, sampler.sample, D2H of the result."
     traj = Trajectory(spec, device, seed=4321)
@@ -702,6 +728,7 @@ def main() -> None:
             r = rk_step_throughput(s, device)
             sweep.append({"workload": name, "shape": list(s["shape"]), "dtype": s["dtype"], "us_per_step": r["us_per_rk_step"], "launches_per_step": r["launches_per_step"], "GBps": r["GBps"], "frac_of_measured_peak": r["GBps"] / peak, "latent_steps_per_s": s["shape"][0] / (r["us_per_rk_step"] * 1e-6), "bytes_per_step_avg": r["bytes_per_step"]})
         line["sweep"] = sweep
+        line["noise_generators"] = noise_generator_times(device)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         res = cpu_oracle_steps(spec, 10_000, 25, 15.0)

@@ -58,6 +58,8 @@ WORKLOADS = {
     "euler_sde_flow_f32_256": dict(sampler="Euler", kw={"stochasticity": 1}, schedule="flow", model="FlowModel", shape=(256, 16, 128, 128), dtype="f32"),
     "euler_sde_flow_bf16_256": dict(sampler="Euler", kw={"stochasticity": 1}, schedule="flow", model="FlowModel", shape=(256, 16, 128, 128), dtype="bf16"),
     "unipc3_sde_flux_bf16": dict(sampler="UniPC", kw={"order": 3, "stochasticity": 1}, schedule="flow", model="FlowModel", shape=(16, 16, 128, 128), dtype="bf16"),
+    "unipc3_sde_flux_f32": dict(sampler="UniPC", kw={"order": 3, "stochasticity": 1}, schedule="flow", model="FlowModel", shape=(16, 16, 128, 128), dtype="f32"),
+    "unipc3_sde_flux64_bf16": dict(sampler="UniPC", kw={"order": 3, "stochasticity": 1}, schedule="flow", model="FlowModel", shape=(64, 16, 128, 128), dtype="bf16"),
 }
 DEFAULT_WORKLOAD = "unipc3_sde_sdxl_bf16"
 SWEEP = ["euler_sde_flow_f32_16", "euler_sde_flow_f32_64", "euler_sde_flow_f32_256", "euler_sde_flow_bf16_256", "adams9_sde_video_bf16", "adams9_sde_video_f32", "unipc3_sde_flux_bf16"]

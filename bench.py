@@ -58,6 +58,7 @@ WORKLOADS = {
     "euler_sde_flow_f32_256": dict(sampler="Euler", kw={"stochasticity": 1}, schedule="flow", model="FlowModel", shape=(256, 16, 128, 128), dtype="f32"),
     "euler_sde_flow_bf16_256": dict(sampler="Euler", kw={"stochasticity": 1}, schedule="flow", model="FlowModel", shape=(256, 16, 128, 128), dtype="bf16"),
     "unipc3_sde_flux_bf16": dict(sampler="UniPC", kw={"order": 3, "stochasticity": 1}, schedule="flow", model="FlowModel", shape=(16, 16, 128, 128), dtype="bf16"),
+    "unipc3_sde_ragged_bf16": dict(sampler="UniPC", kw={"order": 3, "stochasticity": 1}, schedule="scaled", model="NoiseModel", shape=(8, 4, 127, 129), dtype="bf16"),
     "unipc3_sde_flux_f32": dict(sampler="UniPC", kw={"order": 3, "stochasticity": 1}, schedule="flow", model="FlowModel", shape=(16, 16, 128, 128), dtype="f32"),
     "unipc3_sde_flux64_bf16": dict(sampler="UniPC", kw={"order": 3, "stochasticity": 1}, schedule="flow", model="FlowModel", shape=(64, 16, 128, 128), dtype="bf16"),
 }

@@ -82,6 +82,8 @@ struct BProgram {
     uint32_t stage_bytes, use_tma;
     int32_t n_full_tiles;
     int32_t fast_div;  // every divisor has a host-side reciprocal (machine.cuh, div_uniform)
+    int32_t vec_ok;    // every tensor base is 16-byte aligned: whole threads of a guarded tile may use vector accesses
+    int32_t tail_elems;  // elements of the partial last tile (0: the size is a multiple of the tile)
     const void* in_ptr[SKR_MAX_INPUTS];
     void* out_ptr[SKR_MAX_OUTPUTS];
     uint32_t in_off[SKR_MAX_INPUTS];
@@ -374,28 +376,76 @@ static bool shape_matches(const BProgram<CT>& p) {
 
 // ---- one tile of the skeleton -------------------------------------------------------------------------
 
-template <typename CT, int MODE, int V, bool GUARDED>
+// Where a tile's operands come from: the staged shared-memory tile (hot loop), global memory element by element with
+// bounds checks (unaligned tensors, the one thread that straddles the end), or global memory with vector accesses
+// (whole threads of the ragged tail tile - independent loads the compiler can batch).
+enum TilePath : int { TP_STAGED = 0, TP_ELEMENTS = 1, TP_VECTOR = 2 };
+
+template <typename CT, int V>
+__device__ __forceinline__ void fetch_vector(const void* ptr, int dtype, int64_t first, CT (&v)[V]) {
+    switch (dtype) {
+        case SKR_F32: {
+            const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(ptr) + first);
+#pragma unroll
+            for (int i = 0; i < V / 4; ++i) {
+                const float4 q = p[i];
+                v[4 * i] = (CT)q.x; v[4 * i + 1] = (CT)q.y; v[4 * i + 2] = (CT)q.z; v[4 * i + 3] = (CT)q.w;
+            }
+        } break;
+        case SKR_BF16:
+        case SKR_F16: {
+            uint32_t w[V / 2];
+            if constexpr (V == 8) {
+                const uint4 q = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(ptr) + first);
+                w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+            } else {
+                const uint2 q = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(ptr) + first);
+                w[0] = q.x; w[1] = q.y;
+            }
+#pragma unroll
+            for (int i = 0; i < V / 2; ++i) {
+                if (dtype == SKR_BF16) unpack_half2<CT, true>(w[i], v[2 * i], v[2 * i + 1]);
+                else unpack_half2<CT, false>(w[i], v[2 * i], v[2 * i + 1]);
+            }
+        } break;
+        default: {
+            if constexpr (sizeof(CT) == 8) {
+                const double2* p = reinterpret_cast<const double2*>(reinterpret_cast<const double*>(ptr) + first);
+#pragma unroll
+                for (int i = 0; i < V / 2; ++i) {
+                    const double2 q = p[i];
+                    v[2 * i] = (CT)q.x;
+                    v[2 * i + 1] = (CT)q.y;
+                }
+            }
+        } break;
+    }
+}
+
+template <typename CT, int MODE, int V, int PATH, bool PARTIAL = false>
 struct TileIO {
     const BProgram<CT>& prog;
     uint32_t stage;       // shared address of the staged tile
     uint32_t first_elem;  // tid * V
-    int64_t first;
+    int64_t first;  // PARTIAL (the ragged last tile): threads that straddle the end store element by element
     // `in` = input index (pointer / dtype tables), `off` = its byte offset inside the staged tile
     template <int DT = -1>
     __device__ __forceinline__ void load(int in, uint32_t off, CT (&v)[V]) const {
-        if constexpr (GUARDED) fetch_guarded<CT, V>(prog.in_ptr[in], prog.in_dtype[in], first, prog.numel, v);
+        if constexpr (PATH == TP_ELEMENTS) fetch_guarded<CT, V>(prog.in_ptr[in], prog.in_dtype[in], first, prog.numel, v);
+        else if constexpr (PATH == TP_VECTOR) fetch_vector<CT, V>(prog.in_ptr[in], prog.in_dtype[in], first, v);
         else fetch_tile<CT, MODE, V>(stage, off, pinned<DT>(prog.in_dtype[in]), first_elem, v);
     }
     template <int DT = -1>
     __device__ __forceinline__ void store(int out, const CT (&v)[V]) const {
-        if constexpr (GUARDED) store_guarded<CT, V>(prog.out_ptr[out], prog.out_dtype[out], first, prog.numel, v);
+        if constexpr (PATH == TP_ELEMENTS) store_guarded<CT, V>(prog.out_ptr[out], prog.out_dtype[out], first, prog.numel, v);
+        else if (PARTIAL && first + V > prog.numel) store_guarded<CT, V>(prog.out_ptr[out], prog.out_dtype[out], first, prog.numel, v);
         else store_tile<CT, V>(prog.out_ptr[out], pinned<DT>(prog.out_dtype[out]), first, v);
     }
 };
 
-template <typename CT, int MODE, int V, bool GUARDED, bool PHILOX, typename BS>
+template <typename CT, int MODE, int V, int PATH, bool PHILOX, typename BS, bool PARTIAL>
 __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BBlock<CT>& k,
-                                              const TileIO<CT, MODE, V, GUARDED>& io, CT (&X)[V], CT (&P)[V],
+                                              const TileIO<CT, MODE, V, PATH, PARTIAL>& io, CT (&X)[V], CT (&P)[V],
                                               CT (&B)[V], CT (&A)[V], CT (&S)[V], CT (&R)[V]) {
     using Ar = Arith<CT>;
     if (!pinned<BS::enabled>(k.enabled)) return;
@@ -534,10 +584,10 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BB
     }
 }
 
-template <typename CT, int MODE, int V, bool GUARDED, bool PHILOX, typename Sh>
+template <typename CT, int MODE, int V, int PATH, bool PHILOX, typename Sh, bool PARTIAL = false>
 __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t first, uint32_t stage, int tid) {
     using Ar = Arith<CT>;
-    const TileIO<CT, MODE, V, GUARDED> io{prog, stage, (uint32_t)tid * V, first};
+    const TileIO<CT, MODE, V, PATH, PARTIAL> io{prog, stage, (uint32_t)tid * V, first};
 
     CT X[V], P[V], B[V], A[V], S[V], R[V];
 #pragma unroll
@@ -577,15 +627,31 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
     if (pinned<Sh::sp>(h.store_p >= 0)) io.template store<Sh::dt_sp>(h.store_p, P);
     if (pinned<Sh::sp2>(h.store_p2 >= 0)) io.template store<Sh::dt_sp2>(h.store_p2, P);
 
-    run_one_block<CT, MODE, V, GUARDED, PHILOX, typename Sh::B0>(prog, prog.blk[0], io, X, P, B, A, S, R);
-    run_one_block<CT, MODE, V, GUARDED, PHILOX, typename Sh::B1>(prog, prog.blk[1], io, X, P, B, A, S, R);
+    run_one_block<CT, MODE, V, PATH, PHILOX, typename Sh::B0, PARTIAL>(prog, prog.blk[0], io, X, P, B, A, S, R);
+    run_one_block<CT, MODE, V, PATH, PHILOX, typename Sh::B1, PARTIAL>(prog, prog.blk[1], io, X, P, B, A, S, R);
 }
 
-// The ragged tail (and unaligned launches) run out of line so the pipelined loop stays compact.
+// Launches that cannot be staged (unaligned tensor bases, a stage too large for shared memory) run out of line so
+// the pipelined loop stays compact.  Tile t belongs to CTA t % grid.  Threads whose V elements are all inside an
+// aligned tensor use vector accesses; the thread straddling the end, or every thread of an unaligned launch, goes
+// element by element.  One warp needs 5-20 us for a tile on this path (a long dependent instruction stream), which
+// is why the ragged tail of a staged launch goes through the pipeline instead (block_kernel).
 template <typename CT, int MODE, int V, bool PHILOX>
 __device__ __noinline__ void run_guarded_tiles(const BProgram<CT>& prog, int64_t first_tile, int64_t n_tiles, int tid) {
-    for (int64_t tile = first_tile + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        run_block_tile<CT, MODE, V, true, PHILOX, ShAny>(prog, tile * (kThreads * V) + (int64_t)tid * V, 0u, tid);
+    const int64_t grid = gridDim.x;
+    const int64_t start = ((int64_t)blockIdx.x + grid - first_tile % grid) % grid;
+    for (int64_t tile = first_tile + start; tile < n_tiles; tile += grid) {
+        const int64_t first = tile * (kThreads * V) + (int64_t)tid * V;
+        // This path reads operands where the step needs them, one dependent miss after the other; touching this
+        // thread's slice of every input first makes the misses overlap (measured: 12.7 -> see DESIGN on a 16 MB step).
+        if (first < prog.numel) {
+            for (int i = 0; i < prog.n_inputs; ++i) {
+                const char* at = reinterpret_cast<const char*>(prog.in_ptr[i]) + first * (int64_t)dtype_size(prog.in_dtype[i]);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(at));
+            }
+        }
+        if (prog.vec_ok && first + V <= prog.numel) run_block_tile<CT, MODE, V, TP_VECTOR, PHILOX, ShAny>(prog, first, 0u, tid);
+        else if (first < prog.numel) run_block_tile<CT, MODE, V, TP_ELEMENTS, PHILOX, ShAny>(prog, first, 0u, tid);
     }
 }
 
@@ -604,11 +670,16 @@ __global__ void __launch_bounds__(kThreads + kProducerThreads, block_ctas_per_sm
     constexpr int TILE = kThreads * V;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int n_full = prog.use_tma ? prog.n_full_tiles : 0;
+    // staged tiles: the full ones and, when the size is ragged, the partial last one (tail_elems of it are real)
+    const int n_full = prog.n_full_tiles;
+    const int n_staged = prog.use_tma ? n_full + (prog.tail_elems > 0 ? 1 : 0) : 0;
     const int stages = prog.stages;
     const uint32_t stage_bytes = prog.stage_bytes;
     const int grid = (int)gridDim.x, cta = (int)blockIdx.x;
-    const int mine = n_full > cta ? (n_full - cta + grid - 1) / grid : 0;
+    const int mine = n_staged > cta ? (n_staged - cta + grid - 1) / grid : 0;
+    // the partial tile has the highest index: it is the last tile of the CTA that owns it
+    const bool own_partial = n_staged > n_full && n_full % grid == cta;
+    const int mine_full = mine - (own_partial ? 1 : 0);
     const bool producer = warp == kThreads / 32;
 
     // PDL: the next step's grid may start its prologue now; this grid touches global memory only after every
@@ -626,7 +697,6 @@ __global__ void __launch_bounds__(kThreads + kProducerThreads, block_ctas_per_sm
     }
     griddep_wait();
     if (mine > 0) {
-
         if (producer) {
             // one lane per input tensor; lanes beyond n_inputs idle (SKR_MAX_INPUTS == 32 == warp size)
             const bool active = lane < prog.n_inputs;
@@ -638,13 +708,31 @@ __global__ void __launch_bounds__(kThreads + kProducerThreads, block_ctas_per_sm
             const size_t stride = (size_t)grid * bytes;
             int s = 0;
             uint32_t phase = 1;  // a fresh "empty" barrier counts as already released
-            for (int k = 0; k < mine; ++k) {
+            for (int k = 0; k < mine_full; ++k) {
                 mbar_wait(&empty_bar[s], phase);
                 if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
                 __syncwarp();
                 if (active) tma_load_1d(dst + (size_t)s * stage_bytes, src, bytes, &full_bar[s]);
                 src += stride;
                 if (++s == stages) { s = 0; phase ^= 1u; }
+            }
+            if (own_partial) {
+                // The ragged tail: a bulk copy moves multiples of 16 bytes, so each lane brings the whole 16-byte
+                // chunks of its tensor's tail by TMA and the few elements after them with ordinary loads.  The
+                // consumers then run the same staged code as for every other tile.
+                mbar_wait(&empty_bar[s], phase);
+                unsigned char* to = dst + (size_t)s * stage_bytes;
+                const uint32_t real = (uint32_t)prog.tail_elems * esize;
+                const uint32_t bulk = real & ~15u;
+                for (uint32_t at = bulk; at < real; at += 2u)  // element sizes are multiples of 2 bytes
+                    *reinterpret_cast<uint16_t*>(to + at) = *reinterpret_cast<const uint16_t*>(src + at);
+                uint32_t total = bulk;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+                __syncwarp();  // the stores above are ordered before lane 0's arrive (release) below
+                if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], total);
+                __syncwarp();
+                if (active && bulk) tma_load_1d(to, src, bulk, &full_bar[s]);
             }
         } else {
             int s = 0;
@@ -653,20 +741,26 @@ __global__ void __launch_bounds__(kThreads + kProducerThreads, block_ctas_per_sm
             const int64_t stride = (int64_t)grid * TILE;
             const uint32_t smem_addr = (uint32_t)__cvta_generic_to_shared(smem);
             uint32_t stage_addr = smem_addr;
-            for (int k = 0; k < mine; ++k) {
+            for (int k = 0; k < mine_full; ++k) {
                 mbar_wait(&full_bar[s], phase);
-                run_block_tile<CT, MODE, V, false, PHILOX, Sh>(prog, first, stage_addr, tid);
+                run_block_tile<CT, MODE, V, TP_STAGED, PHILOX, Sh>(prog, first, stage_addr, tid);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[s]);
                 first += stride;
                 stage_addr += stage_bytes;
                 if (++s == stages) { s = 0; phase ^= 1u; stage_addr = smem_addr; }
             }
+            if (own_partial) {
+                mbar_wait(&full_bar[s], phase);
+                if (first < prog.numel) run_block_tile<CT, MODE, V, TP_STAGED, PHILOX, Sh, true>(prog, first, stage_addr, tid);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
+            }
         }
     }
-    if (!producer) {
+    if (!producer && !prog.use_tma) {  // unaligned tensors or a stage that does not fit: everything element-wise
         const int64_t n_tiles = (prog.numel + TILE - 1) / TILE;
-        if ((int64_t)n_full < n_tiles) run_guarded_tiles<CT, MODE, V, PHILOX>(prog, n_full, n_tiles, tid);
+        run_guarded_tiles<CT, MODE, V, PHILOX>(prog, 0, n_tiles, tid);
     }
 }
 

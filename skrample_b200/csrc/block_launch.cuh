@@ -38,15 +38,17 @@ static int launch_block_one(const skr_program* p, BProgram<CT>& k, int64_t numel
     const int64_t n_full = numel / TILE;
     if (n_full > 0x7fffffff) return fail(SKR_E_RANGE, "numel too large");
     PipeShape sh = pick_shape(off, dev->max_smem, block_ctas_per_sm<CT, V, Sh>());
-    k.use_tma = (aligned && n_full > 0 && sh.ok) ? 1u : 0u;
+    k.use_tma = (aligned && n_tiles > 0 && sh.ok) ? 1u : 0u;
     k.n_full_tiles = (int32_t)n_full;
+    k.tail_elems = (int32_t)(numel - n_full * TILE);
+    k.vec_ok = aligned ? 1 : 0;
     k.stages = sh.stages;
     size_t smem = k.use_tma ? (size_t)sh.stages * off : 0;
 
     int64_t grid;
     if (k.use_tma) {
         grid = (int64_t)dev->sm_count * sh.ctas_per_sm;
-        if (grid > n_full) grid = n_full;
+        if (grid > n_tiles) grid = n_tiles;  // the ragged last tile is staged like the others
     } else {
         grid = n_tiles < (int64_t)dev->sm_count * 8 ? n_tiles : (int64_t)dev->sm_count * 8;
     }

@@ -156,12 +156,12 @@ def regularize[T: Sample](normal: T, start: float, end: float = 0) -> T:
 
 
 def rescale_positive(x: float) -> float:
-    "-inf..inf -> 0..inf"
+    "Monotone map of the real line onto (0, inf) with 0 -> 1: (|x| + 1) ** sign(x)."
     return (abs(x) + 1) ** math.copysign(1, x)
 
 
 def rescale_subnormal(x: float) -> float:
-    "-inf..inf -> -1..1"
+    "Monotone map of the real line onto (-1, 1) with 0 -> 0."
     return math.copysign(1 - (abs(x) + 1) ** -1, x)
 
 

@@ -322,6 +322,20 @@ class SkrampleWrapperCore(abc.ABC):
         self._handed_out = [*self._handed_out[-3:], (tensor, tensor.data_ptr(), pitch, tensor._version, values.tolist())]
         return tensor
 
+    def _adopt_step_count(self, steps: int | None, timesteps: Any, sigmas: Any, mu: float | None) -> bool:
+        """Shared part of ``set_timesteps``: the step count is given or is the length of a custom timestep / sigma
+        list (their values are ignored, as in the reference: diffusers.py:494-520); then the schedule is re-derived
+        for that count when it is allowed to depend on it.  False when nothing was given."""
+        if steps is None:
+            given = timesteps if timesteps is not None else sigmas
+            if given is None:
+                return False
+            steps = len(given)
+        self._steps = steps
+        if self.allow_dynamic:
+            self.schedule = _dynamic_schedule(self.schedule, steps, mu)  # type: ignore[attr-defined]
+        return True
+
     def _index_without_sync(self, timestep: Tensor) -> int | None:
         "Index of a one-element view of a timesteps tensor this wrapper handed out, or None."
         if timestep.numel() != 1 or timestep.dtype != torch.float64:
@@ -567,16 +581,8 @@ class SkrampleWrapperScheduler[T: TensorNoiseProps | None](SkrampleWrapperCore):
     ) -> None:
         self._index = 0
         self.schedule = self._schedule
-        if num_inference_steps is None:
-            if timesteps is not None:
-                num_inference_steps = len(timesteps)
-            elif sigmas is not None:
-                num_inference_steps = len(sigmas)
-            else:
-                return
-        self._steps = num_inference_steps
-        if self.allow_dynamic:
-            self.schedule = _dynamic_schedule(self.schedule, self._steps, mu)
+        if not self._adopt_step_count(num_inference_steps, timesteps, sigmas, mu):
+            return
         self._previous = []
         self._noise_generator = None
         if device is not None:
@@ -728,16 +734,8 @@ class RKWrapperCore[T: TensorNoiseProps | None, U: functional.FunctionalUnified]
             del self.all_points
             del self.schedule_np_trim
         self.schedule = self._schedule
-        if num_inference_steps is None:
-            if timesteps is not None:
-                num_inference_steps = len(timesteps)
-            elif sigmas is not None:
-                num_inference_steps = len(sigmas)
-            else:
-                return
-        self._steps = num_inference_steps
-        if self.allow_dynamic:
-            self.schedule = _dynamic_schedule(self.schedule, self._steps, mu)
+        if not self._adopt_step_count(num_inference_steps, timesteps, sigmas, mu):
+            return
         self._noise_generator = None
         if device is not None:
             self._device = torch.device(device)

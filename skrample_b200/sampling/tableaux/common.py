@@ -67,22 +67,27 @@ class ButcherCoeffs:
 
     @classmethod
     def deserialize(cls, coeffs: list[float], stages: int, compute_c: bool = False, b_last: bool = True) -> Self:
-        "Read a flat coefficient list laid out as [c...] [b... if not b_last] a-rows [b... if b_last]."
-        t = cls.empty(stages)
-        expected = len(t.c) * (not compute_c) + len(t.b) + sum(len(row) for row in t.a)
-        assert len(coeffs) == expected
-        feed = iter(coeffs)
+        """Read a flat coefficient list: nodes (unless ``compute_c``), then the weights either before or after the
+        coupling rows, rows in order without the empty first one."""
+        table = cls.empty(stages)
+        pending = list(reversed(coeffs))
+
+        def take(target: MutableSequence[float]) -> None:
+            for slot in range(len(target)):
+                target[slot] = pending.pop()
+
         if not compute_c:
-            t.c[:] = [next(feed) for _ in t.c]
+            take(table.c)
         if not b_last:
-            t.b[:] = [next(feed) for _ in t.b]
-        for row in t.a[1:]:
-            row[:] = [next(feed) for _ in row]
-        if compute_c:
-            t.compute_c()
+            take(table.b)
+        for row in table.a[1:]:
+            take(row)
         if b_last:
-            t.b[:] = [next(feed) for _ in t.b]
-        return t
+            take(table.b)
+        assert not pending, f"{len(pending)} coefficients left over for a {stages}-stage tableau"
+        if compute_c:
+            table.compute_c()
+        return table
 
     def serialize(self) -> Sequence[float]:
         return [*self.c, *(x for row in self.a for x in row), *self.b]
@@ -106,26 +111,34 @@ class ButcherCoeffs:
 
 
 def pretty_tableau(tableau: TableauType, label: str | None = None) -> str:
-    def cell(x: float) -> str:
-        return f"{'+' if x >= 0 else '-'}{float(round(abs(x), 4)): <6}"
+    "The tableau as text: one line per stage (node | couplings), a rule, one line per weight row."
 
-    rows = [f"{cell(c)} | {' '.join(cell(x) for x in a)}" for c, a in tableau[0]]
-    sums = ["        | " + " ".join(cell(x) for x in w) for w in tableau[1:]]
-    width = max(len(line) for line in (*sums, *rows))
-    head = [label.rjust((width + len(label)) // 2)] if label is not None else []
-    return "\n".join([*head, *rows, "-" * width, *sums])
+    def cell(value: float) -> str:
+        sign = "-" if value < 0 else "+"
+        return f"{sign}{float(round(abs(value), 4)):<6}"
+
+    body = [f"{cell(stage.c)} | {' '.join(map(cell, stage.a))}" for stage in tableau[0]]
+    foot = [" " * 8 + "| " + " ".join(map(cell, row)) for row in tableau[1:]]
+    width = max(map(len, body + foot))
+    title = [] if label is None else [label.rjust((width + len(label)) // 2)]
+    return "\n".join(title + body + ["-" * width] + foot)
 
 
 def validate_tableau(tab: TableauType, tolerance: float = 1e-12) -> IndexError | ValueError | None:
-    "Structural (lower-triangular) and consistency (row sums, weight sums) checks."
-    for index, stage in enumerate(tab.stages):
-        if index != (stage_len := len(stage.a)):
-            return IndexError(f"{index=}, {stage_len=}, {stage=}")
-        if tolerance < (stage_err := abs(stage.c - math.fsum(stage[1]))):
-            return ValueError(f"{tolerance=}, {stage_err=}, {stage=}")
-    for weight in tab[1:]:
-        if (stage_count := len(tab.stages)) != (weight_len := len(weight)):
-            return IndexError(f"{stage_count=}, {weight_len=}, {weight=}")
-        if tolerance < (weight_err := abs(1 - math.fsum(weight))):
-            return ValueError(f"{tolerance=}, {weight_err=}, {weight=}")
+    """None for a well-formed explicit tableau, else the problem as an exception instance (returned, not raised, like
+    the reference): IndexError for a shape problem (stage i needs i couplings, every weight row one entry per stage),
+    ValueError for an inconsistent one (node != sum of its row, weights not summing to 1)."""
+    count = len(tab.stages)
+    for position, (node, couplings) in enumerate(tab.stages):
+        if len(couplings) != position:
+            return IndexError(f"stage {position} has {len(couplings)} couplings, an explicit method needs {position}: {couplings}")
+        defect = abs(node - math.fsum(couplings))
+        if defect > tolerance:
+            return ValueError(f"stage {position}: node {node} differs from its row sum by {defect} (tolerance {tolerance})")
+    for row_number, row in enumerate(tab[1:]):
+        if len(row) != count:
+            return IndexError(f"weight row {row_number} has {len(row)} entries for {count} stages: {row}")
+        defect = abs(1 - math.fsum(row))
+        if defect > tolerance:
+            return ValueError(f"weight row {row_number} sums to 1 with defect {defect} (tolerance {tolerance}): {row}")
     return None

@@ -1,57 +1,64 @@
 """Mix-in traits shared by structured and functional samplers.
 
-reference: skrample/sampling/traits.py:9-61 (field names, defaults and MRO are
-part of the plugin API - samplers are frozen, hashable dataclasses compared
-with ``==`` - so they are kept as is).
+The names, field order, defaults and base-class order below are the plugin API of the reference
+(skrample/sampling/traits.py:9-61): samplers are frozen, hashable dataclasses that users construct by keyword
+and compare with ``==``, so those must not drift.  Everything else about this module is local.
 """
 
 from __future__ import annotations
 
-import abc
-import dataclasses
+from abc import ABC, abstractmethod
+from dataclasses import dataclass
 
-from skrample_b200 import common
+from skrample_b200.common import Point, Sample
 
-from . import models
+from .models import DataModel, DiffusionModel
+
+frozen = dataclass(frozen=True)
 
 
-@dataclasses.dataclass(frozen=True)
+@frozen
 class SamplingCommon:
-    def add_noise[T: common.Sample](self, sample: T, noise: T, point: common.Point) -> T:
-        "``sample*alpha + noise*sigma`` at ``point`` (one fused launch for device tensors)."
+    "Noise mixing at a schedule point; device tensors take one fused launch (skr_axpby)."
+
+    def add_noise[T: Sample](self, sample: T, noise: T, point: Point) -> T:
+        "``sample * alpha + noise * sigma``"
         return point.add_noise(sample, noise)
 
-    def remove_noise[T: common.Sample](self, sample: T, noise: T, point: common.Point) -> T:
-        "Inverse of :meth:`add_noise`."
+    def remove_noise[T: Sample](self, sample: T, noise: T, point: Point) -> T:
+        "``(sample - noise * sigma) / alpha``"
         return point.remove_noise(sample, noise)
 
 
-@dataclasses.dataclass(frozen=True)
-class HigherOrder(abc.ABC):
+@frozen
+class HigherOrder(ABC):
+    "Samplers with a selectable order; the order effective at a step can be lower (warm-up, end of schedule)."
+
     order: int = 2
-    "Requested solver order; the order actually used at a step can be lower."
 
     @staticmethod
     def min_order() -> int:
         return 1
 
     @staticmethod
-    @abc.abstractmethod
+    @abstractmethod
     def max_order() -> int: ...
 
 
-@dataclasses.dataclass(frozen=True)
+@frozen
 class Stochastic:
+    "``stochasticity`` 0 solves the ODE, 1 the fully stochastic SDE."
+
     stochasticity: float = 0
-    "0 = deterministic ODE, 1 = fully stochastic SDE"
 
 
-@dataclasses.dataclass(frozen=True)
+@frozen
 class DerivativeTransform:
-    derivative_transform: models.DiffusionModel | None = models.DataModel()  # noqa: RUF009 - immutable
-    "Space the solver combines predictions in."
+    "Samplers that may combine predictions in a model space other than the network's own."
+
+    derivative_transform: DiffusionModel | None = DataModel()  # noqa: RUF009 - frozen instance, safe to share
 
 
-@dataclasses.dataclass(frozen=True)
+@frozen
 class UnifiedModelling(DerivativeTransform, Stochastic, HigherOrder):
-    "Order + stochasticity + derivative space, in the reference's field order."
+    "Derivative space + stochasticity + order: the usual combination, with the reference's resolution order."

@@ -290,3 +290,38 @@ def test_full_size_video_latent_adams9_subset_vs_oracle(generator: str) -> None:
         got = res.final.flatten()[pick].float().cpu().numpy()
         assert np.array_equal(got, want), f"step {n}: {int((got != want).sum())} of {got.size} differ"
         x, x_o = res.final, want
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["f32", "bf16"])
+@pytest.mark.parametrize("numel", [5, 1023, 1024 + 8, 3 * 1024 + 11, 148 * 4 * 1024 + 1001], ids=lambda n: f"n{n}")
+def test_ragged_sizes_never_write_past_the_end(numel: int, dtype: torch.dtype, kernel_kind: int) -> None:
+    """Outputs handed to the C ABI as slices of sentinel-filled buffers: whatever path the ragged last tile takes
+    (staged partial tile, vector threads, element-wise thread), nothing outside [0, numel) is written."""
+    import ctypes
+
+    from skrample_b200 import native
+    from skrample_b200.sampling import program as pg
+
+    pad = 64  # elements of sentinel on both sides; keeps the slices 16-byte aligned
+    g = torch.Generator(device="cuda").manual_seed(numel)
+    x, y, z = (torch.randn(numel, device="cuda", generator=g).to(dtype) for _ in range(3))
+    program = pg.Program()
+    program.load(pg.X, x)
+    program.conv(pg.ConvSpec(pg.CONV_USE_X | pg.CONV_MUL_Y | pg.CONV_DIV, 0.0, 0.7, 1.3), y)
+    program.store(pg.P, "compute")
+    program.fwd(0.9, 0.2, pred=pg.P, noise=z, zeta=0.3)
+    program.store(pg.R)
+    sentinel = 12345.0
+    buffers = [torch.full((numel + 2 * pad,), sentinel, device="cuda", dtype=torch.float32), torch.full((numel + 2 * pad,), sentinel, device="cuda", dtype=dtype)]
+    outs = [b[pad : pad + numel] for b in buffers]
+    packed = native.pack_program(program, [x, y, z], outs)
+    status = native.load().skr_program_launch(ctypes.byref(packed), numel, native.raw_stream())
+    native.check(status, "skr_program_launch")
+    torch.cuda.synchronize()
+    for buffer in buffers:
+        assert torch.all(buffer[:pad] == sentinel) and torch.all(buffer[pad + numel :] == sentinel), "wrote outside the tensor"
+    xc, yc, zc = x.cpu().float(), y.cpu().float(), z.cpu().float()  # torch's CPU ops are the reference's arithmetic
+    xhat = (xc - yc * 0.7) / 1.3
+    assert torch.equal(outs[0].cpu(), xhat)
+    want = ((0 + xc * 0.9) + xhat * 0.2) + zc * 0.3
+    assert torch.equal(outs[1].cpu(), want.to(dtype))

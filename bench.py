@@ -398,7 +398,7 @@ def e2e_throughput(spec: dict, device: torch.device, steps: int, warmup: int) ->
         pred = host_pred[n].to(device, non_blocking=True)
         noise = None
         if traj.sampler.require_noise:  # fresh noise every step, generated on the device (fill kernel or in-step draw)
-            noise = traj.noise_source.generate(None) if SUPPLIED_NOISE else traj.noise_source.lazy(None)
+            noise = traj.noise_source.auto(None) if SUPPLIED_NOISE else traj.noise_source.lazy(None)
         final = traj.step(pred, noise)
         result_host.copy_(final, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller consumes the result before the next step
@@ -693,7 +693,7 @@ def main() -> None:
             "sampler_step_GBps": e2e_gbs,
             "ms_per_step": e2e_elapsed / e2e_steps * 1e3,
             "steps": e2e_steps,
-            "api": "structured sampler .sample() per step (the reference's call), pinned-host prediction in, result out",
+            "api": "structured sampler .sample() per step (the reference's call), pinned-host prediction in, result out; noise from BatchTensorNoise.auto (in-kernel Philox draw at this size)",
         },
         "e2e_graphed": {
             "value": e2e_steps * spec["shape"][0] * world / graphed_elapsed,

@@ -387,3 +387,17 @@ def test_in_kernel_noise_unaligned_items() -> None:
     a = sampler.sample(x, o, Step.from_int(2, 9), models.FlowModel(), scheduling.Linear(), drawn)
     b = sampler.sample(x, o, Step.from_int(2, 9), models.FlowModel(), scheduling.Linear(), drawn.materialize())
     assert torch.equal(a.final, b.final)
+
+
+@gpu
+def test_batch_auto_picks_in_kernel_draws_for_small_batches_only() -> None:
+    "BatchTensorNoise.auto: Philox keys below the size threshold, a filled tensor above; identical values either way."
+    small = noise.BatchTensorNoise.from_batch_inputs(noise.Random, (4, 64, 64), [_gen(3), _gen(4)])
+    twin = noise.BatchTensorNoise.from_batch_inputs(noise.Random, (4, 64, 64), [_gen(3), _gen(4)])
+    drawn = small.auto(None)
+    assert getattr(drawn, "is_lazy_noise", False)
+    assert torch.equal(drawn.materialize(), twin.generate(None))
+    big = noise.BatchTensorNoise.from_batch_inputs(noise.Random, (16, 256, 256), [_gen(5), _gen(6)])
+    assert isinstance(big.auto(None), torch.Tensor)
+    mixed = noise.BatchTensorNoise([noise.Random.from_inputs((8,), _gen(1)), noise.Offset.from_inputs((8,), _gen(2))])
+    assert isinstance(mixed.auto(None), torch.Tensor)

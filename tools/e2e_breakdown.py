@@ -28,7 +28,7 @@ def one(record: bool) -> None:
     t.append(time.perf_counter())
     noise = None
     if traj.sampler.require_noise:
-        noise = traj.noise_source.generate(None) if bench.SUPPLIED_NOISE else traj.noise_source.lazy(None)
+        noise = traj.noise_source.auto(None) if bench.SUPPLIED_NOISE else traj.noise_source.lazy(None)
     t.append(time.perf_counter())
     final = traj.step(pred, noise)
     t.append(time.perf_counter())

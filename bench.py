@@ -367,7 +367,7 @@ def noise_generator_times(device: torch.device, unit: tuple[int, ...] = (16, 21,
 
     rows = []
     step = Step.from_int(5, STEPS_PER_TRAJECTORY)
-    for name, props in (("Random", None), ("Offset", noise.OffsetProps()), ("Pyramid", noise.PyramidProps()), ("Colored", noise.ColoredProps())):
+    for name, props in (("Random", None), ("Offset", noise.OffsetProps()), ("Pyramid", noise.PyramidProps()), ("Colored", noise.ColoredProps()), ("Brownian", noise.BrownianProps())):
         cls = getattr(noise, name)
         generator = torch.Generator(device=device).manual_seed(1)
         source = cls.from_inputs(unit, generator, dtype=torch.float32) if props is None else cls.from_inputs(unit, generator, props, dtype=torch.float32)

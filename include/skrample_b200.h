@@ -46,6 +46,7 @@ extern "C" {
 #define SKR_MAX_PHILOX 2
 #define SKR_MAX_PHILOX_ITEMS 32
 #define SKR_MAX_LEVELS 16
+#define SKR_BROWNIAN_MAX_DEPTH 40
 
 /* element types */
 enum { SKR_F32 = 0, SKR_F64 = 1, SKR_BF16 = 2, SKR_F16 = 3 };
@@ -204,6 +205,18 @@ int skr_noise_fill(void* out, int32_t dtype, int64_t numel, uint64_t seed, uint6
  * (noise.py:445-446).  numel = keys->n_items * keys->item_numel.
  */
 int skr_noise_fill_batch(void* out, int32_t dtype, const skr_philox* keys, void* cuda_stream);
+
+/*
+ * Brownian (noise.py:210-252; the reference delegates to torchsde.BrownianInterval(t0=0, t1=1, entropy=seed,
+ * tol=1/(10*max_steps))): out = (W(t1) - W(t0)) * out_scale for the Brownian path W keyed by `seed` alone, so the
+ * same (seed, t0, t1) gives the same tensor on every call, increments over adjoining intervals add up and
+ * increments over disjoint intervals are independent.  W is a Levy bridge tree over dyadic intervals of 0..1,
+ * `depth` levels deep (leaf width 2^-depth plays torchsde's `tol`), node draws = Philox streams 1<<63 | heap
+ * index, one exact bridge draw inside the leaf.  0 <= t0 < t1 <= 1, 1 <= depth <= SKR_BROWNIAN_MAX_DEPTH.
+ * Values are this library's own (torchsde is not available to pin against): parity is statistical.
+ */
+int skr_noise_brownian(void* out, int32_t dtype, int64_t numel, uint64_t seed, double t0, double t1, int32_t depth,
+                       double out_scale, void* cuda_stream);
 
 /* sum / sum^2 of a tensor into device double[2] (pre-zeroed), for Tensor.std() (noise.py:207,365,401). */
 int skr_noise_moments(const void* in, int32_t dtype, int64_t numel, double* moments, void* cuda_stream);

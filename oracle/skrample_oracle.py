@@ -733,3 +733,72 @@ def pyramid_compose(base: np.ndarray, levels: Sequence[np.ndarray], mask: Sequen
         total = total + upsample_linear(level, base.shape, mask) * np.float32(strength**l)
     noise = base.astype(np.float32) + total
     return noise / noise.std(ddof=1)
+
+
+# --------------------------------------------------------------------------------------------
+# Brownian interval noise (reference: skrample/pytorch/noise.py:210-252)
+#
+# PARITY UNPINNED for the values: the reference delegates to the third-party module torchsde
+# (``torchsde>=0.2.6``, pyproject.toml:22; not under /root/reference, not installed), whose interval tree
+# derives its draws from numpy SeedSequence spawning.  What the reference's call site fixes is the contract:
+# ``tree(t0, t1) / sqrt(t1 - t0)`` is a standard normal tensor that is a deterministic function of
+# (entropy, t0, t1), increments over adjoining intervals add up, increments over disjoint intervals are
+# independent.  The product keeps that contract with its own counter-based construction (a Levy bridge tree
+# over dyadic intervals of 0..1 with Philox4x32-10 node draws); this restates that published construction in
+# float64 with ABSOLUTE path values W(t) - an independent route to the same numbers the kernel reaches through
+# relative increments in float32 - so the tree indexing, bridge variances and stream layout are checked
+# element by element, and the contract itself through statistics.
+
+
+def philox4x32_10(counter: np.ndarray, key: tuple[int, int]) -> np.ndarray:
+    "Philox4x32-10 (Salmon et al. 2011) on rows of four uint32 counters; returns rows of four uint32."
+    c = [counter[:, i].astype(np.uint64) for i in range(4)]
+    k0, k1 = np.uint64(key[0]), np.uint64(key[1])
+    m0, m1, mask = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = m0 * c[0], m1 * c[2]
+        c = [(p1 >> np.uint64(32)) ^ c[1] ^ k0, p1 & mask, (p0 >> np.uint64(32)) ^ c[3] ^ k1, p0 & mask]
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & mask, (k1 + np.uint64(0xBB67AE85)) & mask
+    return np.stack(c, axis=1).astype(np.uint32)
+
+
+def philox_normals(seed: int, stream: int, numel: int) -> np.ndarray:
+    """The standard normals of Philox stream (seed, stream): counter = (element // 4, stream), two Box-Muller
+    pairs per block, uniforms (x + 0.5) / 2^32 formed in float32 as the kernels form them."""
+    groups = (numel + 3) // 4
+    index = np.arange(groups, dtype=np.uint64)
+    counter = np.stack(
+        [index & np.uint64(0xFFFFFFFF), index >> np.uint64(32), np.full(groups, stream & 0xFFFFFFFF, np.uint64), np.full(groups, stream >> 32, np.uint64)],
+        axis=1,
+    )
+    bits = philox4x32_10(counter, (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF))
+    u = (bits.astype(np.float32) * np.float32(2.0**-32) + np.float32(2.0**-33)).astype(np.float64)
+    radius0, radius1 = np.sqrt(-2.0 * np.log(u[:, 0])), np.sqrt(-2.0 * np.log(u[:, 2]))
+    angle0, angle1 = 2.0 * np.pi * u[:, 1], 2.0 * np.pi * u[:, 3]
+    z = np.stack([radius0 * np.sin(angle0), radius0 * np.cos(angle0), radius1 * np.sin(angle1), radius1 * np.cos(angle1)], axis=1)
+    return z.reshape(-1)[:numel]
+
+
+BROWNIAN_TREE, BROWNIAN_LEAF = 1 << 63, 1 << 62
+
+
+def brownian_path(seed: int, t: float, depth: int, numel: int) -> np.ndarray:
+    "W(t) of the seed's Brownian path (W(0) = 0, W(1) = the root draw), by midpoint bridges down to the leaf."
+    left, right = 0.0, 1.0
+    w_left, w_right = np.zeros(numel), philox_normals(seed, BROWNIAN_TREE, numel)
+    node = 1
+    for _ in range(depth):
+        mid = 0.5 * (left + right)
+        w_mid = 0.5 * (w_left + w_right) + 0.5 * math.sqrt(right - left) * philox_normals(seed, BROWNIAN_TREE | node, numel)
+        if t >= mid:
+            left, w_left, node = mid, w_mid, 2 * node + 1
+        else:
+            right, w_right, node = mid, w_mid, 2 * node
+    width = right - left
+    deviation = math.sqrt((t - left) * (right - t) / width)
+    return w_left + (t - left) / width * (w_right - w_left) + deviation * philox_normals(seed, BROWNIAN_TREE | BROWNIAN_LEAF | node, numel)
+
+
+def brownian_increment(seed: int, t0: float, t1: float, depth: int, numel: int) -> np.ndarray:
+    "``tree(t0, t1) / sqrt(t1 - t0)`` of noise.py:244-245 for the construction above."
+    return (brownian_path(seed, t1, depth, numel) - brownian_path(seed, t0, depth, numel)) / math.sqrt(t1 - t0)

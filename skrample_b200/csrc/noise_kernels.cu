@@ -6,6 +6,8 @@
 //   skr_noise_pyramid   Pyramid: base + full-resolution level + bilinear-upsampled coarse levels, evaluated
 //                       per element from Philox streams (or supplied buffers), two passes: moments, then
 //                       regenerate + normalise + write - the N-sized intermediate is never stored.
+//   skr_noise_brownian  Brownian: increment of a seed-keyed Brownian path over (t0, t1), a stateless Philox
+//                       bridge tree evaluated per element (replaces torchsde's interval tree on CUDA).
 //   skr_noise_moments   sum / sum^2 of a tensor (for std), warp-shuffle + block reduction, fp64 partials.
 //   skr_noise_scale     out = in * scale (in place allowed), storage-dtype aware.
 //   skr_colored_shape   in-place spectral shaping of an rfftn half-spectrum: multiply each complex bin by
@@ -18,6 +20,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 
@@ -524,6 +527,106 @@ __global__ void __launch_bounds__(256) colored_shape_kernel(const __grid_constan
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Brownian interval   (reference: noise.py:210-252 - torchsde.BrownianInterval over normalised time 0..1)
+//
+// A stateless Levy construction: the increment of a dyadic interval splits into its two halves as
+// d/2 +- sqrt(h)/2 * Z(node), Z(node) = the Philox normals of stream (1 << 63 | heap index of the node).  A query
+// W(t1) - W(t0) walks the tree from the root: while both times fall in the same half only the interval's
+// increment is tracked; below the node that separates them each time descends as a Brownian bridge whose end
+// values are kept RELATIVE to the separating midpoint (so fp32 keeps the precision of the small increment),
+// and inside its leaf (width 2^-depth) each time is placed by one exact bridge draw.  Every (seed, t0, t1)
+// therefore gives the same tensor whenever and wherever it is asked for, increments over adjoining intervals
+// add up, and increments over disjoint intervals are independent.  The host builds the walk; the kernel
+// evaluates it for four elements per thread, one Philox block per visited node.
+
+struct BrownianNode {
+    uint64_t stream;
+    float scale;    // sqrt(width)/2 of the node's interval (signed in the shared prefix: + left half, - right half)
+    int32_t right;  // the walk continues in the right half
+};
+
+struct BrownianWalk {
+    BrownianNode node[SKR_BROWNIAN_MAX_DEPTH];
+    uint64_t leaf_stream;
+    float frac, sd;  // position inside the leaf and the bridge deviation there
+    int32_t n;
+    int32_t pad;
+};
+
+struct BrownianParams {
+    void* out;
+    int64_t numel;
+    uint64_t seed, root_stream;
+    BrownianNode prefix[SKR_BROWNIAN_MAX_DEPTH];
+    BrownianNode split;
+    BrownianWalk from, to;
+    int32_t n_prefix, same_leaf, dtype, aligned;
+    float out_scale;
+};
+
+__device__ __forceinline__ void brownian_descend(const Philox& ph, uint64_t g, const BrownianWalk& w, float (&lo)[4], float (&hi)[4],
+                                                 float (&at)[4]) {
+    float z[4];
+    for (int k = 0; k < w.n; ++k) {
+        normal4(ph(g, w.node[k].stream), z);
+        const float s = w.node[k].scale;
+        const bool right = w.node[k].right != 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float mid = 0.5f * (lo[j] + hi[j]) + s * z[j];
+            lo[j] = right ? mid : lo[j];
+            hi[j] = right ? hi[j] : mid;
+        }
+    }
+    normal4(ph(g, w.leaf_stream), z);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) at[j] = (lo[j] + w.frac * (hi[j] - lo[j])) + w.sd * z[j];
+}
+
+__global__ void __launch_bounds__(256) brownian_kernel(const __grid_constant__ BrownianParams p) {
+    const Philox ph(p.seed);
+    const int64_t groups = (p.numel + 3) >> 2;
+    for (int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t g = (uint64_t)gi;
+        float d[4], z[4], v[4];
+        normal4(ph(g, p.root_stream), d);  // W(1) - W(0)
+        for (int k = 0; k < p.n_prefix; ++k) {
+            normal4(ph(g, p.prefix[k].stream), z);
+            const float s = p.prefix[k].scale;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) d[j] = 0.5f * d[j] + s * z[j];
+        }
+        if (p.same_leaf) {
+            // both times inside one leaf: frac / sd hold the differences of the two placements
+            normal4(ph(g, p.to.leaf_stream), z);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = (p.to.frac * d[j] + p.to.sd * z[j]) * p.out_scale;
+        } else {
+            normal4(ph(g, p.split.stream), z);
+            float lo[4], hi[4], w_from[4], w_to[4];
+            // left half [l, m]: values relative to W(m)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { lo[j] = -(0.5f * d[j] + p.split.scale * z[j]); hi[j] = 0.0f; }
+            float right_end[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) right_end[j] = 0.5f * d[j] - p.split.scale * z[j];
+            brownian_descend(ph, g, p.from, lo, hi, w_from);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { lo[j] = 0.0f; hi[j] = right_end[j]; }
+            brownian_descend(ph, g, p.to, lo, hi, w_to);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = (w_to[j] - w_from[j]) * p.out_scale;
+        }
+        const int64_t first = gi << 2;
+        if (p.aligned && first + 4 <= p.numel) {
+            store4(p.out, p.dtype, first, v);
+        } else {
+            for (int j = 0; j < 4 && first + j < p.numel; ++j) store1(p.out, p.dtype, first + j, v[j]);
+        }
+    }
+}
+
 static unsigned grid_for(int64_t work_items, int threads) {
     const int64_t sms = sm_count_or(148);
     int64_t blocks = (work_items + threads - 1) / threads;
@@ -599,6 +702,60 @@ int skr_noise_fill_batch(void* out, int32_t dtype, const skr_philox* keys, void*
     fill_kphilox(&p.keys, keys, 1);
     batch_fill_kernel<<<grid_for((numel + 3) / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
     return check_launch("noise batch fill");
+}
+
+int skr_noise_brownian(void* out, int32_t dtype, int64_t numel, uint64_t seed, double t0, double t1, int32_t depth, double out_scale,
+                       void* cuda_stream) {
+    using namespace skr;
+    if (numel < 0) return fail(SKR_E_RANGE, "negative numel");
+    if (dtype < 0 || dtype > SKR_F16) return fail(SKR_E_DTYPE, "unknown dtype %d", dtype);
+    if (depth < 1 || depth > SKR_BROWNIAN_MAX_DEPTH) return fail(SKR_E_RANGE, "brownian depth %d outside 1..%d", depth, SKR_BROWNIAN_MAX_DEPTH);
+    if (!(t0 >= 0.0 && t1 <= 1.0 && t0 < t1)) return fail(SKR_E_RANGE, "brownian interval needs 0 <= t0 < t1 <= 1");
+    if (numel == 0) return 0;
+    if (!out) return fail(SKR_E_NULL, "null output");
+    BrownianParams p;
+    memset(&p, 0, sizeof(p));
+    p.out = out; p.numel = numel; p.seed = seed; p.dtype = dtype; p.out_scale = (float)out_scale;
+    p.aligned = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+    const uint64_t tree = 1ull << 63, leaf = 1ull << 62;
+    p.root_stream = tree;  // heap index 0 is unused by the nodes (the root interval is index 1)
+    // interval ends are k / 2^level: exact in double for every depth allowed here
+    double l = 0.0, r = 1.0;
+    uint64_t node = 1;
+    int level = 0;
+    for (; level < depth; ++level) {
+        const double m = 0.5 * (l + r);
+        const bool from_right = t0 >= m, to_right = t1 >= m;
+        if (from_right != to_right) break;
+        const float s = (float)(0.5 * sqrt(r - l));
+        p.prefix[p.n_prefix++] = BrownianNode{tree | node, from_right ? -s : s, from_right ? 1 : 0};
+        if (from_right) { l = m; node = 2 * node + 1; } else { r = m; node = 2 * node; }
+    }
+    if (level == depth) {
+        const double h = r - l;
+        p.same_leaf = 1;
+        p.to.leaf_stream = tree | leaf | node;
+        p.to.frac = (float)((t1 - t0) / h);
+        p.to.sd = (float)(sqrt((t1 - l) * (r - t1) / h) - sqrt((t0 - l) * (r - t0) / h));
+    } else {
+        const double m = 0.5 * (l + r);
+        p.split = BrownianNode{tree | node, (float)(0.5 * sqrt(r - l)), 0};
+        struct Side { BrownianWalk* walk; double t, l, r; uint64_t node; } sides[2] = {{&p.from, t0, l, m, 2 * node}, {&p.to, t1, m, r, 2 * node + 1}};
+        for (Side& side : sides) {
+            for (int k = level + 1; k < depth; ++k) {
+                const double mid = 0.5 * (side.l + side.r);
+                const bool right = side.t >= mid;
+                side.walk->node[side.walk->n++] = BrownianNode{tree | side.node, (float)(0.5 * sqrt(side.r - side.l)), right ? 1 : 0};
+                if (right) { side.l = mid; side.node = 2 * side.node + 1; } else { side.r = mid; side.node = 2 * side.node; }
+            }
+            const double h = side.r - side.l;
+            side.walk->leaf_stream = tree | leaf | side.node;
+            side.walk->frac = (float)((side.t - side.l) / h);
+            side.walk->sd = (float)sqrt((side.t - side.l) * (side.r - side.t) / h);
+        }
+    }
+    brownian_kernel<<<grid_for((numel + 3) / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
+    return check_launch("brownian interval");
 }
 
 int skr_noise_moments(const void* in, int32_t dtype, int64_t numel, double* moments, void* cuda_stream) {

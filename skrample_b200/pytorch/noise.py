@@ -103,6 +103,8 @@ def _lib() -> Any:
         lib.skr_noise_fill.argtypes = [vp, i32, i64, u64, u64, ctypes.POINTER(_SkrOffset), vp, vp]
         lib.skr_noise_fill_batch.restype = ctypes.c_int
         lib.skr_noise_fill_batch.argtypes = [vp, i32, ctypes.POINTER(native.SkrPhilox), vp]
+        lib.skr_noise_brownian.restype = ctypes.c_int
+        lib.skr_noise_brownian.argtypes = [vp, i32, i64, u64, dbl, dbl, i32, dbl, vp]
         lib.skr_noise_moments.restype = ctypes.c_int
         lib.skr_noise_moments.argtypes = [vp, i32, i64, vp, vp]
         lib.skr_noise_scale.restype = ctypes.c_int
@@ -520,13 +522,31 @@ class Pyramid(TensorNoiseCommon[PyramidProps]):
 @dataclass(frozen=True)
 class BrownianProps(TensorNoiseProps):
     max_steps: int = 10_000
+    """Target resolution of the Brownian tree: steps shorter than 1/max_steps fall inside one leaf of the tree
+    and lose exactness (the reference's tolerance caveat, noise.py:211-216)."""
 
 
 @dataclass
 class Brownian(TensorNoiseCommon[BrownianProps]):
-    "torchsde.BrownianInterval pass-through (third-party tree; not accelerated). reference: noise.py:210-252"
+    """Noise that is a deterministic function of the ``Step``: the increment of one Brownian path per seed.
+    reference: noise.py:210-252 (which delegates to ``torchsde.BrownianInterval``).
+
+    With a CUDA generator the increment comes from ``skr_noise_brownian``: a stateless Philox bridge tree over
+    normalised time, ``ceil(log2(10 * max_steps))`` levels deep (the reference's ``tol``), evaluated per element in
+    one launch - no tree object, no cache, no host state.  The same step gives the same tensor on every call,
+    adjoining steps add up to the increment of their union and disjoint steps are independent, which is the
+    contract the reference gets from torchsde.  The VALUES are this library's own: torchsde is a third-party
+    module that is not part of the reference tree, so there is nothing to pin them against (parity statistical).
+    With a CPU generator the reference's torchsde tree is used as is (ImportError without the module).
+    """
 
     def __post_init__(self) -> None:
+        if self.on_device:
+            self._tree = None
+            self._depth = max(1, math.ceil(math.log2(self.props.max_steps * 10)))
+            if self._depth > 40:
+                raise ValueError(f"BrownianProps.max_steps={self.props.max_steps} is beyond the tree depth the kernel walks (40 levels)")
+            return
         import torchsde
 
         self._tree = torchsde.BrownianInterval(
@@ -542,11 +562,29 @@ class Brownian(TensorNoiseCommon[BrownianProps]):
             cache_size=round(math.log2(self.props.max_steps * 10) * 1.3),
         )
 
+    def _increment(self, out: torch.Tensor, step: Step) -> None:
+        scale = 1 / math.sqrt(step.distance())
+        with _DeviceGuard(out.device):
+            status = _lib().skr_noise_brownian(
+                out.data_ptr(), _code(out.dtype), out.numel(), self._key(), step.time_from, step.time_to, self._depth, scale, _stream()
+            )
+        _native().check(status, "skr_noise_brownian")
+
     def generate(self, step: Step | None) -> torch.Tensor:
         if not step:
             return self._randn()
         step = step.normal().clamp()
-        return self._tree(*step) / math.sqrt(step.distance())
+        if self._tree is not None:
+            return self._tree(*step) / math.sqrt(step.distance())
+        out = torch.empty(tuple(self.shape), dtype=self.dtype, device=self.seed.device)
+        self._increment(out, step)
+        return out
+
+    def generate_into(self, out: torch.Tensor, step: Step | None) -> None:
+        if step and self._tree is None and out.is_cuda and out.is_contiguous() and out.numel() == math.prod(self.shape):
+            self._increment(out, step.normal().clamp())
+        else:
+            out.copy_(self.generate(step))
 
     @classmethod
     def from_inputs(

@@ -128,6 +128,39 @@ def test_brownian_needs_torchsde() -> None:
             noise.Brownian.from_inputs((4,), torch.Generator())
 
 
+
+def test_oracle_philox_known_answers() -> None:
+    "Philox4x32-10 known-answer vectors published with Random123 (kat_vectors: zeros, ones, pi digits)."
+    cases = [
+        ((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+        ((0xFFFFFFFF,) * 4, (0xFFFFFFFF, 0xFFFFFFFF), (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+        ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0), (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
+    ]
+    for counter, key, want in cases:
+        got = O.philox4x32_10(np.array([counter], dtype=np.uint32), key)[0]
+        assert tuple(int(x) for x in got) == want
+
+
+def test_oracle_brownian_contract() -> None:
+    """The contract noise.py:244-245 relies on: unit-variance increments that add up over adjoining steps, are
+    independent over disjoint ones, and depend on (seed, t0, t1) only."""
+    n, depth = 1 << 16, 17
+    a = O.brownian_increment(5, 0.20, 0.24, depth, n)
+    b = O.brownian_increment(5, 0.24, 0.28, depth, n)
+    ab = O.brownian_increment(5, 0.20, 0.28, depth, n)
+    assert np.array_equal(a, O.brownian_increment(5, 0.20, 0.24, depth, n))
+    assert np.abs((a + b) * math.sqrt(0.04) - ab * math.sqrt(0.08)).max() < 1e-12
+    for x in (a, b, ab, O.brownian_increment(5, 0.0, 1.0, depth, n), O.brownian_increment(5, 0.5 - 1e-4, 0.5 + 2e-4, depth, n)):
+        assert abs(x.mean()) < 5 / math.sqrt(n) and abs(x.var() - 1) < 2e-2
+        assert abs((x**4).mean() - 3) < 0.15
+    assert abs(np.corrcoef(a, b)[0, 1]) < 5 / math.sqrt(n)
+    assert abs(np.corrcoef(a, O.brownian_increment(6, 0.20, 0.24, depth, n))[0, 1]) < 5 / math.sqrt(n)
+    assert abs(np.corrcoef(a[:-1], a[1:])[0, 1]) < 5 / math.sqrt(n)
+    # overlapping steps are correlated by the shared part: corr = overlap / sqrt(len_a * len_b)
+    c = O.brownian_increment(5, 0.22, 0.26, depth, n)
+    assert np.corrcoef(a, c)[0, 1] == pytest.approx(0.5, abs=0.02)
+
+
 # ------------------------------------------------------------------------------------------- CUDA kernels
 
 gpu = pytest.mark.gpu
@@ -401,3 +434,115 @@ def test_batch_auto_picks_in_kernel_draws_for_small_batches_only() -> None:
     assert isinstance(big.auto(None), torch.Tensor)
     mixed = noise.BatchTensorNoise([noise.Random.from_inputs((8,), _gen(1)), noise.Offset.from_inputs((8,), _gen(2))])
     assert isinstance(mixed.auto(None), torch.Tensor)
+
+
+# ------------------------------------------------------------------------------------------- Brownian (CUDA)
+
+
+def _fill_native(seed: int, stream: int, numel: int) -> torch.Tensor:
+    from skrample_b200 import native
+
+    out = torch.empty(numel, device="cuda")
+    native.check(noise._lib().skr_noise_fill(out.data_ptr(), 0, numel, seed, stream, None, None, noise._stream()), "skr_noise_fill")
+    return out
+
+
+@gpu
+@pytest.mark.parametrize(("seed", "stream", "numel"), [(1234, 0, 4096), (2**63 + 12345, 2**40 + 3, 1027), (7, O.BROWNIAN_TREE | 5, 64)])
+def test_fill_values_match_the_oracle_philox(seed: int, stream: int, numel: int) -> None:
+    "The normals skr_noise_fill writes are the oracle's Philox4x32-10 + Box-Muller stream, element by element."
+    got = _fill_native(seed, stream, numel).cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(got, O.philox_normals(seed, stream, numel), rtol=0, atol=2e-6)
+
+
+BROWNIAN_STEPS = [
+    (0.0, 1.0),
+    (0.0, 0.04),
+    (0.48, 0.52),  # separated at the root
+    (0.96, 1.0),
+    (0.25, 0.5),  # both ends on dyadic points
+    (0.3, 0.3001),
+    (0.7000001, 0.7000003),  # inside one leaf of a 17-level tree
+    (1 / 3, 2 / 3),
+]
+
+
+@gpu
+@pytest.mark.parametrize("step", BROWNIAN_STEPS)
+@pytest.mark.parametrize("max_steps", [10_000, 50])
+def test_brownian_kernel_vs_oracle(step: tuple[float, float], max_steps: int) -> None:
+    "Relative fp32 increments in the kernel against absolute float64 path values in the oracle."
+    shape = (3, 17, 23)  # 1173 elements: ragged last group
+    g = noise.Brownian.from_inputs(shape, _gen(77), noise.BrownianProps(max_steps=max_steps))
+    depth = math.ceil(math.log2(max_steps * 10))
+    got = g.generate(Step(*step))
+    assert got.shape == shape and got.dtype == torch.float32 and got.is_cuda
+    want = O.brownian_increment(77, step[0], step[1], depth, got.numel()).reshape(shape)
+    np.testing.assert_allclose(got.cpu().numpy().astype(np.float64), want, rtol=0, atol=2e-4)
+
+
+@gpu
+def test_brownian_is_a_function_of_the_step() -> None:
+    "reference: noise.py:220 'deterministically over Step' - call order, call count and step direction do not matter."
+    shape = (4, 64, 64)
+    a = noise.Brownian.from_inputs(shape, _gen(3))
+    b = noise.Brownian.from_inputs(shape, _gen(3))
+    s0, s1 = Step.from_int(3, 25), Step.from_int(4, 25)
+    x0, x1 = a.generate(s0), a.generate(s1)
+    assert torch.equal(b.generate(s1), x1) and torch.equal(b.generate(s0), x0) and torch.equal(a.generate(s0), x0)
+    assert torch.equal(a.generate(Step(s0.time_to, s0.time_from)), x0), "Step.normal() orders the ends"
+    assert not torch.equal(x0, x1)
+    assert not torch.equal(noise.Brownian.from_inputs(shape, _gen(4)).generate(s0), x0)
+    # step=None is a plain draw from the generator (noise.py:241-242)
+    assert torch.equal(a.generate(None), noise.Random.from_inputs(shape, _gen(3)).generate(None))
+    # clamp() keeps out-of-range steps inside 0..1 (noise.py:243)
+    torch.testing.assert_close(a.generate(Step(0.98, 1.02)), a.generate(Step(0.96, 1.0)), rtol=0, atol=1e-5)
+    with pytest.raises(ZeroDivisionError):
+        a.generate(Step(0.5, 0.5))
+
+
+@gpu
+def test_brownian_increments_add_up_and_are_independent() -> None:
+    shape = (16, 128, 128)
+    g = noise.Brownian.from_inputs(shape, _gen(11))
+    steps = [Step.from_int(i, 25) for i in range(25)]
+    parts = [g.generate(s).double() for s in steps]
+    n = parts[0].numel()
+    total = sum(p * math.sqrt(s.distance()) for p, s in zip(parts, steps))
+    whole = g.generate(Step(0.0, 1.0)).double()
+    assert (total - whole).abs().max().item() < 5e-6
+    pair = g.generate(Step(steps[6].time_from, steps[7].time_to)).double()
+    assert ((parts[6] + parts[7]) * math.sqrt(steps[6].distance()) - pair * math.sqrt(2 * steps[6].distance())).abs().max().item() < 2e-6
+    for x in (*parts[:4], parts[12], parts[24], whole, pair):
+        x = x.flatten()
+        assert abs(x.mean().item()) < 5 / math.sqrt(n)
+        assert abs(x.var().item() - 1) < 1e-2
+        assert abs((x**3).mean().item()) < 3e-2 and abs((x**4).mean().item() - 3) < 8e-2
+        assert abs((x[:-1] * x[1:]).mean().item()) < 5 / math.sqrt(n)
+    for i, j in [(0, 1), (6, 7), (11, 12), (12, 13), (0, 24), (3, 17)]:
+        assert abs((parts[i] * parts[j]).mean().item()) < 5 / math.sqrt(n), (i, j)
+
+
+@gpu
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float64])
+def test_brownian_storage_dtypes_and_batches(dtype: torch.dtype) -> None:
+    unit = (4, 33, 31)  # odd item size: items 1.. start unaligned
+    step = Step.from_int(7, 20)
+    want = torch.stack([noise.Brownian.from_inputs(unit, _gen(50 + i)).generate(step) for i in range(3)])
+    batch = noise.BatchTensorNoise.from_batch_inputs(noise.Brownian, unit, [_gen(50 + i) for i in range(3)], noise.BrownianProps(), dtype)
+    got = batch.generate(step)
+    assert got.dtype == dtype and got.shape == (3, *unit)
+    assert torch.equal(got, want.to(dtype)), "storage dtypes are the fp32 increment rounded once"
+    out = torch.full((3, *unit), 9.0, device="cuda", dtype=dtype)
+    batch.generate_into(out, step)
+    assert torch.equal(out, got)
+
+
+@gpu
+def test_brownian_abi_rejects_bad_intervals() -> None:
+    lib = noise._lib()
+    out = torch.empty(8, device="cuda")
+    for t0, t1, depth in [(0.5, 0.5, 17), (0.6, 0.5, 17), (-0.1, 0.5, 17), (0.5, 1.1, 17), (0.1, 0.2, 0), (0.1, 0.2, 41), (float("nan"), 0.5, 17)]:
+        assert lib.skr_noise_brownian(out.data_ptr(), 0, 8, 1, t0, t1, depth, 1.0, noise._stream()) < 0
+    assert lib.skr_noise_brownian(out.data_ptr(), 0, 0, 1, 0.1, 0.2, 17, 1.0, noise._stream()) == 0
+    assert lib.skr_noise_brownian(None, 0, 8, 1, 0.1, 0.2, 17, 1.0, noise._stream()) < 0

@@ -190,3 +190,35 @@ def test_timestep_views_resolve_without_a_host_read(wrapper: type, monkeypatch: 
     before = len(reads)
     sched.step(torch.randn(x.shape, generator=g, dtype=torch.float64), edited[0], x, return_dict=False)
     assert len(reads) > before
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize(("steps", "begin"), [(10, 5), (11, 6)])
+@pytest.mark.parametrize("schedule", [scheduling.Sinner(scheduling.Linear()), scheduling.Scaled()], ids=["sinner", "scaled"])
+def test_cuda_wrapper_brownian(steps: int, begin: int, schedule: scheduling.SkrampleSchedule) -> None:
+    """The reference's test_diffusers_brownian (tests/self_sampling.py:503-537) with CUDA generators: the wrapper
+    builds one Brownian generator per batch item, its noise comes from skr_noise_brownian (no torchsde), and because
+    the noise is a function of the step the whole trajectory repeats bit for bit with fresh generators of the same
+    seeds."""
+    from skrample_b200 import native
+
+    finals = []
+    for _ in range(2):
+        wrapper = diffusers.SkrampleWrapperScheduler(
+            sampler=structured.Euler(stochasticity=1), schedule=schedule, model=models.DataModel(), compute_scale=torch.float32, noise_type=noise.Brownian
+        )
+        wrapper.set_timesteps(steps, device="cuda")
+        wrapper.set_begin_index(begin * wrapper.order)
+        generators = [torch.Generator(device="cuda").manual_seed(42), torch.Generator(device="cuda").manual_seed(43)]
+        source = torch.Generator().manual_seed(0)
+        x = torch.randn([2, 16, 128], generator=source).cuda()
+        before = native.launch_count_kind(2)
+        for t in wrapper.timesteps[begin * wrapper.order :]:
+            x = wrapper.step(torch.randn([2, 16, 128], generator=source).cuda(), t, x, return_dict=False, generator=generators)[0]
+        assert native.launch_count_kind(2) - before >= 2 * (steps - begin), "one Brownian launch per item per step"
+        assert wrapper._noise_generator is not None
+        assert len(wrapper._noise_generator.generators) == 2
+        assert all(isinstance(g, noise.Brownian) for g in wrapper._noise_generator.generators)
+        assert torch.isfinite(x).all()
+        finals.append(x)
+    assert torch.equal(finals[0], finals[1])

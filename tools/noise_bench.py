@@ -37,6 +37,7 @@ for label, unit in (("video 16x21x90x160", (16, 21, 90, 160)), ("flux item 16x12
             ("Offset", lambda: noise.Offset.from_inputs(unit, torch.Generator(device=dev).manual_seed(1), noise.OffsetProps(), dtype=dtype)),
             ("Pyramid", lambda: noise.Pyramid.from_inputs(unit, torch.Generator(device=dev).manual_seed(1), noise.PyramidProps(), dtype=dtype)),
             ("Colored", lambda: noise.Colored.from_inputs(unit, torch.Generator(device=dev).manual_seed(1), noise.ColoredProps(), dtype=dtype)),
+            ("Brownian", lambda: noise.Brownian.from_inputs(unit, torch.Generator(device=dev).manual_seed(1), noise.BrownianProps(), dtype=dtype)),
         ]
         for name, make in rows:
             if only and name not in only:

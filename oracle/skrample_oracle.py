@@ -13,6 +13,9 @@ Parity status: PINNED.  ``tests/test_oracle.py`` checks this file against
   * golden tensors produced by importing the reference itself in the build
     container (``tests/golden/make_golden.py`` -> ``tests/golden/*.npz``).
 
+Exception - PARITY UNPINNED: the Brownian section at the end (the reference delegates to the third-party
+``torchsde``, which is neither under /root/reference nor installed; see that section's header).
+
 Numerics model (what "the reference computes" means for tensors):
   * a Python float meeting a float32 array is rounded to float32 first, then every
     binary op is individually rounded - NumPy's weak-scalar promotion gives exactly

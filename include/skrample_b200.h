@@ -218,6 +218,14 @@ int skr_noise_fill_batch(void* out, int32_t dtype, const skr_philox* keys, void*
 int skr_noise_brownian(void* out, int32_t dtype, int64_t numel, uint64_t seed, double t0, double t1, int32_t depth,
                        double out_scale, void* cuda_stream);
 
+/*
+ * The same for a batch in one launch: item i (item_numel elements, starting at element i * item_numel of `out`)
+ * is the path of seeds[i] - BatchTensorNoise over per-item Brownian generators (noise.py:445-446) without the
+ * per-item launches.  1 <= n_items <= SKR_MAX_PHILOX_ITEMS; `seeds` is a host array.
+ */
+int skr_noise_brownian_batch(void* out, int32_t dtype, const uint64_t* seeds, int32_t n_items, int64_t item_numel,
+                             double t0, double t1, int32_t depth, double out_scale, void* cuda_stream);
+
 /* sum / sum^2 of a tensor into device double[2] (pre-zeroed), for Tensor.std() (noise.py:207,365,401). */
 int skr_noise_moments(const void* in, int32_t dtype, int64_t numel, double* moments, void* cuda_stream);
 

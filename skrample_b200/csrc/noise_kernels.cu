@@ -556,12 +556,13 @@ struct BrownianWalk {
 
 struct BrownianParams {
     void* out;
-    int64_t numel;
-    uint64_t seed, root_stream;
+    int64_t numel;  // elements per batch item; item i (blockIdx.y) has its own seed and starts at out + i * numel
+    uint64_t seed[SKR_MAX_PHILOX_ITEMS];
+    uint64_t root_stream;
     BrownianNode prefix[SKR_BROWNIAN_MAX_DEPTH];
     BrownianNode split;
     BrownianWalk from, to;
-    int32_t n_prefix, same_leaf, dtype, aligned;
+    int32_t n_prefix, same_leaf, dtype, pad;
     float out_scale;
 };
 
@@ -585,7 +586,10 @@ __device__ __forceinline__ void brownian_descend(const Philox& ph, uint64_t g, c
 }
 
 __global__ void __launch_bounds__(256) brownian_kernel(const __grid_constant__ BrownianParams p) {
-    const Philox ph(p.seed);
+    const Philox ph(p.seed[blockIdx.y]);
+    const int esize = p.dtype == SKR_F32 ? 4 : p.dtype == SKR_F64 ? 8 : 2;
+    void* const out = reinterpret_cast<char*>(p.out) + (int64_t)blockIdx.y * p.numel * esize;
+    const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
     const int64_t groups = (p.numel + 3) >> 2;
     for (int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gi < groups; gi += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t g = (uint64_t)gi;
@@ -619,10 +623,10 @@ __global__ void __launch_bounds__(256) brownian_kernel(const __grid_constant__ B
             for (int j = 0; j < 4; ++j) v[j] = (w_to[j] - w_from[j]) * p.out_scale;
         }
         const int64_t first = gi << 2;
-        if (p.aligned && first + 4 <= p.numel) {
-            store4(p.out, p.dtype, first, v);
+        if (aligned && first + 4 <= p.numel) {
+            store4(out, p.dtype, first, v);
         } else {
-            for (int j = 0; j < 4 && first + j < p.numel; ++j) store1(p.out, p.dtype, first + j, v[j]);
+            for (int j = 0; j < 4 && first + j < p.numel; ++j) store1(out, p.dtype, first + j, v[j]);
         }
     }
 }
@@ -704,19 +708,22 @@ int skr_noise_fill_batch(void* out, int32_t dtype, const skr_philox* keys, void*
     return check_launch("noise batch fill");
 }
 
-int skr_noise_brownian(void* out, int32_t dtype, int64_t numel, uint64_t seed, double t0, double t1, int32_t depth, double out_scale,
-                       void* cuda_stream) {
+int skr_noise_brownian_batch(void* out, int32_t dtype, const uint64_t* seeds, int32_t n_items, int64_t item_numel, double t0, double t1,
+                             int32_t depth, double out_scale, void* cuda_stream) {
     using namespace skr;
-    if (numel < 0) return fail(SKR_E_RANGE, "negative numel");
+    if (item_numel < 0) return fail(SKR_E_RANGE, "negative numel");
     if (dtype < 0 || dtype > SKR_F16) return fail(SKR_E_DTYPE, "unknown dtype %d", dtype);
+    if (n_items < 1 || n_items > SKR_MAX_PHILOX_ITEMS) return fail(SKR_E_RANGE, "n_items %d out of range", n_items);
+    if (!seeds) return fail(SKR_E_NULL, "null seeds");
     if (depth < 1 || depth > SKR_BROWNIAN_MAX_DEPTH) return fail(SKR_E_RANGE, "brownian depth %d outside 1..%d", depth, SKR_BROWNIAN_MAX_DEPTH);
     if (!(t0 >= 0.0 && t1 <= 1.0 && t0 < t1)) return fail(SKR_E_RANGE, "brownian interval needs 0 <= t0 < t1 <= 1");
-    if (numel == 0) return 0;
+    if (item_numel == 0) return 0;
     if (!out) return fail(SKR_E_NULL, "null output");
+    const int64_t numel = item_numel;
     BrownianParams p;
     memset(&p, 0, sizeof(p));
-    p.out = out; p.numel = numel; p.seed = seed; p.dtype = dtype; p.out_scale = (float)out_scale;
-    p.aligned = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+    p.out = out; p.numel = numel; p.dtype = dtype; p.out_scale = (float)out_scale;
+    for (int i = 0; i < n_items; ++i) p.seed[i] = seeds[i];
     const uint64_t tree = 1ull << 63, leaf = 1ull << 62;
     p.root_stream = tree;  // heap index 0 is unused by the nodes (the root interval is index 1)
     // interval ends are k / 2^level: exact in double for every depth allowed here
@@ -754,8 +761,15 @@ int skr_noise_brownian(void* out, int32_t dtype, int64_t numel, uint64_t seed, d
             side.walk->sd = (float)sqrt((side.t - side.l) * (side.r - side.t) / h);
         }
     }
-    brownian_kernel<<<grid_for((numel + 3) / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
+    unsigned blocks = grid_for((numel + 3) / 4, 256);
+    if (n_items > 1) blocks = (blocks + n_items - 1) / n_items;  // the grid cap is for the whole launch
+    brownian_kernel<<<dim3(blocks, (unsigned)n_items), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
     return check_launch("brownian interval");
+}
+
+int skr_noise_brownian(void* out, int32_t dtype, int64_t numel, uint64_t seed, double t0, double t1, int32_t depth, double out_scale,
+                       void* cuda_stream) {
+    return skr_noise_brownian_batch(out, dtype, &seed, 1, numel, t0, t1, depth, out_scale, cuda_stream);
 }
 
 int skr_noise_moments(const void* in, int32_t dtype, int64_t numel, double* moments, void* cuda_stream) {

@@ -105,6 +105,8 @@ def _lib() -> Any:
         lib.skr_noise_fill_batch.argtypes = [vp, i32, ctypes.POINTER(native.SkrPhilox), vp]
         lib.skr_noise_brownian.restype = ctypes.c_int
         lib.skr_noise_brownian.argtypes = [vp, i32, i64, u64, dbl, dbl, i32, dbl, vp]
+        lib.skr_noise_brownian_batch.restype = ctypes.c_int
+        lib.skr_noise_brownian_batch.argtypes = [vp, i32, ctypes.POINTER(u64), i32, i64, dbl, dbl, i32, dbl, vp]
         lib.skr_noise_moments.restype = ctypes.c_int
         lib.skr_noise_moments.argtypes = [vp, i32, i64, vp, vp]
         lib.skr_noise_scale.restype = ctypes.c_int
@@ -115,6 +117,18 @@ def _lib() -> Any:
         lib.skr_colored_shape.argtypes = [vp, i32, ctypes.POINTER(i64), i32, dbl, vp]
         _bound = True
     return lib
+
+
+def _same_device(generator_device: torch.device, tensor_device: torch.device) -> bool:
+    "A generator made with ``device='cuda'`` carries no index: it lives on the current device."
+    if generator_device.type != tensor_device.type:
+        return False
+    if generator_device.index is None or tensor_device.index is None:
+        current = torch.cuda.current_device() if tensor_device.type == "cuda" else None
+        return (generator_device.index if generator_device.index is not None else current) == (
+            tensor_device.index if tensor_device.index is not None else current
+        )
+    return generator_device.index == tensor_device.index
 
 
 def _stream() -> int:
@@ -750,6 +764,8 @@ class BatchTensorNoise[T: TensorNoiseProps | None](SkrampleTensorNoise):
         same_place = all(g.on_device and g.seed.device == first.seed.device and g.dtype == first.dtype and g.shape == first.shape for g in self.generators)
         if same_place:
             out = torch.empty((len(self.generators), *first.shape), dtype=first.dtype, device=first.seed.device)
+            if step and self._brownian_batch(out, step):
+                return out
             for row, generator in zip(out, self.generators, strict=True):
                 generator.generate_into(row, step)
             return out
@@ -759,7 +775,10 @@ class BatchTensorNoise[T: TensorNoiseProps | None](SkrampleTensorNoise):
         """Write the next batch of noise into ``out`` (``[batch, *unit]``, any floating dtype): the values of
         ``generate(step).to(out.dtype)`` without the intermediate tensor when the batch is plain ``Random`` on
         ``out``'s device."""
-        if out.is_cuda and out.is_contiguous() and self._uniform_random() and out.device == self.generators[0].seed.device:
+        if step and out.is_cuda and out.is_contiguous() and tuple(out.shape) == (len(self.generators), *self.generators[0].shape):
+            if self._brownian_batch(out, step):
+                return
+        if out.is_cuda and out.is_contiguous() and self._uniform_random() and _same_device(self.generators[0].seed.device, out.device):
             drawn = self.lazy(step, _fallback=False)
             if drawn is not None and tuple(out.shape) == drawn.shape:
                 drawn.materialize_into(out)
@@ -767,6 +786,28 @@ class BatchTensorNoise[T: TensorNoiseProps | None](SkrampleTensorNoise):
             out.copy_(drawn.materialize() if drawn is not None else self.generate(step))
             return
         out.copy_(self.generate(step))
+
+    def _brownian_batch(self, out: torch.Tensor, step: Step) -> bool:
+        """Every item a device ``Brownian`` of one shape and tree depth on ``out``'s device: one launch writes the
+        whole batch, item i from the path of its own seed (the values of the per-item calls)."""
+        first = self.generators[0]
+        count = len(self.generators)
+        if count > 32 or not all(
+            type(g) is Brownian and g._tree is None and _same_device(g.seed.device, out.device) and g.shape == first.shape and g._depth == first._depth
+            for g in self.generators
+        ):
+            return False
+        if any(g.dtype != out.dtype and g.dtype not in (torch.float32, torch.float64) for g in self.generators):
+            return False  # a 16-bit generator read into a wider tensor keeps its own rounding: item by item
+        step = step.normal().clamp()
+        scale = 1 / math.sqrt(step.distance())
+        seeds = (ctypes.c_uint64 * count)(*(g._key() for g in self.generators))
+        with _DeviceGuard(out.device):
+            status = _lib().skr_noise_brownian_batch(
+                out.data_ptr(), _code(out.dtype), seeds, count, out.numel() // count, step.time_from, step.time_to, first._depth, scale, _stream()
+            )
+        _native().check(status, "skr_noise_brownian_batch")
+        return True
 
     AUTO_LAZY_MAX_ELEMENTS = 1 << 20
 

@@ -129,6 +129,14 @@ def test_brownian_needs_torchsde() -> None:
 
 
 
+def test_same_device_rule() -> None:
+    "An index-less generator device means the current device; types must agree."
+    same = noise._same_device
+    assert same(torch.device("cpu"), torch.device("cpu"))
+    assert not same(torch.device("cpu"), torch.device("cuda", 0))
+    assert same(torch.device("cuda", 1), torch.device("cuda", 1)) and not same(torch.device("cuda", 0), torch.device("cuda", 1))
+
+
 def test_oracle_philox_known_answers() -> None:
     "Philox4x32-10 known-answer vectors published with Random123 (kat_vectors: zeros, ones, pi digits)."
     cases = [
@@ -526,6 +534,8 @@ def test_brownian_increments_add_up_and_are_independent() -> None:
 @gpu
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float64])
 def test_brownian_storage_dtypes_and_batches(dtype: torch.dtype) -> None:
+    from skrample_b200 import native
+
     unit = (4, 33, 31)  # odd item size: items 1.. start unaligned
     step = Step.from_int(7, 20)
     want = torch.stack([noise.Brownian.from_inputs(unit, _gen(50 + i)).generate(step) for i in range(3)])
@@ -534,8 +544,20 @@ def test_brownian_storage_dtypes_and_batches(dtype: torch.dtype) -> None:
     assert got.dtype == dtype and got.shape == (3, *unit)
     assert torch.equal(got, want.to(dtype)), "storage dtypes are the fp32 increment rounded once"
     out = torch.full((3, *unit), 9.0, device="cuda", dtype=dtype)
+    before = native.launch_count_kind(2)
     batch.generate_into(out, step)
+    assert native.launch_count_kind(2) - before == 1, "one launch for the whole batch"
     assert torch.equal(out, got)
+    # the batch path writes any requested storage type directly; mixed tree depths go item by item
+    wide = noise.BatchTensorNoise.from_batch_inputs(noise.Brownian, unit, [_gen(50 + i) for i in range(3)], noise.BrownianProps())
+    other = torch.empty((3, *unit), device="cuda", dtype=dtype)
+    wide.generate_into(other, step)
+    assert torch.equal(other, got)
+    narrow = torch.empty((3, *unit), device="cuda", dtype=torch.float64)
+    batch.generate_into(narrow, step)
+    assert torch.equal(narrow, got.double()), "a 16-bit generator keeps its rounding when read into a wider tensor"
+    mixed = noise.BatchTensorNoise([noise.Brownian.from_inputs(unit, _gen(50)), noise.Brownian.from_inputs(unit, _gen(51), noise.BrownianProps(max_steps=100))])
+    assert torch.equal(mixed.generate(step)[0], want[0]) and not torch.equal(mixed.generate(step)[1], want[1])
 
 
 @gpu

@@ -26,4 +26,7 @@ capture euler_sde_f32_256x16x128x128 3 --sampler euler --dtype f32 --batch 256 -
 capture unipc3_sde_bf16_16x16x128x128 6 --sampler unipc3 --dtype bf16 --batch 16 --steps 8
 capture unipc3_sde_bf16_2x16x128x128 6 --sampler unipc3 --dtype bf16 --batch 2 --steps 8
 capture adams9_sde_bf16_19x16x128x128 10 --sampler adams9 --dtype bf16 --batch 19 --steps 12
+# the Brownian interval kernel on one 16x21x90x160 video latent (the first timed shape of tools/noise_bench.py)
+python tools/noise_bench.py Brownian > $O/${R}_noise_brownian.txt 2>&1 && ncu --set full --clock-control none --import-source on \
+    -k regex:brownian_kernel -s 30 -c 1 -f -o $O/${R}_brownian_f32_16x21x90x160 python tools/noise_bench.py Brownian > $O/${R}_ncu_brownian.log 2>&1
 ls -la $O/${R}_*

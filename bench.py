@@ -11,10 +11,12 @@ schedule, epsilon model, SDXL latent 8x4x128x128, bf16 storage / fp32 compute, o
              as algorithmic GB/s), inputs resident in HBM, launches replayed from a CUDA graph (device-side time
              between two events; max over ranks).  Trajectories of several latent
              batches are interleaved so consecutive launches never touch the same buffers and the working set
-             (> 2x L2) comes from HBM.
+             (> 2x L2) comes from HBM; the batches are independent requests, so the graph runs them on ``--streams``
+             parallel branches (default 4).  ``one_stream`` is the same launches as a single chain.
   e2e        the same steps through the public API (``sampler.sample``) with HOST buffers: per step the model
              prediction and the noise are copied from pinned host memory and the result is read back.
-  roofline   algorithmic bytes per launch / average launch duration of the step kernel vs the measured HBM copy
+  roofline   algorithmic bytes per launch / average launch duration of the step kernel (taken on the single chain,
+             where a launch's duration is well defined) vs the measured HBM copy
              peak (MEASURED_PEAKS.json); ``sweep`` repeats that for the larger BASELINE shapes.
   cpu_baseline  the CPU oracle port of the reference algorithm (oracle/skrample_oracle.py on torch-CPU tensors,
              all host threads) on a bounded sample of the same workload.
@@ -597,7 +599,7 @@ def main() -> None:
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--sweep", action="store_true", help="also time the larger BASELINE shapes (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=4, help="parallel graph branches of the `concurrent` leg (0 skips it)")
+    ap.add_argument("--streams", type=int, default=4, help="parallel graph branches the latent batches of `value` run on (1: a single chain)")
     ap.add_argument("--fused-noise", action="store_true", help="draw the noise inside the step kernel (PhiloxDraw) instead of reading the tensor skr_noise_fill wrote")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -672,26 +674,32 @@ def main() -> None:
     latent_steps = dev["steps"] * spec["shape"][0] * world / (elapsed_ms / 1e3)
     ms_per_step = elapsed_ms / dev["steps"]
     per_launch_us = elapsed_ms * 1e3 / dev["launches"]
-    achieved = dev["bytes"] / dev["launches"] / (per_launch_us * 1e-6) / 1e9
+    bytes_per_launch = dev["bytes"] / dev["launches"]
+    achieved = bytes_per_launch / (per_launch_us * 1e-6) / 1e9
 
-    concurrent = None
+    # the same launches as one chain on one stream: a launch's duration is well defined there, so the roofline of the
+    # step kernel is taken from this run
+    one_stream = {
+        "value": latent_steps,
+        "unit": "latent-steps/s",
+        "ms_per_step": ms_per_step,
+        "sampler_step_GBps": gbs,
+        "frac_of_measured_peak": gbs / world / peak,
+        "gpu_launches": timed_launches,
+    }
+    branches = 1
     if args.streams > 1:
+        # whole-job throughput: the interleaved latent batches are independent requests, so the graph runs them on
+        # parallel branches and the launch / load / store phases of different batches overlap
         torch.cuda.empty_cache()
         many = graph_throughput(spec, device, args.steps, args.warmup, 2 * L2_BYTES, streams=args.streams)
         many_ms = max_over_ranks(many["elapsed_ms"], device)
-        many_gbs = many["bytes"] * world / (many_ms / 1e3) / 1e9
-        concurrent = {
-            "streams": min(args.streams, many["replicas"]),
-            "value": many["steps"] * spec["shape"][0] * world / (many_ms / 1e3),
-            "unit": "latent-steps/s",
-            "ms_per_step": many_ms / many["steps"],
-            "sampler_step_GBps": many_gbs,
-            "frac_of_measured_peak": many_gbs / world / peak,
-            "gpu_launches": many["launches"],
-            "note": "the same launches with the interleaved latent batches spread over parallel graph branches (independent requests "
-            "overlapping on one GPU); `value` and `roofline` above stay on the one-stream chain, where a launch's duration is well defined",
-        }
-        del many
+        branches = min(args.streams, many["replicas"])
+        dev = many
+        timed_launches = many["launches"]
+        gbs = many["bytes"] * world / (many_ms / 1e3) / 1e9
+        latent_steps = many["steps"] * spec["shape"][0] * world / (many_ms / 1e3)
+        ms_per_step = many_ms / many["steps"]
         torch.cuda.empty_cache()
 
     e2e_steps = min(args.steps, 500)
@@ -715,7 +723,8 @@ def main() -> None:
         "data": "synthetic",
         "config": config
         | {
-            "launch": "CUDA graph replay of the sampler launches",
+            "launch": f"CUDA graph replay of the sampler launches, latent batches on {branches} parallel graph branch(es)",
+            "graph_branches": branches,
             "l2": f"{dev['replicas']} interleaved latent batches, working set per round > 2x L2 (inputs come from HBM)",
             "storage_dtype": spec["dtype"],
         },
@@ -723,7 +732,7 @@ def main() -> None:
         "pct_of_hbm_peak": {"measured": gbs / world / peak, "nominal_8TBs": gbs / world / 8000.0},
         "gpu_launches": timed_launches,
         "clocks": dev["clocks"],
-        "concurrent": concurrent,
+        "one_stream": one_stream,
         "e2e": {
             "value": e2e_steps * spec["shape"][0] * world / e2e_elapsed,
             "unit": "latent-steps/s",
@@ -749,8 +758,9 @@ def main() -> None:
             "frac": achieved / peak,
             "traffic": measured_traffic(),
             "kernel": "skr::block_kernel",
-            "bytes_per_launch": dev["bytes"] / dev["launches"],
+            "bytes_per_launch": bytes_per_launch,
             "us_per_launch": per_launch_us,
+            "measured_on": "the one-stream chain of the same launches (`one_stream`), CUDA events around the timed replays",
             "peak_source": peak_src,
         },
     }

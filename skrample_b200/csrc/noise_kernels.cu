@@ -527,6 +527,43 @@ __global__ void __launch_bounds__(256) colored_shape_kernel(const __grid_constan
     }
 }
 
+// The same for complex64 spectra with many rows: one warp per row of the last (half) axis.  The row's index is
+// decomposed once per warp instead of once per bin, the lanes walk the row with coalesced 8-byte accesses, and the
+// power is exp2(e * log2(r)) on the special-function unit (relative error ~1e-6 against powf; the field is
+// renormalised by its measured std afterwards).
+__global__ void __launch_bounds__(256) colored_shape_rows_kernel(const __grid_constant__ ShapeParams p, const int rows, const float inv_r_max) {
+    const int last = p.ndim - 1;
+    const int last_bins = (int)(p.dims[last] / 2 + 1);
+    const float inv_last = 1.0f / (float)p.dims[last];
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < rows; row += warps) {
+        int rem = row;
+        float row_r2 = 0.0f;
+        for (int d = last - 1; d >= 0; --d) {
+            const int n = (int)p.dims[d];
+            const int q = rem / n;
+            const int k = rem - q * n;
+            rem = q;
+            const int kk = k < (n + 1) / 2 ? k : n - k;
+            const float f = (float)kk / (float)n;
+            row_r2 += f * f;
+        }
+        float2* const line = p.spectrum + (int64_t)row * last_bins;
+        for (int k = lane; k < last_bins; k += 32) {
+            const float f = (float)k * inv_last;
+            float r = sqrtf(row_r2 + f * f);
+            if (p.r_max > 0.0f) r = r * inv_r_max;
+            r = r < p.eps_clip ? p.eps_clip : r;
+            const float w = exp2f(p.exponent_half_neg * __log2f(r));
+            float2 v = line[k];
+            v.x *= w;
+            v.y *= w;
+            line[k] = v;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Brownian interval   (reference: noise.py:210-252 - torchsde.BrownianInterval over normalised time 0..1)
 //
@@ -908,6 +945,12 @@ int skr_colored_shape(void* spectrum, int32_t complex_dtype, const int64_t* dims
     p.eps_clip = (float)(0.5 / (n_eff > 4.0 ? n_eff : 4.0));
     p.r_max = sqrtf((float)rmax2);
     p.exponent_half_neg = (float)(-exponent / 2.0);
+    const int64_t last_bins = dims[ndim - 1] / 2 + 1, rows = bins / last_bins;
+    if (complex_dtype == SKR_F32 && rows >= 2048 && rows < ((int64_t)1 << 27) && last_bins >= 16 && last_bins < (1 << 20)) {
+        colored_shape_rows_kernel<<<grid_for(rows * 32, 256), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(
+            p, (int)rows, p.r_max > 0.0f ? 1.0f / p.r_max : 0.0f);
+        return check_launch("colored shape");
+    }
     if (bins < ((int64_t)1 << 31) - 256 * 148 * 8) colored_shape_kernel<int32_t><<<grid_for(bins, 256), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
     else colored_shape_kernel<int64_t><<<grid_for(bins, 256), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
     return check_launch("colored shape");

@@ -335,7 +335,7 @@ def test_pyramid_philox_statistics(shape: tuple[int, ...]) -> None:
 
 
 @gpu
-@pytest.mark.parametrize(("shape", "exponent", "energy"), [((4, 32, 32), 1.5, None), ((2, 1, 40, 31), -2.0, 3.0), ((4096,), 0.7, None), ((16, 8, 30, 40), 0.25, None)])
+@pytest.mark.parametrize(("shape", "exponent", "energy"), [((4, 32, 32), 1.5, None), ((2, 1, 40, 31), -2.0, 3.0), ((4096,), 0.7, None), ((16, 8, 30, 40), 0.25, None), ((8, 21, 45, 80), -1.0, None), ((3, 700, 37), 2.0, 0.5)])
 def test_colorize_kernel_vs_oracle(shape: tuple[int, ...], exponent: float, energy: float | None) -> None:
     white = torch.randn(shape, generator=torch.Generator().manual_seed(2))
     got = noise.Colored.colorize_noise(white.cuda(), exponent, energy).cpu().numpy()

@@ -603,6 +603,15 @@ def main() -> None:
     ap.add_argument("--fused-noise", action="store_true", help="draw the noise inside the step kernel (PhiloxDraw) instead of reading the tensor skr_noise_fill wrote")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    # stdout carries exactly one JSON line: anything a library prints there while the bench runs (NCCL's version banner
+    # under NCCL_DEBUG=VERSION, for one) goes to stderr instead
+    sys.stdout.flush()
+    result_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line: dict) -> None:
+        sys.stdout.flush()
+        os.write(result_fd, (json.dumps(line) + "\n").encode())
     global SUPPLIED_NOISE
     SUPPLIED_NOISE = not args.fused_noise
 
@@ -651,7 +660,7 @@ def main() -> None:
             },
             "e2e": {"value": lsps, "unit": "latent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }
-        print(json.dumps(line))
+        emit(line)
         return
 
     if not torch.cuda.is_available():
@@ -795,7 +804,7 @@ def main() -> None:
         }
 
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -13,6 +13,7 @@ load, using a CUDA tensor raises ``RuntimeError`` (build with
 from __future__ import annotations
 
 import ctypes
+import struct
 import os
 import threading
 from pathlib import Path
@@ -292,19 +293,38 @@ def _on_device(t: Any) -> bool:
     return t.is_cuda
 
 
+_TENSOR_RECORD = "Qi4x"  # skr_tensor: pointer, dtype code, reserved
+_PACKERS: dict[int, struct.Struct] = {}
+_INPUTS_AT = SkrProgram.inputs.offset
+_OUTPUTS_AT = SkrProgram.outputs.offset
+assert ctypes.sizeof(SkrTensor) == struct.calcsize("<" + _TENSOR_RECORD)
+
+
+def _packer(count: int) -> struct.Struct:
+    "One ``struct`` call writes a whole tensor table into the packed program (field-by-field ctypes stores cost more than the launch)."
+    made = _PACKERS.get(count)
+    if made is None:
+        made = _PACKERS[count] = struct.Struct("<" + _TENSOR_RECORD * count)
+    return made
+
+
 def launch_compiled(compiled: CompiledProgram, inputs: list[Any], draws: list[Any] | None = None) -> list[Any] | None:
     "Bind tensors (and lazy noise draws) to a compiled program and launch it.  None when they do not qualify."
     first = inputs[0]
+    if not _on_device(first):
+        return None
     shape, device = first.shape, first.device
+    where = first.get_device()  # every other operand must report the same ordinal (a CPU tensor reports -1)
     packed = compiled.packed
-    slots = packed.inputs
     any64 = any32 = False
     kind = first.dtype
     mixed = False
-    for i, t in enumerate(inputs):
+    code_of = DTYPE_CODE.get
+    table: list[int] = []
+    for t in inputs:
         dtype = t.dtype
-        code = DTYPE_CODE.get(dtype)
-        if code is None or not _on_device(t) or t.shape != shape or t.device != device or not t.is_contiguous():
+        code = code_of(dtype)
+        if code is None or t.get_device() != where or t.shape != shape or not t.is_contiguous():
             return None
         if code == F64:
             any64 = True
@@ -312,20 +332,21 @@ def launch_compiled(compiled: CompiledProgram, inputs: list[Any], draws: list[An
             any32 = True
         if dtype != kind:
             mixed = True
-        slot = slots[i]
-        slot.ptr = t.data_ptr()
-        slot.dtype = code
+        table.append(t.data_ptr())
+        table.append(code)
+    _packer(len(inputs)).pack_into(packed, _INPUTS_AT, *table)
     default = torch.float64 if any64 else (torch.float32 if any32 or mixed else kind)
     compute = torch.float64 if any64 else torch.float32
     outputs = []
-    slots = packed.outputs
-    for i, want in enumerate(compiled.out_specs):
+    table = []
+    for want in compiled.out_specs:
         dtype = default if want is None else (compute if want.__class__ is str else want)
         out = torch.empty(shape, dtype=dtype, device=device)
-        slot = slots[i]
-        slot.ptr = out.data_ptr()
-        slot.dtype = DTYPE_CODE[dtype]
+        table.append(out.data_ptr())
+        table.append(DTYPE_CODE[dtype])
         outputs.append(out)
+    if outputs:
+        _packer(len(outputs)).pack_into(packed, _OUTPUTS_AT, *table)
     if draws:
         numel = first.numel()
         for d in draws:

@@ -52,3 +52,21 @@ def test_cpu_tensors_match_reference(case: dict) -> None:
         got = getattr(result, field).numpy()
         assert got.dtype == want.dtype
         assert np.array_equal(got, want, equal_nan=True), field
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line() -> None:
+    """bench.py's contract: stdout carries ONE JSON line (library banners are diverted to stderr); the reference arm
+    is the part of the bench that runs without a GPU."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    done = subprocess.run([sys.executable, str(root / "bench.py"), "--impl", "reference", "--steps", "25", "--warmup", "3"], capture_output=True, text=True, timeout=300)
+    assert done.returncode == 0, done.stderr[-2000:]
+    lines = done.stdout.splitlines()
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "latent-steps/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0

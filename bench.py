@@ -404,28 +404,47 @@ def noise_generator_times(device: torch.device, unit: tuple[int, ...] = (16, 21,
     return rows
 
 
-def e2e_throughput(spec: dict, device: torch.device, steps: int, warmup: int) -> dict:
-    "Public API with host buffers: H2D of the step's prediction + noise, sampler.sample, D2H of the result."
-    traj = Trajectory(spec, device, seed=4321)
-    traj.record()
+def e2e_throughput(spec: dict, device: torch.device, steps: int, warmup: int, inflight: int = 1) -> dict:
+    """Public API with host buffers: H2D of the step's prediction, noise drawn on the device, sampler.sample, D2H of the
+    result - every step.  ``inflight`` independent latent batches (requests) are advanced round robin: a request's next
+    step starts only after its previous result has arrived in host memory, but while that copy is in flight the host
+    prepares and launches the other requests' steps.  ``inflight=1`` is the plain synchronous loop."""
+    trajs = [Trajectory(spec, device, seed=4321 + 17 * i) for i in range(inflight)]
+    for traj in trajs:
+        traj.record()
     per_step = step_bytes(spec, device)
-    host_pred = [p.cpu().pin_memory() for p in traj.predictions]
-    result_host = torch.empty(spec["shape"], dtype=traj.dtype).pin_memory()
+    host_pred = [[p.cpu().pin_memory() for p in traj.predictions] for traj in trajs]
+    result_host = [torch.empty(spec["shape"], dtype=trajs[0].dtype).pin_memory() for _ in trajs]
+    arrived = [torch.cuda.Event() for _ in trajs]
+    pending = [False] * inflight
 
     def one(k: int) -> None:
-        n = traj.n
-        pred = host_pred[n].to(device, non_blocking=True)
+        slot = k % inflight
+        traj = trajs[slot]
+        if pending[slot]:
+            arrived[slot].synchronize()  # the caller consumes this request's previous result before its next step
+        pred = host_pred[slot][traj.n].to(device, non_blocking=True)
         noise = None
         if traj.sampler.require_noise:  # fresh noise every step, generated on the device (fill kernel or in-step draw)
             noise = traj.noise_source.auto(None) if SUPPLIED_NOISE else traj.noise_source.lazy(None)
         final = traj.step(pred, noise)
-        result_host.copy_(final, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller consumes the result before the next step
+        result_host[slot].copy_(final, non_blocking=True)
+        if inflight == 1:
+            torch.cuda.current_stream().synchronize()
+        else:
+            arrived[slot].record()
+            pending[slot] = True
+
+    def drain() -> None:
+        torch.cuda.synchronize(device)
+        for slot in range(inflight):
+            pending[slot] = False
 
     for k in range(warmup):
         one(k)
-    traj.reset()
-    torch.cuda.synchronize(device)
+    drain()
+    for traj in trajs:
+        traj.reset()
     barrier()
     t0 = time.perf_counter()
     for k in range(steps):
@@ -434,8 +453,8 @@ def e2e_throughput(spec: dict, device: torch.device, steps: int, warmup: int) ->
     elapsed = time.perf_counter() - t0
     barrier()
     n = numel_of(spec["shape"])
-    esize = traj.dtype.itemsize
-    total_bytes = sum(per_step[k % STEPS_PER_TRAJECTORY] for k in range(steps))
+    esize = trajs[0].dtype.itemsize
+    total_bytes = sum(per_step[(k // inflight) % STEPS_PER_TRAJECTORY] for k in range(steps))
     return {
         "elapsed_s": elapsed,
         "bytes": total_bytes,
@@ -600,6 +619,7 @@ def main() -> None:
     ap.add_argument("--sweep", action="store_true", help="also time the larger BASELINE shapes (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=4, help="parallel graph branches the latent batches of `value` run on (1: a single chain)")
+    ap.add_argument("--inflight", type=int, default=2, help="independent requests advanced round robin by the e2e leg (1: the synchronous loop only)")
     ap.add_argument("--fused-noise", action="store_true", help="draw the noise inside the step kernel (PhiloxDraw) instead of reading the tensor skr_noise_fill wrote")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -712,8 +732,12 @@ def main() -> None:
         torch.cuda.empty_cache()
 
     e2e_steps = min(args.steps, 500)
-    e2e = e2e_throughput(spec, device, e2e_steps, min(args.warmup, 50))
-    e2e_elapsed = max_over_ranks(e2e["elapsed_s"], device)
+    single = e2e_throughput(spec, device, e2e_steps, min(args.warmup, 50))
+    single_elapsed = max_over_ranks(single["elapsed_s"], device)
+    e2e, e2e_elapsed = single, single_elapsed
+    if args.inflight > 1:
+        e2e = e2e_throughput(spec, device, e2e_steps, min(args.warmup, 50), inflight=args.inflight)
+        e2e_elapsed = max_over_ranks(e2e["elapsed_s"], device)
     e2e_gbs = e2e["bytes"] * world / e2e_elapsed / 1e9
     graphed_elapsed = max_over_ranks(e2e_graphed_throughput(spec, device, e2e_steps, min(args.warmup, 50))["elapsed_s"], device)
 
@@ -751,6 +775,12 @@ def main() -> None:
             "ms_per_step": e2e_elapsed / e2e_steps * 1e3,
             "steps": e2e_steps,
             "api": "structured sampler .sample() per step (the reference's call), pinned-host prediction in, result out; noise from BatchTensorNoise.auto (in-kernel Philox draw at this size)",
+            "requests_in_flight": max(1, args.inflight),
+            "one_request": {
+                "value": e2e_steps * spec["shape"][0] * world / single_elapsed,
+                "ms_per_step": single_elapsed / e2e_steps * 1e3,
+                "note": "the plain synchronous loop: every step waits for its result on the host before the next begins",
+            },
         },
         "e2e_graphed": {
             "value": e2e_steps * spec["shape"][0] * world / graphed_elapsed,

@@ -14,7 +14,9 @@ schedule, epsilon model, SDXL latent 8x4x128x128, bf16 storage / fp32 compute, o
              (> 2x L2) comes from HBM; the batches are independent requests, so the graph runs them on ``--streams``
              parallel branches (default 4).  ``one_stream`` is the same launches as a single chain.
   e2e        the same steps through the public API (``sampler.sample``) with HOST buffers: per step the model
-             prediction and the noise are copied from pinned host memory and the result is read back.
+             prediction is copied from pinned host memory, the noise is drawn on the device and the result is read
+             back.  ``--inflight`` independent requests (default 2) are advanced round robin, each waiting for its own
+             previous result; ``e2e.one_request`` is the plain synchronous loop.
   roofline   algorithmic bytes per launch / average launch duration of the step kernel (taken on the single chain,
              where a launch's duration is well defined) vs the measured HBM copy
              peak (MEASURED_PEAKS.json); ``sweep`` repeats that for the larger BASELINE shapes.

@@ -58,3 +58,20 @@ def test_op_codes_in_lockstep() -> None:
         assert getattr(pg, f"OP_{name}") == int(value), name
     for name, value in re.findall(r"SKR_CONV_([A-Z_]+) = (\d+)", HEADER):
         assert getattr(pg, f"CONV_{name}") == int(value), name
+
+
+def test_tensor_tables_are_written_in_the_struct_layout() -> None:
+    "native.launch_compiled writes a whole tensor table with one struct.pack_into; the ctypes fields must read it back."
+    from skrample_b200 import native
+
+    packed = native.SkrProgram()
+    native._packer(3).pack_into(packed, native._INPUTS_AT, 0x1000, native.F32, 0xFFFF_FFFF_FFF0, native.F64, 0x2000, native.DTYPE_CODE[__import__("torch").bfloat16])
+    native._packer(2).pack_into(packed, native._OUTPUTS_AT, 0x3000, native.F32, 0x4000, native.DTYPE_CODE[__import__("torch").float16])
+    assert [(t.ptr, t.dtype, t.reserved) for t in packed.inputs[:4]] == [
+        (0x1000, native.F32, 0),
+        (0xFFFF_FFFF_FFF0, native.F64, 0),
+        (0x2000, native.DTYPE_CODE[__import__("torch").bfloat16], 0),
+        (None, 0, 0),
+    ]
+    assert [(t.ptr, t.dtype) for t in packed.outputs[:3]] == [(0x3000, native.F32), (0x4000, native.DTYPE_CODE[__import__("torch").float16]), (None, 0)]
+    assert packed.n_ops == 0 and packed.n_inputs == 0

@@ -533,6 +533,78 @@ class Pyramid(TensorNoiseCommon[PyramidProps]):
         return noise / noise.std()
 
 
+# -- host side of the Brownian interval (CPU generators without torchsde): the walk of skr_noise_brownian and the
+#    kernel's arithmetic restated with torch CPU ops, so a seed names the same path on the host and on the device.
+
+_BROWNIAN_TREE, _BROWNIAN_LEAF = 1 << 63, 1 << 62
+_M32 = 0xFFFFFFFF
+
+
+def _host_philox_normals(seed: int, stream: int, groups: int) -> torch.Tensor:
+    "[groups, 4] float32 standard normals of Philox stream (seed, stream): counter = (group, stream), as philox.cuh."
+    index = torch.arange(groups, dtype=torch.int64)
+    c0, c1 = index & _M32, (index >> 32) & _M32
+    c2 = torch.full_like(index, stream & _M32)
+    c3 = torch.full_like(index, (stream >> 32) & _M32)
+    k0, k1 = seed & _M32, (seed >> 32) & _M32
+    for _ in range(10):
+        # 32x32-bit products wrap in int64, which keeps their low 64 bits: the halves are recovered with masks
+        p0, p1 = c0 * 0xD2511F53, c2 * 0xCD9E8D57
+        c0, c1, c2, c3 = ((p1 >> 32) & _M32) ^ c1 ^ k0, p1 & _M32, ((p0 >> 32) & _M32) ^ c3 ^ k1, p0 & _M32
+        k0, k1 = (k0 + 0x9E3779B9) & _M32, (k1 + 0xBB67AE85) & _M32
+    u = torch.stack([c0, c1, c2, c3], dim=1).to(torch.float32) * 2.0**-32 + 2.0**-33  # (0, 1]
+    radius = torch.sqrt(-2.0 * torch.log(u[:, 0::2]))
+    angle = (2.0 * math.pi) * u[:, 1::2]
+    z = torch.stack([radius[:, 0] * torch.sin(angle[:, 0]), radius[:, 0] * torch.cos(angle[:, 0]),
+                     radius[:, 1] * torch.sin(angle[:, 1]), radius[:, 1] * torch.cos(angle[:, 1])], dim=1)
+    return z
+
+
+def _host_brownian_increment(seed: int, t0: float, t1: float, depth: int, numel: int) -> torch.Tensor:
+    "(W(t1) - W(t0)) of the seed's path as float32 [numel]: the bridge-tree walk of skr_noise_brownian on the host."
+    groups = (numel + 3) // 4
+
+    def draw(stream: int) -> torch.Tensor:
+        return _host_philox_normals(seed, stream, groups)
+
+    def descend(t: float, left: float, right: float, node: int, level: int, lo: torch.Tensor, hi: torch.Tensor) -> torch.Tensor:
+        for _ in range(level, depth):
+            mid = 0.5 * (left + right)
+            value = 0.5 * (lo + hi) + (0.5 * math.sqrt(right - left)) * draw(_BROWNIAN_TREE | node)
+            if t >= mid:
+                left, lo, node = mid, value, 2 * node + 1
+            else:
+                right, hi, node = mid, value, 2 * node
+        width = right - left
+        spread = math.sqrt((t - left) * (right - t) / width)
+        return lo + ((t - left) / width) * (hi - lo) + spread * draw(_BROWNIAN_TREE | _BROWNIAN_LEAF | node)
+
+    left, right, node, level = 0.0, 1.0, 1, 0
+    increment = draw(_BROWNIAN_TREE)  # W(1) - W(0)
+    while level < depth:
+        mid = 0.5 * (left + right)
+        if (t0 >= mid) != (t1 >= mid):
+            break
+        half = (0.5 * math.sqrt(right - left)) * draw(_BROWNIAN_TREE | node)
+        if t0 >= mid:
+            increment, left, node = 0.5 * increment - half, mid, 2 * node + 1
+        else:
+            increment, right, node = 0.5 * increment + half, mid, 2 * node
+        level += 1
+    if level == depth:  # both times inside one leaf
+        width = right - left
+        spread = math.sqrt((t1 - left) * (right - t1) / width) - math.sqrt((t0 - left) * (right - t0) / width)
+        result = ((t1 - t0) / width) * increment + spread * draw(_BROWNIAN_TREE | _BROWNIAN_LEAF | node)
+    else:  # the node that separates them: both sides relative to W(mid)
+        mid = 0.5 * (left + right)
+        half = (0.5 * math.sqrt(right - left)) * draw(_BROWNIAN_TREE | node)
+        zero = torch.zeros_like(increment)
+        before = descend(t0, left, mid, 2 * node, level + 1, -(0.5 * increment + half), zero)
+        after = descend(t1, mid, right, 2 * node + 1, level + 1, zero, 0.5 * increment - half)
+        result = after - before
+    return result.reshape(-1)[:numel]
+
+
 @dataclass(frozen=True)
 class BrownianProps(TensorNoiseProps):
     max_steps: int = 10_000
@@ -551,7 +623,9 @@ class Brownian(TensorNoiseCommon[BrownianProps]):
     adjoining steps add up to the increment of their union and disjoint steps are independent, which is the
     contract the reference gets from torchsde.  The VALUES are this library's own: torchsde is a third-party
     module that is not part of the reference tree, so there is nothing to pin them against (parity statistical).
-    With a CPU generator the reference's torchsde tree is used as is (ImportError without the module).
+    With a CPU generator the reference's torchsde tree is used as is when the module is installed (the reference's
+    values); without it the same bridge tree is evaluated with torch CPU ops, so a seed names one path on the host and on
+    the device (equal up to float32 rounding of log / sin / cos) instead of raising ImportError.
     """
 
     def __post_init__(self) -> None:
@@ -561,7 +635,12 @@ class Brownian(TensorNoiseCommon[BrownianProps]):
             if self._depth > 40:
                 raise ValueError(f"BrownianProps.max_steps={self.props.max_steps} is beyond the tree depth the kernel walks (40 levels)")
             return
-        import torchsde
+        self._depth = max(1, math.ceil(math.log2(self.props.max_steps * 10)))
+        try:
+            import torchsde
+        except ImportError:
+            self._tree = None  # host evaluation of the library's own construction
+            return
 
         self._tree = torchsde.BrownianInterval(
             t0=0,
@@ -590,12 +669,18 @@ class Brownian(TensorNoiseCommon[BrownianProps]):
         step = step.normal().clamp()
         if self._tree is not None:
             return self._tree(*step) / math.sqrt(step.distance())
+        if not self.on_device:
+            scale = 1 / math.sqrt(step.distance())
+            if not (0.0 <= step.time_from < step.time_to <= 1.0):
+                raise RuntimeError("Brownian: the step must lie inside 0..1 after clamping")
+            walked = _host_brownian_increment(self._key(), step.time_from, step.time_to, self._depth, math.prod(self.shape))
+            return (walked * scale).to(self.dtype).reshape(tuple(self.shape))
         out = torch.empty(tuple(self.shape), dtype=self.dtype, device=self.seed.device)
         self._increment(out, step)
         return out
 
     def generate_into(self, out: torch.Tensor, step: Step | None) -> None:
-        if step and self._tree is None and out.is_cuda and out.is_contiguous() and out.numel() == math.prod(self.shape):
+        if step and self._tree is None and self.on_device and out.is_cuda and out.is_contiguous() and out.numel() == math.prod(self.shape):
             self._increment(out, step.normal().clamp())
         else:
             out.copy_(self.generate(step))
@@ -793,7 +878,7 @@ class BatchTensorNoise[T: TensorNoiseProps | None](SkrampleTensorNoise):
         first = self.generators[0]
         count = len(self.generators)
         if count > 32 or not all(
-            type(g) is Brownian and g._tree is None and _same_device(g.seed.device, out.device) and g.shape == first.shape and g._depth == first._depth
+            type(g) is Brownian and g._tree is None and g.on_device and _same_device(g.seed.device, out.device) and g.shape == first.shape and g._depth == first._depth
             for g in self.generators
         ):
             return False

@@ -120,13 +120,58 @@ def test_colored_exponent_schedule(n: int) -> None:
     assert got == pytest.approx({0: 0.17, 3: -0.16, 6: -0.73, 9: -2.0}[n], abs=6e-3)
 
 
-def test_brownian_needs_torchsde() -> None:
+def _has_torchsde() -> bool:
     try:
         import torchsde  # noqa: F401
     except ImportError:
-        with pytest.raises(ImportError):
-            noise.Brownian.from_inputs((4,), torch.Generator())
+        return False
+    return True
 
+
+BROWNIAN_STEPS = [
+    (0.0, 1.0),
+    (0.0, 0.04),
+    (0.48, 0.52),  # separated at the root
+    (0.96, 1.0),
+    (0.25, 0.5),  # both ends on dyadic points
+    (0.3, 0.3001),
+    (0.7000001, 0.7000003),  # inside one leaf of a 17-level tree
+    (1 / 3, 2 / 3),
+]
+
+
+@pytest.mark.skipif(_has_torchsde(), reason="with torchsde installed a CPU generator uses the reference's tree")
+@pytest.mark.parametrize("step", BROWNIAN_STEPS)
+@pytest.mark.parametrize("max_steps", [10_000, 50])
+def test_brownian_cpu_generator_vs_oracle(step: tuple[float, float], max_steps: int) -> None:
+    """Without torchsde a CPU generator evaluates the library's own bridge tree on the host (reference: noise.py:219-245
+    would raise ImportError): relative float32 increments here, absolute float64 path values in the oracle."""
+    shape = (3, 17, 23)
+    g = noise.Brownian.from_inputs(shape, torch.Generator().manual_seed(77), noise.BrownianProps(max_steps=max_steps))
+    got = g.generate(Step(*step))
+    assert got.shape == shape and got.dtype == torch.float32 and got.device.type == "cpu"
+    want = O.brownian_increment(77, step[0], step[1], math.ceil(math.log2(max_steps * 10)), got.numel()).reshape(shape)
+    np.testing.assert_allclose(got.numpy().astype(np.float64), want, rtol=0, atol=2e-5)
+
+
+@pytest.mark.skipif(_has_torchsde(), reason="with torchsde installed a CPU generator uses the reference's tree")
+def test_brownian_cpu_generator_contract() -> None:
+    shape = (4, 32, 32)
+    a = noise.Brownian.from_inputs(shape, torch.Generator().manual_seed(3), dtype=torch.float64)
+    b = noise.Brownian.from_inputs(shape, torch.Generator().manual_seed(3), dtype=torch.float64)
+    s0, s1 = Step.from_int(3, 25), Step.from_int(4, 25)
+    x0, x1 = a.generate(s0), a.generate(s1)
+    assert x0.dtype == torch.float64
+    assert torch.equal(b.generate(s1), x1) and torch.equal(b.generate(s0), x0) and torch.equal(a.generate(Step(s0.time_to, s0.time_from)), x0)
+    both = a.generate(Step(s0.time_from, s1.time_to))
+    assert ((x0 + x1) * math.sqrt(s0.distance()) - both * math.sqrt(2 * s0.distance())).abs().max().item() < 2e-6
+    assert abs((x0 * x1).mean().item()) < 5 / math.sqrt(x0.numel())
+    assert torch.equal(a.generate(None), torch.randn(shape, generator=torch.Generator().manual_seed(3), dtype=torch.float64))
+    with pytest.raises(ZeroDivisionError):
+        a.generate(Step(0.5, 0.5))
+    batch = noise.BatchTensorNoise.from_batch_inputs(noise.Brownian, shape, [torch.Generator().manual_seed(3), torch.Generator().manual_seed(4)], noise.BrownianProps(), torch.float64)
+    got = batch.generate(s0)
+    assert got.shape == (2, *shape) and torch.equal(got[0], x0) and not torch.equal(got[1], x0)
 
 
 def test_same_device_rule() -> None:
@@ -463,18 +508,6 @@ def test_fill_values_match_the_oracle_philox(seed: int, stream: int, numel: int)
     np.testing.assert_allclose(got, O.philox_normals(seed, stream, numel), rtol=0, atol=2e-6)
 
 
-BROWNIAN_STEPS = [
-    (0.0, 1.0),
-    (0.0, 0.04),
-    (0.48, 0.52),  # separated at the root
-    (0.96, 1.0),
-    (0.25, 0.5),  # both ends on dyadic points
-    (0.3, 0.3001),
-    (0.7000001, 0.7000003),  # inside one leaf of a 17-level tree
-    (1 / 3, 2 / 3),
-]
-
-
 @gpu
 @pytest.mark.parametrize("step", BROWNIAN_STEPS)
 @pytest.mark.parametrize("max_steps", [10_000, 50])
@@ -487,6 +520,17 @@ def test_brownian_kernel_vs_oracle(step: tuple[float, float], max_steps: int) ->
     assert got.shape == shape and got.dtype == torch.float32 and got.is_cuda
     want = O.brownian_increment(77, step[0], step[1], depth, got.numel()).reshape(shape)
     np.testing.assert_allclose(got.cpu().numpy().astype(np.float64), want, rtol=0, atol=2e-4)
+
+
+@gpu
+@pytest.mark.skipif(_has_torchsde(), reason="with torchsde installed a CPU generator uses the reference's tree")
+@pytest.mark.parametrize("step", [(0.0, 0.04), (0.48, 0.52), (0.3, 0.3001)])
+def test_brownian_same_path_on_host_and_device(step: tuple[float, float]) -> None:
+    "A seed names one path: the host evaluation (CPU generator) and the kernel (CUDA generator) agree to float32 rounding."
+    shape = (5, 40, 33)
+    host = noise.Brownian.from_inputs(shape, torch.Generator().manual_seed(21)).generate(Step(*step))
+    device = noise.Brownian.from_inputs(shape, _gen(21)).generate(Step(*step))
+    torch.testing.assert_close(device.cpu(), host, rtol=0, atol=3e-4)
 
 
 @gpu

@@ -5,9 +5,10 @@
 
 Copies /root/reference/tests/*.py (or $SKRAMPLE_REF/tests) to a scratch directory, aliases every
 ``skrample_b200`` module as ``skrample`` in a conftest, and runs the four self-contained files
-(self_sampling, miscellaneous, self_noise, self_scheduling).  Expected outcome here: everything passes except
-the Brownian tests, which need ``torchsde`` (not installed; they fail identically for the reference itself).
-Last run: 4362 passed, 104 failed (all ``*brownian*``).
+(self_sampling, miscellaneous, self_noise, self_scheduling).  Expected outcome here: everything passes, including the
+104 Brownian cases that the reference itself cannot run in this image (they need ``torchsde``, which is not installed;
+this package evaluates its own bridge tree on the host when the module is missing).
+Last run: 4466 passed, 0 failed.
 """
 
 from __future__ import annotations

@@ -111,3 +111,26 @@ def test_nccl_batch_shards_reproduce_the_single_gpu_run(tmp_path: Path) -> None:
     noises = [source.generate(None) for _ in outs]
     whole = _trajectory(x.to(device), [o.to(device) for o in outs], noises)
     assert torch.equal(sharded, whole.cpu())
+
+
+def test_bench_reference_arm_under_torchrun_prints_once() -> None:
+    """The driver launches the reference arm like the product arm (torchrun, one rank per GPU): rank 0 alone measures
+    and prints the line, the other ranks exit 0 without output."""
+    import json
+    import socket
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    with socket.socket() as probe:
+        probe.bind(("127.0.0.1", 0))
+        port = probe.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port),
+           str(root / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "25", "--warmup", "3"]
+    done = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert done.returncode == 0, done.stderr[-2000:]
+    lines = [line for line in done.stdout.splitlines() if line.strip()]
+    assert len(lines) == 1, done.stdout[-2000:]
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0

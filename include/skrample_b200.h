@@ -170,6 +170,35 @@ int skr_program_classify(const skr_program* program);
 int skr_program_describe(const skr_program* program, char* text, int32_t capacity);
 
 /*
+ * Step plans: the same launch with the host work done once.
+ *
+ * The reference re-derives every step from scratch (schedule points, dataclass churn, one ATen call per op:
+ * structured.py:33-34,137-149); a sampling loop takes the SAME step - same ops, same scalars, same tensor types -
+ * once per trajectory, so everything but the tensor addresses can be prepared ahead.  skr_plan_create validates
+ * `program`, recognises the step's structure and chooses the kernel instantiation (only the ops, the counts and the
+ * dtypes of program->inputs / outputs are read; pointers are ignored).  skr_plan_launch binds addresses and launches:
+ * `tensors` holds the n_inputs input pointers followed by the n_outputs output pointers, in the program's order and
+ * of the dtypes given at creation; `draws` = program->n_philox key tables (NULL when the step draws no noise).
+ * A plan is immutable: any number of threads may launch it concurrently.  Same results, bit for bit, as
+ * skr_program_launch on the same program.
+ */
+typedef struct skr_plan skr_plan;
+int skr_plan_create(const skr_program* program, skr_plan** plan);
+int skr_plan_launch(const skr_plan* plan, const void* const* tensors, int64_t numel, const skr_philox* draws, void* stream);
+void skr_plan_destroy(skr_plan* plan);
+/* 0 = structured block kernel, 1 = interpreter (what skr_program_classify says of the program), < 0 = error. */
+int skr_plan_kind(const skr_plan* plan);
+/* Name of the compiled kernel shape the plan launches ("any" = generic instantiation, "interpreter"). */
+const char* skr_plan_shape(const skr_plan* plan);
+
+/*
+ * Development switches (SKR_FORCE_INTERP, SKR_NO_PINNED, SKR_IN_MODE, SKR_STAGES, SKR_CTAS) are read from the
+ * environment once per process; tests and A/B tooling that change them afterwards call this to re-read them.
+ * Existing plans keep the kernel they were created with.
+ */
+void skr_reload_env(void);
+
+/*
  * Point.add_noise / remove_noise (common.py:32-40):
  *   remove == 0: out = sample*alpha + noise*sigma
  *   remove != 0: out = (sample - noise*sigma) / alpha

@@ -482,8 +482,17 @@ def unipc_step(
 
 
 def spowf(x: Any, f: float) -> Any:
-    "reference: common.py:187-190"
-    return np.abs(x) ** f * np.where(x < 0, -1, 1)
+    """reference: common.py:187-190.  torch multiplies the float tensor by an int64 sign tensor and stays in the float
+    type; NumPy would promote float32 * int64 to float64, so the sign is built in the value's own dtype.  Exponents torch
+    special-cases (2, 3, 0.5, ...: exact products / square roots) are the same special cases in NumPy; a general
+    exponent goes through each library's own powf (<= 1 ulp apart, tests state the bound)."""
+    sign = np.where(x < 0, -1, 1)
+    if isinstance(x, np.ndarray):
+        sign = sign.astype(x.dtype)
+        if f == 3:
+            m = np.abs(x)
+            return m * m * m * sign  # torch: pow(x, 3) = x*x*x
+    return np.abs(x) ** f * sign
 
 
 def spc_step(
@@ -583,8 +592,12 @@ def step_tableau(
     noise: Any = None,
     eta: float = 0,
     epsilon: float = 1e-8,
+    store: Callable[[Any], Any] | None = None,
 ) -> list[Any]:
-    "reference: functional.py:55-105"
+    """reference: functional.py:55-105.  ``store`` models latents kept in a 16-bit storage type with fp32 arithmetic (the
+    reference wrapper's compute_scale=float32 numerics, diffusers.py:575-599): every tensor that is handed to the
+    network or returned - the stage inputs and the results - is rounded once by ``store``; derivatives stay fp32."""
+    keep = store if store is not None else (lambda v: v)
     nodes, weights = tab.stages, tab.weights
     if deriv is not None:
         raw, src = net, model
@@ -603,8 +616,8 @@ def step_tableau(
         if abs(frac.timestep) < epsilon or abs(frac.sigma) < epsilon:
             ks.append(model.backward(sample, x, s0, s1))
         else:
-            ks.append(net(x, *frac))
-    return [model.forward(sample, fold_sumprod(ks, w), s0, s1, noise, eta) for w in weights]
+            ks.append(net(keep(x) if coeffs else x, *frac))
+    return [keep(model.forward(sample, fold_sumprod(ks, w), s0, s1, noise, eta)) for w in weights]
 
 
 def dynasaurk_tableau(step: St, order: int = 2, per_step_decay: float = math.log(0.5) / -2, total_step_decay: float = math.log(0.5) / -20) -> Tableau:

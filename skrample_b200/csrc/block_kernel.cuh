@@ -41,7 +41,7 @@ constexpr int kMaxTerms = 36;
 constexpr int kProducerThreads = 32;
 
 enum BlockKind : int32_t { BK_NONE = 0, BK_ACC = 1, BK_UNI = 2, BK_DPM2 = 3, BK_DPM3 = 4 };
-enum BlockLink : int32_t { BL_NONE = 0, BL_X_FROM_R = 1, BL_BLEND = 2, BL_BACK = 3 };
+enum BlockLink : int32_t { BL_NONE = 0, BL_X_FROM_R = 1, BL_BLEND = 2, BL_BACK = 3, BL_BLEND_POW = 4 };
 enum InMode : int { IN_MIXED = 0, IN_F32 = 1, IN_BF16 = 2, IN_F16 = 3 };
 
 template <typename CT>
@@ -60,6 +60,7 @@ struct BBlock {
     int32_t pad;
     CT p_coef, div, gamma, delta, zeta, l0, l1, e0, e1, e2;
     CT div_r, l1_r;  // reciprocals of the divisors `div` and `l1`
+    CT lp, lq;       // BL_BLEND_POW: the power and its inverse (SPC power mean, structured.py:568-575)
     uint32_t sample_off, base_off, noise_off, reserved;  // staged byte offsets of sample_in / base_in / noise_in
     BTerm<CT> terms[kMaxTerms];
     int32_t term_in[kMaxTerms];  // input index of each term (guarded path, host matching)
@@ -451,7 +452,7 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BB
     if (!pinned<BS::enabled>(k.enabled)) return;
     const bool fast_div = prog.fast_div != 0;
     const int link = pinned<BS::link>(k.link);
-    if (link == BL_BLEND) {
+    if (link == BL_BLEND || link == BL_BLEND_POW) {
 #pragma unroll
         for (int j = 0; j < V; ++j) S[j] = X[j];
     }
@@ -573,6 +574,15 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BB
             const CT l0 = k.l0, l1 = k.l1;
 #pragma unroll
             for (int j = 0; j < V; ++j) X[j] = Ar::add(Ar::mul(S[j], l0), Ar::mul(R[j], l1));
+            if (pinned<BS::slink>(k.store_link >= 0)) io.template store<BS::dt_slink>(k.store_link, X);
+        } else if (link == BL_BLEND_POW) {
+            // X = spow(spow(S, pw)*p + spow(R, pw)*c, 1/pw): the signed power mean, the only nonlinear op of a step
+            const CT l0 = k.l0, l1 = k.l1, pw = k.lp, inv = k.lq;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const CT mixed = Ar::add(Ar::mul(Ar::spow(S[j], pw), l0), Ar::mul(Ar::spow(R[j], pw), l1));
+                X[j] = Ar::spow(mixed, inv);
+            }
             if (pinned<BS::slink>(k.store_link >= 0)) io.template store<BS::dt_slink>(k.store_link, X);
         } else {  // BL_BACK
             const CT l0 = k.l0;
@@ -898,10 +908,12 @@ static bool parse_block(OpCursor& cur, BBlock<CT>& k) {
     if (cur.is_mov(SKR_X, SKR_R)) { cur.take(); k.link = BL_X_FROM_R; }
     else if (cur.is(SKR_OP_BLEND)) {
         const skr_op* t = cur.take();
-        if (t->a != 0 || !k.save_s) return false;
-        k.link = BL_BLEND;
+        if (t->a > 1 || !k.save_s) return false;
+        k.link = t->a ? BL_BLEND_POW : BL_BLEND;
         k.l0 = (CT)t->c[0];
         k.l1 = (CT)t->c[1];
+        k.lp = (CT)t->c[2];
+        k.lq = (CT)t->c[3];
         if (cur.is_store(SKR_X)) k.store_link = cur.take()->dst;
     } else if (cur.is(SKR_OP_BACK)) {
         const skr_op* t = cur.take();

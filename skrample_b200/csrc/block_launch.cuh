@@ -4,31 +4,32 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include "../../include/skrample_b200.h"
 #include "block_kernel.cuh"
 #include "host.cuh"
 
 namespace skr {
 
+// A launcher runs one block-kernel instantiation on a descriptor whose control fields, tensor tables (n_inputs,
+// in_ptr / in_dtype, out_ptr / out_dtype) and Philox keys are filled in; it derives everything that depends on the
+// size and the pointers (tile offsets, pipeline shape, grid) and launches.  Choosing the launcher is the expensive
+// part of a launch (matching the pinned shapes): skr_plan_create does it once, skr_plan_launch only calls it.
+template <typename CT>
+using BlockLauncher = int (*)(BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned);
+
 template <typename CT, int MODE, int V, bool PHILOX, typename Sh>
-static int launch_block_one(const skr_program* p, BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned) {
+static int launch_block_one(BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned) {
     constexpr int TILE = kThreads * V;
     k.numel = numel;
-    k.n_inputs = p->n_inputs;
     uint32_t off = 0;
-    for (int i = 0; i < p->n_inputs; ++i) {
-        k.in_ptr[i] = p->inputs[i].ptr;
-        k.in_dtype[i] = p->inputs[i].dtype;
+    for (int i = 0; i < k.n_inputs; ++i) {
         k.in_off[i] = off;
-        off += TILE * dtype_size_host(p->inputs[i].dtype);
-    }
-    for (int i = 0; i < p->n_outputs; ++i) {
-        k.out_ptr[i] = p->outputs[i].ptr;
-        k.out_dtype[i] = p->outputs[i].dtype;
+        off += TILE * dtype_size_host(k.in_dtype[i]);
     }
     k.stage_bytes = off;
     resolve_offsets(k);
-    fill_kphilox(k.philox, p->philox, p->n_philox);
 
     int err = 0;
     DeviceInfo* dev = device_info(&err);
@@ -54,16 +55,17 @@ static int launch_block_one(const skr_program* p, BProgram<CT>& k, int64_t numel
     }
     if (grid < 1) grid = 1;
 
-    static bool attr_set[64] = {};  // per instantiation, per device
-    const int ordinal = dev->ordinal;
-    if (!attr_set[ordinal]) {
+    // per instantiation, one bit per device ordinal; setting the attribute twice from two threads is harmless
+    static std::atomic<uint64_t> attr_set{0};
+    const uint64_t bit = 1ull << (dev->ordinal & 63);
+    if (!(attr_set.load(std::memory_order_acquire) & bit)) {
         cudaFuncAttributes fa;
         cudaError_t e = cudaFuncGetAttributes(&fa, block_kernel<CT, MODE, V, PHILOX, Sh>);
         if (e != cudaSuccess) return fail((int)e, "cudaFuncGetAttributes: %s", cudaGetErrorString(e));
         e = cudaFuncSetAttribute(block_kernel<CT, MODE, V, PHILOX, Sh>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  dev->max_smem - (int)fa.sharedSizeBytes);
         if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set[ordinal] = true;
+        attr_set.fetch_or(bit, std::memory_order_release);
     }
     // Programmatic dependent launch: consecutive steps overlap launch latency and prologue (SKR_PDL=0 disables).
     static const bool pdl = env_int("SKR_PDL", 1) != 0;
@@ -82,6 +84,21 @@ static int launch_block_one(const skr_program* p, BProgram<CT>& k, int64_t numel
     if (e != cudaSuccess) return fail((int)e, "block kernel launch: %s", cudaGetErrorString(e));
     count_launch(0);
     return 0;
+}
+
+// Tensor tables and Philox keys of a launch, from the C ABI's program (pointers + dtypes).
+template <typename CT>
+static void bind_tensors(const skr_program* p, BProgram<CT>& k) {
+    k.n_inputs = p->n_inputs;
+    for (int i = 0; i < p->n_inputs; ++i) {
+        k.in_ptr[i] = p->inputs[i].ptr;
+        k.in_dtype[i] = p->inputs[i].dtype;
+    }
+    for (int i = 0; i < p->n_outputs; ++i) {
+        k.out_ptr[i] = p->outputs[i].ptr;
+        k.out_dtype[i] = p->outputs[i].dtype;
+    }
+    fill_kphilox(k.philox, p->philox, p->n_philox);
 }
 
 template <typename Sh, int MODE, int V>
@@ -114,10 +131,10 @@ static void fill_dtypes(const skr_program* p, BProgram<CT>& k) {
 }
 
 
-// Pinned shapes of one latent storage type (pinned_shapes.cu).  Returns true when a shape matches; with `launch`
-// the kernel has been launched (status in *rc), otherwise only *name is set.
-bool pinned_f32(const skr_program* p, BProgram<float>& k, int64_t numel, cudaStream_t stream, bool aligned, bool launch, int* rc, const char** name);
-bool pinned_bf16(const skr_program* p, BProgram<float>& k, int64_t numel, cudaStream_t stream, bool aligned, bool launch, int* rc, const char** name);
-bool pinned_f16(const skr_program* p, BProgram<float>& k, int64_t numel, cudaStream_t stream, bool aligned, bool launch, int* rc, const char** name);
+// Pinned shapes of one latent storage type (pinned_shapes.cu): the launcher of the first shape that matches the
+// descriptor's control fields and dtypes (its name in *name), or nullptr.
+BlockLauncher<float> pinned_f32(const BProgram<float>& k, const char** name);
+BlockLauncher<float> pinned_bf16(const BProgram<float>& k, const char** name);
+BlockLauncher<float> pinned_f16(const BProgram<float>& k, const char** name);
 
 }  // namespace skr

@@ -1,6 +1,7 @@
 // skrample_b200 - host-side helpers shared by the translation units of the library (defined in step_kernel.cu).
 #pragma once
 
+#include <atomic>
 #include <cstdint>
 
 namespace skr {
@@ -14,7 +15,7 @@ struct DeviceInfo {
     int ordinal = 0;
     int sm_count = 0;
     int max_smem = 0;
-    bool attr_set[2] = {};  // interpreter instantiations (block kernels keep their own flags)
+    std::atomic<bool> attr_set[2] = {};  // interpreter instantiations (block kernels keep their own masks)
 };
 DeviceInfo* device_info(int* err);
 

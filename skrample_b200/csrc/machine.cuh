@@ -18,6 +18,11 @@ constexpr int kMaxStages = 8;
 // ------------------------------------------------------------------------------------------
 // individually rounded arithmetic
 
+// General exponents of the SPC power mean go through double-precision pow, out of line: the code is large and only
+// one uniform branch of the block kernel's generic instantiations and of the interpreter ever reaches it.
+static __device__ __noinline__ float pow_general(float m, float f) { return (float)pow((double)m, (double)f); }
+static __device__ __noinline__ double pow_general(double m, double f) { return pow(m, f); }
+
 template <typename CT> struct Arith;
 template <> struct Arith<float> {
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
@@ -34,7 +39,7 @@ template <> struct Arith<float> {
         else if (f == -0.5f) r = __fdiv_rn(1.0f, __fsqrt_rn(m));
         else if (f == -1.0f) r = __fdiv_rn(1.0f, m);
         else if (f == -2.0f) r = __fdiv_rn(1.0f, __fmul_rn(m, m));
-        else r = (float)pow((double)m, (double)f);
+        else r = pow_general(m, f);
         return x < 0.0f ? -r : r;
     }
 };
@@ -52,7 +57,7 @@ template <> struct Arith<double> {
         else if (f == -0.5) r = __ddiv_rn(1.0, __dsqrt_rn(m));
         else if (f == -1.0) r = __ddiv_rn(1.0, m);
         else if (f == -2.0) r = __ddiv_rn(1.0, __dmul_rn(m, m));
-        else r = pow(m, f);
+        else r = pow_general(m, f);
         return x < 0.0 ? -r : r;
     }
 };

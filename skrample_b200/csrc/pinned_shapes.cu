@@ -53,16 +53,17 @@ static bool for_each_pinned_shape(F&& f) {
            f(ShapeEntry<ShRKFinal<kLP>, kModeLP, kVecLP>{"rk-final/" SKR_LP_NAME});
 }
 
-bool SKR_PINNED_ENTRY(const skr_program* p, BProgram<float>& k, int64_t numel, cudaStream_t stream, bool aligned, bool launch,
-                      int* rc, const char** name) {
+BlockLauncher<float> SKR_PINNED_ENTRY(const BProgram<float>& k, const char** name) {
     const StorageClass storage(k);
-    return for_each_pinned_shape([&](auto entry) {
+    BlockLauncher<float> found = nullptr;
+    for_each_pinned_shape([&](auto entry) {
         using E = decltype(entry);
         if (!storage.allows(E::mode) || !shape_matches<typename E::shape>(k)) return false;
         *name = entry.name;
-        if (launch) *rc = launch_block_one<float, E::mode, E::v, false, typename E::shape>(p, k, numel, stream, aligned);
+        found = &launch_block_one<float, E::mode, E::v, false, typename E::shape>;
         return true;
     });
+    return found;
 }
 
 }  // namespace skr

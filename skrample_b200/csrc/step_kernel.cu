@@ -20,10 +20,14 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
+#include <new>
 
 #include "../../include/skrample_b200.h"
 #include "common.cuh"
@@ -296,10 +300,15 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
 
 // ------------------------------------------------------------------------------------------
 // host side
+//
+// Re-entrant by construction: the only process-wide state is (a) atomic launch counters, (b) the per-device
+// attribute table filled under std::call_once, (c) the development switches read from the environment once
+// (skr_reload_env re-reads them) and (d) per-instantiation "attribute set" bit masks (atomic).  Error text is
+// thread-local; descriptors live on the caller's stack or inside an immutable skr_plan.
 
 static thread_local char g_error[512] = "";
-static int64_t g_launches = 0;
-static int64_t g_launches_kind[3] = {0, 0, 0};  // [0] structured block kernel, [1] interpreter, [2] noise kernels
+static std::atomic<int64_t> g_launches{0};
+static std::atomic<int64_t> g_launches_kind[3];  // [0] structured block kernel, [1] interpreter, [2] noise kernels
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -309,29 +318,51 @@ int fail(int code, const char* fmt, ...) {
     return code;
 }
 
-int env_int(const char* name, int fallback) {
+// Development switches (tests and A/B tooling): read once, re-read by skr_reload_env().
+struct Switches {
+    std::atomic<int> force_interp{0}, no_pinned{0}, in_mode{-1}, stages{0}, ctas{0};
+};
+static Switches g_switches;
+static std::once_flag g_switches_once;
+
+static int env_raw(const char* name, int fallback) {
     const char* v = getenv(name);
     return v && *v ? atoi(v) : fallback;
 }
+static void load_switches() {
+    g_switches.force_interp = env_raw("SKR_FORCE_INTERP", 0);
+    g_switches.no_pinned = env_raw("SKR_NO_PINNED", 0);
+    g_switches.in_mode = env_raw("SKR_IN_MODE", -1);
+    g_switches.stages = env_raw("SKR_STAGES", 0);
+    g_switches.ctas = env_raw("SKR_CTAS", 0);
+}
+static const Switches& switches() {
+    std::call_once(g_switches_once, load_switches);
+    return g_switches;
+}
+
+int env_int(const char* name, int fallback) { return env_raw(name, fallback); }
+
 static DeviceInfo g_devices[64];
+static std::once_flag g_device_once[64];
 
 DeviceInfo* device_info(int* err) {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess || dev < 0 || dev >= 64) { *err = e ? (int)e : 1; return nullptr; }
     DeviceInfo& d = g_devices[dev];
-    if (d.sm_count == 0) {
+    std::call_once(g_device_once[dev], [&] {
         d.ordinal = dev;
         cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev);
         cudaDeviceGetAttribute(&d.max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    }
+    });
     *err = 0;
     return &d;
 }
 
 void count_launch(int kind) {
-    ++g_launches;
-    if (kind >= 0 && kind < 3) ++g_launches_kind[kind];
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (kind >= 0 && kind < 3) g_launches_kind[kind].fetch_add(1, std::memory_order_relaxed);
 }
 
 int sm_count_or(int fallback) {
@@ -411,20 +442,19 @@ static int launch_typed(const skr_program* p, int64_t numel, cudaStream_t stream
     if (grid < 1) grid = 1;
 
     const int which = sizeof(CT) == 8 ? 1 : 0;
-    if (!dev->attr_set[which]) {
+    if (!dev->attr_set[which].load(std::memory_order_acquire)) {
         cudaFuncAttributes fa;
         cudaError_t e = cudaFuncGetAttributes(&fa, step_kernel<CT>);
         if (e != cudaSuccess) return fail((int)e, "cudaFuncGetAttributes: %s", cudaGetErrorString(e));
         e = cudaFuncSetAttribute(step_kernel<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  dev->max_smem - (int)fa.sharedSizeBytes);
         if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        dev->attr_set[which] = true;
+        dev->attr_set[which].store(true, std::memory_order_release);
     }
     step_kernel<CT><<<(unsigned)grid, kThreads, smem, stream>>>(k);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, "step kernel launch: %s", cudaGetErrorString(e));
-    ++g_launches;
-    ++g_launches_kind[1];
+    count_launch(1);
     return 0;
 }
 
@@ -441,148 +471,77 @@ PipeShape pick_shape(uint32_t stage_bytes, int max_smem, int max_ctas) {
     if (stages > want) stages = want;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) stages = 2;
-    sh.stages = env_int("SKR_STAGES", stages);
-    sh.ctas_per_sm = env_int("SKR_CTAS", ctas);
+    const Switches& sw = switches();
+    const int force_stages = sw.stages.load(std::memory_order_relaxed), force_ctas = sw.ctas.load(std::memory_order_relaxed);
+    sh.stages = force_stages > 0 ? force_stages : stages;
+    sh.ctas_per_sm = force_ctas > 0 ? force_ctas : ctas;
     if (sh.stages < 2) sh.stages = 2;
     if (sh.stages > kMaxStages) sh.stages = kMaxStages;
     if ((uint32_t)sh.stages * stage_bytes > usable) sh.stages = (int)(usable / stage_bytes);
     return sh;
 }
 
+// ---- choosing the block-kernel instantiation of a parsed step -----------------------------------------------
+// `k` carries the control fields and the dtypes of every tensor (bind_tensors / fill_dtypes); pointers play no part.
+
 template <typename CT, int MODE, int V>
-static int launch_block_inst(const skr_program* p, BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned) {
-    if (p->n_philox > 0) return launch_block_one<CT, MODE, V, true, ShAny>(p, k, numel, stream, aligned);
-    return launch_block_one<CT, MODE, V, false, ShAny>(p, k, numel, stream, aligned);
+static BlockLauncher<CT> generic_launcher(int n_philox) {
+    if (n_philox > 0) return &launch_block_one<CT, MODE, V, true, ShAny>;
+    return &launch_block_one<CT, MODE, V, false, ShAny>;
 }
 
-// ---- pinned shapes (pinned_shapes.cu), tried before the generic instantiations ------------------------------
-
-static bool pinned_any(const skr_program* p, BProgram<float>& k, int64_t numel, cudaStream_t stream, bool aligned, bool launch,
-                       int* rc, const char** name) {
-    if (p->n_philox > 0 || env_int("SKR_NO_PINNED", 0)) return false;
+static BlockLauncher<float> pinned_any(const BProgram<float>& k, int n_philox, const char** name) {
+    if (n_philox > 0 || switches().no_pinned.load(std::memory_order_relaxed)) return nullptr;
     // the latent storage type is that of the network output (head.y) or, for RK combinations, of the sample
     const int probe = k.head.y_in >= 0 ? k.head.y_in : k.head.x_in;
-    if (probe < 0) return false;
+    if (probe < 0) return nullptr;
     switch (k.in_dtype[probe]) {
-        case SKR_F32: return pinned_f32(p, k, numel, stream, aligned, launch, rc, name);
-        case SKR_BF16: return pinned_bf16(p, k, numel, stream, aligned, launch, rc, name);
-        case SKR_F16: return pinned_f16(p, k, numel, stream, aligned, launch, rc, name);
-        default: return false;
+        case SKR_F32: return pinned_f32(k, name);
+        case SKR_BF16: return pinned_bf16(k, name);
+        case SKR_F16: return pinned_f16(k, name);
+        default: return nullptr;
     }
 }
 
-template <typename CT>
-static int launch_block(const skr_program* p, BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned) {
-    fill_dtypes(p, k);
-    if constexpr (sizeof(CT) == 8) {
-        return launch_block_inst<double, IN_MIXED, 4>(p, k, numel, stream, aligned);
-    } else {
-        const StorageClass storage(k);
-        const int force = env_int("SKR_IN_MODE", -1);  // development switch: 0 / 8 force a mixed instantiation
-        if (force == 0) return launch_block_inst<float, IN_MIXED, 4>(p, k, numel, stream, aligned);
-        if (force == 8) return launch_block_inst<float, IN_MIXED, 8>(p, k, numel, stream, aligned);
-        int rc = 0;
-        const char* name = nullptr;
-        if (pinned_any(p, k, numel, stream, aligned, true, &rc, &name)) return rc;
-        if (storage.all_f32) return launch_block_inst<float, IN_F32, 4>(p, k, numel, stream, aligned);
-        if (storage.all_bf16) return launch_block_inst<float, IN_BF16, 8>(p, k, numel, stream, aligned);
-        if (storage.all_f16) return launch_block_inst<float, IN_F16, 8>(p, k, numel, stream, aligned);
-        // Mixed storage stays at 4 elements per thread: measured on B200 the 8-wide variant loses more to halved
-        // occupancy / doubled stage size than it gains from amortised control (Adams-9 bf16 59 vs 31 us,
-        // UniPC-3 bf16 46 vs 37 us per step); SKR_IN_MODE=8 keeps it reachable for experiments.
-        return launch_block_inst<float, IN_MIXED, 4>(p, k, numel, stream, aligned);
-    }
+static BlockLauncher<double> select_launcher(const BProgram<double>&, int n_philox, const char** name) {
+    *name = "any";
+    return generic_launcher<double, IN_MIXED, 4>(n_philox);
 }
 
-template <typename CT>
-static int launch_any(const skr_program* p, int64_t numel, cudaStream_t stream, bool aligned) {
-    if (!env_int("SKR_FORCE_INTERP", 0)) {
-        BProgram<CT> b;
-        memset(&b, 0, sizeof(b));
-        if (parse_block_program<CT>(p, b)) return launch_block<CT>(p, b, numel, stream, aligned);
-    }
-    return launch_typed<CT>(p, numel, stream, aligned);
+static BlockLauncher<float> select_launcher(const BProgram<float>& k, int n_philox, const char** name) {
+    *name = "any";
+    const StorageClass storage(k);
+    const int force = switches().in_mode.load(std::memory_order_relaxed);  // development switch: 0 / 8 force a mixed instantiation
+    if (force == 0) return generic_launcher<float, IN_MIXED, 4>(n_philox);
+    if (force == 8) return generic_launcher<float, IN_MIXED, 8>(n_philox);
+    if (BlockLauncher<float> pinned = pinned_any(k, n_philox, name)) return pinned;
+    if (storage.all_f32) return generic_launcher<float, IN_F32, 4>(n_philox);
+    if (storage.all_bf16) return generic_launcher<float, IN_BF16, 8>(n_philox);
+    if (storage.all_f16) return generic_launcher<float, IN_F16, 8>(n_philox);
+    // Mixed storage stays at 4 elements per thread: measured on B200 the 8-wide variant loses more to halved
+    // occupancy / doubled stage size than it gains from amortised control (Adams-9 bf16 59 vs 31 us,
+    // UniPC-3 bf16 46 vs 37 us per step); SKR_IN_MODE=8 keeps it reachable for experiments.
+    return generic_launcher<float, IN_MIXED, 4>(n_philox);
 }
 
-}  // namespace skr
+// ---- validation shared by skr_program_launch and skr_plan_create ----------------------------------------------
+// numel < 0: the size is not known yet (plan creation): size-dependent checks are left to the launch.
 
-extern "C" {
-
-int skr_version(void) { return SKR_VERSION; }
-const char* skr_last_error(void) { return skr::g_error; }
-int64_t skr_launch_count(void) { return skr::g_launches; }
-int64_t skr_launch_count_kind(int32_t kind) { return (kind >= 0 && kind <= 2) ? skr::g_launches_kind[kind] : -1; }
-
-int skr_program_classify(const skr_program* p) {
-    using namespace skr;
+static int validate_program(const skr_program* p, int64_t numel, bool need_pointers) {
     if (!p) return fail(SKR_E_NULL, "null program");
-    if (p->n_ops < 0 || p->n_ops > SKR_MAX_OPS) return fail(SKR_E_RANGE, "n_ops %d out of range", p->n_ops);
-    static BProgram<double> b;
-    memset(&b, 0, sizeof(b));
-    return parse_block_program<double>(p, b) ? 0 : 1;
-}
-
-int skr_program_describe(const skr_program* p, char* text, int32_t capacity) {
-    using namespace skr;
-    if (!p || !text || capacity < 1) return fail(SKR_E_NULL, "null argument");
-    if (p->n_ops < 0 || p->n_ops > SKR_MAX_OPS) return fail(SKR_E_RANGE, "n_ops %d out of range", p->n_ops);
-    if (p->n_inputs < 0 || p->n_inputs > SKR_MAX_INPUTS) return fail(SKR_E_RANGE, "n_inputs %d out of range", p->n_inputs);
-    if (p->n_outputs < 0 || p->n_outputs > SKR_MAX_OUTPUTS) return fail(SKR_E_RANGE, "n_outputs %d out of range", p->n_outputs);
-    bool any64 = false;
-    for (int i = 0; i < p->n_inputs; ++i) any64 |= p->inputs[i].dtype == SKR_F64;
-    for (int i = 0; i < p->n_outputs; ++i) any64 |= p->outputs[i].dtype == SKR_F64;
-    static BProgram<float> b;  // host-only scratch; the descriptor is too large for the stack of small threads
-    memset(&b, 0, sizeof(b));
-    if (!parse_block_program<float>(p, b)) {
-        snprintf(text, (size_t)capacity, "interpreter");
-        return 1;
-    }
-    fill_dtypes(p, b);
-    const char* shape_name = "any";
-    int unused = 0;
-    if (!any64) pinned_any(p, b, 0, nullptr, true, false, &unused, &shape_name);
-    const BHead<float>& h = b.head;
-    int n = snprintf(text, (size_t)capacity, "block compute=%s shape=%s fast_div=%d head[x=%d y=%d neg=%d conv=%d sp=%d sp2=%d]",
-                     any64 ? "f64" : "f32", any64 ? "any" : shape_name, any64 ? 0 : b.fast_div,
-                     h.x_in >= 0, h.y_in >= 0, h.neg, h.n_conv, h.store_p >= 0, h.store_p2 >= 0);
-    for (int i = 0; i < 2 && n > 0 && n < capacity; ++i) {
-        const BBlock<float>& k = b.blk[i];
-        if (!k.enabled) continue;
-        n += snprintf(text + n, (size_t)(capacity - n),
-                      " blk%d[kind=%d sample=%d base=%d p_mode=%d div=%d pred_p=%d noise=%d terms=%d store=%d link=%d slink=%d]", i,
-                      k.kind, k.sample_in >= 0, k.base_in >= 0, k.p_mode, k.has_div, k.pred_is_p, k.has_noise, k.n_terms,
-                      k.store_r >= 0, k.link, k.store_link >= 0);
-    }
-    return 0;
-}
-
-int skr_program_launch(const skr_program* p, int64_t numel, void* stream) {
-    using namespace skr;
-    if (!p) return fail(SKR_E_NULL, "null program");
-    if (numel < 0) return fail(SKR_E_RANGE, "negative numel");
     if (p->n_ops < 0 || p->n_ops > SKR_MAX_OPS) return fail(SKR_E_RANGE, "n_ops %d out of range", p->n_ops);
     if (p->n_inputs < 0 || p->n_inputs > SKR_MAX_INPUTS) return fail(SKR_E_RANGE, "n_inputs %d out of range", p->n_inputs);
     if (p->n_outputs < 0 || p->n_outputs > SKR_MAX_OUTPUTS) return fail(SKR_E_RANGE, "n_outputs %d out of range", p->n_outputs);
     if (p->n_philox < 0 || p->n_philox > SKR_MAX_PHILOX) return fail(SKR_E_RANGE, "n_philox %d out of range", p->n_philox);
-    for (int i = 0; i < p->n_philox; ++i) {
-        const skr_philox& d = p->philox[i];
-        if (d.n_items < 1 || d.n_items > SKR_MAX_PHILOX_ITEMS) return fail(SKR_E_RANGE, "philox %d: n_items %d out of range", i, d.n_items);
-        if (d.item_numel < 1 || d.item_numel * d.n_items != numel) return fail(SKR_E_SHAPE, "philox %d: n_items * item_numel != numel", i);
-    }
-    bool any64 = false, aligned = true;
     for (int i = 0; i < p->n_inputs; ++i) {
         const skr_tensor& t = p->inputs[i];
         if (t.dtype < 0 || t.dtype > SKR_F16) return fail(SKR_E_DTYPE, "input %d: unknown dtype %d", i, t.dtype);
-        if (!t.ptr && numel > 0) return fail(SKR_E_NULL, "input %d: null pointer", i);
-        any64 |= t.dtype == SKR_F64;
-        aligned &= (reinterpret_cast<uintptr_t>(t.ptr) & 15u) == 0;
+        if (need_pointers && !t.ptr && numel > 0) return fail(SKR_E_NULL, "input %d: null pointer", i);
     }
     for (int i = 0; i < p->n_outputs; ++i) {
         const skr_tensor& t = p->outputs[i];
         if (t.dtype < 0 || t.dtype > SKR_F16) return fail(SKR_E_DTYPE, "output %d: unknown dtype %d", i, t.dtype);
-        if (!t.ptr && numel > 0) return fail(SKR_E_NULL, "output %d: null pointer", i);
-        any64 |= t.dtype == SKR_F64;
-        aligned &= (reinterpret_cast<uintptr_t>(t.ptr) & 15u) == 0;
+        if (need_pointers && !t.ptr && numel > 0) return fail(SKR_E_NULL, "output %d: null pointer", i);
     }
     for (int i = 0; i < p->n_ops; ++i) {
         const skr_op& o = p->ops[i];
@@ -603,9 +562,204 @@ int skr_program_launch(const skr_program* p, int64_t numel, void* stream) {
         if (o.code == SKR_OP_MOV && o.b > 7) return fail(SKR_E_RANGE, "op %d: register %d out of range", i, (int)o.b);
         if ((o.code == SKR_OP_ACC0 || o.code == SKR_OP_ACC) && o.a > 8) return fail(SKR_E_RANGE, "op %d: register out of range", i);
     }
+    return 0;
+}
+
+static int validate_philox(const skr_philox* draws, int n, int64_t numel) {
+    for (int i = 0; i < n; ++i) {
+        const skr_philox& d = draws[i];
+        if (d.n_items < 1 || d.n_items > SKR_MAX_PHILOX_ITEMS) return fail(SKR_E_RANGE, "philox %d: n_items %d out of range", i, d.n_items);
+        if (d.item_numel < 1 || d.item_numel * d.n_items != numel) return fail(SKR_E_SHAPE, "philox %d: n_items * item_numel != numel", i);
+    }
+    return 0;
+}
+
+static bool any_f64(const skr_program* p) {
+    bool any64 = false;
+    for (int i = 0; i < p->n_inputs; ++i) any64 |= p->inputs[i].dtype == SKR_F64;
+    for (int i = 0; i < p->n_outputs; ++i) any64 |= p->outputs[i].dtype == SKR_F64;
+    return any64;
+}
+
+template <typename CT>
+static int launch_any(const skr_program* p, int64_t numel, cudaStream_t stream, bool aligned) {
+    if (!switches().force_interp.load(std::memory_order_relaxed)) {
+        BProgram<CT> b;
+        memset(&b, 0, sizeof(b));
+        if (parse_block_program<CT>(p, b)) {
+            bind_tensors(p, b);
+            const char* name = nullptr;
+            return select_launcher(b, p->n_philox, &name)(b, numel, stream, aligned);
+        }
+    }
+    return launch_typed<CT>(p, numel, stream, aligned);
+}
+
+}  // namespace skr
+
+// A step whose parsing and kernel selection are done: what the plan-cache hit path of the Python layer launches.
+// Immutable after skr_plan_create, so any number of threads may launch one plan at the same time.
+struct skr_plan {
+    int32_t n_inputs, n_outputs, n_philox;
+    bool f64, block;
+    const char* shape_name;
+    std::unique_ptr<skr::BProgram<float>> bf;
+    std::unique_ptr<skr::BProgram<double>> bd;
+    skr::BlockLauncher<float> lf = nullptr;
+    skr::BlockLauncher<double> ld = nullptr;
+    skr_program source;  // ops + dtypes (the interpreter's input; pointers are filled per launch)
+};
+
+template <typename CT>
+static int launch_planned(const skr::BProgram<CT>& parsed, skr::BlockLauncher<CT> launcher, const skr_plan* plan, const void* const* tensors,
+                          int64_t numel, const skr_philox* draws, cudaStream_t stream, bool aligned) {
+    skr::BProgram<CT> k = parsed;  // the launch's own copy: plans are shared between threads
+    for (int i = 0; i < plan->n_inputs; ++i) k.in_ptr[i] = tensors[i];
+    for (int i = 0; i < plan->n_outputs; ++i) k.out_ptr[i] = const_cast<void*>(tensors[plan->n_inputs + i]);
+    skr::fill_kphilox(k.philox, draws, plan->n_philox);
+    return launcher(k, numel, stream, aligned);
+}
+
+extern "C" {
+
+int skr_version(void) { return SKR_VERSION; }
+const char* skr_last_error(void) { return skr::g_error; }
+int64_t skr_launch_count(void) { return skr::g_launches.load(std::memory_order_relaxed); }
+int64_t skr_launch_count_kind(int32_t kind) {
+    return (kind >= 0 && kind <= 2) ? skr::g_launches_kind[kind].load(std::memory_order_relaxed) : -1;
+}
+void skr_reload_env(void) {
+    skr::switches();
+    skr::load_switches();
+}
+
+int skr_program_classify(const skr_program* p) {
+    using namespace skr;
+    if (!p) return fail(SKR_E_NULL, "null program");
+    if (p->n_ops < 0 || p->n_ops > SKR_MAX_OPS) return fail(SKR_E_RANGE, "n_ops %d out of range", p->n_ops);
+    auto b = std::make_unique<BProgram<double>>();  // too large for the stack of small threads
+    memset(b.get(), 0, sizeof(*b));
+    return parse_block_program<double>(p, *b) ? 0 : 1;
+}
+
+int skr_program_describe(const skr_program* p, char* text, int32_t capacity) {
+    using namespace skr;
+    if (!p || !text || capacity < 1) return fail(SKR_E_NULL, "null argument");
+    if (p->n_ops < 0 || p->n_ops > SKR_MAX_OPS) return fail(SKR_E_RANGE, "n_ops %d out of range", p->n_ops);
+    if (p->n_inputs < 0 || p->n_inputs > SKR_MAX_INPUTS) return fail(SKR_E_RANGE, "n_inputs %d out of range", p->n_inputs);
+    if (p->n_outputs < 0 || p->n_outputs > SKR_MAX_OUTPUTS) return fail(SKR_E_RANGE, "n_outputs %d out of range", p->n_outputs);
+    const bool any64 = any_f64(p);
+    auto b = std::make_unique<BProgram<float>>();
+    memset(b.get(), 0, sizeof(*b));
+    if (!parse_block_program<float>(p, *b)) {
+        snprintf(text, (size_t)capacity, "interpreter");
+        return 1;
+    }
+    fill_dtypes(p, *b);
+    const char* shape_name = "any";
+    if (!any64) select_launcher(*b, p->n_philox, &shape_name);
+    const BHead<float>& h = b->head;
+    int n = snprintf(text, (size_t)capacity, "block compute=%s shape=%s fast_div=%d head[x=%d y=%d neg=%d conv=%d sp=%d sp2=%d]",
+                     any64 ? "f64" : "f32", any64 ? "any" : shape_name, any64 ? 0 : b->fast_div,
+                     h.x_in >= 0, h.y_in >= 0, h.neg, h.n_conv, h.store_p >= 0, h.store_p2 >= 0);
+    for (int i = 0; i < 2 && n > 0 && n < capacity; ++i) {
+        const BBlock<float>& k = b->blk[i];
+        if (!k.enabled) continue;
+        n += snprintf(text + n, (size_t)(capacity - n),
+                      " blk%d[kind=%d sample=%d base=%d p_mode=%d div=%d pred_p=%d noise=%d terms=%d store=%d link=%d slink=%d]", i,
+                      k.kind, k.sample_in >= 0, k.base_in >= 0, k.p_mode, k.has_div, k.pred_is_p, k.has_noise, k.n_terms,
+                      k.store_r >= 0, k.link, k.store_link >= 0);
+    }
+    return 0;
+}
+
+int skr_program_launch(const skr_program* p, int64_t numel, void* stream) {
+    using namespace skr;
+    if (!p) return fail(SKR_E_NULL, "null program");
+    if (numel < 0) return fail(SKR_E_RANGE, "negative numel");
+    if (int rc = validate_program(p, numel, true)) return rc;
+    if (int rc = validate_philox(p->philox, p->n_philox, numel)) return rc;
+    bool aligned = true;
+    for (int i = 0; i < p->n_inputs; ++i) aligned &= (reinterpret_cast<uintptr_t>(p->inputs[i].ptr) & 15u) == 0;
+    for (int i = 0; i < p->n_outputs; ++i) aligned &= (reinterpret_cast<uintptr_t>(p->outputs[i].ptr) & 15u) == 0;
     if (numel == 0 || p->n_ops == 0) return 0;
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-    return any64 ? launch_any<double>(p, numel, s, aligned) : launch_any<float>(p, numel, s, aligned);
+    return any_f64(p) ? launch_any<double>(p, numel, s, aligned) : launch_any<float>(p, numel, s, aligned);
+}
+
+int skr_plan_create(const skr_program* p, skr_plan** out) {
+    using namespace skr;
+    if (!out) return fail(SKR_E_NULL, "null plan slot");
+    *out = nullptr;
+    if (int rc = validate_program(p, -1, false)) return rc;
+    std::unique_ptr<skr_plan> plan(new (std::nothrow) skr_plan());
+    if (!plan) return fail(SKR_E_UNSUPPORTED, "out of host memory");
+    plan->n_inputs = p->n_inputs;
+    plan->n_outputs = p->n_outputs;
+    plan->n_philox = p->n_philox;
+    plan->f64 = any_f64(p);
+    plan->block = false;
+    plan->shape_name = "interpreter";
+    plan->source = *p;
+    for (int i = 0; i < SKR_MAX_INPUTS; ++i) plan->source.inputs[i].ptr = nullptr;
+    for (int i = 0; i < SKR_MAX_OUTPUTS; ++i) plan->source.outputs[i].ptr = nullptr;
+    if (!switches().force_interp.load(std::memory_order_relaxed) && p->n_ops > 0) {
+        if (plan->f64) {
+            plan->bd.reset(new (std::nothrow) BProgram<double>());
+            if (!plan->bd) return fail(SKR_E_UNSUPPORTED, "out of host memory");
+            memset(plan->bd.get(), 0, sizeof(BProgram<double>));
+            if (parse_block_program<double>(p, *plan->bd)) {
+                fill_dtypes(p, *plan->bd);
+                plan->ld = select_launcher(*plan->bd, p->n_philox, &plan->shape_name);
+                plan->block = true;
+            }
+        } else {
+            plan->bf.reset(new (std::nothrow) BProgram<float>());
+            if (!plan->bf) return fail(SKR_E_UNSUPPORTED, "out of host memory");
+            memset(plan->bf.get(), 0, sizeof(BProgram<float>));
+            if (parse_block_program<float>(p, *plan->bf)) {
+                fill_dtypes(p, *plan->bf);
+                plan->lf = select_launcher(*plan->bf, p->n_philox, &plan->shape_name);
+                plan->block = true;
+            }
+        }
+    }
+    *out = plan.release();
+    return 0;
+}
+
+void skr_plan_destroy(skr_plan* plan) { delete plan; }
+
+int skr_plan_kind(const skr_plan* plan) { return !plan ? skr::fail(SKR_E_NULL, "null plan") : plan->block ? 0 : 1; }
+
+const char* skr_plan_shape(const skr_plan* plan) { return plan ? plan->shape_name : ""; }
+
+int skr_plan_launch(const skr_plan* plan, const void* const* tensors, int64_t numel, const skr_philox* draws, void* stream) {
+    using namespace skr;
+    if (!plan) return fail(SKR_E_NULL, "null plan");
+    if (numel < 0) return fail(SKR_E_RANGE, "negative numel");
+    const int n = plan->n_inputs + plan->n_outputs;
+    if (n > 0 && !tensors) return fail(SKR_E_NULL, "null tensor table");
+    if (plan->n_philox > 0) {
+        if (!draws) return fail(SKR_E_NULL, "the plan draws noise in the kernel: Philox keys are required");
+        if (int rc = validate_philox(draws, plan->n_philox, numel)) return rc;
+    }
+    if (numel == 0 || plan->source.n_ops == 0) return 0;
+    bool aligned = true;
+    for (int i = 0; i < n; ++i) {
+        if (!tensors[i]) return fail(SKR_E_NULL, "tensor %d: null pointer", i);
+        aligned &= (reinterpret_cast<uintptr_t>(tensors[i]) & 15u) == 0;
+    }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (plan->block) {
+        if (plan->f64) return launch_planned<double>(*plan->bd, plan->ld, plan, tensors, numel, draws, s, aligned);
+        return launch_planned<float>(*plan->bf, plan->lf, plan, tensors, numel, draws, s, aligned);
+    }
+    skr_program p = plan->source;
+    for (int i = 0; i < plan->n_inputs; ++i) p.inputs[i].ptr = const_cast<void*>(tensors[i]);
+    for (int i = 0; i < plan->n_outputs; ++i) p.outputs[i].ptr = const_cast<void*>(tensors[plan->n_inputs + i]);
+    for (int i = 0; i < plan->n_philox; ++i) p.philox[i] = draws[i];
+    return plan->f64 ? launch_typed<double>(&p, numel, s, aligned) : launch_typed<float>(&p, numel, s, aligned);
 }
 
 int skr_axpby(const void* sample, const void* noise, void* out, int32_t dtype, int64_t numel, double sigma, double alpha,

@@ -101,9 +101,16 @@ EXPORTS = (
     "skr_program_describe",
     "skr_axpby",
     "skr_error_norms",
+    "skr_plan_create",
+    "skr_plan_launch",
+    "skr_plan_destroy",
+    "skr_plan_kind",
+    "skr_plan_shape",
+    "skr_reload_env",
 )
 
 _lib: ctypes.CDLL | None = None
+_switches_touched = False
 
 ACCOUNT = {"on": False, "bytes": 0, "launches": 0}
 "Opt-in byte accounting of launched programs (bench.py derives algorithmic bytes per step from it)."
@@ -143,6 +150,17 @@ def load() -> ctypes.CDLL:
         ctypes.c_int32,
         ctypes.c_void_p,
     ]
+    lib.skr_plan_create.restype = ctypes.c_int
+    lib.skr_plan_create.argtypes = [ctypes.POINTER(SkrProgram), ctypes.POINTER(ctypes.c_void_p)]
+    lib.skr_plan_launch.restype = ctypes.c_int
+    lib.skr_plan_launch.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+    lib.skr_plan_destroy.restype = None
+    lib.skr_plan_destroy.argtypes = [ctypes.c_void_p]
+    lib.skr_plan_kind.restype = ctypes.c_int
+    lib.skr_plan_kind.argtypes = [ctypes.c_void_p]
+    lib.skr_plan_shape.restype = ctypes.c_char_p
+    lib.skr_plan_shape.argtypes = [ctypes.c_void_p]
+    lib.skr_reload_env.restype = None
     lib.skr_error_norms.restype = ctypes.c_int
     lib.skr_error_norms.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
     _lib = lib
@@ -265,10 +283,41 @@ def launch_program(program: "Program") -> list[Any]:
     return outputs
 
 
-class CompiledProgram:
-    "A packed program whose op table is final; only tensor pointers / dtypes change between launches."
+class _NativePlan:
+    """One ``skr_plan`` (the step parsed and its kernel chosen, for one combination of input dtypes) plus the
+    reusable pointer table its launches are bound through."""
 
-    __slots__ = ("n_inputs", "out_specs", "packed")
+    __slots__ = ("handle", "n_inputs", "out_dtypes", "packer", "table")
+
+    def __init__(self, handle: int, n_inputs: int, out_dtypes: tuple) -> None:
+        self.handle = handle
+        self.n_inputs = n_inputs
+        self.out_dtypes = out_dtypes
+        count = n_inputs + len(out_dtypes)
+        self.table = (ctypes.c_uint64 * max(1, count))()
+        self.packer = struct.Struct(f"<{count}Q")
+
+    def __del__(self) -> None:
+        lib, handle = _lib, self.handle
+        if lib is not None and handle:
+            self.handle = 0
+            lib.skr_plan_destroy(handle)
+
+    @property
+    def kind(self) -> int:
+        return int(load().skr_plan_kind(self.handle))
+
+    @property
+    def shape_name(self) -> str:
+        return load().skr_plan_shape(self.handle).decode()
+
+
+class CompiledProgram:
+    """A step program whose op table is final.  Per combination of input dtypes it owns one native plan
+    (``skr_plan_create``: validation, structure recognition and kernel selection happen once); a launch only binds
+    tensor addresses (``skr_plan_launch``)."""
+
+    __slots__ = ("n_inputs", "n_philox", "out_specs", "packed", "plans")
 
     def __init__(self, program: "Program") -> None:
         if len(program.ops) > MAX_OPS or len(program.inputs) > MAX_INPUTS or len(program.outputs) > MAX_OUTPUTS:
@@ -277,95 +326,120 @@ class CompiledProgram:
         packed.n_ops = len(program.ops)
         packed.n_inputs = len(program.inputs)
         packed.n_outputs = len(program.outputs)
+        packed.n_philox = len(getattr(program, "philox", ()))
         for slot, op in zip(packed.ops, program.ops, strict=False):
             slot.code, slot.a, slot.b, slot.src, slot.dst = op.code, op.a, op.b, op.src, op.dst
             for j, value in enumerate(op.c):
                 slot.c[j] = value
         self.packed = packed
         self.n_inputs = len(program.inputs)
+        self.n_philox = packed.n_philox
         self.out_specs = tuple(program.outputs)
+        self.plans: dict[tuple, _NativePlan | None] = {}
+
+    def specialise(self, signature: tuple) -> "_NativePlan | None":
+        "The native plan for inputs of these dtypes (None: a dtype the kernels do not take)."
+        codes = [DTYPE_CODE.get(d) for d in signature]
+        if any(code is None for code in codes):
+            self.plans[signature] = None
+            return None
+        any64 = torch.float64 in signature
+        default = torch.float64 if any64 else (torch.float32 if torch.float32 in signature or len(set(signature)) > 1 else signature[0])
+        compute = torch.float64 if any64 else torch.float32
+        out_dtypes = tuple(default if want is None else (compute if want.__class__ is str else want) for want in self.out_specs)
+        packed = self.packed
+        for slot, code in zip(packed.inputs, codes, strict=False):
+            slot.dtype = code
+        for slot, dtype in zip(packed.outputs, out_dtypes, strict=False):
+            slot.dtype = DTYPE_CODE[dtype]
+        handle = ctypes.c_void_p()
+        check(load().skr_plan_create(ctypes.byref(packed), ctypes.byref(handle)), "skr_plan_create")
+        plan = self.plans[signature] = _NativePlan(handle.value, self.n_inputs, out_dtypes)
+        return plan
 
 
 _ALLOWED = frozenset(DTYPE_CODE)
+_MISSING = object()
+_draw_keys = threading.local()
 
 
-def _on_device(t: Any) -> bool:
-    return t.is_cuda
-
-
-_TENSOR_RECORD = "Qi4x"  # skr_tensor: pointer, dtype code, reserved
-_PACKERS: dict[int, struct.Struct] = {}
-_INPUTS_AT = SkrProgram.inputs.offset
-_OUTPUTS_AT = SkrProgram.outputs.offset
-assert ctypes.sizeof(SkrTensor) == struct.calcsize("<" + _TENSOR_RECORD)
-
-
-def _packer(count: int) -> struct.Struct:
-    "One ``struct`` call writes a whole tensor table into the packed program (field-by-field ctypes stores cost more than the launch)."
-    made = _PACKERS.get(count)
-    if made is None:
-        made = _PACKERS[count] = struct.Struct("<" + _TENSOR_RECORD * count)
-    return made
+def _pack_draw_table(draws: list[Any]) -> Any:
+    "Philox key tables of the lazy noise draws of one launch (reused per thread; the C call copies them)."
+    table = getattr(_draw_keys, "table", None)
+    if table is None:
+        table = _draw_keys.table = (SkrPhilox * MAX_PHILOX)()
+    for slot, draw in zip(table, draws, strict=False):
+        count = len(draw.seeds)
+        slot.n_items = count
+        slot.item_numel = draw.item_numel
+        slot.seed[:count] = draw.seeds
+        slot.stream[:count] = draw.streams
+    return table
 
 
 def launch_compiled(compiled: CompiledProgram, inputs: list[Any], draws: list[Any] | None = None) -> list[Any] | None:
     "Bind tensors (and lazy noise draws) to a compiled program and launch it.  None when they do not qualify."
     first = inputs[0]
-    if not _on_device(first):
+    if not first.is_cuda:
         return None
-    shape, device = first.shape, first.device
+    shape = first.shape
     where = first.get_device()  # every other operand must report the same ordinal (a CPU tensor reports -1)
-    packed = compiled.packed
-    any64 = any32 = False
-    kind = first.dtype
-    mixed = False
-    code_of = DTYPE_CODE.get
-    table: list[int] = []
+    signature = []
+    pointers = []
     for t in inputs:
-        dtype = t.dtype
-        code = code_of(dtype)
-        if code is None or t.get_device() != where or t.shape != shape or not t.is_contiguous():
+        if t.get_device() != where or t.shape != shape or not t.is_contiguous():
             return None
-        if code == F64:
-            any64 = True
-        elif code == F32:
-            any32 = True
-        if dtype != kind:
-            mixed = True
-        table.append(t.data_ptr())
-        table.append(code)
-    _packer(len(inputs)).pack_into(packed, _INPUTS_AT, *table)
-    default = torch.float64 if any64 else (torch.float32 if any32 or mixed else kind)
-    compute = torch.float64 if any64 else torch.float32
+        signature.append(t.dtype)
+        pointers.append(t.data_ptr())
+    signature = tuple(signature)
+    plan = compiled.plans.get(signature, _MISSING)
+    if plan is _MISSING:
+        plan = compiled.specialise(signature)
+    if plan is None:
+        return None
+    if len(draws or ()) != compiled.n_philox:
+        return None
+    device = first.device
     outputs = []
-    table = []
-    for want in compiled.out_specs:
-        dtype = default if want is None else (compute if want.__class__ is str else want)
+    for dtype in plan.out_dtypes:
         out = torch.empty(shape, dtype=dtype, device=device)
-        table.append(out.data_ptr())
-        table.append(DTYPE_CODE[dtype])
+        pointers.append(out.data_ptr())
         outputs.append(out)
-    if outputs:
-        _packer(len(outputs)).pack_into(packed, _OUTPUTS_AT, *table)
+    plan.packer.pack_into(plan.table, 0, *pointers)
+    numel = first.numel()
+    keys = None
     if draws:
-        numel = first.numel()
         for d in draws:
             if d.numel != numel or d.device != device:
                 return None
-        _pack_draws(packed, draws)
+        keys = _pack_draw_table(draws)
     if ACCOUNT["on"]:
         ACCOUNT["launches"] += 1
         ACCOUNT["bytes"] += sum(t.numel() * t.element_size() for t in inputs) + sum(t.numel() * t.element_size() for t in outputs)
     lib = _lib if _lib is not None else load()
-    index = device.index
-    if torch._C._cuda_getDevice() != index:
+    if torch._C._cuda_getDevice() != where:
         with torch.cuda.device(device):
-            status = lib.skr_program_launch(ctypes.byref(packed), first.numel(), torch._C._cuda_getCurrentRawStream(index))
+            status = lib.skr_plan_launch(plan.handle, plan.table, numel, keys, torch._C._cuda_getCurrentRawStream(where))
     else:
-        status = lib.skr_program_launch(ctypes.byref(packed), first.numel(), torch._C._cuda_getCurrentRawStream(index))
+        status = lib.skr_plan_launch(plan.handle, plan.table, numel, keys, torch._C._cuda_getCurrentRawStream(where))
     if status:
-        check(status, "skr_program_launch")
+        check(status, "skr_plan_launch")
     return outputs
+
+
+def reset_switches() -> None:
+    """Re-read the library's development switches (SKR_FORCE_INTERP, SKR_NO_PINNED, ...) from the environment and
+    forget every plan of this thread that was created under the old ones (tests and A/B tooling)."""
+    global _switches_touched
+    if _lib is None and not LIB_PATH.exists():
+        return
+    _switches_touched = True
+    load().skr_reload_env()
+    _compiled.by_ops.clear()
+    from skrample_b200.sampling import functional, plan
+
+    plan.clear()
+    functional._scripts.known.clear()
 
 
 def error_norms(low: Any, high: Any, power: int) -> tuple[float, float]:

@@ -168,7 +168,10 @@ def _drive(sampler: Any, packed: SampleInput, model_transform: Any, schedule: An
     on_device = pg.is_cuda_tensor(packed.sample)
     key = None
     if on_device:
-        out_dtype = _OPTIONS.final_dtype if _OPTIONS.final_dtype is not None else packed.sample.dtype
+        # an explicit final_dtype also asks predictor-correctors for a low-precision x-hat copy: a different program
+        # from the one a sample of that same dtype gets, so the flag is part of the key
+        forced = _OPTIONS.final_dtype is not None
+        out_dtype = (_OPTIONS.final_dtype, True) if forced else (packed.sample.dtype, False)
         key = plan.key_for(sampler, packed, model_transform, schedule, previous, out_dtype)
         hit = plan.lookup(key, sampler, model_transform, schedule)
         if hit is not None:

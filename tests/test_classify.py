@@ -9,6 +9,7 @@ from pathlib import Path
 import pytest
 import torch
 
+import cases
 from skrample_b200 import native
 from skrample_b200.sampling import program as pg
 from test_host_layer import run_product
@@ -34,6 +35,9 @@ def test_structured_programs_are_block_shaped(case: dict, monkeypatch: pytest.Mo
 
     monkeypatch.setattr(pg, "execute", spy)
     run_product(case)
+    if cases.composite(case):  # separately fused launches; only the standalone blend is interpreter-shaped
+        assert seen and 0 in seen and seen.count(1) <= case["steps"], seen
+        return
     assert seen and all(kind == 0 for kind in seen), seen
 
 

@@ -49,6 +49,9 @@ def run(program: pg.Program, interpreter: bool, monkeypatch: pytest.MonkeyPatch)
         monkeypatch.setenv("SKR_FORCE_INTERP", "1")
     else:
         monkeypatch.delenv("SKR_FORCE_INTERP", raising=False)
+    from skrample_b200 import native
+
+    native.reset_switches()
     return [out.cpu().numpy() for out in program.run()]
 
 

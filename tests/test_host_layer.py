@@ -19,10 +19,11 @@ STRUCTURED = np.load(GOLDEN / "structured.npz")
 STRUCTURED_INDEX = json.loads((GOLDEN / "structured.json").read_text())
 
 
-def run_product(case: dict, device: str = "cpu", dtype: torch.dtype | None = None):
-    sampler = cases.make_sampler(structured, models, case)
-    schedule = cases.make_schedule(scheduling, case["schedule"])
-    model = cases.make_model(models, case["model"])
+def run_product(case: dict, device: str = "cpu", dtype: torch.dtype | None = None, objects: tuple | None = None):
+    "``objects`` = (sampler, schedule, model) to reuse (the step-plan cache is keyed on their identity)."
+    if objects is None:
+        objects = (cases.make_sampler(structured, models, case), cases.make_schedule(scheduling, case["schedule"]), cases.make_model(models, case["model"]))
+    sampler, schedule, model = objects
     dtype = dtype or {"f32": torch.float32, "f64": torch.float64}[case["dtype"]]
     x0, outs, noises = cases.trajectory_inputs(case)
     x = torch.from_numpy(x0).to(device=device, dtype=dtype)
@@ -48,10 +49,7 @@ def run_product(case: dict, device: str = "cpu", dtype: torch.dtype | None = Non
 def test_cpu_tensors_match_reference(case: dict) -> None:
     result = run_product(case)
     for field in ("final", "sample", "prediction"):
-        want = STRUCTURED[f"{case['id']}/{field}"]
-        got = getattr(result, field).numpy()
-        assert got.dtype == want.dtype
-        assert np.array_equal(got, want, equal_nan=True), field
+        cases.assert_matches(getattr(result, field).numpy(), STRUCTURED[f"{case['id']}/{field}"], case, field)
 
 
 def test_bench_reference_arm_prints_exactly_one_json_line() -> None:

@@ -431,6 +431,7 @@ def test_in_kernel_noise_equals_materialised_noise(sampler_name: str, kw: dict, 
 
     if kernel == "interpreter":
         monkeypatch.setenv("SKR_FORCE_INTERP", "1")
+    native.reset_switches()
     sampler = getattr(structured, sampler_name)(**kw)
     unit = (4, 33, 31)  # item_numel = 4092: multiple of 4 but not of the tile
     batch = 3

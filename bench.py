@@ -1,36 +1,45 @@
 #!/usr/bin/env python
 """Benchmark of the skrample_b200 sampler step (BASELINE.json metric: sampler-step GB/s and latent-steps/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--sweep]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--quick]
 
-A "step" is ONE solver step of the workload's sampler over one latent batch = one fused kernel launch.
-The default workload is BASELINE.json configs[1]: UniPC order 3, stochastic, Random noise (device Philox), Scaled
-schedule, epsilon model, SDXL latent 8x4x128x128, bf16 storage / fp32 compute, on one B200.
+A "step" is ONE solver step of the workload's sampler over one latent batch.  The default workload is BASELINE.json
+configs[1]: UniPC order 3, stochastic, Random noise (device Philox, one generator per batch item), Scaled schedule,
+epsilon model, SDXL latent 8x4x128x128, bf16 storage / fp32 compute, on one B200.
 
-  value      whole-job latent-steps/s (batch items x solver steps per second; ``sampler_step_GBps`` is the same run
-             as algorithmic GB/s), inputs resident in HBM, launches replayed from a CUDA graph (device-side time
-             between two events; max over ranks).  Trajectories of several latent
-             batches are interleaved so consecutive launches never touch the same buffers and the working set
-             (> 2x L2) comes from HBM; the batches are independent requests, so the graph runs them on ``--streams``
-             parallel branches (default 4).  ``one_stream`` is the same launches as a single chain.
-  e2e        the same steps through the public API (``sampler.sample``) with HOST buffers: per step the model
-             prediction is copied from pinned host memory, the noise is drawn on the device and the result is read
-             back.  ``--inflight`` independent requests (default 2) are advanced round robin, each waiting for its own
-             previous result; ``e2e.one_request`` is the plain synchronous loop.
-  roofline   algorithmic bytes per launch / average launch duration of the step kernel (taken on the single chain,
-             where a launch's duration is well defined) vs the measured HBM copy
-             peak (MEASURED_PEAKS.json); ``sweep`` repeats that for the larger BASELINE shapes.
-  cpu_baseline  the CPU oracle port of the reference algorithm (oracle/skrample_oracle.py on torch-CPU tensors,
-             all host threads) on a bounded sample of the same workload.
+  value        latent-steps/s (batch items x solver steps per second) of ONE dependent chain of launches on ONE stream,
+               the step's noise drawn inside the timed region (in the step kernel itself where the library chooses
+               that, else by its fill kernel), inputs resident in HBM, launches replayed from a CUDA graph, timed with
+               CUDA events; the median of >= 5 timed blocks of >= 0.1 s each (at least --steps steps in total), max over
+               ranks.  Trajectories of several latent batches are interleaved so consecutive launches never touch
+               the same buffers and the working set of a round (> 2x L2) comes from HBM.  ``ms_per_step`` is a real
+               per-step time: the launches are serialised.
+  kernel_only  the same chain with the noise written before the timed region: one launch per step, so a launch's
+               duration is well defined - ``roofline`` (algorithmic bytes per launch / that duration vs the measured
+               HBM copy peak) is taken here.
+  concurrent_requests  the same launches on ``--streams`` parallel graph branches (independent latent batches side by
+               side): a multi-request THROUGHPUT, not a step latency.
+  e2e          the same steps through the public API (``sampler.sample``) with HOST buffers: per step the model
+               prediction is copied from pinned host memory, the noise is drawn on the device and the result is read
+               back.  ``--inflight`` independent requests (default 2) are advanced round robin, each waiting for its own
+               previous result; ``e2e.one_request`` is the plain synchronous loop; ``e2e_graphed`` replays the steps
+               through ``GraphedTrajectory``.  At least 2000 steps and 0.5 s each.
+  rows         the other BASELINE.json shapes (the Euler sweep of configs[4], the video shard of configs[3] with Pyramid
+               and Colored noise drawn per step, UniPC on a Flux-sized latent, the RKUltra(4) step of configs[2]), each
+               with its own roofline fraction; ``noise_generators`` times one draw of every generator.
+  strong_scaling  configs[3] (global batch 8) and the top of configs[4] (global batch 256) split over the N ranks.
+  cpu_baseline the reference's own CPU implementation (the unmodified package under baseline/_ref when it is there, else
+               the oracle port) on all host threads, a bounded sample of the same workload.
 
-Under torchrun every rank runs the same per-GPU batch on its own GPU (weak scaling, no collective on the step
-path); rank 0 prints one JSON line.
+Under torchrun every rank runs the same per-GPU batch on its own GPU (weak scaling, no collective on the step path);
+rank 0 prints one JSON line.
 """
 
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -47,35 +56,68 @@ import torch  # noqa: E402
 
 STEPS_PER_TRAJECTORY = 25
 L2_BYTES = 126 * 1024 * 1024
+METRIC = "sampler latent-steps/s (one batch item advanced one solver step)"
 
+
+def _w(sampler: str, kw: dict, schedule: str, model: str, shape: tuple, dtype: str, noise: str = "Random") -> dict:
+    return dict(sampler=sampler, kw=kw, schedule=schedule, model=model, shape=shape, dtype=dtype, noise=noise)
+
+
+_EULER = ("Euler", {"stochasticity": 1}, "flow", "FlowModel")
+_ADAMS9 = ("Adams", {"order": 9, "stochasticity": 1}, "flow", "FlowModel")
+_UNIPC3 = ("UniPC", {"order": 3, "stochasticity": 1})
+_VIDEO = (1, 16, 21, 90, 160)
 WORKLOADS = {
     # BASELINE.json configs[1]
-    "unipc3_sde_sdxl_bf16": dict(sampler="UniPC", kw={"order": 3, "stochasticity": 1}, schedule="scaled", model="NoiseModel", shape=(8, 4, 128, 128), dtype="bf16"),
+    "unipc3_sde_sdxl_bf16": _w(*_UNIPC3, "scaled", "NoiseModel", (8, 4, 128, 128), "bf16"),
     # BASELINE.json configs[0] (the reference's own CPU-runnable case)
-    "dpm2_scaled_fp32": dict(sampler="DPM", kw={"order": 2}, schedule="scaled", model="NoiseModel", shape=(1, 4, 128, 128), dtype="f32"),
-    # BASELINE.json configs[3], one GPU's shard (one item of 8x16x21x90x160)
-    "adams9_sde_video_bf16": dict(sampler="Adams", kw={"order": 9, "stochasticity": 1}, schedule="flow", model="FlowModel", shape=(1, 16, 21, 90, 160), dtype="bf16"),
-    "adams9_sde_video_f32": dict(sampler="Adams", kw={"order": 9, "stochasticity": 1}, schedule="flow", model="FlowModel", shape=(1, 16, 21, 90, 160), dtype="f32"),
-    # BASELINE.json configs[4] end points of the sweep
-    "euler_sde_flow_f32_16": dict(sampler="Euler", kw={"stochasticity": 1}, schedule="flow", model="FlowModel", shape=(16, 16, 128, 128), dtype="f32"),
-    "euler_sde_flow_f32_64": dict(sampler="Euler", kw={"stochasticity": 1}, schedule="flow", model="FlowModel", shape=(64, 16, 128, 128), dtype="f32"),
-    "euler_sde_flow_f32_256": dict(sampler="Euler", kw={"stochasticity": 1}, schedule="flow", model="FlowModel", shape=(256, 16, 128, 128), dtype="f32"),
-    "euler_sde_flow_bf16_256": dict(sampler="Euler", kw={"stochasticity": 1}, schedule="flow", model="FlowModel", shape=(256, 16, 128, 128), dtype="bf16"),
-    "unipc3_sde_flux_bf16": dict(sampler="UniPC", kw={"order": 3, "stochasticity": 1}, schedule="flow", model="FlowModel", shape=(16, 16, 128, 128), dtype="bf16"),
-    "unipc3_sde_ragged_bf16": dict(sampler="UniPC", kw={"order": 3, "stochasticity": 1}, schedule="scaled", model="NoiseModel", shape=(8, 4, 127, 129), dtype="bf16"),
-    "unipc3_sde_flux_f32": dict(sampler="UniPC", kw={"order": 3, "stochasticity": 1}, schedule="flow", model="FlowModel", shape=(16, 16, 128, 128), dtype="f32"),
-    "unipc3_sde_flux64_bf16": dict(sampler="UniPC", kw={"order": 3, "stochasticity": 1}, schedule="flow", model="FlowModel", shape=(64, 16, 128, 128), dtype="bf16"),
+    "dpm2_scaled_fp32": _w("DPM", {"order": 2}, "scaled", "NoiseModel", (1, 4, 128, 128), "f32"),
+    # BASELINE.json configs[3], one GPU's shard (one item of 8x16x21x90x160), noise generator as named
+    "adams9_sde_video_bf16": _w(*_ADAMS9, _VIDEO, "bf16"),
+    "adams9_sde_video_f32": _w(*_ADAMS9, _VIDEO, "f32"),
+    "adams9_sde_video_bf16_pyramid": _w(*_ADAMS9, _VIDEO, "bf16", "Pyramid"),
+    "adams9_sde_video_bf16_colored": _w(*_ADAMS9, _VIDEO, "bf16", "Colored"),
+    "adams9_sde_video8_bf16_pyramid": _w(*_ADAMS9, (8, *_VIDEO[1:]), "bf16", "Pyramid"),
+    "adams9_sde_video8_bf16_colored": _w(*_ADAMS9, (8, *_VIDEO[1:]), "bf16", "Colored"),
+    # BASELINE.json configs[4]: the Euler sweep
+    "euler_sde_flow_f32_1x4x64": _w(*_EULER, (1, 4, 64, 64), "f32"),
+    "euler_sde_flow_f32_1x4x128": _w(*_EULER, (1, 4, 128, 128), "f32"),
+    "euler_sde_flow_f32_4": _w(*_EULER, (4, 16, 128, 128), "f32"),
+    "euler_sde_flow_f32_16": _w(*_EULER, (16, 16, 128, 128), "f32"),
+    "euler_sde_flow_f32_64": _w(*_EULER, (64, 16, 128, 128), "f32"),
+    "euler_sde_flow_f32_256": _w(*_EULER, (256, 16, 128, 128), "f32"),
+    "euler_sde_flow_bf16_256": _w(*_EULER, (256, 16, 128, 128), "bf16"),
+    "unipc3_sde_flux_bf16": _w(*_UNIPC3, "flow", "FlowModel", (16, 16, 128, 128), "bf16"),
+    "unipc3_sde_ragged_bf16": _w(*_UNIPC3, "scaled", "NoiseModel", (8, 4, 127, 129), "bf16"),
+    "unipc3_sde_flux_f32": _w(*_UNIPC3, "flow", "FlowModel", (16, 16, 128, 128), "f32"),
+    "unipc3_sde_flux64_bf16": _w(*_UNIPC3, "flow", "FlowModel", (64, 16, 128, 128), "bf16"),
 }
 DEFAULT_WORKLOAD = "unipc3_sde_sdxl_bf16"
-SWEEP = ["euler_sde_flow_f32_16", "euler_sde_flow_f32_64", "euler_sde_flow_f32_256", "euler_sde_flow_bf16_256", "adams9_sde_video_bf16", "adams9_sde_video_f32", "unipc3_sde_flux_bf16"]
+ROWS = [
+    "euler_sde_flow_f32_1x4x64",
+    "euler_sde_flow_f32_1x4x128",
+    "euler_sde_flow_f32_4",
+    "euler_sde_flow_f32_16",
+    "euler_sde_flow_f32_64",
+    "euler_sde_flow_f32_256",
+    "euler_sde_flow_bf16_256",
+    "adams9_sde_video_bf16",
+    "adams9_sde_video_f32",
+    "adams9_sde_video_bf16_pyramid",
+    "adams9_sde_video_bf16_colored",
+    "unipc3_sde_flux_bf16",
+]
+# global workloads of the strong-scaling legs: (name, global batch, workload with the per-item shape)
+STRONG = [
+    ("configs[3] video latent 8x16x21x90x160 bf16, Adams-9 SDE, Pyramid noise", 8, "adams9_sde_video_bf16_pyramid"),
+    ("configs[3] video latent 8x16x21x90x160 bf16, Adams-9 SDE, Colored noise", 8, "adams9_sde_video_bf16_colored"),
+    ("configs[4] Euler SDE 256x16x128x128 fp32, Random noise", 256, "euler_sde_flow_f32_256"),
+]
 TORCH_DTYPE = {"bf16": torch.bfloat16, "f32": torch.float32, "f16": torch.float16, "f64": torch.float64}
 
 
 def numel_of(shape: tuple[int, ...]) -> int:
-    n = 1
-    for s in shape:
-        n *= s
-    return n
+    return math.prod(shape)
 
 
 def measured_peak() -> tuple[float, str]:
@@ -85,16 +127,41 @@ def measured_peak() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def workload_text(spec: dict) -> str:
+    kw = ", ".join(f"{k}={v}" for k, v in spec["kw"].items())
+    return (
+        f"{spec['sampler']}({kw}) {spec['schedule']} {spec['model']} latent {'x'.join(map(str, spec['shape']))} {spec['dtype']} storage / fp32 compute, "
+        f"{STEPS_PER_TRAJECTORY}-step trajectories, {spec['noise']} noise (one generator per batch item, a fresh draw every step), "
+        "analytic Gaussian denoiser (pre-recorded, excluded from the timing)"
+    )
+
+
+def config_of(spec: dict, name: str, world: int) -> dict:
+    "The same dictionary on both arms (the driver compares them); arm-specific detail goes under `launch`."
+    return {
+        "workload": workload_text(spec),
+        "name": name,
+        "per_gpu_batch": spec["shape"][0],
+        "global_batch": spec["shape"][0] * world,
+        "parallelism": f"batch-sharded x{world}, no collective on the step path",
+    }
+
+
 # --------------------------------------------------------------------------------------------------------------
 # product arm
 
 
 class Trajectory:
-    """One latent batch walking a 25-step schedule with the analytic Gaussian denoiser's predictions pre-recorded."""
+    """One latent batch walking a 25-step schedule with the analytic Gaussian denoiser's predictions pre-recorded.
 
-    def __init__(self, spec: dict, device: torch.device, seed: int, predictions: int | None = None, supplied_noise: bool = False) -> None:
+    ``noise``: "auto" - a fresh draw every step from the workload's generator, in whichever form the library picks
+    (Philox keys consumed inside the step kernel, or a tensor written by the generator's kernels); "supplied" - the
+    draws are written once, before any timed region (what the CPU arm gets)."""
+
+    def __init__(self, spec: dict, device: torch.device, seed: int, keep: int | None = None, noise: str = "auto", first_item: int = 0) -> None:
         import cases
         from skrample_b200 import scheduling
+        from skrample_b200.pytorch import noise as sk_noise
         from skrample_b200.sampling import models, structured
 
         self.spec = spec
@@ -103,30 +170,35 @@ class Trajectory:
         self.model = cases.make_model(models, spec["model"])
         self.dtype = TORCH_DTYPE[spec["dtype"]]
         self.device = device
+        self.noise_mode = noise if self.sampler.require_noise else "none"
         g = torch.Generator(device=device).manual_seed(seed)
         shape = spec["shape"]
         self.points = self.schedule.schedule(STEPS_PER_TRAJECTORY)
-        sigma_max = self.points[0].sigma
-        self.x0 = (torch.randn(shape, device=device, generator=g) * sigma_max).to(self.dtype)
-        count = predictions or STEPS_PER_TRAJECTORY
-        self.count = count
+        self.x0 = (torch.randn(shape, device=device, generator=g) * self.points[0].sigma).to(self.dtype)
+        self.count = keep or STEPS_PER_TRAJECTORY
         self.predictions: list[torch.Tensor] = []
-        # "Random noise" of the workload: one CUDA generator per batch item (what the diffusers wrapper builds).
-        # The draws are Philox keys; the step kernel generates the normals itself, nothing is written to memory.
-        from skrample_b200.pytorch import noise as sk_noise
-
+        # One CUDA generator per batch item, keyed by the item's GLOBAL index (what the diffusers wrapper builds): any
+        # sharding of the batch draws the same noise for an item.  Random draws are fp32 normals (consumed as such by the
+        # step kernel); the composite generators write the latent's storage type directly.
+        kind = getattr(sk_noise, spec["noise"])
         self.noise_source = sk_noise.BatchTensorNoise.from_batch_inputs(
-            sk_noise.Random,
+            kind,
             tuple(shape[1:]),
-            [torch.Generator(device=device).manual_seed(seed * 1000 + i) for i in range(shape[0])],
-            dtype=torch.float32,
+            [torch.Generator(device=device).manual_seed(seed * 1000 + first_item + i) for i in range(shape[0])],
+            dtype=torch.float32 if kind is sk_noise.Random else self.dtype,
         )
-        self.noises = [self.noise_source.lazy(None) for _ in range(count)] if self.sampler.require_noise else [None] * count
-        if supplied_noise and self.sampler.require_noise:
-            # batches beyond the kernel's Philox table come back as tensors already; either way the workload's noise
-            # is stored in the latent dtype, as a pipeline would hand it over
-            self.noises = [(z.materialize() if hasattr(z, "materialize") else z).to(self.dtype) for z in self.noises]
+        self.noises: list = []
+        if self.noise_mode == "supplied":
+            self.noises = [self.draw(n % STEPS_PER_TRAJECTORY, materialise=True) for n in range(self.count)]
         self.reset()
+
+    def draw(self, n: int, materialise: bool = False):  # noqa: ANN201
+        from skrample_b200.common import Step
+
+        z = self.noise_source.auto(Step.from_int(n, STEPS_PER_TRAJECTORY))
+        if materialise:
+            z = (z.materialize() if hasattr(z, "materialize") else z).to(self.dtype)
+        return z
 
     def reset(self) -> None:
         self.x = self.x0
@@ -157,17 +229,19 @@ class Trajectory:
         from skrample_b200.common import Step
 
         n = self.n
+        if noise is None and self.noise_mode != "none":
+            noise = self.noises[n % self.count] if self.noise_mode == "supplied" else self.draw(n)
         res = self.sampler.sample(
             self.x,
             self.predictions[n % self.count] if prediction is None else prediction,
             Step.from_int(n, STEPS_PER_TRAJECTORY),
             self.model,
             self.schedule,
-            (self.noises[n % self.count] if noise is None else noise) if self.sampler.require_noise else None,
+            noise,
             self.previous,
         )
-        if self.sampler.require_previous:
-            self.previous = (self.previous + [res])[-self.sampler.require_previous :]
+        keep = self.sampler.require_previous
+        self.previous = (self.previous + [res])[-keep:] if keep else []
         self.x = res.final
         self.n += 1
         if self.n == STEPS_PER_TRAJECTORY:
@@ -175,14 +249,11 @@ class Trajectory:
         return res.final
 
 
-SUPPLIED_NOISE = True
-
-
-def step_bytes(traj_spec: dict, device: torch.device) -> list[int]:
+def step_bytes(spec: dict, device: torch.device, noise: str) -> list[int]:
     "Algorithmic bytes (sum of distinct tensor reads + writes) of each of the 25 steps, counted from the launches."
     from skrample_b200 import native
 
-    t = Trajectory(traj_spec, device, seed=99, predictions=1, supplied_noise=SUPPLIED_NOISE)
+    t = Trajectory(spec, device, seed=99, keep=1, noise=noise)
     t.record()
     out: list[int] = []
     for _ in range(STEPS_PER_TRAJECTORY):
@@ -245,22 +316,43 @@ class ClockSampler:
         }
 
 
-def graph_throughput(spec: dict, device: torch.device, steps: int, warmup: int, min_ring_bytes: int, streams: int = 1) -> dict:
-    """Replay `steps` sampler launches from a CUDA graph; returns timing + byte accounting.  With `streams` > 1 the
-    graph has that many parallel branches (latent batch r runs on branch r % streams): independent latent batches
-    overlap the way concurrent requests would, which hides the launch / load / store phases of small steps."""
+class NullClocks:
+    def __enter__(self) -> "NullClocks":
+        return self
+
+    def __exit__(self, *exc: object) -> None:
+        pass
+
+    def summary(self) -> dict:
+        return {}
+
+
+def chain_time(
+    spec: dict,
+    device: torch.device,
+    noise: str,
+    requested_steps: int,
+    warmup: int,
+    streams: int = 1,
+    min_seconds: float = 0.5,
+    blocks: int = 5,
+    clocks: bool = False,
+    min_ring_bytes: int = 2 * L2_BYTES,
+    first_item: int = 0,
+) -> dict:
+    """Replay the sampler launches of `replicas` interleaved 25-step trajectories from a CUDA graph.  One stream: the
+    launches form one dependent chain.  ``streams`` > 1: latent batch r runs on graph branch r % streams (independent
+    requests side by side).  Timed as ``blocks`` blocks of whole replays (CUDA events on the replaying stream); the
+    reported time per step is the MEDIAN block, max over ranks."""
     from skrample_b200 import native
 
-    per_step = step_bytes(spec, device)
+    per_step = step_bytes(spec, device, noise)
     traj_bytes = sum(per_step)
     n = numel_of(spec["shape"])
     esize = TORCH_DTYPE[spec["dtype"]].itemsize
-    # enough interleaved replicas that one round over them touches more than 2x L2
-    replica_touch = max(per_step)
-    replicas = max(2, min(64, -(-min_ring_bytes // replica_touch)))
-    big = n * esize > 64 * 1024 * 1024
-    keep = 2 if big else STEPS_PER_TRAJECTORY  # recorded predictions/noises per replica (memory bound for huge latents)
-    trajs = [Trajectory(spec, device, seed=1234 + i, predictions=keep, supplied_noise=SUPPLIED_NOISE) for i in range(replicas)]
+    replicas = max(2, min(64, -(-min_ring_bytes // max(per_step))))  # one round over them touches more than 2x L2
+    keep = 2 if n * esize > 64 * 1024 * 1024 else STEPS_PER_TRAJECTORY  # recorded predictions / noises per replica
+    trajs = [Trajectory(spec, device, seed=1234 + i, keep=keep, noise=noise, first_item=first_item) for i in range(replicas)]
     for t in trajs:
         t.record()
 
@@ -269,64 +361,76 @@ def graph_throughput(spec: dict, device: torch.device, steps: int, warmup: int, 
     stream = torch.cuda.Stream(device=device)
     branches = [torch.cuda.Stream(device=device) for _ in range(streams)] if streams > 1 else []
 
-    def run(count: int) -> None:
+    def run() -> None:
         if not branches:
-            for k in range(count):
+            for k in range(rounds):
                 trajs[k % replicas].step()
             return
         for branch in branches:  # fork
             branch.wait_stream(stream)
         for b, branch in enumerate(branches):
             with torch.cuda.stream(branch):
-                mine = list(range(b, replicas, streams))
-                for k in range(count // replicas):
-                    for r in mine:
+                for _ in range(STEPS_PER_TRAJECTORY):
+                    for r in range(b, replicas, streams):
                         trajs[r].step()
         for branch in branches:  # join
             stream.wait_stream(branch)
 
     with torch.cuda.stream(stream):
-        run(rounds)  # eager warm-up: caches, allocator
+        run()  # eager warm-up: step plans, allocator, cuFFT plans
         torch.cuda.synchronize(device)
         before = native.launch_count()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=stream):
-            run(rounds)
+            run()
         launches_per_replay = native.launch_count() - before
     torch.cuda.synchronize(device)
 
-    replays = max(1, -(-steps // rounds))
-    warm = max(1, -(-warmup // rounds))
-    for _ in range(warm):
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        for _ in range(max(3, -(-warmup // rounds))):
+            graph.replay()
+        start.record()
         graph.replay()
+        graph.replay()
+        stop.record()
+    torch.cuda.synchronize(device)
+    replay_s = max(start.elapsed_time(stop) / 2e3, 1e-6)
+    per_block = max(1, math.ceil(min_seconds / blocks / replay_s), math.ceil(requested_steps / rounds / blocks))
+    barrier()
+    times: list[float] = []
+    with ClockSampler(device.index or 0) if clocks else NullClocks() as clock:
+        with torch.cuda.stream(stream):
+            for _ in range(blocks):
+                start.record()
+                for _ in range(per_block):
+                    graph.replay()
+                stop.record()
+                stop.synchronize()
+                times.append(start.elapsed_time(stop))
     torch.cuda.synchronize(device)
     barrier()
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(device.index or 0) as clocks:
-        start.record()
-        for _ in range(replays):
-            graph.replay()
-        stop.record()
-        torch.cuda.synchronize(device)
-    barrier()
-    elapsed_ms = start.elapsed_time(stop)
-    total_steps = replays * rounds
-    total_bytes = replays * replicas * traj_bytes
+    block_ms = max_over_ranks(sorted(times)[len(times) // 2], device)
+    steps_per_block = per_block * rounds
     return {
-        "elapsed_ms": elapsed_ms,
-        "steps": total_steps,
-        "bytes": total_bytes,
-        "launches": replays * launches_per_replay,
+        "ms_per_step": block_ms / steps_per_block,
+        "block_ms": block_ms,
+        "blocks_ms": [round(t, 4) for t in times],
+        "steps_per_block": steps_per_block,
+        "timed_steps": steps_per_block * blocks,
+        "launches": per_block * launches_per_replay * blocks,
+        "launches_per_step": launches_per_replay / rounds,
         "replicas": replicas,
+        "branches": streams,
         "bytes_per_step_avg": traj_bytes / STEPS_PER_TRAJECTORY,
         "bytes_per_step_max": max(per_step),
-        "clocks": clocks.summary(),
+        "clocks": clock.summary(),
         "batch": spec["shape"][0],
     }
 
 
 # BASELINE.json configs[2]: an explicit Runge-Kutta step (one launch per stage + the final update)
-RK_SWEEP = {
+RK_ROWS = {
     "rkultra4_flux_bf16": dict(order=4, shape=(16, 16, 128, 128), dtype="bf16"),
     "rkultra4_flux_f32": dict(order=4, shape=(16, 16, 128, 128), dtype="f32"),
 }
@@ -366,73 +470,116 @@ def rk_step_throughput(spec: dict, device: torch.device, replicas: int = 16, rep
         native.ACCOUNT["on"] = False
         launches = native.launch_count() - before
     torch.cuda.synchronize(device)
-    for _ in range(5):
-        graph.replay()
-    torch.cuda.synchronize(device)
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    start.record()
-    for _ in range(reps):
-        graph.replay()
-    stop.record()
-    torch.cuda.synchronize(device)
-    ms = start.elapsed_time(stop) / reps
+    times = []
+    with torch.cuda.stream(stream):
+        for _ in range(5):
+            graph.replay()
+        for _ in range(5):
+            start.record()
+            for _ in range(reps):
+                graph.replay()
+            stop.record()
+            stop.synchronize()
+            times.append(start.elapsed_time(stop) / reps)
+    ms = sorted(times)[len(times) // 2]
     rk_steps = replicas * len(interior)
     return {"us_per_rk_step": ms * 1e3 / rk_steps, "launches_per_step": launches / rk_steps, "GBps": native.ACCOUNT["bytes"] / (ms * 1e-3) / 1e9, "bytes_per_step": native.ACCOUNT["bytes"] / rk_steps}
 
 
 def noise_generator_times(device: torch.device, unit: tuple[int, ...] = (16, 21, 90, 160), reps: int = 30) -> list[dict]:
-    """Device time per draw of each noise generator on one BASELINE.json configs[3] unit (a 16x21x90x160 video latent,
-    fp32 generator dtype): CUDA events around `generate`, after warm-up (cuFFT plans, allocator)."""
+    """Device time per draw of each noise generator on one BASELINE.json configs[3] unit (a 16x21x90x160 video latent):
+    the draws are captured in a CUDA graph (device time, no host launch gaps) and timed with CUDA events."""
     from skrample_b200.common import Step
     from skrample_b200.pytorch import noise
 
     rows = []
     step = Step.from_int(5, STEPS_PER_TRAJECTORY)
-    for name, props in (("Random", None), ("Offset", noise.OffsetProps()), ("Pyramid", noise.PyramidProps()), ("Colored", noise.ColoredProps()), ("Brownian", noise.BrownianProps())):
-        cls = getattr(noise, name)
-        generator = torch.Generator(device=device).manual_seed(1)
-        source = cls.from_inputs(unit, generator, dtype=torch.float32) if props is None else cls.from_inputs(unit, generator, props, dtype=torch.float32)
-        for _ in range(20):
-            out = source.generate(step)
-        torch.cuda.synchronize(device)
-        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        start.record()
-        for _ in range(reps):
-            out = source.generate(step)
-        stop.record()
-        torch.cuda.synchronize(device)
-        us = start.elapsed_time(stop) / reps * 1e3
-        rows.append({"generator": name, "unit_shape": list(unit), "us_per_draw": us, "GBps_written": out.numel() * out.element_size() / us / 1e3})
+    for dtype in (torch.float32, torch.bfloat16):
+        for name, props in (("Random", None), ("Offset", noise.OffsetProps()), ("Pyramid", noise.PyramidProps()), ("Colored", noise.ColoredProps()), ("Brownian", noise.BrownianProps())):
+            cls = getattr(noise, name)
+            generator = torch.Generator(device=device).manual_seed(1)
+            source = cls.from_inputs(unit, generator, dtype=dtype) if props is None else cls.from_inputs(unit, generator, props, dtype=dtype)
+            out = torch.empty(unit, dtype=dtype, device=device)
+            stream = torch.cuda.Stream(device=device)
+            with torch.cuda.stream(stream):
+                for _ in range(3):
+                    source.generate_into(out, step)
+                torch.cuda.synchronize(device)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, stream=stream):
+                    for _ in range(4):
+                        source.generate_into(out, step)
+                for _ in range(3):
+                    graph.replay()
+                start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                start.record()
+                for _ in range(reps):
+                    graph.replay()
+                stop.record()
+            torch.cuda.synchronize(device)
+            us = start.elapsed_time(stop) / (reps * 4) * 1e3
+            rows.append({"generator": name, "unit_shape": list(unit), "dtype": str(dtype).removeprefix("torch."), "us_per_draw": us, "GBps_written": out.numel() * out.element_size() / us / 1e3})
     return rows
 
 
-def e2e_throughput(spec: dict, device: torch.device, steps: int, warmup: int, inflight: int = 1) -> dict:
-    """Public API with host buffers: H2D of the step's prediction, noise drawn on the device, sampler.sample, D2H of the
-    result - every step.  ``inflight`` independent latent batches (requests) are advanced round robin: a request's next
-    step starts only after its previous result has arrived in host memory, but while that copy is in flight the host
-    prepares and launches the other requests' steps.  ``inflight=1`` is the plain synchronous loop."""
+def pin_to_cores(rank: int, world: int) -> list[int]:
+    "Give every rank of one node its own slice of the host cores (they all see the same set by default)."
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        if world > 1 and len(cores) >= world:
+            per = len(cores) // world
+            mine = cores[rank * per : (rank + 1) * per]
+            os.sched_setaffinity(0, mine)
+            return mine
+        return cores
+    except (AttributeError, OSError):
+        return []
+
+
+def e2e_throughput(spec: dict, device: torch.device, min_steps: int, warmup: int, inflight: int, graphed: bool = False, min_seconds: float = 0.5) -> dict:
+    """Public API with host buffers: H2D of the step's prediction, noise drawn on the device, the step, D2H of the result -
+    every step.  ``inflight`` independent latent batches (requests) are advanced round robin: a request's next step
+    starts only after its previous result has arrived in host memory, but while that copy is in flight the host
+    prepares and launches the other requests' steps.  ``inflight=1`` is the plain synchronous loop.  ``graphed``: the
+    step is ``GraphedTrajectory.step()`` instead of ``sampler.sample()``, same buffers and copies."""
+    from skrample_b200.graphs import GraphedTrajectory
+
     trajs = [Trajectory(spec, device, seed=4321 + 17 * i) for i in range(inflight)]
     for traj in trajs:
         traj.record()
-    per_step = step_bytes(spec, device)
+    per_step = step_bytes(spec, device, "auto")
+    dtype = trajs[0].dtype
     host_pred = [[p.cpu().pin_memory() for p in traj.predictions] for traj in trajs]
-    result_host = [torch.empty(spec["shape"], dtype=trajs[0].dtype).pin_memory() for _ in trajs]
+    pred_dev = [torch.empty(spec["shape"], dtype=dtype, device=device) for _ in trajs]
+    result_host = [torch.empty(spec["shape"], dtype=dtype).pin_memory() for _ in trajs]
     arrived = [torch.cuda.Event() for _ in trajs]
     pending = [False] * inflight
+    need_noise = trajs[0].sampler.require_noise
+    graphs = [GraphedTrajectory(t.sampler, t.model, t.schedule, STEPS_PER_TRAJECTORY, like=t.x0) for t in trajs] if graphed else []
+    for g, t in zip(graphs, trajs):
+        g.start(t.x0)
+    current = torch.cuda.current_stream(device)
 
     def one(k: int) -> None:
         slot = k % inflight
         traj = trajs[slot]
         if pending[slot]:
             arrived[slot].synchronize()  # the caller consumes this request's previous result before its next step
-        pred = host_pred[slot][traj.n].to(device, non_blocking=True)
-        noise = None
-        if traj.sampler.require_noise:  # fresh noise every step, generated on the device (fill kernel or in-step draw)
-            noise = traj.noise_source.auto(None) if SUPPLIED_NOISE else traj.noise_source.lazy(None)
-        final = traj.step(pred, noise)
+        if graphed:
+            g = graphs[slot]
+            if g.position == len(g):
+                g.start(traj.x0)
+            g.prediction().copy_(host_pred[slot][g.position], non_blocking=True)
+            if need_noise:
+                traj.noise_source.generate_into(g.noise(), None)  # fresh noise every step, written in place
+            final = g.step()
+        else:
+            pred_dev[slot].copy_(host_pred[slot][traj.n], non_blocking=True)
+            final = traj.step(pred_dev[slot])  # draws this step's noise (Trajectory.draw)
         result_host[slot].copy_(final, non_blocking=True)
         if inflight == 1:
-            torch.cuda.current_stream().synchronize()
+            current.synchronize()
         else:
             arrived[slot].record()
             pending[slot] = True
@@ -442,71 +589,42 @@ def e2e_throughput(spec: dict, device: torch.device, steps: int, warmup: int, in
         for slot in range(inflight):
             pending[slot] = False
 
-    for k in range(warmup):
+    for k in range(max(warmup, 2 * STEPS_PER_TRAJECTORY * inflight)):
         one(k)
     drain()
     for traj in trajs:
         traj.reset()
+    for g, t in zip(graphs, trajs):
+        g.start(t.x0)
+    drain()
     barrier()
+    steps = 0
     t0 = time.perf_counter()
-    for k in range(steps):
-        one(k)
+    while True:
+        for k in range(steps, steps + 500):
+            one(k)
+        steps += 500
+        if steps >= min_steps and time.perf_counter() - t0 >= min_seconds:
+            break
     torch.cuda.synchronize(device)
     elapsed = time.perf_counter() - t0
     barrier()
     n = numel_of(spec["shape"])
-    esize = trajs[0].dtype.itemsize
-    total_bytes = sum(per_step[(k // inflight) % STEPS_PER_TRAJECTORY] for k in range(steps))
     return {
         "elapsed_s": elapsed,
-        "bytes": total_bytes,
-        "h2d": n * esize,
-        "d2h": n * esize,
+        "steps": steps,
+        "bytes": sum(per_step[(k // inflight) % STEPS_PER_TRAJECTORY] for k in range(steps)),
+        "h2d": n * dtype.itemsize,
+        "d2h": n * dtype.itemsize,
     }
 
 
-def e2e_graphed_throughput(spec: dict, device: torch.device, steps: int, warmup: int) -> dict:
-    """The e2e step through skrample_b200.graphs.GraphedTrajectory: the same host buffers and copies, the sampler
-    launches replayed from CUDA graphs captured once."""
-    from skrample_b200.graphs import GraphedTrajectory
-
-    traj = Trajectory(spec, device, seed=4321)
-    traj.record()
-    host_pred = [p.cpu().pin_memory() for p in traj.predictions]
-    result_host = torch.empty(spec["shape"], dtype=traj.dtype).pin_memory()
-    graphed = GraphedTrajectory(traj.sampler, traj.model, traj.schedule, STEPS_PER_TRAJECTORY, like=traj.x0)
-
-    def one() -> None:
-        if graphed.position == len(graphed):
-            graphed.start(traj.x0)
-        graphed.prediction().copy_(host_pred[graphed.position], non_blocking=True)
-        if traj.sampler.require_noise:
-            traj.noise_source.generate_into(graphed.noise(), None)  # fresh noise every step, written in place
-        final = graphed.step()
-        result_host.copy_(final, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-
-    graphed.start(traj.x0)
-    for _ in range(warmup):
-        one()
-    graphed.start(traj.x0)
-    torch.cuda.synchronize(device)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        one()
-    torch.cuda.synchronize(device)
-    elapsed = time.perf_counter() - t0
-    barrier()
-    return {"elapsed_s": elapsed}
-
-
 def measured_traffic() -> float | None:
-    """DRAM bytes per launch of the dominant step kernel on the default workload, from the latest ncu launch list
+    """DRAM bytes per launch of the dominant step kernel on the default workload, from the latest ncu capture
     summarised under profiles/ (tools/profile_round.sh + tools/summarize_profiles.py); None when not captured."""
     if "--workload" in sys.argv:
         return None
-    found = sorted((Path(__file__).resolve().parent / "profiles").glob("r*_traffic.json"))
+    found = sorted((ROOT / "profiles").glob("r*_traffic.json"))
     if not found:
         return None
     try:
@@ -528,42 +646,124 @@ def max_over_ranks(value: float, device: torch.device) -> float:
     return value
 
 
+def strong_scaling(device: torch.device, rank: int, world: int, peak: float) -> list[dict]:
+    """A FIXED global batch split over the ranks in contiguous blocks of whole items; no collective on
+    the step path; the noise of every step is drawn inside the timed region by the workload's generator (keyed by the
+    item's global index).  value = global items x steps / slowest rank's time."""
+    rows = []
+    for title, global_batch, name in STRONG:
+        base = WORKLOADS[name]
+        if global_batch % world:
+            rows.append({"workload": title, "skipped": f"global batch {global_batch} does not split over {world} ranks"})
+            continue
+        per_rank = global_batch // world
+        spec = dict(base, shape=(per_rank, *base["shape"][1:]))
+        torch.cuda.empty_cache()
+        r = chain_time(spec, device, "auto", 0, STEPS_PER_TRAJECTORY, min_seconds=0.3, blocks=3, first_item=rank * per_rank)
+        kernel = chain_time(spec, device, "supplied", 0, STEPS_PER_TRAJECTORY, min_seconds=0.2, blocks=3, first_item=rank * per_rank)
+        us = r["ms_per_step"] * 1e3
+        rows.append(
+            {
+                "workload": title,
+                "global_batch": global_batch,
+                "per_gpu_batch": per_rank,
+                "n_gpus": world,
+                "scaling": "strong",
+                "value": global_batch / (us * 1e-6),
+                "unit": "latent-steps/s",
+                "us_per_step": us,
+                "us_per_step_kernel_only": kernel["ms_per_step"] * 1e3,
+                "launches_per_step": r["launches_per_step"],
+                "sampler_step_GBps_per_gpu": kernel["bytes_per_step_avg"] / (us * 1e-6) / 1e9,
+                "kernel_only_frac_of_measured_peak": kernel["bytes_per_step_avg"] / (kernel["ms_per_step"] * 1e-3) / 1e9 / peak,
+            }
+        )
+    return rows
+
+
 # --------------------------------------------------------------------------------------------------------------
-# CPU oracle arm (reference algorithm restated, torch-CPU tensors so every host thread is used)
+# CPU arm: the reference's own implementation on the host cores
 
 
-def cpu_oracle_steps(spec: dict, steps: int, warmup: int, budget_s: float) -> dict:
+def reference_modules():  # noqa: ANN201
+    "The unmodified reference package from baseline/_ref (tools/install_reference.py), or None."
+    ref = ROOT / "baseline" / "_ref"
+    if not (ref / "skrample" / "__init__.py").exists():
+        return None
+    if str(ref) not in sys.path:
+        sys.path.insert(0, str(ref))
+    try:
+        import skrample.sampling.models as ref_models
+        import skrample.sampling.structured as ref_structured
+        import skrample.scheduling as ref_scheduling
+        from skrample.common import Point as RefPoint
+        from skrample.common import Step as RefStep
+    except Exception:  # noqa: BLE001 - any import problem means "use the port"
+        return None
+    return ref_structured, ref_models, ref_scheduling, RefStep, RefPoint
+
+
+def cpu_reference_steps(spec: dict, steps: int, warmup: int, budget_s: float) -> dict:
+    """The workload through the reference's own ``sampler.sample`` (torch-CPU tensors, every host thread), sampler
+    time only; the oracle port (oracle/skrample_oracle.py) stands in when baseline/_ref is absent."""
     import cases
-    import oracle_run
-    from oracle import skrample_oracle as O
 
     threads = os.cpu_count() or 1
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
     torch.set_num_threads(threads)
-    case = {"sampler": spec["sampler"], "kw": spec["kw"], "schedule": spec["schedule"], "model": spec["model"]}
-    model = oracle_run.MODELS[spec["model"]]
-    sch = oracle_run.schedule(spec["schedule"])
-    need_noise, need_prev = oracle_run.require(case)
     shape = spec["shape"]
     g = torch.Generator().manual_seed(7)
-    pts = sch.schedule(STEPS_PER_TRAJECTORY)
-    x0 = torch.randn(shape, generator=g) * pts[0].sigma
-    noises = [torch.randn(shape, generator=g) for _ in range(STEPS_PER_TRAJECTORY)]
+    mods = reference_modules()
+    case = {"sampler": spec["sampler"], "kw": spec["kw"], "schedule": spec["schedule"], "model": spec["model"]}
     per_step_bytes = reference_step_bytes(spec)
+    if mods is not None:
+        ref_structured, ref_models, ref_scheduling, RefStep, RefPoint = mods
+        sampler = cases.make_sampler(ref_structured, ref_models, case)
+        schedule = cases.make_schedule(ref_scheduling, spec["schedule"])
+        model = cases.make_model(ref_models, spec["model"])
+        points = [tuple(p) for p in schedule.schedule(STEPS_PER_TRAJECTORY)]
+        need_noise, need_prev = sampler.require_noise, sampler.require_previous
+        kind = "reference"
+        what = "the unmodified reference package (baseline/_ref/skrample), sampler.sample on torch-CPU fp32 tensors"
+    else:
+        import oracle_run
+        from oracle import skrample_oracle as O
 
+        model = oracle_run.MODELS[spec["model"]]
+        sch = oracle_run.schedule(spec["schedule"])
+        need_noise, need_prev = oracle_run.require(case)
+        points = [tuple(p) for p in sch.schedule(STEPS_PER_TRAJECTORY)]
+        kind = "port"
+        what = "the oracle port (oracle/skrample_oracle.py) on torch-CPU fp32 tensors"
+    x0 = torch.randn(shape, generator=g) * points[0][1]
+    noises = [torch.randn(shape, generator=g) for _ in range(STEPS_PER_TRAJECTORY)]
     state = {"x": x0, "n": 0, "prev": []}
 
     def one() -> float:
         n = state["n"]
-        p = pts[n]
+        _, sigma, alpha = points[n]
         x = state["x"]
-        xhat = x * (p.alpha / (p.alpha * p.alpha + p.sigma * p.sigma))
-        out = model.from_x(x, xhat, p) if model.kind != "data" else xhat  # analytic denoiser, excluded from timing
-        cur = O.Rec(x, out, O.St.from_int(n, STEPS_PER_TRAJECTORY), noises[n] if need_noise else None)
-        t0 = time.perf_counter()
-        rec = oracle_run.one_step(case, cur, state["prev"], model, sch)
-        dt = time.perf_counter() - t0
-        state["prev"] = (state["prev"] + [rec])[-need_prev:] if need_prev else []
-        state["x"] = rec.final
+        xhat = x * (alpha / (alpha * alpha + sigma * sigma))  # analytic denoiser, excluded from timing
+        if mods is not None:
+            RefStep_ = mods[3]
+            out = xhat if spec["model"] == "DataModel" else model.from_x(x, xhat, RefPoint(*points[n]))
+            t0 = time.perf_counter()
+            res = sampler.sample(x, out, RefStep_.from_int(n, STEPS_PER_TRAJECTORY), model, schedule, noises[n] if need_noise else None, state["prev"])
+            dt = time.perf_counter() - t0
+            final = res.final
+        else:
+            point = O.Pt(*points[n])
+            out = model.from_x(x, xhat, point) if model.kind != "data" else xhat
+            cur = O.Rec(x, out, O.St.from_int(n, STEPS_PER_TRAJECTORY), noises[n] if need_noise else None)
+            t0 = time.perf_counter()
+            res = oracle_run.one_step(case, cur, state["prev"], model, sch)
+            dt = time.perf_counter() - t0
+            final = res.final
+        state["prev"] = (state["prev"] + [res])[-need_prev:] if need_prev else []
+        state["x"] = final
         state["n"] = (n + 1) % STEPS_PER_TRAJECTORY
         if state["n"] == 0:
             state["x"], state["prev"] = x0, []
@@ -572,15 +772,13 @@ def cpu_oracle_steps(spec: dict, steps: int, warmup: int, budget_s: float) -> di
     for _ in range(warmup):
         one()
     state.update(x=x0, n=0, prev=[])
-    spent = 0.0
-    done = 0
-    total_bytes = 0
+    spent, done, total_bytes = 0.0, 0, 0
     wall0 = time.perf_counter()
     while done < steps and (time.perf_counter() - wall0) < budget_s:
         total_bytes += per_step_bytes[state["n"]]
         spent += one()
         done += 1
-    return {"seconds": spent, "steps": done, "bytes": total_bytes, "threads": threads}
+    return {"seconds": spent, "steps": done, "bytes": total_bytes, "threads": threads, "kind": kind, "what": what}
 
 
 def reference_step_bytes(spec: dict) -> list[int]:
@@ -608,6 +806,18 @@ def reference_step_bytes(spec: dict) -> list[int]:
     return out
 
 
+def cpu_baseline_of(res: dict, spec: dict) -> dict:
+    return {
+        "value": res["steps"] * spec["shape"][0] / res["seconds"],
+        "unit": "latent-steps/s",
+        "cores": res["threads"],
+        "kind": res["kind"],
+        "sample": f"{res['steps']} sampler steps of the workload in fp32: {res['what']}, sampler time only",
+        "sampler_step_GBps": res["bytes"] / res["seconds"] / 1e9,
+        "ms_per_step": res["seconds"] / res["steps"] * 1e3,
+    }
+
+
 # --------------------------------------------------------------------------------------------------------------
 
 
@@ -618,11 +828,11 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--sweep", action="store_true", help="also time the larger BASELINE shapes (rank 0, N=1)")
+    ap.add_argument("--quick", action="store_true", help="only the headline measurements (no rows, noise generators, strong-scaling legs)")
+    ap.add_argument("--sweep", action="store_true", help="accepted for compatibility: the rows are part of the default line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=4, help="parallel graph branches the latent batches of `value` run on (1: a single chain)")
+    ap.add_argument("--streams", type=int, default=4, help="parallel graph branches of the `concurrent_requests` leg")
     ap.add_argument("--inflight", type=int, default=2, help="independent requests advanced round robin by the e2e leg (1: the synchronous loop only)")
-    ap.add_argument("--fused-noise", action="store_true", help="draw the noise inside the step kernel (PhiloxDraw) instead of reading the tensor skr_noise_fill wrote")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     # stdout carries exactly one JSON line: anything a library prints there while the bench runs (NCCL's version banner
@@ -634,61 +844,48 @@ def main() -> None:
     def emit(line: dict) -> None:
         sys.stdout.flush()
         os.write(result_fd, (json.dumps(line) + "\n").encode())
-    global SUPPLIED_NOISE
-    SUPPLIED_NOISE = not args.fused_noise
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     spec = WORKLOADS[args.workload]
-    n = numel_of(spec["shape"])
-    config = {
-        "workload": f"{spec['sampler']}({', '.join(f'{k}={v}' for k, v in spec['kw'].items())}) {spec['schedule']} {spec['model']} latent {'x'.join(map(str, spec['shape']))} {spec['dtype']} storage / fp32 compute, {STEPS_PER_TRAJECTORY}-step trajectories, Random noise (Philox, one generator per item; {'drawn inside the step kernel' if args.fused_noise else 'written by skr_noise_fill before the timed region, like the CPU arm'}), analytic Gaussian denoiser (pre-recorded)",
-        "name": args.workload,
-        "per_gpu_batch": spec["shape"][0],
-        "global_batch": spec["shape"][0] * world,
-        "parallelism": f"batch-sharded x{world}, no collective on the step path",
-    }
+    config = config_of(spec, args.workload, world)
 
     if args.impl == "reference":
         if rank != 0:
             return
-        budget = 120.0
-        res = cpu_oracle_steps(spec, args.steps, min(args.warmup, 25), budget)
-        gbs = res["bytes"] / res["seconds"] / 1e9
-        lsps = res["steps"] * spec["shape"][0] / res["seconds"]
-        line = {
-            "impl": "reference",
-            "metric": "sampler latent-steps/s (one batch item advanced one solver step)",
-            "value": lsps,
-            "unit": "latent-steps/s",
-            "n_gpus": args.gpus,
-            "steps": res["steps"],
-            "warmup": min(args.warmup, 25),
-            "ms_per_step": res["seconds"] / res["steps"] * 1e3,
-            "higher_is_better": True,
-            "scaling": "weak",
-            "vs_baseline": None,
-            "dtype": "f32",
-            "data": "synthetic",
-            "config": config,
-            "sampler_step_GBps": gbs,
-            "cpu_baseline": {
-                "value": lsps,
+        warm = min(max(args.warmup, 3 * STEPS_PER_TRAJECTORY), 8 * STEPS_PER_TRAJECTORY)  # the CPU path needs whole trajectories to warm its thread pool and allocator
+        res = cpu_reference_steps(spec, args.steps, warm, 120.0)
+        base = cpu_baseline_of(res, spec)
+        emit(
+            {
+                "impl": "reference",
+                "metric": METRIC,
+                "value": base["value"],
                 "unit": "latent-steps/s",
-                "cores": res["threads"],
-                "kind": "port",
-                "sample": f"{res['steps']} sampler steps of the workload in fp32 on torch-CPU tensors (oracle/skrample_oracle.py), sampler time only",
-            },
-            "e2e": {"value": lsps, "unit": "latent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }
-        emit(line)
+                "n_gpus": args.gpus,
+                "steps": args.steps,
+                "timed_steps": res["steps"],
+                "warmup": warm,
+                "ms_per_step": base["ms_per_step"],
+                "higher_is_better": True,
+                "scaling": "weak",
+                "vs_baseline": None,
+                "dtype": "f32",
+                "data": "synthetic",
+                "config": config,
+                "sampler_step_GBps": base["sampler_step_GBps"],
+                "cpu_baseline": base,
+                "e2e": {"value": base["value"], "unit": "latent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            }
+        )
         return
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device for --impl ours (there is no CPU fallback)")
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
+    cores = pin_to_cores(local, world)
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=device)
 
@@ -696,59 +893,50 @@ def main() -> None:
 
     native.load()
     peak, peak_src = measured_peak()
-
+    batch = spec["shape"][0]
     launches_before = native.launch_count()
-    dev = graph_throughput(spec, device, args.steps, args.warmup, 2 * L2_BYTES)
-    timed_launches = dev["launches"]
-    elapsed_ms = max_over_ranks(dev["elapsed_ms"], device)
-    gbs = dev["bytes"] * world / (elapsed_ms / 1e3) / 1e9
-    latent_steps = dev["steps"] * spec["shape"][0] * world / (elapsed_ms / 1e3)
-    ms_per_step = elapsed_ms / dev["steps"]
-    per_launch_us = elapsed_ms * 1e3 / dev["launches"]
-    bytes_per_launch = dev["bytes"] / dev["launches"]
+
+    # headline: one dependent chain, the noise of every step drawn inside the timed region
+    chain = chain_time(spec, device, "auto", args.steps, args.warmup, clocks=True)
+    ms_per_step = chain["ms_per_step"]
+    value = batch * world / (ms_per_step * 1e-3)
+    gbs = chain["bytes_per_step_avg"] * world / (ms_per_step * 1e-3) / 1e9
+    # the same chain with the noise written beforehand: one launch per step, the step kernel's own duration
+    torch.cuda.empty_cache()
+    kernel = chain_time(spec, device, "supplied", args.steps, args.warmup)
+    per_launch_us = kernel["ms_per_step"] * 1e3 / kernel["launches_per_step"]
+    bytes_per_launch = kernel["bytes_per_step_avg"] / kernel["launches_per_step"]
     achieved = bytes_per_launch / (per_launch_us * 1e-6) / 1e9
-
-    # the same launches as one chain on one stream: a launch's duration is well defined there, so the roofline of the
-    # step kernel is taken from this run
-    one_stream = {
-        "value": latent_steps,
-        "unit": "latent-steps/s",
-        "ms_per_step": ms_per_step,
-        "sampler_step_GBps": gbs,
-        "frac_of_measured_peak": gbs / world / peak,
-        "gpu_launches": timed_launches,
-    }
-    branches = 1
+    concurrent = None
     if args.streams > 1:
-        # whole-job throughput: the interleaved latent batches are independent requests, so the graph runs them on
-        # parallel branches and the launch / load / store phases of different batches overlap
         torch.cuda.empty_cache()
-        many = graph_throughput(spec, device, args.steps, args.warmup, 2 * L2_BYTES, streams=args.streams)
-        many_ms = max_over_ranks(many["elapsed_ms"], device)
-        branches = min(args.streams, many["replicas"])
-        dev = many
-        timed_launches = many["launches"]
-        gbs = many["bytes"] * world / (many_ms / 1e3) / 1e9
-        latent_steps = many["steps"] * spec["shape"][0] * world / (many_ms / 1e3)
-        ms_per_step = many_ms / many["steps"]
-        torch.cuda.empty_cache()
+        many = chain_time(spec, device, "auto", args.steps, args.warmup, streams=args.streams)
+        concurrent = {
+            "value": batch * world / (many["ms_per_step"] * 1e-3),
+            "unit": "latent-steps/s",
+            "inverse_throughput_ms_per_step": many["ms_per_step"],
+            "graph_branches": many["branches"],
+            "sampler_step_GBps": many["bytes_per_step_avg"] * world / (many["ms_per_step"] * 1e-3) / 1e9,
+            "note": "independent latent batches on parallel graph branches: a multi-request throughput, not a step latency",
+        }
+    torch.cuda.empty_cache()
 
-    e2e_steps = min(args.steps, 500)
-    single = e2e_throughput(spec, device, e2e_steps, min(args.warmup, 50))
+    single = e2e_throughput(spec, device, 2000, min(args.warmup, 100), 1)
     single_elapsed = max_over_ranks(single["elapsed_s"], device)
     e2e, e2e_elapsed = single, single_elapsed
     if args.inflight > 1:
-        e2e = e2e_throughput(spec, device, e2e_steps, min(args.warmup, 50), inflight=args.inflight)
+        e2e = e2e_throughput(spec, device, 2000, min(args.warmup, 100), args.inflight)
         e2e_elapsed = max_over_ranks(e2e["elapsed_s"], device)
-    e2e_gbs = e2e["bytes"] * world / e2e_elapsed / 1e9
-    graphed_elapsed = max_over_ranks(e2e_graphed_throughput(spec, device, e2e_steps, min(args.warmup, 50))["elapsed_s"], device)
+    graphed = e2e_throughput(spec, device, 2000, min(args.warmup, 100), max(1, args.inflight), graphed=True)
+    graphed_elapsed = max_over_ranks(graphed["elapsed_s"], device)
 
     line = {
-        "metric": "sampler latent-steps/s (one batch item advanced one solver step)",
-        "value": latent_steps,
+        "metric": METRIC,
+        "value": value,
         "unit": "latent-steps/s",
         "n_gpus": world,
-        "steps": dev["steps"],
+        "steps": args.steps,
+        "timed_steps": chain["timed_steps"],
         "warmup": args.warmup,
         "ms_per_step": ms_per_step,
         "higher_is_better": True,
@@ -756,39 +944,53 @@ def main() -> None:
         "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic",
-        "config": config
-        | {
-            "launch": f"CUDA graph replay of the sampler launches, latent batches on {branches} parallel graph branch(es)",
-            "graph_branches": branches,
-            "l2": f"{dev['replicas']} interleaved latent batches, working set per round > 2x L2 (inputs come from HBM)",
+        "config": config,
+        "launch": {
+            "how": "one dependent chain of sampler launches on one stream, replayed from a CUDA graph; the median of 5 timed blocks",
+            "noise": "a fresh draw every step inside the timed region: Philox keys consumed by the step kernel where BatchTensorNoise.auto picks that, else written by the generator's kernels",
+            "launches_per_step": chain["launches_per_step"],
+            "blocks_ms": chain["blocks_ms"],
+            "steps_per_block": chain["steps_per_block"],
+            "l2": f"{chain['replicas']} interleaved latent batches, working set per round > 2x L2 (inputs come from HBM)",
             "storage_dtype": spec["dtype"],
+            "host_cores_of_rank0": len(cores),
         },
         "sampler_step_GBps": gbs,
         "pct_of_hbm_peak": {"measured": gbs / world / peak, "nominal_8TBs": gbs / world / 8000.0},
-        "gpu_launches": timed_launches,
-        "clocks": dev["clocks"],
-        "one_stream": one_stream,
+        "gpu_launches": chain["launches"],
+        "clocks": chain["clocks"],
+        "kernel_only": {
+            "value": batch * world / (kernel["ms_per_step"] * 1e-3),
+            "unit": "latent-steps/s",
+            "ms_per_step": kernel["ms_per_step"],
+            "launches_per_step": kernel["launches_per_step"],
+            "sampler_step_GBps": kernel["bytes_per_step_avg"] * world / (kernel["ms_per_step"] * 1e-3) / 1e9,
+            "note": "the noise tensors are written before the timed region (what the CPU arm gets): the step kernel alone",
+        },
+        "concurrent_requests": concurrent,
         "e2e": {
-            "value": e2e_steps * spec["shape"][0] * world / e2e_elapsed,
+            "value": e2e["steps"] * batch * world / e2e_elapsed,
             "unit": "latent-steps/s",
             "h2d_bytes_per_step": e2e["h2d"],
             "d2h_bytes_per_step": e2e["d2h"],
-            "sampler_step_GBps": e2e_gbs,
-            "ms_per_step": e2e_elapsed / e2e_steps * 1e3,
-            "steps": e2e_steps,
-            "api": "structured sampler .sample() per step (the reference's call), pinned-host prediction in, result out; noise from BatchTensorNoise.auto (in-kernel Philox draw at this size)",
+            "sampler_step_GBps": e2e["bytes"] * world / e2e_elapsed / 1e9,
+            "ms_per_step": e2e_elapsed / e2e["steps"] * 1e3,
+            "steps": e2e["steps"],
+            "api": "structured sampler .sample() per step (the reference's call), pinned-host prediction in, result out; noise from BatchTensorNoise.auto",
             "requests_in_flight": max(1, args.inflight),
             "one_request": {
-                "value": e2e_steps * spec["shape"][0] * world / single_elapsed,
-                "ms_per_step": single_elapsed / e2e_steps * 1e3,
+                "value": single["steps"] * batch * world / single_elapsed,
+                "ms_per_step": single_elapsed / single["steps"] * 1e3,
+                "steps": single["steps"],
                 "note": "the plain synchronous loop: every step waits for its result on the host before the next begins",
             },
         },
         "e2e_graphed": {
-            "value": e2e_steps * spec["shape"][0] * world / graphed_elapsed,
+            "value": graphed["steps"] * batch * world / graphed_elapsed,
             "unit": "latent-steps/s",
-            "ms_per_step": graphed_elapsed / e2e_steps * 1e3,
-            "steps": e2e_steps,
+            "ms_per_step": graphed_elapsed / graphed["steps"] * 1e3,
+            "steps": graphed["steps"],
+            "requests_in_flight": max(1, args.inflight),
             "api": "skrample_b200.graphs.GraphedTrajectory.step(): same host buffers and copies, launches replayed from CUDA graphs",
         },
         "roofline": {
@@ -801,39 +1003,50 @@ def main() -> None:
             "kernel": "skr::block_kernel",
             "bytes_per_launch": bytes_per_launch,
             "us_per_launch": per_launch_us,
-            "measured_on": "the one-stream chain of the same launches (`one_stream`), CUDA events around the timed replays",
+            "measured_on": "the `kernel_only` chain (one step-kernel launch per step), CUDA events around the timed blocks",
             "peak_source": peak_src,
         },
     }
     assert native.launch_count() > launches_before
 
-    if rank == 0 and world == 1 and args.sweep:
-        sweep = []
-        for name in SWEEP:
-            s = WORKLOADS[name]
+    if not args.quick:
+        # the other BASELINE shapes; every rank runs them (they must stay in lock-step for the strong-scaling legs)
+        rows = []
+        if world == 1:
+            for name in ROWS:
+                s = WORKLOADS[name]
+                torch.cuda.empty_cache()
+                k = chain_time(s, device, "supplied", 0, STEPS_PER_TRAJECTORY, min_seconds=0.15, blocks=3)
+                w = chain_time(s, device, "auto", 0, STEPS_PER_TRAJECTORY, min_seconds=0.15, blocks=3)
+                us_k, us_w = k["ms_per_step"] * 1e3, w["ms_per_step"] * 1e3
+                ach = k["bytes_per_step_avg"] / (us_k * 1e-6) / 1e9
+                rows.append(
+                    {
+                        "workload": name,
+                        "shape": list(s["shape"]),
+                        "dtype": s["dtype"],
+                        "noise": s["noise"],
+                        "us_per_step_kernel_only": us_k,
+                        "GBps": ach,
+                        "frac_of_measured_peak": ach / peak,
+                        "bytes_per_step_avg": k["bytes_per_step_avg"],
+                        "us_per_step_with_noise": us_w,
+                        "launches_per_step_with_noise": w["launches_per_step"],
+                        "latent_steps_per_s_with_noise": s["shape"][0] / (us_w * 1e-6),
+                    }
+                )
+            for name, s in RK_ROWS.items():
+                torch.cuda.empty_cache()
+                r = rk_step_throughput(s, device)
+                rows.append({"workload": name, "shape": list(s["shape"]), "dtype": s["dtype"], "noise": "none (ODE)", "us_per_step_kernel_only": r["us_per_rk_step"], "launches_per_step": r["launches_per_step"], "GBps": r["GBps"], "frac_of_measured_peak": r["GBps"] / peak, "bytes_per_step_avg": r["bytes_per_step"], "latent_steps_per_s": s["shape"][0] / (r["us_per_rk_step"] * 1e-6)})
             torch.cuda.empty_cache()
-            r = graph_throughput(s, device, STEPS_PER_TRAJECTORY * 8, STEPS_PER_TRAJECTORY * 2, 2 * L2_BYTES)
-            us = r["elapsed_ms"] * 1e3 / r["launches"]
-            ach = r["bytes"] / r["launches"] / (us * 1e-6) / 1e9
-            sweep.append({"workload": name, "shape": list(s["shape"]), "dtype": s["dtype"], "us_per_step": us, "GBps": ach, "frac_of_measured_peak": ach / peak, "latent_steps_per_s": s["shape"][0] / (us * 1e-6), "bytes_per_step_avg": r["bytes_per_step_avg"]})
-        for name, s in RK_SWEEP.items():
-            torch.cuda.empty_cache()
-            r = rk_step_throughput(s, device)
-            sweep.append({"workload": name, "shape": list(s["shape"]), "dtype": s["dtype"], "us_per_step": r["us_per_rk_step"], "launches_per_step": r["launches_per_step"], "GBps": r["GBps"], "frac_of_measured_peak": r["GBps"] / peak, "latent_steps_per_s": s["shape"][0] / (r["us_per_rk_step"] * 1e-6), "bytes_per_step_avg": r["bytes_per_step"]})
-        line["sweep"] = sweep
-        line["noise_generators"] = noise_generator_times(device)
+            line["rows"] = rows
+            line["noise_generators"] = noise_generator_times(device)
+        torch.cuda.empty_cache()
+        line["strong_scaling"] = strong_scaling(device, rank, world, peak)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        res = cpu_oracle_steps(spec, 10_000, 25, 15.0)
-        line["cpu_baseline"] = {
-            "value": res["steps"] * spec["shape"][0] / res["seconds"],
-            "unit": "latent-steps/s",
-            "cores": res["threads"],
-            "kind": "port",
-            "sample": f"{res['steps']} sampler steps of the workload in fp32 on torch-CPU tensors (oracle/skrample_oracle.py), sampler time only",
-            "sampler_step_GBps": res["bytes"] / res["seconds"] / 1e9,
-            "ms_per_step": res["seconds"] / res["steps"] * 1e3,
-        }
+        line["cpu_baseline"] = cpu_baseline_of(cpu_reference_steps(spec, 10_000, 4 * STEPS_PER_TRAJECTORY, 15.0), spec)
 
     if rank == 0:
         emit(line)

@@ -30,7 +30,9 @@ import torch
 from skrample_b200.common import Step, divf, rescale_positive
 
 _SUBSTREAMS = 64
-"Philox offset units consumed per generate() call on a CUDA generator."
+"Philox stream ids consumed per generate() call on a CUDA generator."
+_RESERVED_CALLS = 64
+"generate() calls whose stream ids one advance of the generator's offset reserves (see TensorNoiseCommon._tick)."
 
 
 @dataclass(frozen=True)
@@ -214,14 +216,21 @@ class PhiloxDraw:
     def materialize_into(self, out: torch.Tensor) -> None:
         "Write the draw into ``out`` (contiguous, on this draw's device; rounded once to ``out``'s dtype)."
         keys = _philox_scratch()
-        count = len(self.seeds)
-        keys.n_items = count
-        keys.item_numel = self.item_numel
-        keys.seed[:count] = self.seeds
-        keys.stream[:count] = self.streams
+        total = len(self.seeds)
+        item_numel = self.item_numel
+        limit = _native().MAX_PHILOX_ITEMS  # items one launch's key table holds
+        code, base, esize = _code(out.dtype), out.data_ptr(), out.element_size()
         with _DeviceGuard(self.device):
-            status = _lib().skr_noise_fill_batch(out.data_ptr(), _code(out.dtype), ctypes.byref(keys), _stream())
-        _native().check(status, "skr_noise_fill_batch")
+            lib, stream = _lib(), _stream()
+            for first in range(0, total, limit):
+                count = min(limit, total - first)
+                keys.n_items = count
+                keys.item_numel = item_numel
+                keys.seed[:count] = self.seeds[first : first + count]
+                keys.stream[:count] = self.streams[first : first + count]
+                status = lib.skr_noise_fill_batch(base + first * item_numel * esize, code, ctypes.byref(keys), stream)
+                if status:
+                    _native().check(status, "skr_noise_fill_batch")
 
     def to(self, *args: Any, **kwargs: Any) -> torch.Tensor:
         return self.materialize().to(*args, **kwargs)
@@ -254,12 +263,31 @@ class TensorNoiseCommon[T: TensorNoiseProps | None](SkrampleTensorNoise):
 
     # -- device helpers
     def _tick(self) -> int:
-        "Reserve this call's block of Philox streams by advancing the generator's offset."
-        at = int(self.seed.get_offset())
-        self.seed.set_offset(at + 4 * _SUBSTREAMS)
-        return at // 4
+        """This call's block of Philox streams (``_SUBSTREAMS`` stream ids starting at the returned one).
+
+        The generator's own offset is advanced so interleaved ``torch.randn`` calls on it stay independent, but not
+        once per call: ``_RESERVED_CALLS`` calls' worth of streams are reserved at a time, and a call inside the
+        reservation costs one ``get_offset()`` - the check that nobody else drew from (or re-seeded) the generator in
+        between; if somebody did, a fresh reservation starts at the generator's current state.  While this source
+        is the generator's only user the stream ids are exactly those of advancing once per call."""
+        seed = self.seed
+        held = self.__dict__.get("_skr_reserved")
+        if held is not None and held[1] < held[2] and seed.get_offset() == held[0]:
+            tick = held[1]
+            held[1] = tick + _SUBSTREAMS
+            return tick
+        at = int(seed.get_offset())
+        tick = at // 4
+        after = at + 4 * _SUBSTREAMS * _RESERVED_CALLS
+        seed.set_offset(after)
+        self.__dict__["_skr_reserved"] = [after, tick + _SUBSTREAMS, tick + _SUBSTREAMS * _RESERVED_CALLS, int(seed.initial_seed()) & 0xFFFFFFFFFFFFFFFF]
+        return tick
 
     def _key(self) -> int:
+        "Philox key = the generator's seed (read once per reservation: re-seeding resets the offset, which ends it)."
+        held = self.__dict__.get("_skr_reserved")
+        if held is not None and self.seed.get_offset() == held[0]:
+            return held[3]
         return int(self.seed.initial_seed()) & 0xFFFFFFFFFFFFFFFF
 
     def _fill(self, out: torch.Tensor, stream: int, offset: _SkrOffset | None = None, moments: torch.Tensor | None = None) -> None:
@@ -317,7 +345,8 @@ class Random(TensorNoiseCommon[None]):
         "The next draw as Philox keys for in-kernel generation (CUDA generators); a tensor otherwise."
         if not self.on_device:
             return self.generate(step)
-        return PhiloxDraw(tuple(self.shape), (self._key(),), (self._tick(),), self.dtype, self.seed.device)
+        tick = self._tick()
+        return PhiloxDraw(tuple(self.shape), (self.__dict__["_skr_reserved"][3],), (tick,), self.dtype, self.seed.device)
 
 
 @dataclass(frozen=True)
@@ -902,7 +931,8 @@ class BatchTensorNoise[T: TensorNoiseProps | None](SkrampleTensorNoise):
         tensor's traffic is worth more than the extra arithmetic in the step kernel (measured on B200, 8x4x128x128:
         101 us against 115 us per end-to-end step) - and a filled tensor above ``AUTO_LAZY_MAX_ELEMENTS``, where the step
         kernel is bound by memory or issue rate and the fill kernel is the cheaper producer.  Same values either way."""
-        if self._uniform_random() and len(self.generators) * math.prod(self.generators[0].shape) <= self.AUTO_LAZY_MAX_ELEMENTS:
+        count = len(self.generators)
+        if self._uniform_random() and count <= _native().MAX_PHILOX_ITEMS and count * math.prod(self.generators[0].shape) <= self.AUTO_LAZY_MAX_ELEMENTS:
             return self.lazy(step)
         return self.generate(step)
 
@@ -912,7 +942,7 @@ class BatchTensorNoise[T: TensorNoiseProps | None](SkrampleTensorNoise):
         cached = self.__dict__.get("_skr_uniform")
         if cached is None or cached[0] != stamp:
             first = self.generators[0]
-            ok = len(self.generators) <= 32 and all(
+            ok = all(
                 type(g) is Random and g.on_device and g.seed.device == first.seed.device and g.dtype == first.dtype and g.shape == first.shape
                 for g in self.generators
             )
@@ -926,13 +956,9 @@ class BatchTensorNoise[T: TensorNoiseProps | None](SkrampleTensorNoise):
         if not self._uniform_random():
             return self.generate(step) if _fallback else None
         first = self.generators[0]
-        return PhiloxDraw(
-            (len(self.generators), *first.shape),
-            tuple(g._key() for g in self.generators),
-            tuple(g._tick() for g in self.generators),
-            first.dtype,
-            first.seed.device,
-        )
+        streams = tuple([g._tick() for g in self.generators])  # each tick (re)validates its generator's reservation,
+        seeds = tuple([g.__dict__["_skr_reserved"][3] for g in self.generators])  # which also holds the seed
+        return PhiloxDraw((len(self.generators), *first.shape), seeds, streams, first.dtype, first.seed.device)
 
     @classmethod
     def from_batch_inputs[U: TensorNoiseProps | None](

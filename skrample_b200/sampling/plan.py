@@ -56,17 +56,36 @@ def _noise_kind(noise: Any) -> int:
     return 0 if noise is None else (2 if getattr(noise, "is_lazy_noise", False) else 1)
 
 
+_ENTRY_KEY = "_skr_plan_key"
+
+
+def _entry_key(entry: Any) -> tuple:
+    "What a history entry contributes to the key: its step, the kind of its noise, whether it carries an x-hat cache."
+    held = entry.__dict__
+    key = held.get(_ENTRY_KEY)
+    if key is None:  # entries are frozen: computed once (the x-hat cache is attached before an entry can be history)
+        key = held[_ENTRY_KEY] = (entry.step, _noise_kind(entry.noise), XHAT_ATTR in held)
+    elif key[2] != (XHAT_ATTR in held):  # an x-hat was converted on demand and remembered since
+        key = held[_ENTRY_KEY] = (entry.step, key[1], XHAT_ATTR in held)
+    return key
+
+
 def key_for(sampler: Any, packed: Any, model_transform: Any, schedule: Any, previous: Any, out_dtype: Any) -> tuple:
-    keep = sampler.require_previous
-    tail = previous[len(previous) - keep :] if keep and previous else ()
+    count = len(previous)
+    if count:
+        keep = sampler.require_previous
+        tail = tuple([_entry_key(p) for p in (previous[count - keep :] if keep < count else previous)]) if keep else ()
+    else:
+        tail = ()
+    noise = packed.noise
     return (
         id(sampler),
         id(model_transform),
         id(schedule),
         packed.step,
-        len(previous),
-        _noise_kind(packed.noise),
-        tuple((p.step, _noise_kind(p.noise), XHAT_ATTR in p.__dict__) for p in tail),
+        count,
+        0 if noise is None else (2 if getattr(noise, "is_lazy_noise", False) else 1),
+        tail,
         out_dtype,
     )
 

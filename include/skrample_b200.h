@@ -44,7 +44,7 @@ extern "C" {
 #define SKR_MAX_OUTPUTS 8
 #define SKR_MAX_DIMS 8
 #define SKR_MAX_PHILOX 2
-#define SKR_MAX_PHILOX_ITEMS 32
+#define SKR_MAX_PHILOX_ITEMS 256
 #define SKR_MAX_LEVELS 16
 #define SKR_BROWNIAN_MAX_DEPTH 40
 
@@ -124,7 +124,9 @@ typedef struct skr_philox {
     uint64_t stream[SKR_MAX_PHILOX_ITEMS];
     int64_t item_numel; /* elements per batch item; numel == n_items * item_numel */
     int32_t n_items;    /* 1..SKR_MAX_PHILOX_ITEMS */
-    int32_t reserved;
+    int32_t dtype;      /* storage type of the tensor this stands for: SKR_BF16 / SKR_F16 round every normal to that
+                           type before it is used, exactly what reading the filled tensor would give; SKR_F32 (0) and
+                           SKR_F64 use the fp32 normal as drawn */
 } skr_philox;
 
 typedef struct skr_program {

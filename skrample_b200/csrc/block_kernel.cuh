@@ -92,7 +92,6 @@ struct BProgram {
     int32_t out_dtype[SKR_MAX_OUTPUTS];
     BHead<CT> head;
     BBlock<CT> blk[2];
-    KPhilox philox[SKR_MAX_PHILOX];
 };
 
 // ---- staged operand fetch, V elements per thread ---------------------------------------------------
@@ -445,7 +444,7 @@ struct TileIO {
 };
 
 template <typename CT, int MODE, int V, int PATH, bool PHILOX, typename BS, bool PARTIAL>
-__device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BBlock<CT>& k,
+__device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const PhiloxKeys<PHILOX>& keys, const BBlock<CT>& k,
                                               const TileIO<CT, MODE, V, PATH, PARTIAL>& io, CT (&X)[V], CT (&P)[V],
                                               CT (&B)[V], CT (&A)[V], CT (&S)[V], CT (&R)[V]) {
     using Ar = Arith<CT>;
@@ -558,8 +557,14 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BB
     }
     const int has_noise = pinned<BS::noise>(k.has_noise);
     if (has_noise) {
-        if (PHILOX && has_noise == 2) draw_normals<CT, V>(prog.philox[k.noise_in], io.first, prog.numel, in);
-        else io.template load<BS::dt_noise>(k.noise_in, k.noise_off, in);
+        bool drawn = false;
+        if constexpr (PHILOX) {
+            if (has_noise == 2) {
+                draw_normals<CT, V>(keys.table[k.noise_in], io.first, prog.numel, in);
+                drawn = true;
+            }
+        }
+        if (!drawn) io.template load<BS::dt_noise>(k.noise_in, k.noise_off, in);
         const CT zeta = k.zeta;
 #pragma unroll
         for (int j = 0; j < V; ++j) R[j] = Ar::add(R[j], Ar::mul(in[j], zeta));
@@ -595,7 +600,7 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const BB
 }
 
 template <typename CT, int MODE, int V, int PATH, bool PHILOX, typename Sh, bool PARTIAL = false>
-__device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t first, uint32_t stage, int tid) {
+__device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, const PhiloxKeys<PHILOX>& keys, int64_t first, uint32_t stage, int tid) {
     using Ar = Arith<CT>;
     const TileIO<CT, MODE, V, PATH, PARTIAL> io{prog, stage, (uint32_t)tid * V, first};
 
@@ -637,8 +642,8 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
     if (pinned<Sh::sp>(h.store_p >= 0)) io.template store<Sh::dt_sp>(h.store_p, P);
     if (pinned<Sh::sp2>(h.store_p2 >= 0)) io.template store<Sh::dt_sp2>(h.store_p2, P);
 
-    run_one_block<CT, MODE, V, PATH, PHILOX, typename Sh::B0, PARTIAL>(prog, prog.blk[0], io, X, P, B, A, S, R);
-    run_one_block<CT, MODE, V, PATH, PHILOX, typename Sh::B1, PARTIAL>(prog, prog.blk[1], io, X, P, B, A, S, R);
+    run_one_block<CT, MODE, V, PATH, PHILOX, typename Sh::B0, PARTIAL>(prog, keys, prog.blk[0], io, X, P, B, A, S, R);
+    run_one_block<CT, MODE, V, PATH, PHILOX, typename Sh::B1, PARTIAL>(prog, keys, prog.blk[1], io, X, P, B, A, S, R);
 }
 
 // Launches that cannot be staged (unaligned tensor bases, a stage too large for shared memory) run out of line so
@@ -647,7 +652,7 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, int64_t
 // element by element.  One warp needs 5-20 us for a tile on this path (a long dependent instruction stream), which
 // is why the ragged tail of a staged launch goes through the pipeline instead (block_kernel).
 template <typename CT, int MODE, int V, bool PHILOX>
-__device__ __noinline__ void run_guarded_tiles(const BProgram<CT>& prog, int64_t first_tile, int64_t n_tiles, int tid) {
+__device__ __noinline__ void run_guarded_tiles(const BProgram<CT>& prog, const PhiloxKeys<PHILOX>& keys, int64_t first_tile, int64_t n_tiles, int tid) {
     const int64_t grid = gridDim.x;
     const int64_t start = ((int64_t)blockIdx.x + grid - first_tile % grid) % grid;
     for (int64_t tile = first_tile + start; tile < n_tiles; tile += grid) {
@@ -660,8 +665,8 @@ __device__ __noinline__ void run_guarded_tiles(const BProgram<CT>& prog, int64_t
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(at));
             }
         }
-        if (prog.vec_ok && first + V <= prog.numel) run_block_tile<CT, MODE, V, TP_VECTOR, PHILOX, ShAny>(prog, first, 0u, tid);
-        else if (first < prog.numel) run_block_tile<CT, MODE, V, TP_ELEMENTS, PHILOX, ShAny>(prog, first, 0u, tid);
+        if (prog.vec_ok && first + V <= prog.numel) run_block_tile<CT, MODE, V, TP_VECTOR, PHILOX, ShAny>(prog, keys, first, 0u, tid);
+        else if (first < prog.numel) run_block_tile<CT, MODE, V, TP_ELEMENTS, PHILOX, ShAny>(prog, keys, first, 0u, tid);
     }
 }
 
@@ -672,7 +677,7 @@ constexpr int block_ctas_per_sm() {
 }
 
 template <typename CT, int MODE, int V, bool PHILOX, typename Sh>
-__global__ void __launch_bounds__(kThreads + kProducerThreads, block_ctas_per_sm<CT, V, Sh>()) block_kernel(const __grid_constant__ BProgram<CT> prog) {
+__global__ void __launch_bounds__(kThreads + kProducerThreads, block_ctas_per_sm<CT, V, Sh>()) block_kernel(const __grid_constant__ BProgram<CT> prog, const __grid_constant__ PhiloxKeys<PHILOX> keys) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t full_bar[kMaxStages];
     __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
@@ -753,7 +758,7 @@ __global__ void __launch_bounds__(kThreads + kProducerThreads, block_ctas_per_sm
             uint32_t stage_addr = smem_addr;
             for (int k = 0; k < mine_full; ++k) {
                 mbar_wait(&full_bar[s], phase);
-                run_block_tile<CT, MODE, V, TP_STAGED, PHILOX, Sh>(prog, first, stage_addr, tid);
+                run_block_tile<CT, MODE, V, TP_STAGED, PHILOX, Sh>(prog, keys, first, stage_addr, tid);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[s]);
                 first += stride;
@@ -762,7 +767,7 @@ __global__ void __launch_bounds__(kThreads + kProducerThreads, block_ctas_per_sm
             }
             if (own_partial) {
                 mbar_wait(&full_bar[s], phase);
-                if (first < prog.numel) run_block_tile<CT, MODE, V, TP_STAGED, PHILOX, Sh, true>(prog, first, stage_addr, tid);
+                if (first < prog.numel) run_block_tile<CT, MODE, V, TP_STAGED, PHILOX, Sh, true>(prog, keys, first, stage_addr, tid);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[s]);
             }
@@ -770,7 +775,7 @@ __global__ void __launch_bounds__(kThreads + kProducerThreads, block_ctas_per_sm
     }
     if (!producer && !prog.use_tma) {  // unaligned tensors or a stage that does not fit: everything element-wise
         const int64_t n_tiles = (prog.numel + TILE - 1) / TILE;
-        run_guarded_tiles<CT, MODE, V, PHILOX>(prog, 0, n_tiles, tid);
+        run_guarded_tiles<CT, MODE, V, PHILOX>(prog, keys, 0, n_tiles, tid);
     }
 }
 

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cstring>
 
 #include "../../include/skrample_b200.h"
 #include "block_kernel.cuh"
@@ -17,10 +18,10 @@ namespace skr {
 // size and the pointers (tile offsets, pipeline shape, grid) and launches.  Choosing the launcher is the expensive
 // part of a launch (matching the pinned shapes): skr_plan_create does it once, skr_plan_launch only calls it.
 template <typename CT>
-using BlockLauncher = int (*)(BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned);
+using BlockLauncher = int (*)(BProgram<CT>& k, const skr_philox* draws, int n_draws, int64_t numel, cudaStream_t stream, bool aligned);
 
 template <typename CT, int MODE, int V, bool PHILOX, typename Sh>
-static int launch_block_one(BProgram<CT>& k, int64_t numel, cudaStream_t stream, bool aligned) {
+static int launch_block_one(BProgram<CT>& k, const skr_philox* draws, int n_draws, int64_t numel, cudaStream_t stream, bool aligned) {
     constexpr int TILE = kThreads * V;
     k.numel = numel;
     uint32_t off = 0;
@@ -79,14 +80,19 @@ static int launch_block_one(BProgram<CT>& k, int64_t numel, cudaStream_t stream,
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, block_kernel<CT, MODE, V, PHILOX, Sh>, k);
+    PhiloxKeys<PHILOX> keys;
+    if constexpr (PHILOX) {
+        memset(&keys, 0, sizeof(keys));
+        fill_kphilox(keys.table, draws, n_draws < SKR_MAX_PHILOX ? n_draws : SKR_MAX_PHILOX);
+    }
+    cudaError_t e = cudaLaunchKernelEx(&cfg, block_kernel<CT, MODE, V, PHILOX, Sh>, k, keys);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail((int)e, "block kernel launch: %s", cudaGetErrorString(e));
     count_launch(0);
     return 0;
 }
 
-// Tensor tables and Philox keys of a launch, from the C ABI's program (pointers + dtypes).
+// Tensor tables of a launch, from the C ABI's program (pointers + dtypes).
 template <typename CT>
 static void bind_tensors(const skr_program* p, BProgram<CT>& k) {
     k.n_inputs = p->n_inputs;
@@ -98,7 +104,6 @@ static void bind_tensors(const skr_program* p, BProgram<CT>& k) {
         k.out_ptr[i] = p->outputs[i].ptr;
         k.out_dtype[i] = p->outputs[i].dtype;
     }
-    fill_kphilox(k.philox, p->philox, p->n_philox);
 }
 
 template <typename Sh, int MODE, int V>
@@ -133,8 +138,9 @@ static void fill_dtypes(const skr_program* p, BProgram<CT>& k) {
 
 // Pinned shapes of one latent storage type (pinned_shapes.cu): the launcher of the first shape that matches the
 // descriptor's control fields and dtypes (its name in *name), or nullptr.
-BlockLauncher<float> pinned_f32(const BProgram<float>& k, const char** name);
-BlockLauncher<float> pinned_bf16(const BProgram<float>& k, const char** name);
-BlockLauncher<float> pinned_f16(const BProgram<float>& k, const char** name);
+// `philox`: the step draws noise inside the kernel (instantiations with the Philox code).
+BlockLauncher<float> pinned_f32(const BProgram<float>& k, bool philox, const char** name);
+BlockLauncher<float> pinned_bf16(const BProgram<float>& k, bool philox, const char** name);
+BlockLauncher<float> pinned_f16(const BProgram<float>& k, bool philox, const char** name);
 
 }  // namespace skr

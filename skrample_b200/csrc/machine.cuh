@@ -237,8 +237,24 @@ struct KPhilox {
     int64_t item_numel;
     int32_t n_items;
     int32_t aligned;  // bit 0: item_numel % 4 == 0 (four consecutive elements share one Philox block);
-                      // bit 1: numel < 2^31 (32-bit index arithmetic)
+                      // bit 1: numel < 2^31 (32-bit index arithmetic);
+                      // bits 8-9: round every normal to bf16 (1) / fp16 (2), like the tensor skr_noise_fill writes
 };
+
+// The key tables of a launch that draws noise in the kernel travel as a second kernel parameter, so the
+// instantiations that read their noise from memory carry no table at all (their parameter block stays ~3 KB).
+template <bool ON>
+struct PhiloxKeys {};
+template <>
+struct PhiloxKeys<true> {
+    KPhilox table[SKR_MAX_PHILOX];
+};
+
+__device__ __forceinline__ float round_as_stored(float z, int mode) {
+    if (mode == 1) return __bfloat162float(__float2bfloat16_rn(z));
+    if (mode == 2) return __half2float(__float2half_rn(z));
+    return z;
+}
 
 // Four normals of the virtual noise tensor starting at element e (e % 4 == 0, item_numel % 4 == 0).
 __device__ __forceinline__ float4 draw_group(const KPhilox& d, int64_t e) {
@@ -253,13 +269,18 @@ __device__ __forceinline__ float4 draw_group(const KPhilox& d, int64_t e) {
     }
     float z[4];
     normal4(Philox(d.seed[item])((uint64_t)local >> 2, d.stream[item]), z);
+    const int mode = (d.aligned >> 8) & 3;
+    if (mode) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) z[j] = round_as_stored(z[j], mode);
+    }
     return make_float4(z[0], z[1], z[2], z[3]);
 }
 
 __device__ __forceinline__ float draw_single(const KPhilox& d, int64_t e) {
     const int64_t item = e / d.item_numel;
     const int64_t local = e - item * d.item_numel;
-    return normal_at(Philox(d.seed[item]), (uint64_t)local, d.stream[item]);
+    return round_as_stored(normal_at(Philox(d.seed[item]), (uint64_t)local, d.stream[item]), (d.aligned >> 8) & 3);
 }
 
 // V consecutive elements starting at global element `first` (a multiple of 4) of the virtual noise tensor.
@@ -284,11 +305,13 @@ __device__ __forceinline__ void draw_normals(const KPhilox& d, int64_t first, in
 
 static inline void fill_kphilox(KPhilox* out, const skr_philox* in, int count) {
     for (int i = 0; i < count; ++i) {
-        for (int j = 0; j < SKR_MAX_PHILOX_ITEMS; ++j) { out[i].seed[j] = in[i].seed[j]; out[i].stream[j] = in[i].stream[j]; }
+        const int n = in[i].n_items < SKR_MAX_PHILOX_ITEMS ? in[i].n_items : SKR_MAX_PHILOX_ITEMS;
+        for (int j = 0; j < n; ++j) { out[i].seed[j] = in[i].seed[j]; out[i].stream[j] = in[i].stream[j]; }
         out[i].item_numel = in[i].item_numel;
         out[i].n_items = in[i].n_items;
+        const int round_to = in[i].dtype == SKR_BF16 ? 1 : in[i].dtype == SKR_F16 ? 2 : 0;
         out[i].aligned = ((in[i].item_numel % 4) == 0 ? 1 : 0) |
-                         (in[i].item_numel * in[i].n_items < (int64_t)0x7fffffff ? 2 : 0);
+                         (in[i].item_numel * in[i].n_items < (int64_t)0x7fffffff ? 2 : 0) | (round_to << 8);
     }
 }
 

@@ -33,13 +33,41 @@ struct Philox {
 
 __device__ __forceinline__ float u01(uint32_t x) { return (float)x * 2.3283064365386963e-10f + 1.1641532182693481e-10f; }  // (0, 1]
 
+// Box-Muller on the special-function unit.  A standard normal is needed to ~1e-5, not to the last bit (nothing pins the
+// VALUES of device noise: torch's CUDA generator cannot be reproduced either; the contract is seed determinism, the
+// moments, and that every kernel of this library draws the SAME value for the same (seed, stream, element)).  The
+// full-precision logf + sqrtf + sincospif of the first version cost ~50 instructions per element and made the fill
+// kernel issue-bound at 1.3 TB/s; this form is ~12 (MUFU.LG2 / SQRT / SIN / COS + a few FMAs), so a fill is bound by
+// its HBM writes and a draw inside a step kernel hides under the step's loads.
+//   -2 ln u:  lg2.approx has an ABSOLUTE error of ~2^-22 on [0.5, 2), which would swamp the result where u -> 1; there
+//             the series 2t + t^2 + (2/3)t^3, t = 1 - u (exact: Sterbenz), is used instead (t < 2^-9: remainder < 2e-11).
+//   sin/cos:  sin.approx / cos.approx of 2 pi v, absolute error ~4e-7 on [0, 2 pi].
+// Resulting absolute error of a normal against exact arithmetic on the same uniforms: <= ~5e-6 (tests pin 1e-5).
+__device__ __forceinline__ float neg2_log(float u) {
+    float lg;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u));
+    const float t = 1.0f - u;
+    const float series = __fmul_rn(t, __fmaf_rn(t, __fmaf_rn(t, 0.6666667f, 1.0f), 2.0f));
+    return t < 0x1p-9f ? series : __fmul_rn(lg, -1.3862943611198906f);
+}
+__device__ __forceinline__ float sqrt_fast(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void sincos_turns(float v, float& s, float& c) {  // sin / cos of 2 pi v, v in (0, 1]
+    const float a = __fmul_rn(v, 6.283185307179586f);
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(a));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(a));
+}
+
 // four standard normals from one Philox block (two Box-Muller pairs)
 __device__ __forceinline__ void normal4(const uint4 r, float (&z)[4]) {
-    const float r0 = sqrtf(-2.0f * logf(u01(r.x)));
-    const float r1 = sqrtf(-2.0f * logf(u01(r.z)));
+    const float r0 = sqrt_fast(neg2_log(u01(r.x)));
+    const float r1 = sqrt_fast(neg2_log(u01(r.z)));
     float s0, c0, s1, c1;
-    sincospif(2.0f * u01(r.y), &s0, &c0);
-    sincospif(2.0f * u01(r.w), &s1, &c1);
+    sincos_turns(u01(r.y), s0, c0);
+    sincos_turns(u01(r.w), s1, c1);
     z[0] = r0 * s0;
     z[1] = r0 * c0;
     z[2] = r1 * s1;

@@ -53,9 +53,33 @@ static bool for_each_pinned_shape(F&& f) {
            f(ShapeEntry<ShRKFinal<kLP>, kModeLP, kVecLP>{"rk-final/" SKR_LP_NAME});
 }
 
-BlockLauncher<float> SKR_PINNED_ENTRY(const BProgram<float>& k, const char** name) {
+// The samplers that take noise, again with the in-kernel Philox draw compiled in (the draw replaces the noise
+// tensor's read here and its write by the fill kernel; for UniPC the corrector re-draws the previous step's noise).
+template <typename F>
+static bool for_each_pinned_philox_shape(F&& f) {
+    return f(ShapeEntry<ShUniPC<kLP, 2>, IN_MIXED, 4>{"unipc3+philox/" SKR_LP_NAME}) ||
+           f(ShapeEntry<ShUniPC<kLP, 1>, IN_MIXED, 4>{"unipc2+philox/" SKR_LP_NAME}) ||
+           f(ShapeEntry<ShUniPC<kLP>, IN_MIXED, 4>{"unipc+philox/" SKR_LP_NAME}) ||
+           f(ShapeEntry<ShUniP<kLP>, IN_MIXED, 4>{"unip+philox/" SKR_LP_NAME}) ||
+           f(ShapeEntry<ShAcc<kLP>, IN_MIXED, 4>{"acc+philox/" SKR_LP_NAME}) ||
+           f(ShapeEntry<ShDpm2<kLP>, IN_MIXED, 4>{"dpm2+philox/" SKR_LP_NAME}) ||
+           f(ShapeEntry<ShDpm3<kLP>, IN_MIXED, 4>{"dpm3+philox/" SKR_LP_NAME}) ||
+           f(ShapeEntry<ShEuler<kLP>, kModeLP, kVecLP>{"euler+philox/" SKR_LP_NAME});
+}
+
+BlockLauncher<float> SKR_PINNED_ENTRY(const BProgram<float>& k, bool philox, const char** name) {
     const StorageClass storage(k);
     BlockLauncher<float> found = nullptr;
+    if (philox) {
+        for_each_pinned_philox_shape([&](auto entry) {
+            using E = decltype(entry);
+            if (!storage.allows(E::mode) || !shape_matches<typename E::shape>(k)) return false;
+            *name = entry.name;
+            found = &launch_block_one<float, E::mode, E::v, true, typename E::shape>;
+            return true;
+        });
+        return found;
+    }
     for_each_pinned_shape([&](auto entry) {
         using E = decltype(entry);
         if (!storage.allows(E::mode) || !shape_matches<typename E::shape>(k)) return false;

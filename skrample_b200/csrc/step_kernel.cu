@@ -491,14 +491,14 @@ static BlockLauncher<CT> generic_launcher(int n_philox) {
 }
 
 static BlockLauncher<float> pinned_any(const BProgram<float>& k, int n_philox, const char** name) {
-    if (n_philox > 0 || switches().no_pinned.load(std::memory_order_relaxed)) return nullptr;
+    if (switches().no_pinned.load(std::memory_order_relaxed)) return nullptr;
     // the latent storage type is that of the network output (head.y) or, for RK combinations, of the sample
     const int probe = k.head.y_in >= 0 ? k.head.y_in : k.head.x_in;
     if (probe < 0) return nullptr;
     switch (k.in_dtype[probe]) {
-        case SKR_F32: return pinned_f32(k, name);
-        case SKR_BF16: return pinned_bf16(k, name);
-        case SKR_F16: return pinned_f16(k, name);
+        case SKR_F32: return pinned_f32(k, n_philox > 0, name);
+        case SKR_BF16: return pinned_bf16(k, n_philox > 0, name);
+        case SKR_F16: return pinned_f16(k, n_philox > 0, name);
         default: return nullptr;
     }
 }
@@ -589,7 +589,7 @@ static int launch_any(const skr_program* p, int64_t numel, cudaStream_t stream, 
         if (parse_block_program<CT>(p, b)) {
             bind_tensors(p, b);
             const char* name = nullptr;
-            return select_launcher(b, p->n_philox, &name)(b, numel, stream, aligned);
+            return select_launcher(b, p->n_philox, &name)(b, p->philox, p->n_philox, numel, stream, aligned);
         }
     }
     return launch_typed<CT>(p, numel, stream, aligned);
@@ -616,8 +616,7 @@ static int launch_planned(const skr::BProgram<CT>& parsed, skr::BlockLauncher<CT
     skr::BProgram<CT> k = parsed;  // the launch's own copy: plans are shared between threads
     for (int i = 0; i < plan->n_inputs; ++i) k.in_ptr[i] = tensors[i];
     for (int i = 0; i < plan->n_outputs; ++i) k.out_ptr[i] = const_cast<void*>(tensors[plan->n_inputs + i]);
-    skr::fill_kphilox(k.philox, draws, plan->n_philox);
-    return launcher(k, numel, stream, aligned);
+    return launcher(k, draws, plan->n_philox, numel, stream, aligned);
 }
 
 extern "C" {

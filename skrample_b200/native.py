@@ -52,7 +52,7 @@ class SkrTensor(ctypes.Structure):
 
 
 MAX_PHILOX = 2
-MAX_PHILOX_ITEMS = 32
+MAX_PHILOX_ITEMS = 256
 
 
 class SkrPhilox(ctypes.Structure):
@@ -61,7 +61,7 @@ class SkrPhilox(ctypes.Structure):
         ("stream", ctypes.c_uint64 * MAX_PHILOX_ITEMS),
         ("item_numel", ctypes.c_int64),
         ("n_items", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("dtype", ctypes.c_int32),
     ]
 
 
@@ -89,6 +89,7 @@ def _pack_draws(packed: SkrProgram, draws: list[Any]) -> None:
         slot.item_numel = draw.item_numel
         slot.seed[:count] = draw.seeds
         slot.stream[:count] = draw.streams
+        slot.dtype = DTYPE_CODE.get(draw.dtype, F32)
 
 
 EXPORTS = (
@@ -374,6 +375,7 @@ def _pack_draw_table(draws: list[Any]) -> Any:
         slot.item_numel = draw.item_numel
         slot.seed[:count] = draw.seeds
         slot.stream[:count] = draw.streams
+        slot.dtype = DTYPE_CODE.get(draw.dtype, F32)
     return table
 
 

@@ -74,7 +74,7 @@ CONV_DIV = 8
 MAX_OPS = 64
 MAX_INPUTS = 32
 MAX_OUTPUTS = 8
-MAX_PHILOX_ITEMS = 32
+MAX_PHILOX_ITEMS = 256
 
 
 @dataclasses.dataclass(frozen=True, slots=True)
@@ -190,7 +190,7 @@ class Program:
     def fwd(self, gamma: float, delta: float, pred: int = A, noise: Any = None, zeta: float = 0.0) -> None:
         if noise is not None and is_lazy_noise(noise):
             if (len(self.philox) >= 2 and not any(known is noise for known in self.philox)) or len(noise.seeds) > MAX_PHILOX_ITEMS:
-                noise = noise.materialize()  # the kernel draws at most two noise tensors itself, of at most 32 items each
+                noise = noise.materialize()  # the kernel draws at most two noise tensors itself, of at most 256 items each
             else:
                 self.ops.append(Op(OP_FWD, pred, 2, src=self.draw(noise), c=(gamma, delta, zeta)))
                 return

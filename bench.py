@@ -379,6 +379,8 @@ def chain_time(
     with torch.cuda.stream(stream):
         run()  # eager warm-up: step plans, allocator, cuFFT plans
         torch.cuda.synchronize(device)
+        for t in trajs:  # a captured region can only consume Philox streams reserved beforehand
+            t.noise_source.reserve(2 * STEPS_PER_TRAJECTORY)
         before = native.launch_count()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=stream):
@@ -506,6 +508,7 @@ def noise_generator_times(device: torch.device, unit: tuple[int, ...] = (16, 21,
                 for _ in range(3):
                     source.generate_into(out, step)
                 torch.cuda.synchronize(device)
+                source.reserve(8)  # a captured region can only consume Philox streams reserved beforehand
                 graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(graph, stream=stream):
                     for _ in range(4):

@@ -38,6 +38,58 @@ NVCC_FLAGS = [
 ]
 
 
+FAST = CSRC.parent / "_fast.so"
+"CPython extension with the plan-cache hit path (csrc/fast_launch.cpp): torch tensors -> skr_plan_launch in one call."
+
+
+def build_fast(force: bool = False) -> Path | None:
+    """Compile ``_fast.so`` in-tree with g++ against the installed torch (ATen + pybind11).  Host glue only: when it
+    cannot be built here the Python layer runs the same sequence itself, so a failure is reported, not raised."""
+    source = CSRC / "fast_launch.cpp"
+    if not force and FAST.exists() and FAST.stat().st_mtime >= source.stat().st_mtime:
+        return FAST
+    try:
+        import sysconfig
+
+        import torch
+        from torch.utils import cpp_extension
+
+        includes = [*cpp_extension.include_paths(), sysconfig.get_paths()["include"], "/usr/local/cuda/include"]
+        libdir = str(Path(torch.__file__).resolve().parent / "lib")
+        cmd = [
+            shutil.which("g++") or "g++",
+            "-O2",
+            "-std=c++17",
+            "-shared",
+            "-fPIC",
+            "-fvisibility=hidden",
+            f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+            "-DTORCH_EXTENSION_NAME=_fast",
+            "-DTORCH_API_INCLUDE_EXTENSION_H",
+            *(f"-I{path}" for path in includes),
+            str(source),
+            "-o",
+            str(FAST),
+            f"-L{libdir}",
+            f"-Wl,-rpath,{libdir}",
+            "-lc10",
+            "-lc10_cuda",
+            "-ltorch_cpu",
+            "-ltorch_cuda",
+            "-ltorch",
+            "-ltorch_python",
+        ]
+        done = subprocess.run(cmd, capture_output=True, text=True)
+        if done.returncode != 0:
+            sys.stderr.write(done.stderr[-4000:])
+            sys.stderr.write("\nskrample_b200: _fast.so was not built (the Python hit path is used instead)\n")
+            return None
+        return FAST
+    except Exception as error:  # noqa: BLE001 - optional host-side accelerator
+        sys.stderr.write(f"skrample_b200: _fast.so was not built: {error}\n")
+        return None
+
+
 def _stale() -> bool:
     if not LIB.exists():
         return True
@@ -51,6 +103,8 @@ def build(force: bool = False, verbose: bool = False, defines: tuple[str, ...] =
     experiment variant next to the product library (load it with ``SKRAMPLE_B200_LIB=<path>``); the default call
     builds the product."""
     target = out if out is not None else LIB
+    if out is None:
+        build_fast(force)
     if out is None and not force and not _stale():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"

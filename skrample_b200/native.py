@@ -318,7 +318,7 @@ class CompiledProgram:
     (``skr_plan_create``: validation, structure recognition and kernel selection happen once); a launch only binds
     tensor addresses (``skr_plan_launch``)."""
 
-    __slots__ = ("n_inputs", "n_philox", "out_specs", "packed", "plans")
+    __slots__ = ("fast", "n_inputs", "n_philox", "out_specs", "packed", "plans")
 
     def __init__(self, program: "Program") -> None:
         if len(program.ops) > MAX_OPS or len(program.inputs) > MAX_INPUTS or len(program.outputs) > MAX_OUTPUTS:
@@ -337,6 +337,7 @@ class CompiledProgram:
         self.n_philox = packed.n_philox
         self.out_specs = tuple(program.outputs)
         self.plans: dict[tuple, _NativePlan | None] = {}
+        self.fast: dict[int, tuple] = {}  # the same plans keyed the way _fast.launch looks them up
 
     def specialise(self, signature: tuple) -> "_NativePlan | None":
         "The native plan for inputs of these dtypes (None: a dtype the kernels do not take)."
@@ -356,11 +357,16 @@ class CompiledProgram:
         handle = ctypes.c_void_p()
         check(load().skr_plan_create(ctypes.byref(packed), ctypes.byref(handle)), "skr_plan_create")
         plan = self.plans[signature] = _NativePlan(handle.value, self.n_inputs, out_dtypes)
+        packed_signature = 0
+        for position, code in enumerate(codes):
+            packed_signature |= code << (2 * position)
+        self.fast[packed_signature] = (plan.handle, bytes(DTYPE_CODE[d] for d in out_dtypes))
         return plan
 
 
 _ALLOWED = frozenset(DTYPE_CODE)
 _MISSING = object()
+_fast: Any = _MISSING
 _draw_keys = threading.local()
 
 
@@ -379,11 +385,56 @@ def _pack_draw_table(draws: list[Any]) -> Any:
     return table
 
 
+_DTYPE_OF_CODE = {code: dtype for dtype, code in DTYPE_CODE.items()}
+
+
+def _fast_module() -> Any:
+    "The C++ hit path (``_fast.so``, built by skrample_b200.build), bound to this library's skr_plan_launch; or None."
+    global _fast
+    if _fast is _MISSING:
+        try:
+            if os.environ.get("SKRAMPLE_B200_NO_FAST"):
+                raise ImportError("disabled")
+            from skrample_b200 import _fast as module
+
+            module.bind(ctypes.cast(load().skr_plan_launch, ctypes.c_void_p).value)
+            _fast = module
+        except ImportError:
+            _fast = None
+    return _fast
+
+
 def launch_compiled(compiled: CompiledProgram, inputs: list[Any], draws: list[Any] | None = None) -> list[Any] | None:
     "Bind tensors (and lazy noise draws) to a compiled program and launch it.  None when they do not qualify."
     first = inputs[0]
     if not first.is_cuda:
         return None
+    fast = _fast if _fast is not _MISSING else _fast_module()
+    if fast is not None and inputs.__class__ is list:
+        keys = 0
+        if compiled.n_philox:
+            if not draws or len(draws) != compiled.n_philox:
+                return None
+            numel, device = first.numel(), first.device
+            for d in draws:
+                if d.numel != numel or d.device != device:
+                    return None
+            keys = ctypes.addressof(_pack_draw_table(draws))
+        elif draws:
+            return None
+        account = ACCOUNT["on"]
+        got = fast.launch(compiled.fast, inputs, keys, account)
+        if got.__class__ is int:  # no plan yet for this combination of input dtypes
+            if compiled.specialise(tuple(t.dtype for t in inputs)) is None:
+                return None
+            got = fast.launch(compiled.fast, inputs, keys, account)
+        if got.__class__ is list or got is None:
+            return got
+        if len(got) == 1:
+            check(got[0], "skr_plan_launch")
+        ACCOUNT["launches"] += 1
+        ACCOUNT["bytes"] += got[1]
+        return got[0]
     shape = first.shape
     where = first.get_device()  # every other operand must report the same ordinal (a CPU tensor reports -1)
     signature = []

@@ -188,23 +188,19 @@ class PhiloxDraw:
     """
 
     is_lazy_noise = True
-    __slots__ = ("device", "dtype", "seeds", "shape", "streams", "_tensor")
+    __slots__ = ("device", "dtype", "item_numel", "numel", "seeds", "shape", "streams", "_tensor")
 
-    def __init__(self, shape: tuple[int, ...], seeds: tuple[int, ...], streams: tuple[int, ...], dtype: torch.dtype, device: torch.device) -> None:
-        self.shape = tuple(shape)
+    def __init__(
+        self, shape: tuple[int, ...], seeds: tuple[int, ...], streams: tuple[int, ...], dtype: torch.dtype, device: torch.device, numel: int | None = None
+    ) -> None:
+        self.shape = shape if shape.__class__ is tuple else tuple(shape)
         self.seeds = seeds
         self.streams = streams
         self.dtype = dtype
         self.device = device
+        self.numel = math.prod(self.shape) if numel is None else numel
+        self.item_numel = self.numel // len(seeds)
         self._tensor: torch.Tensor | None = None
-
-    @property
-    def numel(self) -> int:
-        return math.prod(self.shape)
-
-    @property
-    def item_numel(self) -> int:
-        return self.numel // len(self.seeds)
 
     def materialize(self) -> torch.Tensor:
         if self._tensor is None:
@@ -272,22 +268,39 @@ class TensorNoiseCommon[T: TensorNoiseProps | None](SkrampleTensorNoise):
         is the generator's only user the stream ids are exactly those of advancing once per call."""
         seed = self.seed
         held = self.__dict__.get("_skr_reserved")
-        if held is not None and held[1] < held[2] and seed.get_offset() == held[0]:
-            tick = held[1]
-            held[1] = tick + _SUBSTREAMS
-            return tick
+        if held is not None and held[1] < held[2]:
+            try:
+                untouched = seed.get_offset() == held[0]
+            except RuntimeError:  # a CUDA graph is being captured: generator state cannot be read (see `reserve`)
+                untouched = True
+            if untouched:
+                tick = held[1]
+                held[1] = tick + _SUBSTREAMS
+                return tick
+        return self.reserve(_RESERVED_CALLS, _take=True)
+
+    def reserve(self, calls: int, _take: bool = False) -> int:
+        """Reserve the Philox streams of the next ``calls`` generate() calls with one advance of the generator's offset.
+        Needed before capturing draws into a CUDA graph: torch refuses to read or move a generator's offset during
+        capture, so a captured region can only consume streams that were reserved beforehand."""
+        seed = self.seed
         at = int(seed.get_offset())
         tick = at // 4
-        after = at + 4 * _SUBSTREAMS * _RESERVED_CALLS
+        after = at + 4 * _SUBSTREAMS * max(1, calls)
         seed.set_offset(after)
-        self.__dict__["_skr_reserved"] = [after, tick + _SUBSTREAMS, tick + _SUBSTREAMS * _RESERVED_CALLS, int(seed.initial_seed()) & 0xFFFFFFFFFFFFFFFF]
+        first = tick + _SUBSTREAMS if _take else tick
+        self.__dict__["_skr_reserved"] = [after, first, tick + _SUBSTREAMS * max(1, calls), int(seed.initial_seed()) & 0xFFFFFFFFFFFFFFFF]
         return tick
 
     def _key(self) -> int:
         "Philox key = the generator's seed (read once per reservation: re-seeding resets the offset, which ends it)."
         held = self.__dict__.get("_skr_reserved")
-        if held is not None and self.seed.get_offset() == held[0]:
-            return held[3]
+        if held is not None:
+            try:
+                if self.seed.get_offset() == held[0]:
+                    return held[3]
+            except RuntimeError:  # capturing: the reservation made before the capture stands
+                return held[3]
         return int(self.seed.initial_seed()) & 0xFFFFFFFFFFFFFFFF
 
     def _fill(self, out: torch.Tensor, stream: int, offset: _SkrOffset | None = None, moments: torch.Tensor | None = None) -> None:
@@ -923,42 +936,65 @@ class BatchTensorNoise[T: TensorNoiseProps | None](SkrampleTensorNoise):
         _native().check(status, "skr_noise_brownian_batch")
         return True
 
+    def reserve(self, calls: int) -> None:
+        "Reserve the Philox streams of the next ``calls`` draws of every item (required before CUDA-graph capture)."
+        for g in self.generators:
+            if g.on_device:
+                g.reserve(calls)
+
     AUTO_LAZY_MAX_ELEMENTS = 1 << 20
 
     def auto(self, step: Step | None) -> "PhiloxDraw | torch.Tensor":
         """The next batch of noise in whichever form steps faster: Philox keys drawn inside the step kernel for small
         batches - where a step is bound by host time and launch latency, and skipping the fill launch and the noise
-        tensor's traffic is worth more than the extra arithmetic in the step kernel (measured on B200, 8x4x128x128:
-        101 us against 115 us per end-to-end step) - and a filled tensor above ``AUTO_LAZY_MAX_ELEMENTS``, where the step
-        kernel is bound by memory or issue rate and the fill kernel is the cheaper producer.  Same values either way."""
-        count = len(self.generators)
-        if self._uniform_random() and count <= _native().MAX_PHILOX_ITEMS and count * math.prod(self.generators[0].shape) <= self.AUTO_LAZY_MAX_ELEMENTS:
+        tensor's traffic is worth more than the extra arithmetic in the step kernel - and a filled tensor above
+        ``AUTO_LAZY_MAX_ELEMENTS``, where the fill kernel is the cheaper producer.  Same values either way."""
+        info = self._uniform_info()
+        if info is not None and info[0] <= _native().MAX_PHILOX_ITEMS and info[2] <= self.AUTO_LAZY_MAX_ELEMENTS:
             return self.lazy(step)
         return self.generate(step)
 
-    def _uniform_random(self) -> bool:
-        "Every item is a plain ``Random`` with one shape / dtype on one CUDA device (checked once per generator list)."
-        stamp = tuple(id(g) for g in self.generators)
+    def _uniform_info(self) -> tuple | None:
+        """(count, shape, numel, dtype, device) when every item is a plain ``Random`` with one shape / dtype on one CUDA
+        device, else None.  Checked once per generator list (identity of the list, its length and its ends)."""
+        generators = self.generators
         cached = self.__dict__.get("_skr_uniform")
-        if cached is None or cached[0] != stamp:
-            first = self.generators[0]
-            ok = all(
-                type(g) is Random and g.on_device and g.seed.device == first.seed.device and g.dtype == first.dtype and g.shape == first.shape
-                for g in self.generators
-            )
-            cached = (stamp, ok)
-            self.__dict__["_skr_uniform"] = cached
-        return cached[1]
+        if cached is not None and cached[0] is generators and cached[1] == len(generators) and cached[2] is generators[0] and cached[3] is generators[-1]:
+            return cached[4]
+        first = generators[0]
+        ok = all(type(g) is Random and g.on_device and g.seed.device == first.seed.device and g.dtype == first.dtype and g.shape == first.shape for g in generators)
+        shape = (len(generators), *first.shape)
+        info = (len(generators), shape, math.prod(shape), first.dtype, first.seed.device) if ok else None
+        self.__dict__["_skr_uniform"] = (generators, len(generators), first, generators[-1], info)
+        return info
+
+    def _uniform_random(self) -> bool:
+        return self._uniform_info() is not None
 
     def lazy(self, step: Step | None, _fallback: bool = True) -> "PhiloxDraw | torch.Tensor | None":
-        """The next batch of noise as Philox keys when every item is a plain ``Random`` on one CUDA device (and the
-        batch fits the kernel's key table); otherwise the materialised tensor."""
-        if not self._uniform_random():
+        """The next batch of noise as Philox keys when every item is a plain ``Random`` on one CUDA device; otherwise the
+        materialised tensor."""
+        info = self._uniform_info()
+        if info is None:
             return self.generate(step) if _fallback else None
-        first = self.generators[0]
-        streams = tuple([g._tick() for g in self.generators])  # each tick (re)validates its generator's reservation,
-        seeds = tuple([g.__dict__["_skr_reserved"][3] for g in self.generators])  # which also holds the seed
-        return PhiloxDraw((len(self.generators), *first.shape), seeds, streams, first.dtype, first.seed.device)
+        streams, seeds = [], []
+        try:
+            for g in self.generators:  # TensorNoiseCommon._tick, inlined for its common case
+                held = g.__dict__.get("_skr_reserved")
+                if held is not None and held[1] < held[2] and g.seed.get_offset() == held[0]:
+                    tick = held[1]
+                    held[1] = tick + _SUBSTREAMS
+                else:
+                    tick = g._tick()
+                    held = g.__dict__["_skr_reserved"]
+                streams.append(tick)
+                seeds.append(held[3])
+        except RuntimeError:  # a CUDA graph is being captured: the reservations made beforehand stand (see `reserve`)
+            streams, seeds = [], []
+            for g in self.generators:
+                streams.append(g._tick())
+                seeds.append(g.__dict__["_skr_reserved"][3])
+        return PhiloxDraw(info[1], tuple(seeds), tuple(streams), info[3], info[4], info[2])
 
     @classmethod
     def from_batch_inputs[U: TensorNoiseProps | None](

@@ -57,6 +57,7 @@ def _noise_kind(noise: Any) -> int:
 
 
 _ENTRY_KEY = "_skr_plan_key"
+_KEEP = "_skr_keep"
 
 
 def _entry_key(entry: Any) -> tuple:
@@ -70,13 +71,24 @@ def _entry_key(entry: Any) -> tuple:
     return key
 
 
+def history_depth(sampler: Any) -> int:
+    "``sampler.require_previous``, remembered on the (frozen) sampler object: the property walks the sampler tree."
+    keep = sampler.__dict__.get(_KEEP)
+    if keep is None:
+        keep = sampler.require_previous
+        object.__setattr__(sampler, _KEEP, keep)
+    return keep
+
+
 def key_for(sampler: Any, packed: Any, model_transform: Any, schedule: Any, previous: Any, out_dtype: Any) -> tuple:
     count = len(previous)
+    tail: tuple = ()
     if count:
-        keep = sampler.require_previous
-        tail = tuple([_entry_key(p) for p in (previous[count - keep :] if keep < count else previous)]) if keep else ()
-    else:
-        tail = ()
+        keep = sampler.__dict__.get(_KEEP)
+        if keep is None:
+            keep = history_depth(sampler)
+        if keep:
+            tail = tuple([_entry_key(p) for p in (previous[count - keep :] if keep < count else previous)])
     noise = packed.noise
     return (
         id(sampler),
@@ -122,7 +134,7 @@ def roles_of(inputs: list[Any], packed: Any, previous: Any) -> tuple | None:
         for f, name in enumerate(_FIELDS):
             ok = ok and note(getattr(entry, name), (4, back, f))
         held = entry.__dict__.get(XHAT_ATTR)
-        if held is not None:
+        if held is not None and held[1] is not entry.prediction:  # a trivial conversion remembers the prediction itself
             ok = ok and note(held[1], (4, back, XHAT, held[0]))
     if not ok:
         return None
@@ -144,23 +156,27 @@ def store(key: tuple, anchors: tuple, compiled: Any, roles: tuple, result: tuple
 def bind(plan: Plan, packed: Any, previous: Any) -> list[Any] | None:
     "The input tensors of this call in program order, or None when the plan does not apply after all."
     bound = []
+    add = bound.append
     for role in plan.roles:
         kind = role[0]
         if kind == SAMPLE:
-            value = packed.sample
+            add(packed.sample)
         elif kind == PREDICTION:
-            value = packed.prediction
+            add(packed.prediction)
         elif kind == NOISE:
-            value = packed.noise
+            add(packed.noise)
         else:
             entry = previous[-role[1]]
             field = role[2]
             if field == XHAT:
                 held = entry.__dict__.get(XHAT_ATTR)
-                if held is None or held[0] != role[3]:
+                if held is None or (held[0] is not role[3] and held[0] != role[3]):
                     return None
-                value = held[1]
+                add(held[1])
+            elif field == 0:
+                add(entry.sample)
+            elif field == 1:
+                add(entry.prediction)
             else:
-                value = getattr(entry, _FIELDS[field])
-        bound.append(value)
+                add(entry.noise)
     return bound

@@ -235,9 +235,17 @@ def is_lazy_noise(value: Any) -> bool:
     return getattr(value, "is_lazy_noise", False)
 
 
+_TENSOR: Any = None
+
+
 def is_cuda_tensor(value: Any) -> bool:
-    torch = _torch()
-    return torch is not None and isinstance(value, torch.Tensor) and value.is_cuda
+    global _TENSOR
+    if _TENSOR is None:
+        torch = _torch()
+        if torch is None:
+            return False
+        _TENSOR = torch.Tensor
+    return isinstance(value, _TENSOR) and value.is_cuda
 
 
 def any_cuda(values: Sequence[Any]) -> bool:

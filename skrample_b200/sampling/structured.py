@@ -162,37 +162,65 @@ def _assemble(packed: SampleInput, outs: list[Any], spec: tuple) -> "SKSamples":
     return result
 
 
+_native: Any = None
+
+
 def _drive(sampler: Any, packed: SampleInput, model_transform: Any, schedule: Any, previous: Any, build: Any) -> "SKSamples":
     """Run one fused step: replay a cached plan when this exact step was taken before (device tensors only),
     otherwise emit the program with ``build(ctx) -> spec``, run it, and remember the plan."""
-    on_device = pg.is_cuda_tensor(packed.sample)
+    global _native
+    sample = packed.sample
     key = None
-    if on_device:
+    if pg.is_cuda_tensor(sample):
+        if _native is None:
+            from skrample_b200 import native
+
+            _native = native
         # an explicit final_dtype also asks predictor-correctors for a low-precision x-hat copy: a different program
         # from the one a sample of that same dtype gets, so the flag is part of the key
-        forced = _OPTIONS.final_dtype is not None
-        out_dtype = (_OPTIONS.final_dtype, True) if forced else (packed.sample.dtype, False)
-        key = plan.key_for(sampler, packed, model_transform, schedule, previous, out_dtype)
+        forced = _OPTIONS.final_dtype
+        key = plan.key_for(sampler, packed, model_transform, schedule, previous, (sample.dtype, False) if forced is None else (forced, True))
         hit = plan.lookup(key, sampler, model_transform, schedule)
         if hit is not None:
             bound = plan.bind(hit, packed, previous)
             if bound is not None:
-                from skrample_b200 import native
-
-                count = hit.compiled.n_inputs
-                outs = native.launch_compiled(hit.compiled, bound[:count], bound[count:])
+                compiled = hit.compiled
+                count = compiled.n_inputs
+                outs = _native.launch_compiled(compiled, bound, None) if len(bound) == count else _native.launch_compiled(compiled, bound[:count], bound[count:])
                 if outs is not None:
-                    return _assemble(packed, outs, hit.result)
-    ctx = _Ctx(packed.sample)
+                    # _assemble, inlined: (final, sample, prediction, x-hat cache, x-hat key, low-precision x-hat)
+                    final_slot, sample_slot, pred_slot, cache_slot, cache_key, lowp_slot = hit.result
+                    result = SKSamples(
+                        sample if sample_slot is None else outs[sample_slot],
+                        packed.prediction if pred_slot is None else outs[pred_slot],
+                        packed.step,
+                        packed.noise,
+                        outs[final_slot],
+                    )
+                    if cache_slot is not None:
+                        result.__dict__[_XHAT_ATTR] = (cache_key, outs[cache_slot])
+                    if lowp_slot is not None:
+                        result.__dict__["_skr_pred_lowp"] = outs[lowp_slot]
+                    return result
+    ctx = _Ctx(sample)
     spec = build(ctx)
     outs = ctx.prog.run()
     if key is not None and pg._fusable(ctx.prog.inputs):
         roles = plan.roles_of([*ctx.prog.inputs, *ctx.prog.philox], packed, previous)
         if roles is not None:
-            from skrample_b200 import native
-
-            plan.store(key, (sampler, model_transform, schedule), native.CompiledProgram(ctx.prog), roles, spec)
+            plan.store(key, (sampler, model_transform, schedule), _native.CompiledProgram(ctx.prog), roles, spec)
     return _assemble(packed, outs, spec)
+
+
+def _convert_for(sampler: Any, model_transform: Any) -> "models.ModelConvert | None":
+    """``ModelConvert(model_transform, sampler.derivative_transform)`` (None without a derivative space), remembered on
+    the frozen sampler object per model instance: predictor-correctors build it on every call otherwise."""
+    held = sampler.__dict__.get("_skr_convert")
+    if held is not None and held[0] is model_transform:
+        return held[1]
+    convert = models.ModelConvert(model_transform, sampler.derivative_transform) if sampler.derivative_transform else None
+    object.__setattr__(sampler, "_skr_convert", (model_transform, convert))
+    return convert
 
 
 def _remember_xhat(entry: SKSamples, key: Any, value: Any) -> None:
@@ -251,7 +279,7 @@ class StructuredSampler(ABC, traits.SamplingCommon):
     ) -> SKSamples[T]:
         "Shorthand for :meth:`sample_packed`."
         return self.sample_packed(
-            SampleInput(sample=sample, prediction=prediction, step=Step(*step), noise=noise),
+            SampleInput(sample, prediction, step if step.__class__ is Step else Step(*step), noise),
             model_transform=model_transform,
             schedule=schedule,
             previous=previous,
@@ -361,6 +389,9 @@ class StructuredUnified(traits.UnifiedModelling, StructuredStochastic, Structure
                 found.append(entry.prediction)
                 continue
             origin = _point_from(entry.step, schedule)
+            if _trivial(convert.specs_to(origin)):  # e.g. Data -> Data between distinct instances: x-hat IS the prediction
+                found.append(entry.prediction)
+                continue
             key = (convert.transform_from, convert.transform_to, origin)
             value = _recall_xhat(entry, key)
             if value is None:
@@ -674,7 +705,7 @@ class UniPC(UniP):
         schedule: SkrampleSchedule,
         previous: Sequence[SKSamples[T]] = (),
     ) -> SKSamples[T]:
-        convert = models.ModelConvert(model_transform, self.derivative_transform) if self.derivative_transform else None
+        convert = _convert_for(self, model_transform)
         inner_model = convert.transform_to if convert is not None else model_transform
         def build(ctx: _Ctx) -> tuple:
             ctx.depth = 1
@@ -748,7 +779,7 @@ class SPC(traits.DerivativeTransform, StructuredSampler):
         schedule: SkrampleSchedule,
         previous: Sequence[SKSamples[T]] = (),
     ) -> SKSamples[T]:
-        convert = models.ModelConvert(model_transform, self.derivative_transform) if self.derivative_transform else None
+        convert = _convert_for(self, model_transform)
         inner_model = convert.transform_to if convert is not None else model_transform
         origin = _point_from(packed.step, schedule)
         def build(ctx: _Ctx) -> tuple:

@@ -563,12 +563,19 @@ def e2e_throughput(spec: dict, device: torch.device, min_steps: int, warmup: int
     for g, t in zip(graphs, trajs):
         g.start(t.x0)
     current = torch.cuda.current_stream(device)
+    # one stream per request, as a server would: the copy engines move request A's result out while request B's
+    # prediction comes in and its step runs (on ONE stream the three would queue behind each other)
+    lanes = [torch.cuda.Stream(device=device) for _ in trajs] if inflight > 1 else [current]
+    for lane in lanes:
+        lane.wait_stream(current)
 
     def one(k: int) -> None:
         slot = k % inflight
         traj = trajs[slot]
         if pending[slot]:
             arrived[slot].synchronize()  # the caller consumes this request's previous result before its next step
+        if inflight > 1:
+            torch.cuda.set_stream(lanes[slot])
         if graphed:
             g = graphs[slot]
             if g.position == len(g):
@@ -584,7 +591,7 @@ def e2e_throughput(spec: dict, device: torch.device, min_steps: int, warmup: int
         if inflight == 1:
             current.synchronize()
         else:
-            arrived[slot].record()
+            arrived[slot].record(lanes[slot])
             pending[slot] = True
 
     def drain() -> None:
@@ -611,6 +618,7 @@ def e2e_throughput(spec: dict, device: torch.device, min_steps: int, warmup: int
             break
     torch.cuda.synchronize(device)
     elapsed = time.perf_counter() - t0
+    torch.cuda.set_stream(current)
     barrier()
     n = numel_of(spec["shape"])
     return {

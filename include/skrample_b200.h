@@ -47,6 +47,10 @@ extern "C" {
 #define SKR_MAX_PHILOX_ITEMS 256
 #define SKR_MAX_LEVELS 16
 #define SKR_BROWNIAN_MAX_DEPTH 40
+/* Accumulators of grid-wide sums (`moments`, `sums` below): device double[SKR_MOMENTS_DOUBLES], zeroed before first use.
+ * [0], [1] hold the two sums; the rest is scratch for a summation in a fixed order (bit-reproducible results). */
+#define SKR_MOMENT_BLOCKS 2048
+#define SKR_MOMENTS_DOUBLES (4 + 2 * SKR_MOMENT_BLOCKS)
 
 /* element types */
 enum { SKR_F32 = 0, SKR_F64 = 1, SKR_BF16 = 2, SKR_F16 = 3 };
@@ -225,7 +229,7 @@ typedef struct skr_offset {
 
 /*
  * Random / Offset (noise.py:73-74,104-113): out[e] = normal(seed, stream)[e] (+ offset term).
- * `moments` (optional, device double[2], pre-zeroed) accumulates sum and sum of squares of the values written.
+ * `moments` (optional, device double[SKR_MOMENTS_DOUBLES], zeroed) accumulates sum and sum of squares of the values written.
  */
 int skr_noise_fill(void* out, int32_t dtype, int64_t numel, uint64_t seed, uint64_t stream, const skr_offset* offset,
                    double* moments, void* cuda_stream);
@@ -257,20 +261,20 @@ int skr_noise_brownian(void* out, int32_t dtype, int64_t numel, uint64_t seed, d
 int skr_noise_brownian_batch(void* out, int32_t dtype, const uint64_t* seeds, int32_t n_items, int64_t item_numel,
                              double t0, double t1, int32_t depth, double out_scale, void* cuda_stream);
 
-/* sum / sum^2 of a tensor into device double[2] (pre-zeroed), for Tensor.std() (noise.py:207,365,401). */
+/* sum / sum^2 of a tensor into device double[SKR_MOMENTS_DOUBLES] (zeroed), for Tensor.std() (noise.py:207,365,401). */
 int skr_noise_moments(const void* in, int32_t dtype, int64_t numel, double* moments, void* cuda_stream);
 
 /*
  * Error norms of an embedded Runge-Kutta pair in one pass (FunctionalAdaptive.mae/.mse applied to (low, high) and
  * (0, high), functional.py:197-214, used by RKMoire.sample_model functional.py:437-441):
- *   sums[0] += sum |low - high|^power,  sums[1] += sum |high|^power      (power = 1 or 2; device double[2], pre-zeroed)
+ *   sums[0] += sum |low - high|^power,  sums[1] += sum |high|^power   (power = 1 or 2; device double[SKR_MOMENTS_DOUBLES], zeroed)
  */
 int skr_error_norms(const void* low, const void* high, int32_t dtype, int64_t numel, int32_t power, double* sums,
                     void* cuda_stream);
 
 /*
  * out = in * s, s = numerator [* std(num_moments, num_count)] [/ std(moments, count)], each factor applied when
- * its pointer is given (unbiased std from device double[2] accumulators); s stays 1 when the denominator std
+ * its pointer is given (unbiased std from the first two doubles of an accumulator); s stays 1 when the denominator std
  * is <= min_std.  In place allowed; casts in_dtype -> out_dtype.  (noise.py:207, 369, 402-405)
  */
 int skr_noise_scale(const void* in, int32_t in_dtype, void* out, int32_t out_dtype, int64_t numel, double numerator,
@@ -293,18 +297,25 @@ typedef struct skr_pyramid {
     uint64_t base_stream;         /* the plain randn(shape) term                                      */
     const float* base_buffer;     /* non-null: supplied base draw                                     */
     float* scratch;               /* optional, numel floats (may alias base_buffer): see below        */
+    float* levels_scratch;        /* optional, room for every weighted level smaller than the unit (each rounded up
+                                     to a multiple of 4 floats): levels without a buffer are drawn into it by one
+                                     launch instead of inside the composition                          */
     skr_pyramid_level levels[SKR_MAX_LEVELS];
 } skr_pyramid;
 
 /*
  * Pyramid (noise.py:146-207): out = (base + sum_l weight_l * upsample(level_l)) / std, bilinear/linear
  * upsampling with align_corners=False semantics, unbiased std over the whole tensor.  `moments` = device
- * double[2], pre-zeroed.  Two kernels either way:
+ * double[SKR_MOMENTS_DOUBLES], zeroed.  Without `levels_scratch`, two kernels either way:
  *   - without `scratch`: moments pass, then a second pass that regenerates, normalises and writes (nothing
  *     N-sized besides `out` exists; every interpolation corner is a Philox draw: compute-bound);
  *   - with `scratch`: one composition pass writes the unnormalised field to scratch and accumulates the moments,
- *     then a scale pass writes scratch / std to `out`.  Meant to be used with the base and the levels supplied
- *     as buffers (skr_noise_fill with the level's stream gives the same values the in-kernel draw would).
+ *     then a scale pass writes scratch / std to `out`.  With `levels_scratch` as well (and a last extent that is a
+ *     multiple of 4) this is the fast path, three launches: the coarse level grids are drawn into levels_scratch, the
+ *     composition draws the base and the unit-sized levels in registers and interpolates the coarse grids, the scale
+ *     pass normalises.  Buffers supplied for the base / levels are read instead of drawn (skr_noise_fill with the
+ *     level's stream gives the same values the in-kernel draw would).
+ * `moments`: SKR_MOMENTS_DOUBLES doubles, zeroed.
  */
 int skr_noise_pyramid(void* out, int32_t dtype, const skr_pyramid* desc, double* moments, void* cuda_stream);
 

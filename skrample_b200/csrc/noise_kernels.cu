@@ -99,6 +99,101 @@ __device__ __forceinline__ void block_sum2(double& a, double& b) {
     }
 }
 
+// Grid-wide sum of two doubles with a FIXED summation order, so the std that normalises Pyramid / Colored noise and
+// the RKMoire error ratio are bit-reproducible from run to run (atomicAdd on doubles would add the block sums in
+// arrival order).  `buf` is the caller's accumulator, SKR_MOMENTS_DOUBLES doubles, zeroed before first use:
+//   buf[0..1]  the two sums (added to what is there: several launches may accumulate into one buffer, in stream order)
+//   buf[2]     arrival counter (bit pattern of an unsigned integer), left at zero again
+//   buf[4 + 2b], buf[5 + 2b]  partial sums of block b
+// Every block stores its partials; the block that arrives last adds them up in block order (each lane a fixed strided
+// subset, then a fixed shuffle tree) and publishes the totals.  gridDim.x <= SKR_MOMENT_BLOCKS.
+__device__ __forceinline__ void publish_sums(double a, double b, double* buf) {
+    __shared__ bool last;
+    block_sum2(a, b);
+    if (threadIdx.x == 0) {
+        buf[4 + 2 * blockIdx.x] = a;
+        buf[5 + 2 * blockIdx.x] = b;
+        __threadfence();
+        const unsigned int ticket = atomicAdd(reinterpret_cast<unsigned int*>(buf + 2), 1u);
+        last = ticket == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (last && threadIdx.x < 32) {
+        __threadfence();
+        double ta = 0.0, tb = 0.0;
+        for (unsigned int i = threadIdx.x; i < gridDim.x; i += 32) {
+            ta += __ldcg(buf + 4 + 2 * i);
+            tb += __ldcg(buf + 5 + 2 * i);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ta += __shfl_down_sync(0xffffffffu, ta, o);
+            tb += __shfl_down_sync(0xffffffffu, tb, o);
+        }
+        if (threadIdx.x == 0) {
+            buf[0] += ta;
+            buf[1] += tb;
+            *reinterpret_cast<unsigned int*>(buf + 2) = 0u;
+        }
+    }
+}
+
+// 128-bit loads / stores of VEC consecutive elements of a storage type, as floats
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+    static constexpr int N = 4;
+    static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+        const float4 q = *reinterpret_cast<const float4*>(p);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    }
+    static __device__ __forceinline__ void store(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+    static __device__ __forceinline__ float get(const float* p) { return *p; }
+    static __device__ __forceinline__ void put(float* p, float v) { *p = v; }
+};
+template <> struct Vec<__nv_bfloat16> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+        const uint4 q = *reinterpret_cast<const uint4*>(p);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    static __device__ __forceinline__ float get(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+    static __device__ __forceinline__ void put(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+template <> struct Vec<__half> {
+    static constexpr int N = 8;
+    static __device__ __forceinline__ void load(const __half* p, float (&v)[8]) {
+        const uint4 q = *reinterpret_cast<const uint4*>(p);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
+    }
+    static __device__ __forceinline__ void store(__half* p, const float (&v)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    static __device__ __forceinline__ float get(const __half* p) { return __half2float(*p); }
+    static __device__ __forceinline__ void put(__half* p, float v) { *p = __float2half_rn(v); }
+};
+
 // ---------------------------------------------------------------------------------------------------------
 // Random / Offset fill   (reference: noise.py:36-42,73-74,104-113)
 
@@ -123,6 +218,8 @@ __device__ __forceinline__ int64_t reduced_index(const FillParams& p, int64_t e)
     return r;
 }
 
+// OFFSET / MOMENTS are compile-time so that the plain Random fill carries neither the offset lookup nor the sums.
+template <bool OFFSET, bool MOMENTS>
 __global__ void __launch_bounds__(256) fill_kernel(const __grid_constant__ FillParams p) {
     const Philox ph(p.seed);
     double s1 = 0.0, s2 = 0.0;
@@ -131,7 +228,7 @@ __global__ void __launch_bounds__(256) fill_kernel(const __grid_constant__ FillP
         float z[4];
         normal4(ph((uint64_t)g, p.stream), z);
         const int64_t first = g << 2;
-        if (p.offset_scale != 0.0f) {
+        if constexpr (OFFSET) {
             const int64_t row = p.inner > 0 ? first / p.inner : -1;
             if (row >= 0 && first + 3 < (row + 1) * p.inner) {
                 // the usual case (offsets along leading axes): the four elements share one offset draw
@@ -147,20 +244,18 @@ __global__ void __launch_bounds__(256) fill_kernel(const __grid_constant__ FillP
         }
         if (p.aligned && first + 4 <= p.numel) {
             store4(p.out, p.dtype, first, z);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { s1 += z[j]; s2 += (double)z[j] * z[j]; }
+            if constexpr (MOMENTS) {  // four values in fp32 (exact enough: |z| < 7), then one fp64 add per sum
+                s1 += (double)((z[0] + z[1]) + (z[2] + z[3]));
+                s2 += (double)((z[0] * z[0] + z[1] * z[1]) + (z[2] * z[2] + z[3] * z[3]));
+            }
         } else {
             for (int j = 0; j < 4 && first + j < p.numel; ++j) {
                 store1(p.out, p.dtype, first + j, z[j]);
-                s1 += z[j];
-                s2 += (double)z[j] * z[j];
+                if constexpr (MOMENTS) { s1 += z[j]; s2 += (double)z[j] * z[j]; }
             }
         }
     }
-    if (p.moments) {
-        block_sum2(s1, s2);
-        if (threadIdx.x == 0) { atomicAdd(&p.moments[0], s1); atomicAdd(&p.moments[1], s2); }
-    }
+    if constexpr (MOMENTS) publish_sums(s1, s2, p.moments);
 }
 
 // Batched Random fill: one launch for every batch item, each with its own (seed, stream) - the same values
@@ -193,15 +288,40 @@ struct MomentParams {
     double* moments;
 };
 
+// T: storage type.  128-bit loads (4 fp32 / 8 half elements per thread and iteration) when the base is 16-byte aligned;
+// per-thread sums of a vector in fp32, accumulated in fp64.
+template <typename T>
 __global__ void __launch_bounds__(256) moments_kernel(const __grid_constant__ MomentParams p) {
+    constexpr int N = Vec<T>::N;
+    const T* in = reinterpret_cast<const T*>(p.in);
     double s1 = 0.0, s2 = 0.0;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.numel; e += (int64_t)gridDim.x * blockDim.x) {
-        const double v = p.dtype == SKR_F64 ? reinterpret_cast<const double*>(p.in)[e] : (double)load1(p.in, p.dtype, e);
+    const bool vec = (reinterpret_cast<uintptr_t>(in) & 15u) == 0;
+    const int64_t groups = vec ? p.numel / N : 0;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+        float v[N];
+        Vec<T>::load(in + g * N, v);
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int j = 0; j < N; ++j) { a += v[j]; b += v[j] * v[j]; }
+        s1 += (double)a;
+        s2 += (double)b;
+    }
+    for (int64_t e = groups * N + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.numel; e += (int64_t)gridDim.x * blockDim.x) {
+        const double v = (double)Vec<T>::get(in + e);
         s1 += v;
         s2 += v * v;
     }
-    block_sum2(s1, s2);
-    if (threadIdx.x == 0) { atomicAdd(&p.moments[0], s1); atomicAdd(&p.moments[1], s2); }
+    publish_sums(s1, s2, p.moments);
+}
+
+__global__ void __launch_bounds__(256) moments_kernel_f64(const __grid_constant__ MomentParams p) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.numel; e += (int64_t)gridDim.x * blockDim.x) {
+        const double v = reinterpret_cast<const double*>(p.in)[e];
+        s1 += v;
+        s2 += v * v;
+    }
+    publish_sums(s1, s2, p.moments);
 }
 
 // Error norms of an embedded Runge-Kutta pair in one pass: sums[0] += sum |low - high|^p, sums[1] += sum |high|^p
@@ -215,23 +335,47 @@ struct ErrorNormParams {
     double* sums;
 };
 
+template <typename T>
 __global__ void __launch_bounds__(256) error_norm_kernel(const __grid_constant__ ErrorNormParams p) {
+    constexpr int N = Vec<T>::N;
+    const T* low = reinterpret_cast<const T*>(p.low);
+    const T* high = reinterpret_cast<const T*>(p.high);
+    double s1 = 0.0, s2 = 0.0;
+    const bool vec = ((reinterpret_cast<uintptr_t>(low) | reinterpret_cast<uintptr_t>(high)) & 15u) == 0;
+    const int64_t groups = vec ? p.numel / N : 0;
+    const bool square = p.power == 2;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+        float lo[N], hi[N];
+        Vec<T>::load(low + g * N, lo);
+        Vec<T>::load(high + g * N, hi);
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const float d = fabsf(lo[j] - hi[j]), h = fabsf(hi[j]);
+            a += square ? d * d : d;
+            b += square ? h * h : h;
+        }
+        s1 += (double)a;
+        s2 += (double)b;
+    }
+    for (int64_t e = groups * N + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.numel; e += (int64_t)gridDim.x * blockDim.x) {
+        const double lo = (double)Vec<T>::get(low + e), hi = (double)Vec<T>::get(high + e);
+        const double d = fabs(lo - hi), h = fabs(hi);
+        s1 += square ? d * d : d;
+        s2 += square ? h * h : h;
+    }
+    publish_sums(s1, s2, p.sums);
+}
+
+__global__ void __launch_bounds__(256) error_norm_kernel_f64(const __grid_constant__ ErrorNormParams p) {
     double s1 = 0.0, s2 = 0.0;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.numel; e += (int64_t)gridDim.x * blockDim.x) {
-        double lo, hi;
-        if (p.dtype == SKR_F64) {
-            lo = reinterpret_cast<const double*>(p.low)[e];
-            hi = reinterpret_cast<const double*>(p.high)[e];
-        } else {
-            lo = (double)load1(p.low, p.dtype, e);
-            hi = (double)load1(p.high, p.dtype, e);
-        }
+        const double lo = reinterpret_cast<const double*>(p.low)[e], hi = reinterpret_cast<const double*>(p.high)[e];
         const double d = fabs(lo - hi), h = fabs(hi);
         s1 += p.power == 2 ? d * d : d;
         s2 += p.power == 2 ? h * h : h;
     }
-    block_sum2(s1, s2);
-    if (threadIdx.x == 0) { atomicAdd(&p.sums[0], s1); atomicAdd(&p.sums[1], s2); }
+    publish_sums(s1, s2, p.sums);
 }
 
 struct ScaleParams {
@@ -254,22 +398,53 @@ __device__ __forceinline__ double std_from(const double* m, int64_t n) {
     return sqrt(var > 0.0 ? var : 0.0);
 }
 
-__global__ void __launch_bounds__(256) scale_kernel(const __grid_constant__ ScaleParams p) {
+__device__ __forceinline__ double scale_factor(const ScaleParams& p) {
     double scale = p.numerator;
     if (p.num_moments) scale *= std_from(p.num_moments, p.num_count);
     if (p.moments) {
         const double sd = std_from(p.moments, p.count);
         scale = sd > p.min_std ? scale / sd : 1.0;
     }
-    const float fs = (float)scale;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.numel; e += (int64_t)gridDim.x * blockDim.x) {
-        if (p.in_dtype == SKR_F64 || p.out_dtype == SKR_F64) {
-            const double v = p.in_dtype == SKR_F64 ? reinterpret_cast<const double*>(p.in)[e] : (double)load1(p.in, p.in_dtype, e);
-            if (p.out_dtype == SKR_F64) reinterpret_cast<double*>(p.out)[e] = v * scale;
-            else store1(p.out, p.out_dtype, e, (float)(v * scale));
-        } else {
-            store1(p.out, p.out_dtype, e, load1(p.in, p.in_dtype, e) * fs);
+    return scale;
+}
+
+// TI -> TO with 128-bit accesses on both sides: a thread moves max(N_in, N_out) consecutive elements per iteration.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) scale_kernel(const __grid_constant__ ScaleParams p) {
+    constexpr int NI = Vec<TI>::N, NO = Vec<TO>::N, N = NI > NO ? NI : NO;
+    const TI* in = reinterpret_cast<const TI*>(p.in);
+    TO* out = reinterpret_cast<TO*>(p.out);
+    const float fs = (float)scale_factor(p);
+    const bool vec = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+    const int64_t groups = vec ? p.numel / N : 0;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+        float v[N];
+#pragma unroll
+        for (int k = 0; k < N / NI; ++k) {
+            float part[NI];
+            Vec<TI>::load(in + g * N + k * NI, part);
+#pragma unroll
+            for (int j = 0; j < NI; ++j) v[k * NI + j] = part[j] * fs;
         }
+#pragma unroll
+        for (int k = 0; k < N / NO; ++k) {
+            float part[NO];
+#pragma unroll
+            for (int j = 0; j < NO; ++j) part[j] = v[k * NO + j];
+            Vec<TO>::store(out + g * N + k * NO, part);
+        }
+    }
+    for (int64_t e = groups * N + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.numel; e += (int64_t)gridDim.x * blockDim.x)
+        Vec<TO>::put(out + e, Vec<TI>::get(in + e) * fs);
+}
+
+// anything involving fp64 storage: element-wise, scaled in double
+__global__ void __launch_bounds__(256) scale_kernel_any(const __grid_constant__ ScaleParams p) {
+    const double scale = scale_factor(p);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < p.numel; e += (int64_t)gridDim.x * blockDim.x) {
+        const double v = p.in_dtype == SKR_F64 ? reinterpret_cast<const double*>(p.in)[e] : (double)load1(p.in, p.in_dtype, e);
+        if (p.out_dtype == SKR_F64) reinterpret_cast<double*>(p.out)[e] = v * scale;
+        else store1(p.out, p.out_dtype, e, (float)(v * scale));
     }
 }
 
@@ -295,6 +470,7 @@ struct PyramidParams {
     double* moments;
     int32_t m_axis[2];                                  // the resized axes in order (-1: only one)
     int32_t same_size[SKR_MAX_LEVELS];                  // 1: the level has the unit shape (interpolation is the identity)
+    float ratio[SKR_MAX_LEVELS][2];                     // level extent / unit extent along the resized axes (fp32, like ATen)
     int64_t lstride[SKR_MAX_LEVELS][SKR_MAX_DIMS];      // row-major strides of each level grid
 };
 
@@ -331,6 +507,10 @@ __device__ __forceinline__ float pyramid_value(const PyramidParams& p, const Phi
     for (int l = 0; l < p.n_levels; ++l) {
         const float wl = p.weight[l];
         if (wl == 0.0f) continue;
+        if (p.same_size[l]) {  // a level of the unit's own size: interpolation is the identity (weights 1 and 0)
+            pyramid += level_value(p, ph, l, (int64_t)e) * wl;
+            continue;
+        }
         I outer = 0;  // offset of this element's slice inside the level grid (all but the resized axes)
         for (int d = 0; d < p.ndim; ++d)
             if (!p.masked[d]) outer += idx[d] * (I)p.lstride[l][d];
@@ -369,22 +549,56 @@ __global__ void __launch_bounds__(256) pyramid_kernel(const __grid_constant__ Py
         if (p.mode == 1) store1(p.out, p.dtype, e, v * inv_std);
         else if (p.mode == 2) p.scratch[e] = v;  // may alias base_buffer: element e is read before it is written
     }
-    if (p.mode != 1) {
-        block_sum2(s1, s2);
-        if (threadIdx.x == 0) { atomicAdd(&p.moments[0], s1); atomicAdd(&p.moments[1], s2); }
+    if (p.mode != 1) publish_sums(s1, s2, p.moments);
+}
+
+// F.interpolate(align_corners=False) source position along one axis in 32-bit arithmetic (extents < 2^31)
+__device__ __forceinline__ void source_index32(int dst, int in_size, float scale, int& i0, int& i1, float& w1) {
+    float src = scale * ((float)dst + 0.5f) - 0.5f;
+    src = src < 0.0f ? 0.0f : src;
+    i0 = (int)src;
+    if (i0 > in_size - 1) i0 = in_size - 1;
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    w1 = src - (float)i0;
+}
+
+// All the coarse level grids of one pyramid in ONE launch: blockIdx.y = level, the level's normals written as fp32
+// (the values skr_noise_fill writes for (seed, stream[level])).
+struct LevelsFillParams {
+    uint64_t seed;
+    uint64_t stream[SKR_MAX_LEVELS];
+    float* out[SKR_MAX_LEVELS];
+    int32_t numel[SKR_MAX_LEVELS];
+};
+
+__global__ void __launch_bounds__(256) levels_fill_kernel(const __grid_constant__ LevelsFillParams p) {
+    const int l = blockIdx.y;
+    const int32_t numel = p.numel[l];
+    float* const out = p.out[l];
+    if (!out) return;
+    const Philox ph(p.seed);
+    const int32_t groups = (numel + 3) >> 2;
+    for (int32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
+        float z[4];
+        normal4(ph((uint64_t)g, p.stream[l]), z);
+        const int32_t first = g << 2;
+        if (first + 4 <= numel) *reinterpret_cast<float4*>(out + first) = make_float4(z[0], z[1], z[2], z[3]);  // grids are 16-byte aligned
+        else for (int j = 0; j < 4 && first + j < numel; ++j) out[first + j] = z[j];
     }
 }
 
-// Composition pass over supplied grids, four consecutive elements of the last axis per thread (last extent % 4 == 0,
-// fewer than 2^31 elements): the coordinate decomposition, the slice offset and the source rows of the other resized
-// axis are shared by the four, base / same-size levels / result move as 128-bit accesses.  Same arithmetic, in the
-// same order, as pyramid_value.
+// The composition pass, four consecutive elements of the last axis per thread (last extent % 4 == 0, fewer than 2^31
+// elements).  The base draw and every level of the unit's own size (level 0 always is) are drawn in registers from
+// their Philox streams - element 4g..4g+3 of a stream is block g - unless a buffer is supplied; coarse levels are
+// interpolated from their grids (small: they stay in L1 / L2).  Writes the unnormalised field to `scratch` and
+// accumulates its sum / sum of squares.  Same arithmetic, in the same order, as pyramid_value.
 __global__ void __launch_bounds__(256) pyramid_compose4_kernel(const __grid_constant__ PyramidParams p) {
     const int last = p.ndim - 1;
     const int m0 = p.m_axis[0], m1 = p.m_axis[1];
     const bool last_resized = p.masked[last] != 0;
     const int other = last_resized ? (m1 >= 0 ? m0 : -1) : -1;  // the resized axis that is not the last one
     const int32_t groups = (int32_t)(p.numel >> 2);
+    const Philox ph(p.seed);
     double s1 = 0.0, s2 = 0.0;
     for (int32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
         const int32_t e0 = g << 2;
@@ -402,8 +616,14 @@ __global__ void __launch_bounds__(256) pyramid_compose4_kernel(const __grid_cons
             if (wl == 0.0f) continue;
             const float* grid = p.buffer[l];
             if (p.same_size[l]) {
-                const float4 q = *reinterpret_cast<const float4*>(grid + e0);
-                acc[0] += q.x * wl; acc[1] += q.y * wl; acc[2] += q.z * wl; acc[3] += q.w * wl;
+                float q[4];
+                if (grid) {
+                    const float4 v = *reinterpret_cast<const float4*>(grid + e0);
+                    q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
+                } else {
+                    normal4(ph((uint64_t)g, p.stream[l]), q);
+                }
+                acc[0] += q[0] * wl; acc[1] += q[1] * wl; acc[2] += q[2] * wl; acc[3] += q[3] * wl;
                 continue;
             }
             int32_t outer = 0;  // slice offset from the axes that are neither resized nor the last one
@@ -411,10 +631,10 @@ __global__ void __launch_bounds__(256) pyramid_compose4_kernel(const __grid_cons
                 if (!p.masked[d]) outer += idx[d] * (int32_t)p.lstride[l][d];
             if (!last_resized) {
                 // the four elements sit in four consecutive slices: same interpolation footprint in each
-                int64_t h0, h1, w0 = 0, w1 = 0;
+                int h0, h1, w0 = 0, w1 = 0;
                 float wh, ww = 0.0f;
-                source_index((int64_t)idx[m0], p.extent[l][0], p.shape[m0], h0, h1, wh);
-                if (m1 >= 0) source_index((int64_t)idx[m1], p.extent[l][1], p.shape[m1], w0, w1, ww);
+                source_index32(idx[m0], (int)p.extent[l][0], p.ratio[l][0], h0, h1, wh);
+                if (m1 >= 0) source_index32(idx[m1], (int)p.extent[l][1], p.ratio[l][1], w0, w1, ww);
                 const int32_t sh = (int32_t)p.lstride[l][m0], sw = m1 >= 0 ? (int32_t)p.lstride[l][m1] : 0;
                 const int32_t sl = (int32_t)p.lstride[l][last];
 #pragma unroll
@@ -422,51 +642,131 @@ __global__ void __launch_bounds__(256) pyramid_compose4_kernel(const __grid_cons
                     const int32_t o = outer + (idx[last] + j) * sl;
                     float v;
                     if (m1 < 0) {
-                        v = (1.0f - wh) * grid[o + (int32_t)h0 * sh] + wh * grid[o + (int32_t)h1 * sh];
+                        v = (1.0f - wh) * grid[o + h0 * sh] + wh * grid[o + h1 * sh];
                     } else {
-                        const int32_t r0 = o + (int32_t)h0 * sh, r1 = o + (int32_t)h1 * sh;
-                        const float top = (1.0f - ww) * grid[r0 + (int32_t)w0 * sw] + ww * grid[r0 + (int32_t)w1 * sw];
-                        const float bot = (1.0f - ww) * grid[r1 + (int32_t)w0 * sw] + ww * grid[r1 + (int32_t)w1 * sw];
+                        const int32_t r0 = o + h0 * sh, r1 = o + h1 * sh;
+                        const float top = (1.0f - ww) * grid[r0 + w0 * sw] + ww * grid[r0 + w1 * sw];
+                        const float bot = (1.0f - ww) * grid[r1 + w0 * sw] + ww * grid[r1 + w1 * sw];
                         v = (1.0f - wh) * top + wh * bot;
                     }
                     acc[j] += v * wl;
                 }
             } else {
-                int64_t h0 = 0, h1 = 0;
+                int h0 = 0, h1 = 0;
                 float wh = 0.0f;
                 int32_t r0 = outer, r1 = outer;
                 if (other >= 0) {
-                    source_index((int64_t)idx[other], p.extent[l][0], p.shape[other], h0, h1, wh);
+                    source_index32(idx[other], (int)p.extent[l][0], p.ratio[l][0], h0, h1, wh);
                     const int32_t sh = (int32_t)p.lstride[l][other];
-                    r0 = outer + (int32_t)h0 * sh;
-                    r1 = outer + (int32_t)h1 * sh;
+                    r0 = outer + h0 * sh;
+                    r1 = outer + h1 * sh;
                 }
-                const int64_t extent_last = p.extent[l][other >= 0 ? 1 : 0];
+                const int which = other >= 0 ? 1 : 0;
+                const int extent_last = (int)p.extent[l][which];
+                const float ratio_last = p.ratio[l][which];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    int64_t w0, w1;
+                    int w0, w1;
                     float ww;
-                    source_index((int64_t)(idx[last] + j), extent_last, p.shape[last], w0, w1, ww);
+                    source_index32(idx[last] + j, extent_last, ratio_last, w0, w1, ww);
                     float v;
                     if (other < 0) {
-                        v = (1.0f - ww) * grid[outer + (int32_t)w0] + ww * grid[outer + (int32_t)w1];
+                        v = (1.0f - ww) * grid[outer + w0] + ww * grid[outer + w1];
                     } else {
-                        const float top = (1.0f - ww) * grid[r0 + (int32_t)w0] + ww * grid[r0 + (int32_t)w1];
-                        const float bot = (1.0f - ww) * grid[r1 + (int32_t)w0] + ww * grid[r1 + (int32_t)w1];
+                        const float top = (1.0f - ww) * grid[r0 + w0] + ww * grid[r0 + w1];
+                        const float bot = (1.0f - ww) * grid[r1 + w0] + ww * grid[r1 + w1];
                         v = (1.0f - wh) * top + wh * bot;
                     }
                     acc[j] += v * wl;
                 }
             }
         }
-        const float4 b = *reinterpret_cast<const float4*>(p.base_buffer + e0);
-        const float4 v = make_float4(b.x + acc[0], b.y + acc[1], b.z + acc[2], b.w + acc[3]);
+        float b[4];
+        if (p.base_buffer) {
+            const float4 q = *reinterpret_cast<const float4*>(p.base_buffer + e0);
+            b[0] = q.x; b[1] = q.y; b[2] = q.z; b[3] = q.w;
+        } else {
+            normal4(ph((uint64_t)g, p.base_stream), b);
+        }
+        const float4 v = make_float4(b[0] + acc[0], b[1] + acc[1], b[2] + acc[2], b[3] + acc[3]);
         *reinterpret_cast<float4*>(p.scratch + e0) = v;
-        s1 += (double)v.x + (double)v.y + (double)v.z + (double)v.w;
-        s2 += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+        s1 += (double)((v.x + v.y) + (v.z + v.w));
+        s2 += (double)((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
     }
-    block_sum2(s1, s2);
-    if (threadIdx.x == 0) { atomicAdd(&p.moments[0], s1); atomicAdd(&p.moments[1], s2); }
+    publish_sums(s1, s2, p.moments);
+}
+
+// The same composition for the usual layout - the resized axes are the trailing ones, everything before them only
+// selects a slice: the tensor is [slices, H, W] (AXES == 2) or [slices, W] (AXES == 1).  Coordinates live in
+// registers (no index arrays), two or one integer divisions per four elements.
+template <int AXES>
+__global__ void __launch_bounds__(256) pyramid_compose_trailing_kernel(const __grid_constant__ PyramidParams p) {
+    const int32_t groups = (int32_t)(p.numel >> 2);
+    const int32_t width = (int32_t)p.shape[AXES], height = AXES == 2 ? (int32_t)p.shape[1] : 1;
+    const Philox ph(p.seed);
+    double s1 = 0.0, s2 = 0.0;
+    for (int32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
+        const int32_t e0 = g << 2;
+        const int32_t row = e0 / width;          // slice * height + y
+        const int32_t x = e0 - row * width;
+        int32_t slice = row, y = 0;
+        if constexpr (AXES == 2) {
+            slice = row / height;
+            y = row - slice * height;
+        }
+        float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        for (int l = 0; l < p.n_levels; ++l) {
+            const float wl = p.weight[l];
+            if (wl == 0.0f) continue;
+            const float* grid = p.buffer[l];
+            if (p.same_size[l]) {
+                float q[4];
+                if (grid) {
+                    const float4 v = *reinterpret_cast<const float4*>(grid + e0);
+                    q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
+                } else {
+                    normal4(ph((uint64_t)g, p.stream[l]), q);
+                }
+                acc[0] += q[0] * wl; acc[1] += q[1] * wl; acc[2] += q[2] * wl; acc[3] += q[3] * wl;
+                continue;
+            }
+            const int lw = (int)p.extent[l][AXES - 1];
+            const float rw = p.ratio[l][AXES - 1];
+            const float* r0 = grid + slice * (int32_t)p.lstride[l][0];
+            const float* r1 = r0;
+            float wh = 0.0f;
+            if constexpr (AXES == 2) {
+                int h0, h1;
+                source_index32(y, (int)p.extent[l][0], p.ratio[l][0], h0, h1, wh);
+                r1 = r0 + h1 * lw;
+                r0 = r0 + h0 * lw;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int w0, w1;
+                float ww;
+                source_index32(x + j, lw, rw, w0, w1, ww);
+                float v = (1.0f - ww) * r0[w0] + ww * r0[w1];
+                if constexpr (AXES == 2) {
+                    const float bot = (1.0f - ww) * r1[w0] + ww * r1[w1];
+                    v = (1.0f - wh) * v + wh * bot;
+                }
+                acc[j] += v * wl;
+            }
+        }
+        float b[4];
+        if (p.base_buffer) {
+            const float4 q = *reinterpret_cast<const float4*>(p.base_buffer + e0);
+            b[0] = q.x; b[1] = q.y; b[2] = q.z; b[3] = q.w;
+        } else {
+            normal4(ph((uint64_t)g, p.base_stream), b);
+        }
+        const float4 v = make_float4(b[0] + acc[0], b[1] + acc[1], b[2] + acc[2], b[3] + acc[3]);
+        *reinterpret_cast<float4*>(p.scratch + e0) = v;
+        s1 += (double)((v.x + v.y) + (v.z + v.w));
+        s2 += (double)((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
+    }
+    publish_sums(s1, s2, p.moments);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -671,7 +971,8 @@ __global__ void __launch_bounds__(256) brownian_kernel(const __grid_constant__ B
 static unsigned grid_for(int64_t work_items, int threads) {
     const int64_t sms = sm_count_or(148);
     int64_t blocks = (work_items + threads - 1) / threads;
-    const int64_t cap = sms * 8;
+    int64_t cap = sms * 8;
+    if (cap > SKR_MOMENT_BLOCKS) cap = SKR_MOMENT_BLOCKS;  // kernels that publish grid-wide sums keep one partial per block
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return (unsigned)blocks;
@@ -723,7 +1024,16 @@ int skr_noise_fill(void* out, int32_t dtype, int64_t numel, uint64_t seed, uint6
         }
         p.inner = prefix ? inner : 0;
     }
-    fill_kernel<<<grid_for((numel + 3) / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
+    const unsigned grid = grid_for((numel + 3) / 4, 256);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const bool shifted = p.offset_scale != 0.0f;
+    if (moments) {
+        if (shifted) fill_kernel<true, true><<<grid, 256, 0, s>>>(p);
+        else fill_kernel<false, true><<<grid, 256, 0, s>>>(p);
+    } else {
+        if (shifted) fill_kernel<true, false><<<grid, 256, 0, s>>>(p);
+        else fill_kernel<false, false><<<grid, 256, 0, s>>>(p);
+    }
     return check_launch("noise fill");
 }
 
@@ -817,7 +1127,14 @@ int skr_noise_moments(const void* in, int32_t dtype, int64_t numel, double* mome
     if (numel == 0) return 0;
     if (!in) return fail(SKR_E_NULL, "null input");
     MomentParams p{in, numel, dtype, moments};
-    moments_kernel<<<grid_for(numel, 256 * 4), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const unsigned grid = grid_for(numel, 256 * 8);
+    switch (dtype) {
+        case SKR_F32: moments_kernel<float><<<grid, 256, 0, s>>>(p); break;
+        case SKR_BF16: moments_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(p); break;
+        case SKR_F16: moments_kernel<__half><<<grid, 256, 0, s>>>(p); break;
+        default: moments_kernel_f64<<<grid, 256, 0, s>>>(p); break;
+    }
     return check_launch("noise moments");
 }
 
@@ -830,7 +1147,14 @@ int skr_error_norms(const void* low, const void* high, int32_t dtype, int64_t nu
     if (numel == 0) return 0;
     if (!low || !high) return fail(SKR_E_NULL, "null input");
     ErrorNormParams p{low, high, numel, dtype, power, sums};
-    error_norm_kernel<<<grid_for(numel, 256 * 4), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const unsigned grid = grid_for(numel, 256 * 8);
+    switch (dtype) {
+        case SKR_F32: error_norm_kernel<float><<<grid, 256, 0, s>>>(p); break;
+        case SKR_BF16: error_norm_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(p); break;
+        case SKR_F16: error_norm_kernel<__half><<<grid, 256, 0, s>>>(p); break;
+        default: error_norm_kernel_f64<<<grid, 256, 0, s>>>(p); break;
+    }
     return check_launch("error norms");
 }
 
@@ -842,7 +1166,20 @@ int skr_noise_scale(const void* in, int32_t in_dtype, void* out, int32_t out_dty
     if (numel == 0) return 0;
     if (!in || !out) return fail(SKR_E_NULL, "null tensor");
     ScaleParams p{in, out, numel, in_dtype, out_dtype, numerator, num_moments, num_count, moments, count, min_std};
-    scale_kernel<<<grid_for(numel, 256 * 4), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+    const unsigned grid = grid_for(numel, 256 * 8);
+#define SKR_SCALE_CASE(TI, TO) scale_kernel<TI, TO><<<grid, 256, 0, s>>>(p)
+    if (in_dtype == SKR_F64 || out_dtype == SKR_F64) scale_kernel_any<<<grid, 256, 0, s>>>(p);
+    else if (in_dtype == SKR_F32 && out_dtype == SKR_F32) SKR_SCALE_CASE(float, float);
+    else if (in_dtype == SKR_F32 && out_dtype == SKR_BF16) SKR_SCALE_CASE(float, __nv_bfloat16);
+    else if (in_dtype == SKR_F32 && out_dtype == SKR_F16) SKR_SCALE_CASE(float, __half);
+    else if (in_dtype == SKR_BF16 && out_dtype == SKR_BF16) SKR_SCALE_CASE(__nv_bfloat16, __nv_bfloat16);
+    else if (in_dtype == SKR_BF16 && out_dtype == SKR_F32) SKR_SCALE_CASE(__nv_bfloat16, float);
+    else if (in_dtype == SKR_F16 && out_dtype == SKR_F16) SKR_SCALE_CASE(__half, __half);
+    else if (in_dtype == SKR_F16 && out_dtype == SKR_F32) SKR_SCALE_CASE(__half, float);
+    else if (in_dtype == SKR_BF16 && out_dtype == SKR_F16) SKR_SCALE_CASE(__nv_bfloat16, __half);
+    else SKR_SCALE_CASE(__half, __nv_bfloat16);
+#undef SKR_SCALE_CASE
     return check_launch("noise scale");
 }
 
@@ -897,15 +1234,73 @@ int skr_noise_pyramid(void* out, int32_t dtype, const skr_pyramid* desc, double*
         else pyramid_kernel<int64_t><<<grid_for(numel, 256), 256, 0, s>>>(p);
         return check_launch(what);
     };
-    bool grids = p.scratch && p.base_buffer && narrow && (p.shape[desc->ndim - 1] & 3) == 0 &&
-                 ((reinterpret_cast<uintptr_t>(p.scratch) | reinterpret_cast<uintptr_t>(p.base_buffer)) & 15u) == 0;
     for (int l = 0; l < desc->n_levels; ++l) {
         p.same_size[l] = p.extent[l][0] == p.shape[p.m_axis[0]] && (p.m_axis[1] < 0 || p.extent[l][1] == p.shape[p.m_axis[1]]);
-        if (p.weight[l] == 0.0f) continue;
-        grids = grids && p.buffer[l] && (!p.same_size[l] || (reinterpret_cast<uintptr_t>(p.buffer[l]) & 15u) == 0);
+        p.ratio[l][0] = (float)p.extent[l][0] / (float)p.shape[p.m_axis[0]];
+        p.ratio[l][1] = p.m_axis[1] >= 0 ? (float)p.extent[l][1] / (float)p.shape[p.m_axis[1]] : 1.0f;
     }
-    if (grids) {  // everything supplied as grids: four elements per thread
-        pyramid_compose4_kernel<<<grid_for(numel / 4, 256), 256, 0, s>>>(p);
+    // The fused path: base draw and unit-sized levels in registers, coarse levels from grids (supplied, or drawn here
+    // into `levels_scratch` by one launch), four elements per thread.
+    bool fused = p.scratch && narrow && (p.shape[desc->ndim - 1] & 3) == 0 && (reinterpret_cast<uintptr_t>(p.scratch) & 15u) == 0 &&
+                 (!p.base_buffer || (reinterpret_cast<uintptr_t>(p.base_buffer) & 15u) == 0);
+    if (desc->levels_scratch && (reinterpret_cast<uintptr_t>(desc->levels_scratch) & 15u) == 0) {
+        // coarse levels without a buffer: all drawn into levels_scratch by one launch (both composition kernels then
+        // interpolate grids instead of drawing every corner)
+        LevelsFillParams fill;
+        memset(&fill, 0, sizeof(fill));
+        fill.seed = desc->seed;
+        float* cursor = desc->levels_scratch;
+        int64_t largest = 0;
+        for (int l = 0; l < desc->n_levels; ++l) {
+            if (p.weight[l] == 0.0f || p.same_size[l] || p.buffer[l]) continue;
+            const int64_t count = p.lstride[l][0] * (p.masked[0] ? p.extent[l][0] : p.shape[0]);
+            if (count >= ((int64_t)1 << 31)) continue;  // stays an in-kernel draw
+            fill.stream[l] = p.stream[l];
+            fill.out[l] = cursor;
+            fill.numel[l] = (int32_t)count;
+            p.buffer[l] = cursor;
+            cursor += (count + 3) & ~(int64_t)3;
+            largest = count > largest ? count : largest;
+        }
+        if (largest > 0) {
+            const unsigned blocks = grid_for((largest + 3) / 4, 256);
+            levels_fill_kernel<<<dim3(blocks, (unsigned)desc->n_levels), 256, 0, s>>>(fill);
+            int rc = check_launch("pyramid levels");
+            if (rc) return rc;
+        }
+    }
+    for (int l = 0; l < desc->n_levels && fused; ++l) {
+        if (p.weight[l] == 0.0f) continue;
+        if (p.same_size[l]) fused = !p.buffer[l] || (reinterpret_cast<uintptr_t>(p.buffer[l]) & 15u) == 0;
+        else fused = p.buffer[l] != nullptr;
+    }
+    if (fused) {
+        // leading axes that are not resized only select a slice: collapse them so the kernel decomposes 2-3 indices
+        int lead = 0;
+        while (lead < desc->ndim && !p.masked[lead]) ++lead;
+        bool trailing = lead + masked == desc->ndim;
+        if (trailing) {
+            int64_t slices = 1;
+            for (int d = 0; d < lead; ++d) slices *= p.shape[d];
+            const int nd = masked + 1;
+            for (int l = 0; l < desc->n_levels; ++l) {
+                const int64_t inner = masked == 2 ? p.extent[l][0] * p.extent[l][1] : p.extent[l][0];
+                p.lstride[l][0] = inner;
+                if (masked == 2) { p.lstride[l][1] = p.extent[l][1]; p.lstride[l][2] = 1; }
+                else p.lstride[l][1] = 1;
+            }
+            const int64_t resized[2] = {p.shape[lead], masked == 2 ? p.shape[lead + 1] : 1};
+            for (int k = 0; k < masked; ++k) { p.shape[1 + k] = resized[k]; p.masked[1 + k] = 1; }
+            p.shape[0] = slices;
+            p.masked[0] = 0;
+            p.ndim = nd;
+            p.m_axis[0] = 1;
+            p.m_axis[1] = masked == 2 ? 2 : -1;
+            if (masked == 2) pyramid_compose_trailing_kernel<2><<<grid_for(numel / 4, 256), 256, 0, s>>>(p);
+            else pyramid_compose_trailing_kernel<1><<<grid_for(numel / 4, 256), 256, 0, s>>>(p);
+        } else {
+            pyramid_compose4_kernel<<<grid_for(numel / 4, 256), 256, 0, s>>>(p);
+        }
         int rc = check_launch("pyramid compose");
         if (rc) return rc;
         return skr_noise_scale(p.scratch, SKR_F32, out, dtype, numel, 1.0, nullptr, 0, moments, numel, 0.0, cuda_stream);

@@ -18,12 +18,13 @@ struct Philox {
         uint32_t a = k0, b = k1;
 #pragma unroll
         for (int r = 0; r < 10; ++r) {
-            const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-            c0 = hi1 ^ c1 ^ a;
-            c1 = lo1;
-            c2 = hi0 ^ c3 ^ b;
-            c3 = lo0;
+            // one 32x32 -> 64-bit multiply (IMAD.WIDE.U32) per product instead of a high and a low multiply
+            const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+            const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+            c0 = (uint32_t)(p1 >> 32) ^ c1 ^ a;
+            c1 = (uint32_t)p1;
+            c2 = (uint32_t)(p0 >> 32) ^ c3 ^ b;
+            c3 = (uint32_t)p0;
             a += 0x9E3779B9u;
             b += 0xBB67AE85u;
         }

@@ -52,6 +52,9 @@ class SkrTensor(ctypes.Structure):
 
 
 MAX_PHILOX = 2
+MOMENT_BLOCKS = 2048
+MOMENTS_DOUBLES = 4 + 2 * MOMENT_BLOCKS
+"Doubles in an accumulator of grid-wide sums (SKR_MOMENTS_DOUBLES): [0], [1] are the sums, the rest is reduction scratch."
 MAX_PHILOX_ITEMS = 256
 
 
@@ -501,10 +504,10 @@ def error_norms(low: Any, high: Any, power: int) -> tuple[float, float]:
     if low.shape != high.shape or low.dtype != high.dtype or low.device != high.device:
         raise ValueError("error_norms needs two tensors of one shape, dtype and device")
     low, high = low.contiguous(), high.contiguous()
-    sums = torch.zeros(2, dtype=torch.float64, device=high.device)
+    sums = torch.zeros(MOMENTS_DOUBLES, dtype=torch.float64, device=high.device)
     with torch.cuda.device(high.device):
         status = load().skr_error_norms(low.data_ptr(), high.data_ptr(), DTYPE_CODE[high.dtype], high.numel(), power, sums.data_ptr(), raw_stream())
     check(status, "skr_error_norms")
     count = max(high.numel(), 1)
-    total = sums.tolist()  # the adaptive controller needs the value: the one synchronisation of the step
+    total = sums[:2].tolist()  # the adaptive controller needs the value: the one synchronisation of the step
     return total[0] / count, total[1] / count

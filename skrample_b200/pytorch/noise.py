@@ -29,6 +29,8 @@ import torch
 
 from skrample_b200.common import Step, divf, rescale_positive
 
+_MOMENTS = 4 + 2 * 2048
+"Doubles in an accumulator of grid-wide sums (SKR_MOMENTS_DOUBLES in the C header)."
 _SUBSTREAMS = 64
 "Philox stream ids consumed per generate() call on a CUDA generator."
 _RESERVED_CALLS = 64
@@ -88,6 +90,7 @@ class _SkrPyramid(ctypes.Structure):
         ("base_stream", ctypes.c_uint64),
         ("base_buffer", ctypes.c_void_p),
         ("scratch", ctypes.c_void_p),
+        ("levels_scratch", ctypes.c_void_p),
         ("levels", _SkrPyramidLevel * 16),
     ]
 
@@ -529,17 +532,16 @@ class Pyramid(TensorNoiseCommon[PyramidProps]):
         for n, d in enumerate(self.shape):
             desc.shape[n] = d
             desc.masked[n] = int(mask[n])
-        # The base draw and every kept level are written once as fp32 grids (the levels are small: each is the unit
-        # shape shrunk by the level's ratio along the resized axes); the composition kernel then only interpolates.
-        # Drawing each interpolation corner inside the kernel instead costs ~32 Philox blocks per element.
+        # Three launches: the coarse level grids (small: each is the unit shape shrunk by the level's ratio along the
+        # resized axes) are drawn by one launch into scratch memory; the composition kernel draws the base and the
+        # unit-sized level 0 in registers, interpolates the coarse grids, writes the unnormalised field and sums it; the
+        # scale pass divides by the std.  (Drawing every interpolation corner inside the kernel instead - no scratch at
+        # all, `_use_grids = False` - costs ~32 Philox blocks per element.)
         numel = math.prod(self.shape)
         align = lambda n: (n + 3) & ~3  # noqa: E731 - keep every grid 16-byte aligned for vector stores
-        sizes = [math.prod(shape) if level >= first and self._use_grids else 0 for level, shape in enumerate(shapes)]
-        scratch = torch.empty(align(numel) + sum(align(n) for n in sizes), dtype=torch.float32, device=out.device)
+        coarse = [math.prod(shape) if level >= first and tuple(shape) != tuple(self.shape) and self._use_grids else 0 for level, shape in enumerate(shapes)]
+        scratch = torch.empty(align(numel) + sum(align(n) for n in coarse), dtype=torch.float32, device=out.device) if self._use_grids else None
         with _DeviceGuard(out.device):
-            if self._use_grids:
-                self._fill(scratch[:numel], base)
-            cursor = align(numel)
             for level, shape in enumerate(shapes):
                 slot = desc.levels[level]
                 slot.stream = level_tick + 2 + level
@@ -547,15 +549,10 @@ class Pyramid(TensorNoiseCommon[PyramidProps]):
                 slot.extent[0] = extents[0]
                 slot.extent[1] = extents[1] if len(extents) > 1 else 1
                 slot.weight = self.props.strength**level if level >= first else 0.0
-                if sizes[level]:
-                    grid = scratch[cursor : cursor + sizes[level]]
-                    self._fill(grid, slot.stream)
-                    slot.buffer = grid.data_ptr()
-                    cursor += align(sizes[level])
-            if self._use_grids:
-                desc.base_buffer = scratch.data_ptr()
-                desc.scratch = scratch.data_ptr()  # composed in place over the base draw
-            moments = torch.zeros(2, dtype=torch.float64, device=out.device)
+            if scratch is not None:
+                desc.scratch = scratch.data_ptr()
+                desc.levels_scratch = scratch.data_ptr() + 4 * align(numel)
+            moments = torch.zeros(_MOMENTS, dtype=torch.float64, device=out.device)
             status = _lib().skr_noise_pyramid(out.data_ptr(), _code(out.dtype), ctypes.byref(desc), moments.data_ptr(), _stream())
         _native().check(status, "skr_noise_pyramid")
 
@@ -801,7 +798,7 @@ class Colored(TensorNoiseCommon[ColoredProps]):
         with _DeviceGuard(white.device):
             stream = _stream()
             if white_moments is None:
-                white_moments = torch.zeros(2, dtype=torch.float64, device=white.device)
+                white_moments = torch.zeros(_MOMENTS, dtype=torch.float64, device=white.device)
                 native.check(lib.skr_noise_moments(white.data_ptr(), _code(white.dtype), n, white_moments.data_ptr(), stream), "skr_noise_moments")
             if exponent == 0.0:
                 if energy is None:
@@ -824,7 +821,7 @@ class Colored(TensorNoiseCommon[ColoredProps]):
             # norm="forward": no 1/N pass on the inverse; the field is renormalised by its own std just below, so a
             # constant factor only has to be carried into the degenerate-std threshold
             colored = torch.fft.irfftn(spectrum, s=w.shape, norm="forward").contiguous()
-            colored_moments = torch.zeros(2, dtype=torch.float64, device=white.device)
+            colored_moments = torch.zeros(_MOMENTS, dtype=torch.float64, device=white.device)
             native.check(lib.skr_noise_moments(colored.data_ptr(), _code(colored.dtype), n, colored_moments.data_ptr(), stream), "skr_noise_moments")
             out = torch.empty(white.shape, dtype=out_dtype, device=white.device)
             native.check(
@@ -862,7 +859,7 @@ class Colored(TensorNoiseCommon[ColoredProps]):
         if self.on_device:
             work_dtype = self.dtype if self.dtype in (torch.float32, torch.float64) else torch.float32
             white = torch.empty(tuple(self.shape), dtype=work_dtype, device=self.seed.device)
-            moments = torch.zeros(2, dtype=torch.float64, device=white.device)
+            moments = torch.zeros(_MOMENTS, dtype=torch.float64, device=white.device)
             self._fill(white, self._tick(), moments=moments)
             return self._colorize_device(white, exponent, self.props.energy, moments, self.dtype)
         return self.colorize_noise(self._randn(), exponent=exponent, energy=self.props.energy)

@@ -297,9 +297,13 @@ typedef struct skr_pyramid {
     uint64_t base_stream;         /* the plain randn(shape) term                                      */
     const float* base_buffer;     /* non-null: supplied base draw                                     */
     float* scratch;               /* optional, numel floats (may alias base_buffer): see below        */
-    float* levels_scratch;        /* optional, room for every weighted level smaller than the unit (each rounded up
-                                     to a multiple of 4 floats): levels without a buffer are drawn into it by one
-                                     launch instead of inside the composition                          */
+    float* levels_scratch;        /* optional work area of levels_scratch_floats floats.  Weighted levels smaller
+                                     than the unit that come without a buffer are drawn into it by one launch
+                                     (each rounded up to a multiple of 4 floats) instead of inside the composition;
+                                     when the resized axes are the trailing ones and room is left, each such level
+                                     is also stretched to the unit's width there (slices x level height x width
+                                     floats) so the composition interpolates whole rows                  */
+    int64_t levels_scratch_floats;
     skr_pyramid_level levels[SKR_MAX_LEVELS];
 } skr_pyramid;
 

@@ -218,12 +218,34 @@ __device__ __forceinline__ int64_t reduced_index(const FillParams& p, int64_t e)
     return r;
 }
 
-// OFFSET / MOMENTS are compile-time so that the plain Random fill carries neither the offset lookup nor the sums.
-template <bool OFFSET, bool MOMENTS>
+// four consecutive elements in storage type T
+template <typename T> __device__ __forceinline__ void put4(T* p, const float (&v)[4]);
+template <> __device__ __forceinline__ void put4<float>(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+template <> __device__ __forceinline__ void put4<double>(double* p, const float (&v)[4]) {
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+}
+template <> __device__ __forceinline__ void put4<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[4]) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+template <> __device__ __forceinline__ void put4<__half>(__half* p, const float (&v)[4]) {
+    const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+template <typename T> __device__ __forceinline__ void put1(T* p, float v) { *p = (T)v; }
+template <> __device__ __forceinline__ void put1<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ void put1<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+
+// T (the storage type), OFFSET and MOMENTS are compile-time so that the plain Random fill carries neither a dtype
+// dispatch, nor the offset lookup, nor the sums: its loop is Philox + Box-Muller + one 128-bit store.
+template <typename T, bool OFFSET, bool MOMENTS>
 __global__ void __launch_bounds__(256) fill_kernel(const __grid_constant__ FillParams p) {
     const Philox ph(p.seed);
+    T* const out = reinterpret_cast<T*>(p.out);
     double s1 = 0.0, s2 = 0.0;
     const int64_t groups = (p.numel + 3) >> 2;
+    const int64_t whole = p.aligned ? p.numel >> 2 : 0;  // groups stored with one vector access
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
         float z[4];
         normal4(ph((uint64_t)g, p.stream), z);
@@ -242,20 +264,31 @@ __global__ void __launch_bounds__(256) fill_kernel(const __grid_constant__ FillP
                 }
             }
         }
-        if (p.aligned && first + 4 <= p.numel) {
-            store4(p.out, p.dtype, first, z);
+        if (g < whole) {
+            put4<T>(out + first, z);
             if constexpr (MOMENTS) {  // four values in fp32 (exact enough: |z| < 7), then one fp64 add per sum
                 s1 += (double)((z[0] + z[1]) + (z[2] + z[3]));
                 s2 += (double)((z[0] * z[0] + z[1] * z[1]) + (z[2] * z[2] + z[3] * z[3]));
             }
         } else {
             for (int j = 0; j < 4 && first + j < p.numel; ++j) {
-                store1(p.out, p.dtype, first + j, z[j]);
+                put1<T>(out + first + j, z[j]);
                 if constexpr (MOMENTS) { s1 += z[j]; s2 += (double)z[j] * z[j]; }
             }
         }
     }
     if constexpr (MOMENTS) publish_sums(s1, s2, p.moments);
+}
+
+template <typename T>
+static void launch_fill(const FillParams& p, bool shifted, bool moments, unsigned grid, cudaStream_t s) {
+    if (moments) {
+        if (shifted) fill_kernel<T, true, true><<<grid, 256, 0, s>>>(p);
+        else fill_kernel<T, false, true><<<grid, 256, 0, s>>>(p);
+    } else {
+        if (shifted) fill_kernel<T, true, false><<<grid, 256, 0, s>>>(p);
+        else fill_kernel<T, false, false><<<grid, 256, 0, s>>>(p);
+    }
 }
 
 // Batched Random fill: one launch for every batch item, each with its own (seed, stream) - the same values
@@ -267,14 +300,17 @@ struct BatchFillParams {
     KPhilox keys;
 };
 
+template <typename T>
 __global__ void __launch_bounds__(256) batch_fill_kernel(const __grid_constant__ BatchFillParams p) {
+    T* const out = reinterpret_cast<T*>(p.out);
     const int64_t groups = (p.numel + 3) >> 2;
+    const int64_t whole = p.aligned ? p.numel >> 2 : 0;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
         const int64_t first = g << 2;
         float z[4];
         draw_normals<float, 4>(p.keys, first, p.numel, z);
-        if (p.aligned && first + 4 <= p.numel) store4(p.out, p.dtype, first, z);
-        else for (int j = 0; j < 4 && first + j < p.numel; ++j) store1(p.out, p.dtype, first + j, z[j]);
+        if (g < whole) put4<T>(out + first, z);
+        else for (int j = 0; j < 4 && first + j < p.numel; ++j) put1<T>(out + first + j, z[j]);
     }
 }
 
@@ -471,6 +507,8 @@ struct PyramidParams {
     int32_t m_axis[2];                                  // the resized axes in order (-1: only one)
     int32_t same_size[SKR_MAX_LEVELS];                  // 1: the level has the unit shape (interpolation is the identity)
     float ratio[SKR_MAX_LEVELS][2];                     // level extent / unit extent along the resized axes (fp32, like ATen)
+    const float* wide[SKR_MAX_LEVELS];                  // trailing layout: the level already interpolated along the last axis
+                                                        // ([slices, level height, unit width]); null: interpolate here
     int64_t lstride[SKR_MAX_LEVELS][SKR_MAX_DIMS];      // row-major strides of each level grid
 };
 
@@ -584,6 +622,44 @@ __global__ void __launch_bounds__(256) levels_fill_kernel(const __grid_constant_
         const int32_t first = g << 2;
         if (first + 4 <= numel) *reinterpret_cast<float4*>(out + first) = make_float4(z[0], z[1], z[2], z[3]);  // grids are 16-byte aligned
         else for (int j = 0; j < 4 && first + j < numel; ++j) out[first + j] = z[j];
+    }
+}
+
+// Bilinear interpolation is separable: a coarse level is first stretched along the last axis to the unit's width
+// (this kernel: [rows, level width] -> [rows, unit width], rows = slices x level height, all levels in one launch,
+// blockIdx.y = level), so the composition only interpolates between two ROWS - two 128-bit loads and four lerps per
+// level and group of four elements instead of sixteen gathers and four index computations.
+struct LevelsWidenParams {
+    const float* in[SKR_MAX_LEVELS];
+    float* out[SKR_MAX_LEVELS];
+    int32_t rows[SKR_MAX_LEVELS];
+    int32_t in_width[SKR_MAX_LEVELS];
+    float ratio[SKR_MAX_LEVELS];
+    int32_t width;  // unit width, a multiple of 4
+};
+
+__global__ void __launch_bounds__(256) levels_widen_kernel(const __grid_constant__ LevelsWidenParams p) {
+    const int l = blockIdx.y;
+    const float* const in = p.in[l];
+    if (!in) return;
+    float* const out = p.out[l];
+    const int32_t width = p.width, lw = p.in_width[l];
+    const float ratio = p.ratio[l];
+    const int32_t groups = p.rows[l] * (width >> 2);
+    for (int32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
+        const int32_t e0 = g << 2;
+        const int32_t row = e0 / width;
+        const int32_t x = e0 - row * width;
+        const float* const line = in + row * lw;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int w0, w1;
+            float ww;
+            source_index32(x + j, lw, ratio, w0, w1, ww);
+            v[j] = (1.0f - ww) * line[w0] + ww * line[w1];
+        }
+        *reinterpret_cast<float4*>(out + e0) = make_float4(v[0], v[1], v[2], v[3]);
     }
 }
 
@@ -728,6 +804,26 @@ __global__ void __launch_bounds__(256) pyramid_compose_trailing_kernel(const __g
                     normal4(ph((uint64_t)g, p.stream[l]), q);
                 }
                 acc[0] += q[0] * wl; acc[1] += q[1] * wl; acc[2] += q[2] * wl; acc[3] += q[3] * wl;
+                continue;
+            }
+            if (const float* wide = p.wide[l]) {
+                // already at the unit's width: interpolate between two rows (AXES == 2) or just add (AXES == 1)
+                float4 top;
+                if constexpr (AXES == 2) {
+                    int h0, h1;
+                    float wh;
+                    source_index32(y, (int)p.extent[l][0], p.ratio[l][0], h0, h1, wh);
+                    const int32_t base = slice * (int32_t)p.extent[l][0];
+                    top = *reinterpret_cast<const float4*>(wide + (base + h0) * width + x);
+                    const float4 bot = *reinterpret_cast<const float4*>(wide + (base + h1) * width + x);
+                    top.x = (1.0f - wh) * top.x + wh * bot.x;
+                    top.y = (1.0f - wh) * top.y + wh * bot.y;
+                    top.z = (1.0f - wh) * top.z + wh * bot.z;
+                    top.w = (1.0f - wh) * top.w + wh * bot.w;
+                } else {
+                    top = *reinterpret_cast<const float4*>(wide + e0);
+                }
+                acc[0] += top.x * wl; acc[1] += top.y * wl; acc[2] += top.z * wl; acc[3] += top.w * wl;
                 continue;
             }
             const int lw = (int)p.extent[l][AXES - 1];
@@ -1027,12 +1123,11 @@ int skr_noise_fill(void* out, int32_t dtype, int64_t numel, uint64_t seed, uint6
     const unsigned grid = grid_for((numel + 3) / 4, 256);
     cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
     const bool shifted = p.offset_scale != 0.0f;
-    if (moments) {
-        if (shifted) fill_kernel<true, true><<<grid, 256, 0, s>>>(p);
-        else fill_kernel<false, true><<<grid, 256, 0, s>>>(p);
-    } else {
-        if (shifted) fill_kernel<true, false><<<grid, 256, 0, s>>>(p);
-        else fill_kernel<false, false><<<grid, 256, 0, s>>>(p);
+    switch (dtype) {
+        case SKR_F32: launch_fill<float>(p, shifted, moments != nullptr, grid, s); break;
+        case SKR_BF16: launch_fill<__nv_bfloat16>(p, shifted, moments != nullptr, grid, s); break;
+        case SKR_F16: launch_fill<__half>(p, shifted, moments != nullptr, grid, s); break;
+        default: launch_fill<double>(p, shifted, moments != nullptr, grid, s); break;
     }
     return check_launch("noise fill");
 }
@@ -1051,7 +1146,14 @@ int skr_noise_fill_batch(void* out, int32_t dtype, const skr_philox* keys, void*
     p.out = out; p.numel = numel; p.dtype = dtype;
     p.aligned = (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
     fill_kphilox(&p.keys, keys, 1);
-    batch_fill_kernel<<<grid_for((numel + 3) / 4, 256), 256, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(p);
+    const unsigned grid = grid_for((numel + 3) / 4, 256);
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+    switch (dtype) {
+        case SKR_F32: batch_fill_kernel<float><<<grid, 256, 0, s>>>(p); break;
+        case SKR_BF16: batch_fill_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>(p); break;
+        case SKR_F16: batch_fill_kernel<__half><<<grid, 256, 0, s>>>(p); break;
+        default: batch_fill_kernel<double><<<grid, 256, 0, s>>>(p); break;
+    }
     return check_launch("noise batch fill");
 }
 
@@ -1241,6 +1343,7 @@ int skr_noise_pyramid(void* out, int32_t dtype, const skr_pyramid* desc, double*
     }
     // The fused path: base draw and unit-sized levels in registers, coarse levels from grids (supplied, or drawn here
     // into `levels_scratch` by one launch), four elements per thread.
+    float* levels_cursor = nullptr;  // first free float of levels_scratch after the level grids
     bool fused = p.scratch && narrow && (p.shape[desc->ndim - 1] & 3) == 0 && (reinterpret_cast<uintptr_t>(p.scratch) & 15u) == 0 &&
                  (!p.base_buffer || (reinterpret_cast<uintptr_t>(p.base_buffer) & 15u) == 0);
     if (desc->levels_scratch && (reinterpret_cast<uintptr_t>(desc->levels_scratch) & 15u) == 0) {
@@ -1254,7 +1357,8 @@ int skr_noise_pyramid(void* out, int32_t dtype, const skr_pyramid* desc, double*
         for (int l = 0; l < desc->n_levels; ++l) {
             if (p.weight[l] == 0.0f || p.same_size[l] || p.buffer[l]) continue;
             const int64_t count = p.lstride[l][0] * (p.masked[0] ? p.extent[l][0] : p.shape[0]);
-            if (count >= ((int64_t)1 << 31)) continue;  // stays an in-kernel draw
+            const int64_t used = cursor - desc->levels_scratch;
+            if (count >= ((int64_t)1 << 31) || used + ((count + 3) & ~(int64_t)3) > desc->levels_scratch_floats) continue;  // stays an in-kernel draw
             fill.stream[l] = p.stream[l];
             fill.out[l] = cursor;
             fill.numel[l] = (int32_t)count;
@@ -1268,6 +1372,7 @@ int skr_noise_pyramid(void* out, int32_t dtype, const skr_pyramid* desc, double*
             int rc = check_launch("pyramid levels");
             if (rc) return rc;
         }
+        levels_cursor = cursor;
     }
     for (int l = 0; l < desc->n_levels && fused; ++l) {
         if (p.weight[l] == 0.0f) continue;
@@ -1296,6 +1401,35 @@ int skr_noise_pyramid(void* out, int32_t dtype, const skr_pyramid* desc, double*
             p.ndim = nd;
             p.m_axis[0] = 1;
             p.m_axis[1] = masked == 2 ? 2 : -1;
+            // stretch the coarse levels to the unit's width first, when the scratch area has room after the grids
+            {
+                LevelsWidenParams widen;
+                memset(&widen, 0, sizeof(widen));
+                widen.width = (int32_t)p.shape[masked];
+                float* cursor = levels_cursor;
+                int64_t room = levels_cursor ? desc->levels_scratch_floats - (levels_cursor - desc->levels_scratch) : 0;
+                int64_t largest = 0;
+                for (int l = 0; l < desc->n_levels; ++l) {
+                    if (p.weight[l] == 0.0f || p.same_size[l] || !p.buffer[l]) continue;
+                    const int64_t rows = slices * (masked == 2 ? p.extent[l][0] : 1);
+                    const int64_t count = rows * widen.width;
+                    if (count > room || count >= ((int64_t)1 << 31)) continue;
+                    widen.in[l] = p.buffer[l];
+                    widen.out[l] = cursor;
+                    widen.rows[l] = (int32_t)rows;
+                    widen.in_width[l] = (int32_t)p.extent[l][masked - 1];
+                    widen.ratio[l] = p.ratio[l][masked - 1];
+                    p.wide[l] = cursor;
+                    cursor += count;
+                    room -= count;
+                    largest = count > largest ? count : largest;
+                }
+                if (largest > 0) {
+                    levels_widen_kernel<<<dim3(grid_for(largest / 4, 256), (unsigned)desc->n_levels), 256, 0, s>>>(widen);
+                    int rc = check_launch("pyramid widen");
+                    if (rc) return rc;
+                }
+            }
             if (masked == 2) pyramid_compose_trailing_kernel<2><<<grid_for(numel / 4, 256), 256, 0, s>>>(p);
             else pyramid_compose_trailing_kernel<1><<<grid_for(numel / 4, 256), 256, 0, s>>>(p);
         } else {

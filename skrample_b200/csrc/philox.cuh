@@ -18,13 +18,14 @@ struct Philox {
         uint32_t a = k0, b = k1;
 #pragma unroll
         for (int r = 0; r < 10; ++r) {
-            // one 32x32 -> 64-bit multiply (IMAD.WIDE.U32) per product instead of a high and a low multiply
-            const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
-            const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
-            c0 = (uint32_t)(p1 >> 32) ^ c1 ^ a;
-            c1 = (uint32_t)p1;
-            c2 = (uint32_t)(p0 >> 32) ^ c3 ^ b;
-            c3 = (uint32_t)p0;
+            // one 32x32 -> 64-bit multiply per product (mul.wide.u32 -> IMAD.WIDE.U32), halves split without arithmetic
+            uint32_t lo0, hi0, lo1, hi1;
+            asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo0), "=r"(hi0) : "r"(c0), "r"(0xD2511F53u));
+            asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo1), "=r"(hi1) : "r"(c2), "r"(0xCD9E8D57u));
+            c0 = hi1 ^ c1 ^ a;
+            c1 = lo1;
+            c2 = hi0 ^ c3 ^ b;
+            c3 = lo0;
             a += 0x9E3779B9u;
             b += 0xBB67AE85u;
         }
@@ -32,7 +33,9 @@ struct Philox {
     }
 };
 
-__device__ __forceinline__ float u01(uint32_t x) { return (float)x * 2.3283064365386963e-10f + 1.1641532182693481e-10f; }  // (0, 1]
+// (0, 1]; one fused multiply-add, written explicitly so that every translation unit (whatever its -fmad setting) gets
+// the same bits
+__device__ __forceinline__ float u01(uint32_t x) { return __fmaf_rn((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
 
 // Box-Muller on the special-function unit.  A standard normal is needed to ~1e-5, not to the last bit (nothing pins the
 // VALUES of device noise: torch's CUDA generator cannot be reproduced either; the contract is seed determinism, the
@@ -69,10 +72,10 @@ __device__ __forceinline__ void normal4(const uint4 r, float (&z)[4]) {
     float s0, c0, s1, c1;
     sincos_turns(u01(r.y), s0, c0);
     sincos_turns(u01(r.w), s1, c1);
-    z[0] = r0 * s0;
-    z[1] = r0 * c0;
-    z[2] = r1 * s1;
-    z[3] = r1 * c1;
+    z[0] = __fmul_rn(r0, s0);
+    z[1] = __fmul_rn(r0, c0);
+    z[2] = __fmul_rn(r1, s1);
+    z[3] = __fmul_rn(r1, c1);
 }
 
 // the normal at element `e` of stream (seed, stream)

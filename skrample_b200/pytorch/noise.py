@@ -91,6 +91,7 @@ class _SkrPyramid(ctypes.Structure):
         ("base_buffer", ctypes.c_void_p),
         ("scratch", ctypes.c_void_p),
         ("levels_scratch", ctypes.c_void_p),
+        ("levels_scratch_floats", ctypes.c_int64),
         ("levels", _SkrPyramidLevel * 16),
     ]
 
@@ -540,7 +541,12 @@ class Pyramid(TensorNoiseCommon[PyramidProps]):
         numel = math.prod(self.shape)
         align = lambda n: (n + 3) & ~3  # noqa: E731 - keep every grid 16-byte aligned for vector stores
         coarse = [math.prod(shape) if level >= first and tuple(shape) != tuple(self.shape) and self._use_grids else 0 for level, shape in enumerate(shapes)]
-        scratch = torch.empty(align(numel) + sum(align(n) for n in coarse), dtype=torch.float32, device=out.device) if self._use_grids else None
+        # ... plus room to stretch each coarse level to the unit's width (rows of the level x unit width) when the
+        # resized axes are the trailing ones: the composition then interpolates whole rows
+        width = self.shape[-1]
+        widened = [n // shape[-1] * width if n and mask[-1] else 0 for n, shape in zip(coarse, shapes)]
+        levels_room = sum(align(n) for n in coarse) + sum(align(n) for n in widened)
+        scratch = torch.empty(align(numel) + levels_room, dtype=torch.float32, device=out.device) if self._use_grids else None
         with _DeviceGuard(out.device):
             for level, shape in enumerate(shapes):
                 slot = desc.levels[level]
@@ -552,6 +558,7 @@ class Pyramid(TensorNoiseCommon[PyramidProps]):
             if scratch is not None:
                 desc.scratch = scratch.data_ptr()
                 desc.levels_scratch = scratch.data_ptr() + 4 * align(numel)
+                desc.levels_scratch_floats = levels_room
             moments = torch.zeros(_MOMENTS, dtype=torch.float64, device=out.device)
             status = _lib().skr_noise_pyramid(out.data_ptr(), _code(out.dtype), ctypes.byref(desc), moments.data_ptr(), _stream())
         _native().check(status, "skr_noise_pyramid")
@@ -939,15 +946,13 @@ class BatchTensorNoise[T: TensorNoiseProps | None](SkrampleTensorNoise):
             if g.on_device:
                 g.reserve(calls)
 
-    AUTO_LAZY_MAX_ELEMENTS = 1 << 20
-
     def auto(self, step: Step | None) -> "PhiloxDraw | torch.Tensor":
-        """The next batch of noise in whichever form steps faster: Philox keys drawn inside the step kernel for small
-        batches - where a step is bound by host time and launch latency, and skipping the fill launch and the noise
-        tensor's traffic is worth more than the extra arithmetic in the step kernel - and a filled tensor above
-        ``AUTO_LAZY_MAX_ELEMENTS``, where the fill kernel is the cheaper producer.  Same values either way."""
+        """The next batch of noise in the form a sampler makes the most of: Philox keys (a ``PhiloxDraw``) when every
+        item is a plain ``Random`` on one CUDA device - the step then draws the normals inside its own kernel, or has
+        them written by the fill kernel first where that is faster for the step at hand (``Program.settle_noise``) - and
+        the generated tensor otherwise.  Same values either way."""
         info = self._uniform_info()
-        if info is not None and info[0] <= _native().MAX_PHILOX_ITEMS and info[2] <= self.AUTO_LAZY_MAX_ELEMENTS:
+        if info is not None and info[0] <= _native().MAX_PHILOX_ITEMS:
             return self.lazy(step)
         return self.generate(step)
 

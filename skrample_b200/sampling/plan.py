@@ -18,6 +18,7 @@ import threading
 from typing import Any
 
 SAMPLE, PREDICTION, NOISE, XHAT = 0, 1, 2, 3
+MATERIALISED = 9  # role (MATERIALISED, inner role): the tensor of a lazy noise draw, written by its fill kernel on demand
 _FIELDS = ("sample", "prediction", "noise")
 _MAX_PLANS = 512
 XHAT_ATTR = "_skr_xhat"
@@ -121,11 +122,14 @@ def roles_of(inputs: list[Any], packed: Any, previous: Any) -> tuple | None:
     where: dict[int, tuple] = {}
 
     def note(value: Any, role: tuple) -> bool:
-        if value is None or not (hasattr(value, "data_ptr") or getattr(value, "is_lazy_noise", False)):
+        lazy = getattr(value, "is_lazy_noise", False)
+        if value is None or not (hasattr(value, "data_ptr") or lazy):
             return True
         if id(value) in where:
             return False  # one tensor in two roles: a later call may pass different tensors, do not cache
         where[id(value)] = role
+        if lazy and value._tensor is not None:  # a draw the step chose to read from memory (Program.settle_noise)
+            where[id(value._tensor)] = (MATERIALISED, role)
         return True
 
     ok = note(packed.sample, (SAMPLE,)) and note(packed.prediction, (PREDICTION,)) and note(packed.noise, (NOISE,))
@@ -165,6 +169,12 @@ def bind(plan: Plan, packed: Any, previous: Any) -> list[Any] | None:
             add(packed.prediction)
         elif kind == NOISE:
             add(packed.noise)
+        elif kind == MATERIALISED:
+            inner = role[1]
+            draw = packed.noise if inner[0] == NOISE else previous[-inner[1]].noise
+            if not getattr(draw, "is_lazy_noise", False):
+                return None
+            add(draw.materialize())  # remembered on the draw: the next step's corrector reads the same tensor
         else:
             entry = previous[-role[1]]
             field = role[2]

@@ -214,6 +214,26 @@ class Program:
     def axpby(self, value: Any, c0: float, c1: float, remove: bool = False) -> None:
         self.ops.append(Op(OP_AXPBY, int(remove), src=self.input(value), c=(c0, c1)))
 
+    # -- in-kernel noise or a noise tensor?
+    SETTLE_ELEMENTS = 1 << 20
+    "Below this many elements a step is launch-bound and an in-kernel draw is free."
+
+    def settle_noise(self) -> None:
+        """Decide where this step's lazy noise draws (Philox keys) turn into values.  Inside the step kernel removes
+        the noise tensor's write and its reads, at ~35 instructions per drawn element.  Steps that stream few
+        instructions per byte (Euler, DPM, Adams: bound by HBM) hide that under their loads at any size; the
+        divided-difference steps (UniP / UniPC: bound by instruction issue on large latents) would be slowed by
+        exactly the time the fill kernel takes, so above ``SETTLE_ELEMENTS`` they read a filled tensor instead."""
+        if not self.philox:
+            return
+        heavy = sum(1 for op in self.ops if op.code in (OP_UNI, OP_UNIC)) >= 2 or any(op.code == OP_BLEND for op in self.ops)
+        if not heavy or self.philox[0].numel <= self.SETTLE_ELEMENTS:
+            return
+        draws, self.philox = self.philox, []
+        for index, op in enumerate(self.ops):
+            if op.code == OP_FWD and op.b & 2:
+                self.ops[index] = Op(OP_FWD, op.a, 1, src=self.input(draws[op.src].materialize()), c=op.c)
+
     # -- execution
     def run(self) -> list[Any]:
         "Execute and return one value per ``store``."

@@ -204,6 +204,8 @@ def _drive(sampler: Any, packed: SampleInput, model_transform: Any, schedule: An
                     return result
     ctx = _Ctx(sample)
     spec = build(ctx)
+    if key is not None:
+        ctx.prog.settle_noise()
     outs = ctx.prog.run()
     if key is not None and pg._fusable(ctx.prog.inputs):
         roles = plan.roles_of([*ctx.prog.inputs, *ctx.prog.philox], packed, previous)

@@ -583,6 +583,7 @@ class Pyramid(TensorNoiseCommon[PyramidProps]):
 #    kernel's arithmetic restated with torch CPU ops, so a seed names the same path on the host and on the device.
 
 _BROWNIAN_TREE, _BROWNIAN_LEAF = 1 << 63, 1 << 62
+_warned_no_torchsde = False
 _M32 = 0xFFFFFFFF
 
 
@@ -685,6 +686,23 @@ class Brownian(TensorNoiseCommon[BrownianProps]):
         try:
             import torchsde
         except ImportError:
+            # The reference raises ImportError here (noise.py:223).  This library instead evaluates its own bridge tree
+            # on the host - the SAME path the CUDA kernel walks for this seed - and says so once: the values are not
+            # torchsde's (set SKRAMPLE_B200_REQUIRE_TORCHSDE=1 to get the reference's ImportError instead).
+            import os
+            import warnings
+
+            if os.environ.get("SKRAMPLE_B200_REQUIRE_TORCHSDE"):
+                raise
+            global _warned_no_torchsde
+            if not _warned_no_torchsde:
+                _warned_no_torchsde = True
+                warnings.warn(
+                    "skrample_b200: torchsde is not installed; Brownian noise on a CPU generator comes from this library's own "
+                    "Philox bridge tree (the path its CUDA kernel walks for the same seed), not from torchsde.BrownianInterval",
+                    RuntimeWarning,
+                    stacklevel=3,
+                )
             self._tree = None  # host evaluation of the library's own construction
             return
 
@@ -800,6 +818,7 @@ class Colored(TensorNoiseCommon[ColoredProps]):
     ) -> torch.Tensor:
         lib = _lib()
         native = _native()
+        white = white.contiguous()  # raw pointers below: a transposed / expanded view would be read in storage order
         n = white.numel()
         out_dtype = out_dtype or white.dtype
         with _DeviceGuard(white.device):

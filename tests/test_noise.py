@@ -325,8 +325,9 @@ def test_offset_structure() -> None:
     assert not torch.equal(d0, d1)
 
 
-def _pyramid_supplied(base: np.ndarray, levels: list[np.ndarray], mask: list[bool], strength: float, depth: int) -> torch.Tensor:
-    "Drive skr_noise_pyramid with supplied draws (test hook of the C ABI)."
+def _pyramid_supplied(base: np.ndarray, levels: list[np.ndarray], mask: list[bool], strength: float, depth: int, fused: bool = False) -> torch.Tensor:
+    """Drive skr_noise_pyramid with supplied draws (test hook of the C ABI).  ``fused``: give it the scratch areas of the
+    fast path (composition into scratch + scale pass; trailing resized axes: levels stretched to the unit's width first)."""
     from skrample_b200 import native
 
     lib = noise._lib()
@@ -348,19 +349,27 @@ def _pyramid_supplied(base: np.ndarray, levels: list[np.ndarray], mask: list[boo
         desc.levels[l].extent[1] = ext[1] if len(ext) > 1 else 1
         desc.levels[l].weight = strength**l if l >= skip else 0.0
     out = torch.empty(base.shape, device="cuda")
-    moments = torch.zeros(2, dtype=torch.float64, device="cuda")
+    if fused:
+        room = sum(int(np.prod(lv.shape)) // lv.shape[-1] * base.shape[-1] + 4 for lv in levels)
+        scratch = torch.empty(base.size + 4 + room, device="cuda")
+        desc.scratch = scratch.data_ptr()
+        desc.levels_scratch = scratch.data_ptr() + 4 * ((base.size + 3) & ~3)
+        desc.levels_scratch_floats = room
+    moments = torch.zeros(native.MOMENTS_DOUBLES, dtype=torch.float64, device="cuda")
     native.check(lib.skr_noise_pyramid(out.data_ptr(), 0, ctypes.byref(desc), moments.data_ptr(), torch.cuda.current_stream().cuda_stream), "pyramid")
     return out
 
 
 @gpu
 @pytest.mark.parametrize(("shape", "dims", "depth"), [((4, 64, 64), (-1, -2), 99), ((3, 40, 56), (-1, -2), 1), ((5, 96), (-1,), 99), ((48, 4, 48), (0, 2), 99)])
-def test_pyramid_kernel_vs_oracle_on_supplied_draws(shape: tuple[int, ...], dims: tuple[int, ...], depth: int) -> None:
-    "Identical supplied draws -> the kernel's upsample / weights / std equal the oracle's (fp32 rounding only)."
+@pytest.mark.parametrize("fused", [False, True], ids=["two-pass", "fused"])
+def test_pyramid_kernel_vs_oracle_on_supplied_draws(shape: tuple[int, ...], dims: tuple[int, ...], depth: int, fused: bool) -> None:
+    """Identical supplied draws -> the kernels' upsample / weights / std equal the oracle's (fp32 rounding only): the
+    generic two-pass kernel, and the fused path (separable upsampling for trailing axes, four-wide otherwise)."""
     props = noise.PyramidProps(dims=dims, depth=depth)
     _out, base, levels, _ratios = _record_pyramid(shape, props, 21)
     mask = [n in [len(shape) + d if d < 0 else d for d in dims] for n in range(len(shape))]
-    got = _pyramid_supplied(base, levels, mask, props.strength, depth).cpu().numpy()
+    got = _pyramid_supplied(base, levels, mask, props.strength, depth, fused).cpu().numpy()
     want = O.pyramid_compose(base, levels, mask, props.strength, depth)
     np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-6)
 
@@ -477,17 +486,59 @@ def test_in_kernel_noise_unaligned_items() -> None:
 
 
 @gpu
-def test_batch_auto_picks_in_kernel_draws_for_small_batches_only() -> None:
-    "BatchTensorNoise.auto: Philox keys below the size threshold, a filled tensor above; identical values either way."
+def test_batch_auto_hands_out_philox_keys_and_the_step_decides() -> None:
+    """BatchTensorNoise.auto: Philox keys whenever every item is a plain Random on one device (identical values to the
+    filled tensor); the STEP decides where they become values - inside its kernel (one launch), or, for the
+    issue-bound divided-difference steps on large latents, through the fill kernel first (Program.settle_noise)."""
+    from skrample_b200 import native, scheduling
+    from skrample_b200.common import Step
+    from skrample_b200.sampling import models, structured
+
     small = noise.BatchTensorNoise.from_batch_inputs(noise.Random, (4, 64, 64), [_gen(3), _gen(4)])
     twin = noise.BatchTensorNoise.from_batch_inputs(noise.Random, (4, 64, 64), [_gen(3), _gen(4)])
     drawn = small.auto(None)
     assert getattr(drawn, "is_lazy_noise", False)
     assert torch.equal(drawn.materialize(), twin.generate(None))
-    big = noise.BatchTensorNoise.from_batch_inputs(noise.Random, (16, 256, 256), [_gen(5), _gen(6)])
-    assert isinstance(big.auto(None), torch.Tensor)
     mixed = noise.BatchTensorNoise([noise.Random.from_inputs((8,), _gen(1)), noise.Offset.from_inputs((8,), _gen(2))])
     assert isinstance(mixed.auto(None), torch.Tensor)
+
+    unit = (16, 256, 256)  # 2 x 1 Mi elements: above Program.SETTLE_ELEMENTS
+    schedule, model = scheduling.FlowShift(scheduling.Linear()), models.FlowModel()
+    for sampler, fills in ((structured.Euler(stochasticity=1), 0), (structured.UniPC(order=2, stochasticity=1), 1)):
+        big = noise.BatchTensorNoise.from_batch_inputs(noise.Random, unit, [_gen(5), _gen(6)])
+        ref = noise.BatchTensorNoise.from_batch_inputs(noise.Random, unit, [_gen(5), _gen(6)])
+        x = torch.randn((2, *unit), device="cuda")
+        previous: list = []
+        previous_ref: list = []
+        for n in range(3):
+            out = torch.randn((2, *unit), device="cuda")
+            lazy = big.auto(None)
+            assert getattr(lazy, "is_lazy_noise", False)
+            before = native.launch_count_kind(2)
+            got = sampler.sample(x, out, Step.from_int(n, 8), model, schedule, lazy, previous)
+            assert native.launch_count_kind(2) - before == fills, f"{type(sampler).__name__} step {n}"
+            want = sampler.sample(x, out, Step.from_int(n, 8), model, schedule, ref.generate(None), previous_ref)
+            assert torch.equal(got.final, want.final)
+            previous = (previous + [got])[-sampler.require_previous :] if sampler.require_previous else []
+            previous_ref = (previous_ref + [want])[-sampler.require_previous :] if sampler.require_previous else []
+            x = got.final
+
+
+@pytest.mark.skipif(_has_torchsde(), reason="torchsde present: the reference's tree is used")
+def test_brownian_without_torchsde_says_so(monkeypatch: pytest.MonkeyPatch) -> None:
+    """The reference raises ImportError without torchsde (noise.py:223); this library evaluates its own bridge tree
+    instead, warns once that the values are not torchsde's, and raises like the reference on request."""
+    import warnings
+
+    monkeypatch.setattr(noise, "_warned_no_torchsde", False)
+    with pytest.warns(RuntimeWarning, match="torchsde is not installed"):
+        noise.Brownian.from_inputs((4, 8), torch.Generator().manual_seed(1))
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        noise.Brownian.from_inputs((4, 8), torch.Generator().manual_seed(1))  # said once
+    monkeypatch.setenv("SKRAMPLE_B200_REQUIRE_TORCHSDE", "1")
+    with pytest.raises(ImportError):
+        noise.Brownian.from_inputs((4, 8), torch.Generator().manual_seed(1))
 
 
 # ------------------------------------------------------------------------------------------- Brownian (CUDA)

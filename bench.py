@@ -107,6 +107,7 @@ ROWS = [
     "adams9_sde_video_bf16_colored",
     "unipc3_sde_flux_bf16",
 ]
+CONTRACTED_ROWS = ["unipc3_sde_flux_bf16", "unipc3_sde_sdxl_bf16"]
 # global workloads of the strong-scaling legs: (name, global batch, workload with the per-item shape)
 STRONG = [
     ("configs[3] video latent 8x16x21x90x160 bf16, Adams-9 SDE, Pyramid noise", 8, "adams9_sde_video_bf16_pyramid"),
@@ -161,6 +162,7 @@ class Trajectory:
     def __init__(self, spec: dict, device: torch.device, seed: int, keep: int | None = None, noise: str = "auto", first_item: int = 0) -> None:
         import cases
         from skrample_b200 import scheduling
+        from skrample_b200.common import Step
         from skrample_b200.pytorch import noise as sk_noise
         from skrample_b200.sampling import models, structured
 
@@ -187,15 +189,15 @@ class Trajectory:
             [torch.Generator(device=device).manual_seed(seed * 1000 + first_item + i) for i in range(shape[0])],
             dtype=torch.float32 if kind is sk_noise.Random else self.dtype,
         )
+        self.steps = [Step.from_int(n, STEPS_PER_TRAJECTORY) for n in range(STEPS_PER_TRAJECTORY)]
+        self.keep = self.sampler.require_previous
         self.noises: list = []
         if self.noise_mode == "supplied":
             self.noises = [self.draw(n % STEPS_PER_TRAJECTORY, materialise=True) for n in range(self.count)]
         self.reset()
 
     def draw(self, n: int, materialise: bool = False):  # noqa: ANN201
-        from skrample_b200.common import Step
-
-        z = self.noise_source.auto(Step.from_int(n, STEPS_PER_TRAJECTORY))
+        z = self.noise_source.auto(self.steps[n])
         if materialise:
             z = (z.materialize() if hasattr(z, "materialize") else z).to(self.dtype)
         return z
@@ -226,21 +228,19 @@ class Trajectory:
         self.reset()
 
     def step(self, prediction: torch.Tensor | None = None, noise: torch.Tensor | None = None) -> torch.Tensor:
-        from skrample_b200.common import Step
-
         n = self.n
         if noise is None and self.noise_mode != "none":
             noise = self.noises[n % self.count] if self.noise_mode == "supplied" else self.draw(n)
         res = self.sampler.sample(
             self.x,
             self.predictions[n % self.count] if prediction is None else prediction,
-            Step.from_int(n, STEPS_PER_TRAJECTORY),
+            self.steps[n],
             self.model,
             self.schedule,
             noise,
             self.previous,
         )
-        keep = self.sampler.require_previous
+        keep = self.keep
         self.previous = (self.previous + [res])[-keep:] if keep else []
         self.x = res.final
         self.n += 1
@@ -1046,6 +1046,17 @@ def main() -> None:
                         "latent_steps_per_s_with_noise": s["shape"][0] / (us_w * 1e-6),
                     }
                 )
+            for name in CONTRACTED_ROWS:  # the issue-bound steps again with the opt-in contracted arithmetic
+                s = WORKLOADS[name]
+                torch.cuda.empty_cache()
+                native.set_arithmetic("contracted")
+                try:
+                    k = chain_time(s, device, "supplied", 0, STEPS_PER_TRAJECTORY, min_seconds=0.15, blocks=3)
+                finally:
+                    native.set_arithmetic("exact")
+                us_k = k["ms_per_step"] * 1e3
+                ach = k["bytes_per_step_avg"] / (us_k * 1e-6) / 1e9
+                rows.append({"workload": name + " (arithmetic: contracted, opt-in)", "shape": list(s["shape"]), "dtype": s["dtype"], "noise": s["noise"], "us_per_step_kernel_only": us_k, "GBps": ach, "frac_of_measured_peak": ach / peak, "bytes_per_step_avg": k["bytes_per_step_avg"]})
             for name, s in RK_ROWS.items():
                 torch.cuda.empty_cache()
                 r = rk_step_throughput(s, device)

@@ -205,6 +205,18 @@ const char* skr_plan_shape(const skr_plan* plan);
 void skr_reload_env(void);
 
 /*
+ * Arithmetic of the fused step, process-wide; plans keep the mode they were created under.
+ *   0  exact (default): every product, sum and quotient individually rounded in the reference's order - fp32 / fp64
+ *      results are bit-identical to the reference's torch-CPU path;
+ *   1  contracted: the divided-difference and weighted-sum steps (UniP / UniPC / SPC / Adams on fp32 compute) fuse
+ *      a*b + c into one multiply-add and divide by multiplying with the reciprocal: a few fp32 ulp per step (inside the
+ *      1e-5 relative per step the north star asks for), ~30% fewer instructions where the step is issue-bound.
+ * The environment variable SKR_ARITH=contracted selects mode 1 at start-up.
+ */
+int skr_set_arithmetic(int32_t mode);
+int skr_get_arithmetic(void);
+
+/*
  * Point.add_noise / remove_noise (common.py:32-40):
  *   remove == 0: out = sample*alpha + noise*sigma
  *   remove != 0: out = (sample - noise*sigma) / alpha

@@ -265,6 +265,7 @@ struct BlkOff : BlkAny {
     static constexpr int enabled = 0;
 };
 struct ShAny {
+    static constexpr bool contract = false;  // arithmetic policy (machine.cuh): exact unless a shape opts in
     static constexpr int ctas8 = 2;  // CTAs per SM the 8-elements-per-thread instantiation is compiled for
     static constexpr int x = -1, y = -1, neg = -1, n_conv = -1, sp = -1, sp2 = -1;
     static constexpr int dt_x = -1, dt_y = -1, dt_sp = -1, dt_sp2 = -1;
@@ -336,6 +337,12 @@ template <int LP>
 using ShRKStage = ShRaw<LP, 0, BlkPin<BK_ACC, 0, 0, 0, 1, 0, 1, BL_NONE, 0, LP, LP, LP>>;
 template <int LP>
 using ShRKFinal = ShRaw<LP, 0, BlkPin<BK_ACC, 0, 0, 0, 0, 0, 1, BL_NONE, 0, LP, LP, LP>>;
+
+// The same shape with contracted arithmetic (fp32 compute only).
+template <typename Base>
+struct Contracted : Base {
+    static constexpr bool contract = true;
+};
 
 template <typename BS, typename CT>
 static bool block_matches(const BBlock<CT>& k, const int32_t* in_dt, const int32_t* out_dt) {
@@ -443,11 +450,17 @@ struct TileIO {
     }
 };
 
-template <typename CT, int MODE, int V, int PATH, bool PHILOX, typename BS, bool PARTIAL>
+template <typename CT, int V, bool CONTRACT>
+__device__ __forceinline__ void divide(CT (&a)[V], CT d, CT r, bool fast) {
+    if constexpr (CONTRACT && sizeof(CT) == 4) div_reciprocal<V>(a, d, r, fast);
+    else div_uniform<V>(a, d, r, fast);
+}
+
+template <typename CT, int MODE, int V, int PATH, bool PHILOX, typename BS, bool PARTIAL, bool CONTRACT>
 __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const PhiloxKeys<PHILOX>& keys, const BBlock<CT>& k,
                                               const TileIO<CT, MODE, V, PATH, PARTIAL>& io, CT (&X)[V], CT (&P)[V],
                                               CT (&B)[V], CT (&A)[V], CT (&S)[V], CT (&R)[V]) {
-    using Ar = Arith<CT>;
+    using Ar = Policy<CT, CONTRACT && sizeof(CT) == 4>;
     if (!pinned<BS::enabled>(k.enabled)) return;
     const bool fast_div = prog.fast_div != 0;
     const int link = pinned<BS::link>(k.link);
@@ -474,27 +487,27 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const Ph
             if (p_mode == 1 || n_terms == 0) {
                 const CT c = k.p_coef;
 #pragma unroll
-                for (int j = 0; j < V; ++j) A[j] = Ar::add((CT)0, Ar::mul(P[j], c));
+                for (int j = 0; j < V; ++j) A[j] = Ar::head(P[j], c);
             } else {
                 io.template load<BS::dt_state>(k.term_in[0], k.terms[0].off, in);
                 const CT c = k.terms[0].c0;
 #pragma unroll
-                for (int j = 0; j < V; ++j) A[j] = Ar::add((CT)0, Ar::mul(in[j], c));
+                for (int j = 0; j < V; ++j) A[j] = Ar::head(in[j], c);
                 t = 1;
             }
             for (; t < n_terms; ++t) {
                 io.template load<BS::dt_state>(k.term_in[t], k.terms[t].off, in);
                 const CT c = k.terms[t].c0;
 #pragma unroll
-                for (int j = 0; j < V; ++j) A[j] = Ar::add(A[j], Ar::mul(in[j], c));
+                for (int j = 0; j < V; ++j) A[j] = Ar::madd(A[j], in[j], c);
             }
             if (p_mode == 2 && n_terms > 0) {
                 const CT c = k.p_coef;
 #pragma unroll
-                for (int j = 0; j < V; ++j) A[j] = Ar::add(A[j], Ar::mul(P[j], c));
+                for (int j = 0; j < V; ++j) A[j] = Ar::madd(A[j], P[j], c);
             }
             if (pinned<BS::has_div>(k.has_div)) {
-                div_uniform<V>(A, k.div, k.div_r, fast_div);
+                divide<CT, V, CONTRACT>(A, k.div, k.div_r, fast_div);
             }
         } else if (kind == BK_UNI) {
 #pragma unroll
@@ -504,9 +517,17 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const Ph
                 const CT rho = k.terms[t].c1;
 #pragma unroll
                 for (int j = 0; j < V; ++j) in[j] = Ar::sub(in[j], B[j]);
-                div_uniform<V>(in, k.terms[t].c0, k.terms[t].r0, fast_div);
+                if constexpr (Ar::contract) {
+                    if (fast_div) {  // ((x - B) / rk) * rho as one multiply-add with the constant rho / rk
+                        const CT scale = Ar::mul(rho, k.terms[t].r0);
 #pragma unroll
-                for (int j = 0; j < V; ++j) A[j] = Ar::add(A[j], Ar::mul(in[j], rho));
+                        for (int j = 0; j < V; ++j) A[j] = Ar::madd(A[j], in[j], scale);
+                        return;
+                    }
+                }
+                divide<CT, V, CONTRACT>(in, k.terms[t].c0, k.terms[t].r0, fast_div);
+#pragma unroll
+                for (int j = 0; j < V; ++j) A[j] = Ar::madd(A[j], in[j], rho);
             };
             if constexpr (BS::n_terms >= 0) {
 #pragma unroll
@@ -517,10 +538,7 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const Ph
             if (p_mode == 1) {
                 const CT rho = k.p_coef;
 #pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    const CT term = Ar::mul(Ar::sub(P[j], B[j]), rho);
-                    A[j] = Ar::add(A[j], term);
-                }
+                for (int j = 0; j < V; ++j) A[j] = Ar::madd(A[j], Ar::sub(P[j], B[j]), rho);
             }
             const bool empty = k.empty_sum != 0;
 #pragma unroll
@@ -553,7 +571,7 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const Ph
 #pragma unroll
     for (int j = 0; j < V; ++j) {
         const CT pred = from_p ? P[j] : A[j];
-        R[j] = Ar::add(Ar::add((CT)0, Ar::mul(X[j], gamma)), Ar::mul(pred, delta));
+        R[j] = Ar::madd(Ar::head(X[j], gamma), pred, delta);
     }
     const int has_noise = pinned<BS::noise>(k.has_noise);
     if (has_noise) {
@@ -567,7 +585,7 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const Ph
         if (!drawn) io.template load<BS::dt_noise>(k.noise_in, k.noise_off, in);
         const CT zeta = k.zeta;
 #pragma unroll
-        for (int j = 0; j < V; ++j) R[j] = Ar::add(R[j], Ar::mul(in[j], zeta));
+        for (int j = 0; j < V; ++j) R[j] = Ar::madd(R[j], in[j], zeta);
     }
     if (pinned<BS::store>(k.store_r >= 0)) io.template store<BS::dt_store>(k.store_r, R);
 
@@ -578,7 +596,7 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const Ph
         } else if (link == BL_BLEND) {
             const CT l0 = k.l0, l1 = k.l1;
 #pragma unroll
-            for (int j = 0; j < V; ++j) X[j] = Ar::add(Ar::mul(S[j], l0), Ar::mul(R[j], l1));
+            for (int j = 0; j < V; ++j) X[j] = Ar::madd(Ar::mul(S[j], l0), R[j], l1);
             if (pinned<BS::slink>(k.store_link >= 0)) io.template store<BS::dt_slink>(k.store_link, X);
         } else if (link == BL_BLEND_POW) {
             // X = spow(spow(S, pw)*p + spow(R, pw)*c, 1/pw): the signed power mean, the only nonlinear op of a step
@@ -592,8 +610,8 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const Ph
         } else {  // BL_BACK
             const CT l0 = k.l0;
 #pragma unroll
-            for (int j = 0; j < V; ++j) P[j] = Ar::sub(R[j], Ar::mul(X[j], l0));
-            div_uniform<V>(P, k.l1, k.l1_r, fast_div);
+            for (int j = 0; j < V; ++j) P[j] = Ar::msub(R[j], X[j], l0);
+            divide<CT, V, CONTRACT>(P, k.l1, k.l1_r, fast_div);
             if (pinned<BS::slink>(k.store_link >= 0)) io.template store<BS::dt_slink>(k.store_link, P);
         }
     }
@@ -601,7 +619,8 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const Ph
 
 template <typename CT, int MODE, int V, int PATH, bool PHILOX, typename Sh, bool PARTIAL = false>
 __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, const PhiloxKeys<PHILOX>& keys, int64_t first, uint32_t stage, int tid) {
-    using Ar = Arith<CT>;
+    constexpr bool CONTRACT = Sh::contract && sizeof(CT) == 4;
+    using Ar = Policy<CT, CONTRACT>;
     const TileIO<CT, MODE, V, PATH, PARTIAL> io{prog, stage, (uint32_t)tid * V, first};
 
     CT X[V], P[V], B[V], A[V], S[V], R[V];
@@ -629,21 +648,20 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, const P
                 for (int j = 0; j < V; ++j) {
                     if (f & SKR_CONV_USE_X) {
                         const CT lhs = (f & SKR_CONV_MUL_X) ? Ar::mul(c0, X[j]) : X[j];
-                        const CT rhs = (f & SKR_CONV_MUL_Y) ? Ar::mul(c1, P[j]) : P[j];
-                        P[j] = Ar::sub(lhs, rhs);
+                        P[j] = (f & SKR_CONV_MUL_Y) ? Ar::msub(lhs, c1, P[j]) : Ar::sub(lhs, P[j]);
                     } else {
                         P[j] = (f & SKR_CONV_MUL_Y) ? Ar::mul(P[j], c1) : P[j];
                     }
                 }
-                if (f & SKR_CONV_DIV) div_uniform<V>(P, c2, h.conv_r[c], fast_div);
+                if (f & SKR_CONV_DIV) divide<CT, V, CONTRACT>(P, c2, h.conv_r[c], fast_div);
             }
         }
     }
     if (pinned<Sh::sp>(h.store_p >= 0)) io.template store<Sh::dt_sp>(h.store_p, P);
     if (pinned<Sh::sp2>(h.store_p2 >= 0)) io.template store<Sh::dt_sp2>(h.store_p2, P);
 
-    run_one_block<CT, MODE, V, PATH, PHILOX, typename Sh::B0, PARTIAL>(prog, keys, prog.blk[0], io, X, P, B, A, S, R);
-    run_one_block<CT, MODE, V, PATH, PHILOX, typename Sh::B1, PARTIAL>(prog, keys, prog.blk[1], io, X, P, B, A, S, R);
+    run_one_block<CT, MODE, V, PATH, PHILOX, typename Sh::B0, PARTIAL, CONTRACT>(prog, keys, prog.blk[0], io, X, P, B, A, S, R);
+    run_one_block<CT, MODE, V, PATH, PHILOX, typename Sh::B1, PARTIAL, CONTRACT>(prog, keys, prog.blk[1], io, X, P, B, A, S, R);
 }
 
 // Launches that cannot be staged (unaligned tensor bases, a stage too large for shared memory) run out of line so

@@ -138,9 +138,10 @@ static void fill_dtypes(const skr_program* p, BProgram<CT>& k) {
 
 // Pinned shapes of one latent storage type (pinned_shapes.cu): the launcher of the first shape that matches the
 // descriptor's control fields and dtypes (its name in *name), or nullptr.
-// `philox`: the step draws noise inside the kernel (instantiations with the Philox code).
-BlockLauncher<float> pinned_f32(const BProgram<float>& k, bool philox, const char** name);
-BlockLauncher<float> pinned_bf16(const BProgram<float>& k, bool philox, const char** name);
-BlockLauncher<float> pinned_f16(const BProgram<float>& k, bool philox, const char** name);
+// `philox`: the step draws noise inside the kernel (instantiations with the Philox code); `contracted`: the caller
+// opted into contracted arithmetic (skr_set_arithmetic) - shapes that have such an instantiation use it.
+BlockLauncher<float> pinned_f32(const BProgram<float>& k, bool philox, bool contracted, const char** name);
+BlockLauncher<float> pinned_bf16(const BProgram<float>& k, bool philox, bool contracted, const char** name);
+BlockLauncher<float> pinned_f16(const BProgram<float>& k, bool philox, bool contracted, const char** name);
 
 }  // namespace skr

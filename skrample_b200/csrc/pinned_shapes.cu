@@ -67,9 +67,30 @@ static bool for_each_pinned_philox_shape(F&& f) {
            f(ShapeEntry<ShEuler<kLP>, kModeLP, kVecLP>{"euler+philox/" SKR_LP_NAME});
 }
 
-BlockLauncher<float> SKR_PINNED_ENTRY(const BProgram<float>& k, bool philox, const char** name) {
+// The issue-bound steps again with contracted arithmetic (machine.cuh, Policy): opt-in through skr_set_arithmetic.
+template <typename F>
+static bool for_each_pinned_contracted_shape(F&& f) {
+    return f(ShapeEntry<Contracted<ShUniPC<kLP, 2>>, IN_MIXED, 4>{"unipc3~contracted/" SKR_LP_NAME}) ||
+           f(ShapeEntry<Contracted<ShUniPC<kLP, 1>>, IN_MIXED, 4>{"unipc2~contracted/" SKR_LP_NAME}) ||
+           f(ShapeEntry<Contracted<ShUniPC<kLP>>, IN_MIXED, 4>{"unipc~contracted/" SKR_LP_NAME}) ||
+           f(ShapeEntry<Contracted<ShUniP<kLP>>, IN_MIXED, 4>{"unip~contracted/" SKR_LP_NAME}) ||
+           f(ShapeEntry<Contracted<ShAcc<kLP>>, IN_MIXED, 4>{"acc~contracted/" SKR_LP_NAME}) ||
+           f(ShapeEntry<Contracted<ShSPC<kLP>>, IN_MIXED, 4>{"spc~contracted/" SKR_LP_NAME});
+}
+
+BlockLauncher<float> SKR_PINNED_ENTRY(const BProgram<float>& k, bool philox, bool contracted, const char** name) {
     const StorageClass storage(k);
     BlockLauncher<float> found = nullptr;
+    if (contracted && !philox) {
+        for_each_pinned_contracted_shape([&](auto entry) {
+            using E = decltype(entry);
+            if (!storage.allows(E::mode) || !shape_matches<typename E::shape>(k)) return false;
+            *name = entry.name;
+            found = &launch_block_one<float, E::mode, E::v, false, typename E::shape>;
+            return true;
+        });
+        if (found) return found;  // other steps keep the exact kernels
+    }
     if (philox) {
         for_each_pinned_philox_shape([&](auto entry) {
             using E = decltype(entry);

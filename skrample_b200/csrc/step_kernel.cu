@@ -321,6 +321,7 @@ int fail(int code, const char* fmt, ...) {
 // Development switches (tests and A/B tooling): read once, re-read by skr_reload_env().
 struct Switches {
     std::atomic<int> force_interp{0}, no_pinned{0}, in_mode{-1}, stages{0}, ctas{0};
+    std::atomic<int> arithmetic{0};  // 0 exact, 1 contracted (skr_set_arithmetic; initial value from SKR_ARITH)
 };
 static Switches g_switches;
 static std::once_flag g_switches_once;
@@ -335,6 +336,8 @@ static void load_switches() {
     g_switches.in_mode = env_raw("SKR_IN_MODE", -1);
     g_switches.stages = env_raw("SKR_STAGES", 0);
     g_switches.ctas = env_raw("SKR_CTAS", 0);
+    const char* arith = getenv("SKR_ARITH");
+    g_switches.arithmetic = (arith && (arith[0] == 'c' || arith[0] == '1')) ? 1 : 0;
 }
 static const Switches& switches() {
     std::call_once(g_switches_once, load_switches);
@@ -495,10 +498,11 @@ static BlockLauncher<float> pinned_any(const BProgram<float>& k, int n_philox, c
     // the latent storage type is that of the network output (head.y) or, for RK combinations, of the sample
     const int probe = k.head.y_in >= 0 ? k.head.y_in : k.head.x_in;
     if (probe < 0) return nullptr;
+    const bool contracted = switches().arithmetic.load(std::memory_order_relaxed) == 1;
     switch (k.in_dtype[probe]) {
-        case SKR_F32: return pinned_f32(k, n_philox > 0, name);
-        case SKR_BF16: return pinned_bf16(k, n_philox > 0, name);
-        case SKR_F16: return pinned_f16(k, n_philox > 0, name);
+        case SKR_F32: return pinned_f32(k, n_philox > 0, contracted, name);
+        case SKR_BF16: return pinned_bf16(k, n_philox > 0, contracted, name);
+        case SKR_F16: return pinned_f16(k, n_philox > 0, contracted, name);
         default: return nullptr;
     }
 }
@@ -631,6 +635,13 @@ void skr_reload_env(void) {
     skr::switches();
     skr::load_switches();
 }
+int skr_set_arithmetic(int32_t mode) {
+    if (mode != 0 && mode != 1) return skr::fail(SKR_E_RANGE, "arithmetic mode %d: 0 (exact) or 1 (contracted)", mode);
+    skr::switches();
+    skr::g_switches.arithmetic.store(mode, std::memory_order_relaxed);
+    return 0;
+}
+int skr_get_arithmetic(void) { return skr::switches().arithmetic.load(std::memory_order_relaxed); }
 
 int skr_program_classify(const skr_program* p) {
     using namespace skr;

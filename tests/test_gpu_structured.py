@@ -429,3 +429,70 @@ def test_config2_rkultra4_flux_bf16_subset_vs_oracle() -> None:
             x, x_o = got, want
         if walk == 0:
             assert functional._scripts.known, "the first walk should have recorded its launch scripts"
+
+
+CONTRACTED = [c for c in STRUCTURED_INDEX if c["dtype"] == "f32" and c["sampler"] in ("UniPC", "UniP", "Adams", "SPC") and cases.tolerance(c) is None and not cases.composite(c)]
+
+
+def test_contracted_arithmetic_is_opt_in_and_inside_the_stated_tolerance() -> None:
+    """``native.set_arithmetic("contracted")``: the divided-difference / weighted-sum steps run kernels that fuse
+    a*b + c and multiply by reciprocals.  Against the reference's golden trajectories (12 steps) every field stays within
+    1e-5 of the tensor's scale - the per-STEP tolerance of the specification, here spent on a whole trajectory - the
+    results are NOT the exact path's bits (so the contracted kernels really ran), and switching back restores them."""
+    from skrample_b200 import native
+
+    assert native.get_arithmetic() == "exact"
+    differing = 0
+    try:
+        native.set_arithmetic("contracted")
+        for case in CONTRACTED:
+            result = run_product(case, device="cuda")
+            for field in ("final", "sample", "prediction"):
+                want = STRUCTURED[f"{case['id']}/{field}"]
+                got = getattr(result, field).cpu().numpy()
+                assert got.dtype == want.dtype and np.isfinite(got).all()
+                worst = float(np.abs(got.astype(np.float64) - want.astype(np.float64)).max())
+                assert worst <= 1e-5 * float(np.abs(want).max()), f"{case['id']} {field}: {worst:.3e}"
+                differing += int(not np.array_equal(got, want))
+    finally:
+        native.set_arithmetic("exact")
+    assert differing > len(CONTRACTED), "contracted mode produced the exact path's bits: its kernels did not run"
+    case = CONTRACTED[0]
+    result = run_product(case, device="cuda")
+    assert np.array_equal(result.final.cpu().numpy(), STRUCTURED[f"{case['id']}/final"])
+
+
+def test_contracted_shapes_are_selected_only_on_request() -> None:
+    from skrample_b200 import native, scheduling
+    from skrample_b200.common import Step
+    from skrample_b200.sampling import models, structured
+
+    def shape_of_steady_step() -> str:
+        sampler = structured.UniPC(order=3, stochasticity=1)
+        schedule, model = scheduling.Scaled(), models.NoiseModel()
+        x = torch.randn(4096, device="cuda").bfloat16()
+        previous: list = []
+        names = []
+        real = native.CompiledProgram.specialise
+
+        def spy(self, signature):  # noqa: ANN001, ANN202
+            plan = real(self, signature)
+            names.append(plan.shape_name)
+            return plan
+
+        native.CompiledProgram.specialise = spy
+        try:
+            for n in range(5):
+                res = sampler.sample(x, torch.randn(4096, device="cuda").bfloat16(), Step.from_int(n, 10), model, schedule, torch.randn(4096, device="cuda").bfloat16(), previous)
+                previous = (previous + [res])[-sampler.require_previous :]
+                x = res.final
+        finally:
+            native.CompiledProgram.specialise = real
+        return names[-1]
+
+    assert shape_of_steady_step() == "unipc3/bf16"
+    try:
+        native.set_arithmetic("contracted")
+        assert shape_of_steady_step() == "unipc3~contracted/bf16"
+    finally:
+        native.set_arithmetic("exact")

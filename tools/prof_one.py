@@ -19,6 +19,7 @@ ap.add_argument("--sampler", default="euler")
 ap.add_argument("--dtype", default="f32")
 ap.add_argument("--batch", type=int, default=256)
 ap.add_argument("--steps", type=int, default=12)
+ap.add_argument("--lazy-noise", action="store_true", help="hand the sampler Philox keys (BatchTensorNoise.auto): the step draws its noise itself where it chooses to")
 args = ap.parse_args()
 
 sampler = {
@@ -35,7 +36,14 @@ outs = [torch.randn(shape, device="cuda", generator=g).to(dtype) for _ in range(
 noise = torch.randn(shape, device="cuda", generator=g).to(dtype)
 flow = scheduling.FlowShift(scheduling.Linear())
 prev: list = []
+source = None
+if args.lazy_noise:
+    from skrample_b200.pytorch import noise as sk_noise
+
+    source = sk_noise.BatchTensorNoise.from_batch_inputs(sk_noise.Random, shape[1:], [torch.Generator(device="cuda").manual_seed(100 + i) for i in range(shape[0])])
 for n in range(args.steps):
+    if source is not None:
+        noise = source.auto(Step.from_int(n, 25))
     res = sampler.sample(x, outs[n % 2], Step.from_int(n, 25), models.FlowModel(), flow, noise if sampler.require_noise else None, prev)
     prev = (prev + [res])[-sampler.require_previous :] if sampler.require_previous else []
     x = res.final

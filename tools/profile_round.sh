@@ -42,4 +42,7 @@ capture noise_scale_f32_16x21x90x160 scale_kernel 25 $N Pyramid
 capture noise_colored_shape_16x21x90x160 colored_shape 25 $N Colored
 capture noise_moments_f32_16x21x90x160 moments_kernel 25 $N Colored
 capture noise_brownian_f32_16x21x90x160 brownian_kernel 30 $N Brownian
-ls -la $O/${R}_*
+# summarise here: only gpurun_out/ travels back and the reports are far larger than its 64 MiB limit
+SKR_PROFILES_OUT=$O/${R}_summary python tools/summarize_profiles.py $R > $O/${R}_summarize.log 2>&1
+rm -f $O/${R}_*.ncu-rep
+du -sh $O; ls $O/${R}_summary

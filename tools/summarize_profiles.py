@@ -13,9 +13,13 @@ import subprocess
 import sys
 from pathlib import Path
 
+import os
+
 ROOT = Path(__file__).resolve().parent.parent
 OUT = ROOT / "gpurun_out"
-PROFILES = ROOT / "profiles"
+# On the GPU box the summaries go under gpurun_out/ (the only directory that travels back; the .ncu-rep files are far
+# over its 64 MiB limit and are deleted there after summarising): SKR_PROFILES_OUT=gpurun_out/r02_summary
+PROFILES = Path(os.environ.get("SKR_PROFILES_OUT", ROOT / "profiles"))
 
 KEEP = (
     "gpu__time_duration.sum",
@@ -37,6 +41,10 @@ KEEP = (
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
     "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "sm__cycles_active.avg",
+    "l1tex__t_sector_hit_rate.pct",
 )
 
 
@@ -119,15 +127,16 @@ def full_captures(round_name: str) -> None:
 
 
 def bench_lines(round_name: str) -> None:
-    for name in ("bench", "bench_reference", "bench_fused_noise"):
-        src = OUT / f"{round_name}_{name}.json"
-        if src.exists() and src.stat().st_size:
-            shutil.copy(src, PROFILES / src.name)
+    for name in ("bench", "bench_reference", "bench_fused_noise", "e2e_breakdown", "step_floor"):
+        for suffix in (".json", ".txt"):
+            src = OUT / f"{round_name}_{name}{suffix}"
+            if src.exists() and src.stat().st_size and src.resolve().parent != PROFILES.resolve():
+                shutil.copy(src, PROFILES / src.name)
 
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "r01"
-    PROFILES.mkdir(exist_ok=True)
+    PROFILES.mkdir(parents=True, exist_ok=True)
     bench_lines(which)
     launches(which)
     full_captures(which)

@@ -206,6 +206,10 @@ def _drive(sampler: Any, packed: SampleInput, model_transform: Any, schedule: An
     spec = build(ctx)
     if key is not None:
         ctx.prog.settle_noise()
+        if len(ctx.prog.ops) > pg.MAX_OPS or len(ctx.prog.inputs) > pg.MAX_INPUTS or len(ctx.prog.outputs) > pg.MAX_OUTPUTS:
+            # deeper compositions than one launch can describe (e.g. SPC over two high-order UniPCs on a long
+            # schedule): predictor-correctors fall back to separately fused launches, in the reference's order
+            raise CannotFuse(f"step program too large for one launch ({len(ctx.prog.ops)} ops, {len(ctx.prog.inputs)} inputs)")
     outs = ctx.prog.run()
     if key is not None and pg._fusable(ctx.prog.inputs):
         roles = plan.roles_of([*ctx.prog.inputs, *ctx.prog.philox], packed, previous)

@@ -496,3 +496,22 @@ def test_contracted_shapes_are_selected_only_on_request() -> None:
         assert shape_of_steady_step() == "unipc3~contracted/bf16"
     finally:
         native.set_arithmetic("exact")
+
+
+@pytest.mark.parametrize("name", ["UniPC(order=3,stochasticity=1)|scaled|NoiseModel|f32|12", "SPC()|flow|FlowModel|f32|12"])
+def test_oversized_step_programs_fall_back_to_composed_launches(name: str, monkeypatch: pytest.MonkeyPatch) -> None:
+    """A predictor-corrector step that does not fit one launch's op table (SKR_MAX_OPS; e.g. SPC over two high-order
+    UniPCs on a long schedule) runs as separately fused launches in the reference's order instead of raising: forced
+    here by shrinking the limit, the trajectory still equals the reference's golden tensors bit for bit."""
+    from skrample_b200 import native
+    from skrample_b200.sampling import plan
+    from skrample_b200.sampling import program as pg
+
+    case = next(c for c in STRUCTURED_INDEX if c["id"] == name)
+    monkeypatch.setattr(pg, "MAX_OPS", 9)
+    plan.clear()
+    before = native.launch_count()
+    result = run_product(case, device="cuda")
+    assert native.launch_count() - before > case["steps"], "expected more than one launch per step"
+    for field in ("final", "sample", "prediction"):
+        cases.assert_matches(getattr(result, field).cpu().numpy(), STRUCTURED[f"{case['id']}/{field}"], case, field)

@@ -194,10 +194,8 @@ int skr_plan_launch(const skr_plan* plan, const void* const* tensors, int64_t nu
 void skr_plan_destroy(skr_plan* plan);
 /* 0 = structured block kernel, 1 = interpreter (what skr_program_classify says of the program), < 0 = error. */
 int skr_plan_kind(const skr_plan* plan);
-/* Name of the compiled kernel shape the plan launches ("any" = generic instantiation, "interpreter"); latents of many
- * tiles (>= 6 per SM) may run a different instantiation of the same step (the "+early" shapes): the second name. */
+/* Name of the compiled kernel shape the plan launches ("any" = generic instantiation, "interpreter"). */
 const char* skr_plan_shape(const skr_plan* plan);
-const char* skr_plan_shape_large(const skr_plan* plan);
 
 /*
  * Development switches (SKR_FORCE_INTERP, SKR_NO_PINNED, SKR_IN_MODE, SKR_STAGES, SKR_CTAS) are read from the

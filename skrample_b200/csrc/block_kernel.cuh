@@ -266,8 +266,6 @@ struct BlkOff : BlkAny {
 };
 struct ShAny {
     static constexpr bool contract = false;  // arithmetic policy (machine.cuh): exact unless a shape opts in
-    static constexpr bool early = false;     // see Early<> below
-    static constexpr int ctas4 = 4;          // CTAs per SM the 4-elements-per-thread fp32 instantiations are compiled for
     static constexpr int ctas8 = 2;  // CTAs per SM the 8-elements-per-thread instantiation is compiled for
     static constexpr int x = -1, y = -1, neg = -1, n_conv = -1, sp = -1, sp2 = -1;
     static constexpr int dt_x = -1, dt_y = -1, dt_sp = -1, dt_sp2 = -1;
@@ -340,21 +338,6 @@ using ShRKStage = ShRaw<LP, 0, BlkPin<BK_ACC, 0, 0, 0, 1, 0, 1, BL_NONE, 0, LP, 
 template <int LP>
 using ShRKFinal = ShRaw<LP, 0, BlkPin<BK_ACC, 0, 0, 0, 0, 0, 1, BL_NONE, 0, LP, LP, LP>>;
 
-// The same shape, but a tile's operands are all read from shared memory into registers first and the stage is handed
-// back to the producer BEFORE the arithmetic, not after it.  A step with ~100 instructions per element (UniPC) otherwise
-// sits on its stage for most of a tile's lifetime: with the two stages four CTAs per SM leave room for, only about half
-// of the shared memory is a landing buffer for loads at any time, and the step runs at what that many bytes in flight
-// buy (0.76 of the HBM peak; cutting a third of its instructions changed that by 7 %).  Holding the operands in
-// registers costs ~32 of them, so these instantiations are compiled for three CTAs per SM (72 registers) and run
-// three stages.  Only for shapes whose operand list is fixed at compile time (UniPC with a pinned term count; the
-// predictor re-uses the corrector's history registers, which shape_matches verifies on the host).
-template <typename Base>
-struct Early : Base {
-    static constexpr bool early = true;
-    static constexpr int ctas4 = 3;
-    static_assert(Base::B0::n_terms >= 0 && Base::B0::n_terms == Base::B1::n_terms, "operand list must be pinned");
-};
-
 // The same shape with contracted arithmetic (fp32 compute only).
 template <typename Base>
 struct Contracted : Base {
@@ -394,18 +377,8 @@ static bool shape_matches(const BProgram<CT>& p) {
     if (Sh::dt_y >= 0 && h.y_in >= 0 && p.in_dtype[h.y_in] != Sh::dt_y) return false;
     if (Sh::dt_sp >= 0 && h.store_p >= 0 && p.out_dtype[h.store_p] != Sh::dt_sp) return false;
     if (Sh::dt_sp2 >= 0 && h.store_p2 >= 0 && p.out_dtype[h.store_p2] != Sh::dt_sp2) return false;
-    if (!(block_matches<typename Sh::B0>(p.blk[0], p.in_dtype, p.out_dtype) && block_matches<typename Sh::B1>(p.blk[1], p.in_dtype, p.out_dtype)))
-        return false;
-    if constexpr (Sh::early) {
-        // the predictor's history is the corrector's, shifted by one: its term t is the corrector's base (t == 0) or
-        // the corrector's term t - 1; and both blocks take their noise from tensors or not at all
-        const BBlock<CT>& c = p.blk[0];
-        const BBlock<CT>& q = p.blk[1];
-        if (c.base_in < 0 || c.has_noise == 2 || q.has_noise == 2) return false;
-        for (int t = 0; t < q.n_terms; ++t)
-            if (q.term_in[t] != (t == 0 ? c.base_in : c.term_in[t - 1])) return false;
-    }
-    return true;
+    return block_matches<typename Sh::B0>(p.blk[0], p.in_dtype, p.out_dtype) &&
+           block_matches<typename Sh::B1>(p.blk[1], p.in_dtype, p.out_dtype);
 }
 
 // ---- one tile of the skeleton -------------------------------------------------------------------------
@@ -477,35 +450,15 @@ struct TileIO {
     }
 };
 
-// Operands of an Early<> tile, read from the stage before the arithmetic starts.
-template <typename CT, int V, int NT, bool ON>
-struct Preload {
-    static constexpr bool on = false;
-};
-template <typename CT, int V, int NT>
-struct Preload<CT, V, NT, true> {
-    static constexpr bool on = true;
-    CT x[V], y[V];                  // head: sample, network output
-    CT sample[V], base[V];          // corrector: previous sample, previous x-hat (= the predictor's first term)
-    CT term[NT > 0 ? NT : 1][V];    // corrector's history terms (term t = the predictor's term t + 1)
-    CT noise[2][V];                 // corrector's / predictor's noise
-};
-
-template <typename CT, int V>
-__device__ __forceinline__ void copy_vec(const CT (&from)[V], CT (&to)[V]) {
-#pragma unroll
-    for (int j = 0; j < V; ++j) to[j] = from[j];
-}
-
 template <typename CT, int V, bool CONTRACT>
 __device__ __forceinline__ void divide(CT (&a)[V], CT d, CT r, bool fast) {
     if constexpr (CONTRACT && sizeof(CT) == 4) div_reciprocal<V>(a, d, r, fast);
     else div_uniform<V>(a, d, r, fast);
 }
 
-template <typename CT, int MODE, int V, int PATH, bool PHILOX, typename BS, bool PARTIAL, bool CONTRACT, int BLK, typename PRE>
+template <typename CT, int MODE, int V, int PATH, bool PHILOX, typename BS, bool PARTIAL, bool CONTRACT>
 __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const PhiloxKeys<PHILOX>& keys, const BBlock<CT>& k,
-                                              const TileIO<CT, MODE, V, PATH, PARTIAL>& io, const PRE& pre, CT (&X)[V], CT (&P)[V],
+                                              const TileIO<CT, MODE, V, PATH, PARTIAL>& io, CT (&X)[V], CT (&P)[V],
                                               CT (&B)[V], CT (&A)[V], CT (&S)[V], CT (&R)[V]) {
     using Ar = Policy<CT, CONTRACT && sizeof(CT) == 4>;
     if (!pinned<BS::enabled>(k.enabled)) return;
@@ -515,10 +468,7 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const Ph
 #pragma unroll
         for (int j = 0; j < V; ++j) S[j] = X[j];
     }
-    if (pinned<BS::sample>(k.sample_in >= 0)) {
-        if constexpr (PRE::on) copy_vec<CT, V>(pre.sample, X);
-        else io.template load<BS::dt_sample>(k.sample_in, k.sample_off, X);
-    }
+    if (pinned<BS::sample>(k.sample_in >= 0)) io.template load<BS::dt_sample>(k.sample_in, k.sample_off, X);
 
     CT in[V];
     const int kind = pinned<BS::kind>(k.kind);
@@ -526,10 +476,8 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const Ph
         const int n_terms = pinned<BS::n_terms>(k.n_terms);
         const int p_mode = pinned<BS::p_mode>(k.p_mode);
         if (kind != BK_ACC) {
-            if (pinned<BS::base>(k.base_in >= 0)) {
-                if constexpr (PRE::on) copy_vec<CT, V>(pre.base, B);
-                else io.template load<BS::dt_state>(k.base_in, k.base_off, B);
-            } else {
+            if (pinned<BS::base>(k.base_in >= 0)) io.template load<BS::dt_state>(k.base_in, k.base_off, B);
+            else {
 #pragma unroll
                 for (int j = 0; j < V; ++j) B[j] = P[j];
             }
@@ -565,14 +513,7 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const Ph
 #pragma unroll
             for (int j = 0; j < V; ++j) A[j] = (CT)0;  // 0 + first term, like the reference's running sum
             auto term = [&](int t) {
-                if constexpr (PRE::on) {
-                    // corrector (BLK 0): its own terms; predictor (BLK 1): the corrector's base, then its terms
-                    if (BLK == 0) copy_vec<CT, V>(pre.term[t], in);
-                    else if (t == 0) copy_vec<CT, V>(pre.base, in);
-                    else copy_vec<CT, V>(pre.term[t > 0 ? t - 1 : 0], in);
-                } else {
-                    io.template load<BS::dt_state>(k.term_in[t], k.terms[t].off, in);
-                }
+                io.template load<BS::dt_state>(k.term_in[t], k.terms[t].off, in);
                 const CT rho = k.terms[t].c1;
 #pragma unroll
                 for (int j = 0; j < V; ++j) in[j] = Ar::sub(in[j], B[j]);
@@ -641,10 +582,7 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const Ph
                 drawn = true;
             }
         }
-        if (!drawn) {
-            if constexpr (PRE::on) copy_vec<CT, V>(pre.noise[BLK], in);
-            else io.template load<BS::dt_noise>(k.noise_in, k.noise_off, in);
-        }
+        if (!drawn) io.template load<BS::dt_noise>(k.noise_in, k.noise_off, in);
         const CT zeta = k.zeta;
 #pragma unroll
         for (int j = 0; j < V; ++j) R[j] = Ar::madd(R[j], in[j], zeta);
@@ -680,10 +618,8 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const Ph
 }
 
 template <typename CT, int MODE, int V, int PATH, bool PHILOX, typename Sh, bool PARTIAL = false>
-__device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, const PhiloxKeys<PHILOX>& keys, int64_t first, uint32_t stage, int tid,
-                                               uint64_t* release = nullptr) {
+__device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, const PhiloxKeys<PHILOX>& keys, int64_t first, uint32_t stage, int tid) {
     constexpr bool CONTRACT = Sh::contract && sizeof(CT) == 4;
-    constexpr bool EARLY = Sh::early && PATH == TP_STAGED;
     using Ar = Policy<CT, CONTRACT>;
     const TileIO<CT, MODE, V, PATH, PARTIAL> io{prog, stage, (uint32_t)tid * V, first};
 
@@ -691,35 +627,12 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, const P
 #pragma unroll
     for (int j = 0; j < V; ++j) X[j] = P[j] = B[j] = A[j] = S[j] = R[j] = (CT)0;
 
-    const BHead<CT>& h = prog.head;
-    Preload<CT, V, Sh::B0::n_terms, EARLY> pre;
-    if constexpr (EARLY) {
-        // everything this tile reads, now; then the stage goes back to the producer while the arithmetic runs
-        using C = typename Sh::B0;
-        using Q = typename Sh::B1;
-        const BBlock<CT>& c = prog.blk[0];
-        const BBlock<CT>& q = prog.blk[1];
-        io.template load<Sh::dt_x>(h.x_in, h.x_off, pre.x);
-        io.template load<Sh::dt_y>(h.y_in, h.y_off, pre.y);
-        io.template load<C::dt_sample>(c.sample_in, c.sample_off, pre.sample);
-        io.template load<C::dt_state>(c.base_in, c.base_off, pre.base);
-#pragma unroll
-        for (int t = 0; t < C::n_terms; ++t) io.template load<C::dt_state>(c.term_in[t], c.terms[t].off, pre.term[t]);
-        if (pinned<C::noise>(c.has_noise)) io.template load<C::dt_noise>(c.noise_in, c.noise_off, pre.noise[0]);
-        if (pinned<Q::noise>(q.has_noise)) io.template load<Q::dt_noise>(q.noise_in, q.noise_off, pre.noise[1]);
-        __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(release);
-    }
-
     // ---- head ---------------------------------------------------------------------------------
+    const BHead<CT>& h = prog.head;
     const bool fast_div = prog.fast_div != 0;
-    if (pinned<Sh::x>(h.x_in >= 0)) {
-        if constexpr (EARLY) copy_vec<CT, V>(pre.x, X);
-        else io.template load<Sh::dt_x>(h.x_in, h.x_off, X);
-    }
+    if (pinned<Sh::x>(h.x_in >= 0)) io.template load<Sh::dt_x>(h.x_in, h.x_off, X);
     if (pinned<Sh::y>(h.y_in >= 0)) {
-        if constexpr (EARLY) copy_vec<CT, V>(pre.y, P);
-        else io.template load<Sh::dt_y>(h.y_in, h.y_off, P);
+        io.template load<Sh::dt_y>(h.y_in, h.y_off, P);
         const bool neg = pinned<Sh::neg>(h.neg) != 0;
 #pragma unroll
         for (int j = 0; j < V; ++j) P[j] = neg ? -P[j] : P[j];
@@ -747,8 +660,8 @@ __device__ __forceinline__ void run_block_tile(const BProgram<CT>& prog, const P
     if (pinned<Sh::sp>(h.store_p >= 0)) io.template store<Sh::dt_sp>(h.store_p, P);
     if (pinned<Sh::sp2>(h.store_p2 >= 0)) io.template store<Sh::dt_sp2>(h.store_p2, P);
 
-    run_one_block<CT, MODE, V, PATH, PHILOX, typename Sh::B0, PARTIAL, CONTRACT, 0>(prog, keys, prog.blk[0], io, pre, X, P, B, A, S, R);
-    run_one_block<CT, MODE, V, PATH, PHILOX, typename Sh::B1, PARTIAL, CONTRACT, 1>(prog, keys, prog.blk[1], io, pre, X, P, B, A, S, R);
+    run_one_block<CT, MODE, V, PATH, PHILOX, typename Sh::B0, PARTIAL, CONTRACT>(prog, keys, prog.blk[0], io, X, P, B, A, S, R);
+    run_one_block<CT, MODE, V, PATH, PHILOX, typename Sh::B1, PARTIAL, CONTRACT>(prog, keys, prog.blk[1], io, X, P, B, A, S, R);
 }
 
 // Launches that cannot be staged (unaligned tensor bases, a stage too large for shared memory) run out of line so
@@ -778,7 +691,7 @@ __device__ __noinline__ void run_guarded_tiles(const BProgram<CT>& prog, const P
 // Occupancy each instantiation is compiled for (register cap) and launched with (pipeline shape).
 template <typename CT, int V, typename Sh>
 constexpr int block_ctas_per_sm() {
-    return sizeof(CT) == 8 ? 2 : V == 8 ? Sh::ctas8 : Sh::ctas4;
+    return sizeof(CT) == 8 ? 2 : V == 8 ? Sh::ctas8 : 4;
 }
 
 template <typename CT, int MODE, int V, bool PHILOX, typename Sh>
@@ -863,26 +776,18 @@ __global__ void __launch_bounds__(kThreads + kProducerThreads, block_ctas_per_sm
             uint32_t stage_addr = smem_addr;
             for (int k = 0; k < mine_full; ++k) {
                 mbar_wait(&full_bar[s], phase);
-                run_block_tile<CT, MODE, V, TP_STAGED, PHILOX, Sh>(prog, keys, first, stage_addr, tid, &empty_bar[s]);
-                if constexpr (!Sh::early) {  // Early<> shapes hand the stage back as soon as their operands are in registers
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty_bar[s]);
-                }
+                run_block_tile<CT, MODE, V, TP_STAGED, PHILOX, Sh>(prog, keys, first, stage_addr, tid);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
                 first += stride;
                 stage_addr += stage_bytes;
                 if (++s == stages) { s = 0; phase ^= 1u; stage_addr = smem_addr; }
             }
             if (own_partial) {
                 mbar_wait(&full_bar[s], phase);
-                if constexpr (Sh::early) {
-                    // every lane takes part (the hand-back inside is a warp-wide step); lanes past the end compute on
-                    // whatever the stage holds and store nothing (guarded stores)
-                    run_block_tile<CT, MODE, V, TP_STAGED, PHILOX, Sh, true>(prog, keys, first, stage_addr, tid, &empty_bar[s]);
-                } else {
-                    if (first < prog.numel) run_block_tile<CT, MODE, V, TP_STAGED, PHILOX, Sh, true>(prog, keys, first, stage_addr, tid);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty_bar[s]);
-                }
+                if (first < prog.numel) run_block_tile<CT, MODE, V, TP_STAGED, PHILOX, Sh, true>(prog, keys, first, stage_addr, tid);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
             }
         }
     }

@@ -140,10 +140,8 @@ static void fill_dtypes(const skr_program* p, BProgram<CT>& k) {
 // descriptor's control fields and dtypes (its name in *name), or nullptr.
 // `philox`: the step draws noise inside the kernel (instantiations with the Philox code); `contracted`: the caller
 // opted into contracted arithmetic (skr_set_arithmetic) - shapes that have such an instantiation use it.
-// `early`: instantiations that hand a stage back before the arithmetic (Early<>, three CTAs per SM) may be chosen -
-// they pay off on latents of many tiles per CTA, not on a single wave.
-BlockLauncher<float> pinned_f32(const BProgram<float>& k, bool philox, bool contracted, bool early, const char** name);
-BlockLauncher<float> pinned_bf16(const BProgram<float>& k, bool philox, bool contracted, bool early, const char** name);
-BlockLauncher<float> pinned_f16(const BProgram<float>& k, bool philox, bool contracted, bool early, const char** name);
+BlockLauncher<float> pinned_f32(const BProgram<float>& k, bool philox, bool contracted, const char** name);
+BlockLauncher<float> pinned_bf16(const BProgram<float>& k, bool philox, bool contracted, const char** name);
+BlockLauncher<float> pinned_f16(const BProgram<float>& k, bool philox, bool contracted, const char** name);
 
 }  // namespace skr

@@ -39,9 +39,7 @@ constexpr int kLP = SKR_F16, kModeLP = IN_F16, kVecLP = 8;
 // latent type use 8 elements per thread for 16-bit storage (every shared-memory read 128-bit).
 template <typename F>
 static bool for_each_pinned_shape(F&& f) {
-    return f(ShapeEntry<Early<ShUniPC<kLP, 2>>, IN_MIXED, 4>{"unipc3+early/" SKR_LP_NAME}) ||
-           f(ShapeEntry<Early<ShUniPC<kLP, 1>>, IN_MIXED, 4>{"unipc2+early/" SKR_LP_NAME}) ||
-           f(ShapeEntry<ShUniPC<kLP, 2>, IN_MIXED, 4>{"unipc3/" SKR_LP_NAME}) ||
+    return f(ShapeEntry<ShUniPC<kLP, 2>, IN_MIXED, 4>{"unipc3/" SKR_LP_NAME}) ||
            f(ShapeEntry<ShUniPC<kLP, 1>, IN_MIXED, 4>{"unipc2/" SKR_LP_NAME}) ||
            f(ShapeEntry<ShUniPC<kLP>, IN_MIXED, 4>{"unipc/" SKR_LP_NAME}) ||
            f(ShapeEntry<ShUniP<kLP>, IN_MIXED, 4>{"unip/" SKR_LP_NAME}) ||
@@ -72,9 +70,7 @@ static bool for_each_pinned_philox_shape(F&& f) {
 // The issue-bound steps again with contracted arithmetic (machine.cuh, Policy): opt-in through skr_set_arithmetic.
 template <typename F>
 static bool for_each_pinned_contracted_shape(F&& f) {
-    return f(ShapeEntry<Contracted<Early<ShUniPC<kLP, 2>>>, IN_MIXED, 4>{"unipc3+early~contracted/" SKR_LP_NAME}) ||
-           f(ShapeEntry<Contracted<Early<ShUniPC<kLP, 1>>>, IN_MIXED, 4>{"unipc2+early~contracted/" SKR_LP_NAME}) ||
-           f(ShapeEntry<Contracted<ShUniPC<kLP, 2>>, IN_MIXED, 4>{"unipc3~contracted/" SKR_LP_NAME}) ||
+    return f(ShapeEntry<Contracted<ShUniPC<kLP, 2>>, IN_MIXED, 4>{"unipc3~contracted/" SKR_LP_NAME}) ||
            f(ShapeEntry<Contracted<ShUniPC<kLP, 1>>, IN_MIXED, 4>{"unipc2~contracted/" SKR_LP_NAME}) ||
            f(ShapeEntry<Contracted<ShUniPC<kLP>>, IN_MIXED, 4>{"unipc~contracted/" SKR_LP_NAME}) ||
            f(ShapeEntry<Contracted<ShUniP<kLP>>, IN_MIXED, 4>{"unip~contracted/" SKR_LP_NAME}) ||
@@ -82,13 +78,12 @@ static bool for_each_pinned_contracted_shape(F&& f) {
            f(ShapeEntry<Contracted<ShSPC<kLP>>, IN_MIXED, 4>{"spc~contracted/" SKR_LP_NAME});
 }
 
-BlockLauncher<float> SKR_PINNED_ENTRY(const BProgram<float>& k, bool philox, bool contracted, bool early, const char** name) {
+BlockLauncher<float> SKR_PINNED_ENTRY(const BProgram<float>& k, bool philox, bool contracted, const char** name) {
     const StorageClass storage(k);
     BlockLauncher<float> found = nullptr;
     if (contracted && !philox) {
         for_each_pinned_contracted_shape([&](auto entry) {
             using E = decltype(entry);
-            if (E::shape::early && !early) return false;
             if (!storage.allows(E::mode) || !shape_matches<typename E::shape>(k)) return false;
             *name = entry.name;
             found = &launch_block_one<float, E::mode, E::v, false, typename E::shape>;
@@ -108,7 +103,6 @@ BlockLauncher<float> SKR_PINNED_ENTRY(const BProgram<float>& k, bool philox, boo
     }
     for_each_pinned_shape([&](auto entry) {
         using E = decltype(entry);
-        if (E::shape::early && !early) return false;
         if (!storage.allows(E::mode) || !shape_matches<typename E::shape>(k)) return false;
         *name = entry.name;
         found = &launch_block_one<float, E::mode, E::v, false, typename E::shape>;

@@ -493,35 +493,32 @@ static BlockLauncher<CT> generic_launcher(int n_philox) {
     return &launch_block_one<CT, MODE, V, false, ShAny>;
 }
 
-// Latents of at least this many 1024-element tiles (two rounds of three CTAs on every SM) may use the Early<> shapes.
-static bool is_large(int64_t numel) { return numel / kTile >= (int64_t)sm_count_or(148) * 6; }
-
-static BlockLauncher<float> pinned_any(const BProgram<float>& k, int n_philox, bool large, const char** name) {
+static BlockLauncher<float> pinned_any(const BProgram<float>& k, int n_philox, const char** name) {
     if (switches().no_pinned.load(std::memory_order_relaxed)) return nullptr;
     // the latent storage type is that of the network output (head.y) or, for RK combinations, of the sample
     const int probe = k.head.y_in >= 0 ? k.head.y_in : k.head.x_in;
     if (probe < 0) return nullptr;
     const bool contracted = switches().arithmetic.load(std::memory_order_relaxed) == 1;
     switch (k.in_dtype[probe]) {
-        case SKR_F32: return pinned_f32(k, n_philox > 0, contracted, large, name);
-        case SKR_BF16: return pinned_bf16(k, n_philox > 0, contracted, large, name);
-        case SKR_F16: return pinned_f16(k, n_philox > 0, contracted, large, name);
+        case SKR_F32: return pinned_f32(k, n_philox > 0, contracted, name);
+        case SKR_BF16: return pinned_bf16(k, n_philox > 0, contracted, name);
+        case SKR_F16: return pinned_f16(k, n_philox > 0, contracted, name);
         default: return nullptr;
     }
 }
 
-static BlockLauncher<double> select_launcher(const BProgram<double>&, int n_philox, bool, const char** name) {
+static BlockLauncher<double> select_launcher(const BProgram<double>&, int n_philox, const char** name) {
     *name = "any";
     return generic_launcher<double, IN_MIXED, 4>(n_philox);
 }
 
-static BlockLauncher<float> select_launcher(const BProgram<float>& k, int n_philox, bool large, const char** name) {
+static BlockLauncher<float> select_launcher(const BProgram<float>& k, int n_philox, const char** name) {
     *name = "any";
     const StorageClass storage(k);
     const int force = switches().in_mode.load(std::memory_order_relaxed);  // development switch: 0 / 8 force a mixed instantiation
     if (force == 0) return generic_launcher<float, IN_MIXED, 4>(n_philox);
     if (force == 8) return generic_launcher<float, IN_MIXED, 8>(n_philox);
-    if (BlockLauncher<float> pinned = pinned_any(k, n_philox, large, name)) return pinned;
+    if (BlockLauncher<float> pinned = pinned_any(k, n_philox, name)) return pinned;
     if (storage.all_f32) return generic_launcher<float, IN_F32, 4>(n_philox);
     if (storage.all_bf16) return generic_launcher<float, IN_BF16, 8>(n_philox);
     if (storage.all_f16) return generic_launcher<float, IN_F16, 8>(n_philox);
@@ -596,7 +593,7 @@ static int launch_any(const skr_program* p, int64_t numel, cudaStream_t stream, 
         if (parse_block_program<CT>(p, b)) {
             bind_tensors(p, b);
             const char* name = nullptr;
-            return select_launcher(b, p->n_philox, is_large(numel), &name)(b, p->philox, p->n_philox, numel, stream, aligned);
+            return select_launcher(b, p->n_philox, &name)(b, p->philox, p->n_philox, numel, stream, aligned);
         }
     }
     return launch_typed<CT>(p, numel, stream, aligned);
@@ -612,9 +609,8 @@ struct skr_plan {
     const char* shape_name;
     std::unique_ptr<skr::BProgram<float>> bf;
     std::unique_ptr<skr::BProgram<double>> bd;
-    skr::BlockLauncher<float> lf = nullptr, lf_large = nullptr;  // the latter for latents of many tiles (Early<> shapes)
+    skr::BlockLauncher<float> lf = nullptr;
     skr::BlockLauncher<double> ld = nullptr;
-    const char* shape_name_large = nullptr;
     skr_program source;  // ops + dtypes (the interpreter's input; pointers are filled per launch)
 };
 
@@ -671,17 +667,11 @@ int skr_program_describe(const skr_program* p, char* text, int32_t capacity) {
     }
     fill_dtypes(p, *b);
     const char* shape_name = "any";
-    const char* large_name = "any";
-    if (!any64) {
-        select_launcher(*b, p->n_philox, false, &shape_name);
-        select_launcher(*b, p->n_philox, true, &large_name);
-    }
+    if (!any64) select_launcher(*b, p->n_philox, &shape_name);
     const BHead<float>& h = b->head;
     int n = snprintf(text, (size_t)capacity, "block compute=%s shape=%s fast_div=%d head[x=%d y=%d neg=%d conv=%d sp=%d sp2=%d]",
                      any64 ? "f64" : "f32", any64 ? "any" : shape_name, any64 ? 0 : b->fast_div,
                      h.x_in >= 0, h.y_in >= 0, h.neg, h.n_conv, h.store_p >= 0, h.store_p2 >= 0);
-    if (!any64 && strcmp(shape_name, large_name) != 0 && n > 0 && n < capacity)
-        n += snprintf(text + n, (size_t)(capacity - n), " large=%s", large_name);
     for (int i = 0; i < 2 && n > 0 && n < capacity; ++i) {
         const BBlock<float>& k = b->blk[i];
         if (!k.enabled) continue;
@@ -730,7 +720,7 @@ int skr_plan_create(const skr_program* p, skr_plan** out) {
             memset(plan->bd.get(), 0, sizeof(BProgram<double>));
             if (parse_block_program<double>(p, *plan->bd)) {
                 fill_dtypes(p, *plan->bd);
-                plan->ld = select_launcher(*plan->bd, p->n_philox, false, &plan->shape_name);
+                plan->ld = select_launcher(*plan->bd, p->n_philox, &plan->shape_name);
                 plan->block = true;
             }
         } else {
@@ -739,8 +729,7 @@ int skr_plan_create(const skr_program* p, skr_plan** out) {
             memset(plan->bf.get(), 0, sizeof(BProgram<float>));
             if (parse_block_program<float>(p, *plan->bf)) {
                 fill_dtypes(p, *plan->bf);
-                plan->lf = select_launcher(*plan->bf, p->n_philox, false, &plan->shape_name);
-                plan->lf_large = select_launcher(*plan->bf, p->n_philox, true, &plan->shape_name_large);
+                plan->lf = select_launcher(*plan->bf, p->n_philox, &plan->shape_name);
                 plan->block = true;
             }
         }
@@ -754,7 +743,6 @@ void skr_plan_destroy(skr_plan* plan) { delete plan; }
 int skr_plan_kind(const skr_plan* plan) { return !plan ? skr::fail(SKR_E_NULL, "null plan") : plan->block ? 0 : 1; }
 
 const char* skr_plan_shape(const skr_plan* plan) { return plan ? plan->shape_name : ""; }
-const char* skr_plan_shape_large(const skr_plan* plan) { return !plan ? "" : plan->shape_name_large ? plan->shape_name_large : plan->shape_name; }
 
 int skr_plan_launch(const skr_plan* plan, const void* const* tensors, int64_t numel, const skr_philox* draws, void* stream) {
     using namespace skr;
@@ -775,7 +763,7 @@ int skr_plan_launch(const skr_plan* plan, const void* const* tensors, int64_t nu
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (plan->block) {
         if (plan->f64) return launch_planned<double>(*plan->bd, plan->ld, plan, tensors, numel, draws, s, aligned);
-        return launch_planned<float>(*plan->bf, is_large(numel) ? plan->lf_large : plan->lf, plan, tensors, numel, draws, s, aligned);
+        return launch_planned<float>(*plan->bf, plan->lf, plan, tensors, numel, draws, s, aligned);
     }
     skr_program p = plan->source;
     for (int i = 0; i < plan->n_inputs; ++i) p.inputs[i].ptr = const_cast<void*>(tensors[i]);

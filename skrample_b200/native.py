@@ -110,7 +110,6 @@ EXPORTS = (
     "skr_plan_destroy",
     "skr_plan_kind",
     "skr_plan_shape",
-    "skr_plan_shape_large",
     "skr_reload_env",
     "skr_set_arithmetic",
     "skr_get_arithmetic",
@@ -167,8 +166,6 @@ def load() -> ctypes.CDLL:
     lib.skr_plan_kind.argtypes = [ctypes.c_void_p]
     lib.skr_plan_shape.restype = ctypes.c_char_p
     lib.skr_plan_shape.argtypes = [ctypes.c_void_p]
-    lib.skr_plan_shape_large.restype = ctypes.c_char_p
-    lib.skr_plan_shape_large.argtypes = [ctypes.c_void_p]
     lib.skr_reload_env.restype = None
     lib.skr_set_arithmetic.restype = ctypes.c_int
     lib.skr_set_arithmetic.argtypes = [ctypes.c_int32]
@@ -322,11 +319,6 @@ class _NativePlan:
     @property
     def shape_name(self) -> str:
         return load().skr_plan_shape(self.handle).decode()
-
-    @property
-    def shape_name_large(self) -> str:
-        "The instantiation latents of many tiles run (differs from ``shape_name`` for the '+early' shapes)."
-        return load().skr_plan_shape_large(self.handle).decode()
 
 
 class CompiledProgram:

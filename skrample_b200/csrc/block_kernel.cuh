@@ -518,7 +518,7 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const Ph
 #pragma unroll
                 for (int j = 0; j < V; ++j) in[j] = Ar::sub(in[j], B[j]);
                 if constexpr (Ar::contract) {
-                    if (fast_div) {  // ((x - B) / rk) * rho as one multiply-add with the constant rho / rk
+                    if (fast_div && k.terms[t].r0 != (CT)0) {  // ((x - B) / rk) * rho as one multiply-add with the constant rho / rk
                         const CT scale = Ar::mul(rho, k.terms[t].r0);
 #pragma unroll
                         for (int j = 0; j < V; ++j) A[j] = Ar::madd(A[j], in[j], scale);

@@ -108,7 +108,9 @@ __device__ __forceinline__ void div_uniform(float (&a)[V], float d, float r, boo
 #pragma unroll
     for (int j = 0; j < V; ++j) a[j] = __fdiv_rn(a[j], d);
 #else
-    bool ok = fast;
+    // r == 0: the host found THIS divisor outside the range it computes reciprocals for (the other divisions of the
+    // launch keep the fast sequence)
+    bool ok = fast && r != 0.0f;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
         const float m = fabsf(a[j]);
@@ -121,6 +123,13 @@ __device__ __forceinline__ void div_uniform(float (&a)[V], float d, float r, boo
             const float e = __fmaf_rn(-q0, d, a[j]);
             a[j] = __fmaf_rn(e, r, q0);
         }
+    } else if (r == 0.0f && fabsf(d) == __int_as_float(0x7f800000)) {
+        // an infinite divisor - lambda = ln(alpha / sigma) of a flow schedule's first point, so the first `order` steps
+        // of every flow-matching trajectory have one: x / +-inf IS x * +-0 in IEEE arithmetic (signed zeros for finite
+        // x, NaN for inf / inf), so these steps need not leave the fast path either
+        const float zero = copysignf(0.0f, d);
+#pragma unroll
+        for (int j = 0; j < V; ++j) a[j] = __fmul_rn(a[j], zero);
     } else {
         static_assert(V % 4 == 0, "elements per thread come in groups of four");
 #pragma unroll
@@ -136,7 +145,7 @@ __device__ __forceinline__ void div_uniform(float (&a)[V], float d, float r, boo
 // the host computes reciprocals for).
 template <int V>
 __device__ __forceinline__ void div_reciprocal(float (&a)[V], float d, float r, bool fast) {
-    if (fast) {
+    if (fast && r != 0.0f) {
 #pragma unroll
         for (int j = 0; j < V; ++j) a[j] = __fmul_rn(a[j], r);
     } else {
@@ -151,10 +160,10 @@ __device__ __forceinline__ void div_uniform(double (&a)[V], double d, double, bo
     for (int j = 0; j < V; ++j) a[j] = __ddiv_rn(a[j], d);
 }
 
-// Host side: r = RN(1/d) in the compute type, or 0 (and *fast = false) when d is outside the guarded range.
-static inline float uniform_reciprocal(float d, bool* fast) {
+// Host side: r = RN(1/d) in the compute type, or 0 when d is outside the guarded range.
+static inline float uniform_reciprocal(float d, bool*) {
     const float m = d < 0 ? -d : d;
-    if (!(m >= 0x1p-20f && m <= 0x1p20f)) { *fast = false; return 0.0f; }
+    if (!(m >= 0x1p-20f && m <= 0x1p20f)) return 0.0f;  // this divisor takes IEEE division (or the +-inf shortcut)
     return 1.0f / d;  // IEEE division on the host: correctly rounded
 }
 static inline double uniform_reciprocal(double, bool*) { return 0.0; }

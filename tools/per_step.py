@@ -32,7 +32,7 @@ real = native.CompiledProgram.specialise
 
 def spy(self, signature):  # noqa: ANN001, ANN201
     plan = real(self, signature)
-    shapes.append(plan.shape_name_large)
+    shapes.append(plan.shape_name)
     return plan
 
 

@@ -543,6 +543,46 @@ def test_brownian_without_torchsde_says_so(monkeypatch: pytest.MonkeyPatch) -> N
         noise.Brownian.from_inputs((4, 8), torch.Generator().manual_seed(1))
 
 
+@gpu
+@pytest.mark.parametrize(("items", "unit"), [(64, (4, 32, 32)), (256, (3, 5, 8)), (40, (16, 64, 64))], ids=["64-items", "256-items", "40-items-2.6M"])
+def test_in_kernel_noise_beyond_32_items_and_a_million_elements(items: int, unit: tuple[int, ...]) -> None:
+    """Round 1 limited in-kernel draws to 32 batch items and 2^20 elements.  The key tables are now a kernel parameter of
+    their own (256 items), and a batched fill takes any number of items (chunks of 256): an Euler SDE step that draws
+    its noise from Philox keys equals the step on the materialised tensor bit for bit, item by item."""
+    from skrample_b200 import native, scheduling
+    from skrample_b200.sampling import models, structured
+
+    gens = lambda: [_gen(900 + i) for i in range(items)]  # noqa: E731
+    lazy = noise.BatchTensorNoise.from_batch_inputs(noise.Random, unit, gens())
+    full = noise.BatchTensorNoise.from_batch_inputs(noise.Random, unit, gens())
+    single = noise.Random.from_inputs(unit, _gen(900 + items - 1))
+    sampler = structured.Euler(stochasticity=1)
+    schedule, model = scheduling.FlowShift(scheduling.Linear()), models.FlowModel()
+    x = torch.randn((items, *unit), device="cuda")
+    out = torch.randn((items, *unit), device="cuda")
+    drawn = lazy.auto(None)
+    assert getattr(drawn, "is_lazy_noise", False) and len(drawn.seeds) == items
+    fills = native.launch_count_kind(2)
+    got = sampler.sample(x, out, (0.2, 0.3), model, schedule, drawn)
+    assert native.launch_count_kind(2) == fills, "the step drew its own noise: no fill kernel"
+    tensor = full.generate(None)
+    assert torch.equal(tensor[-1], single.generate(None)), "item i of a batch is its own generator's stream"
+    want = sampler.sample(x, out, (0.2, 0.3), model, schedule, tensor)
+    assert torch.equal(got.final, want.final)
+
+
+@gpu
+def test_batched_fill_of_more_items_than_one_key_table() -> None:
+    "300 per-item generators: the batched fill runs in chunks of 256 items; every item is its own generator's stream."
+    unit = (2, 6, 10)
+    batch = noise.BatchTensorNoise.from_batch_inputs(noise.Random, unit, [_gen(3000 + i) for i in range(300)])
+    assert isinstance(batch.auto(None), torch.Tensor)  # more items than the step kernel's key table: a tensor
+    batch = noise.BatchTensorNoise.from_batch_inputs(noise.Random, unit, [_gen(3000 + i) for i in range(300)])
+    got = batch.generate(None)
+    for i in (0, 1, 255, 256, 257, 299):
+        assert torch.equal(got[i], noise.Random.from_inputs(unit, _gen(3000 + i)).generate(None)), i
+
+
 # ------------------------------------------------------------------------------------------- Brownian (CUDA)
 
 

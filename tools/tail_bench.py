@@ -11,6 +11,6 @@ import bench
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(dev)
 for numel in (511 * 1024, 511 * 1024 + 992, 511 * 1024 + 5, 512 * 1024):
-    spec = dict(sampler="UniPC", kw={"order": 3, "stochasticity": 1}, schedule="scaled", model="NoiseModel", shape=(1, numel), dtype="bf16")
-    r = bench.graph_throughput(spec, dev, 200, 50, 2 * bench.L2_BYTES)
-    print(f"numel {numel}: {r['elapsed_ms'] * 1e3 / r['launches']:.2f} us/step")
+    spec = dict(sampler="UniPC", kw={"order": 3, "stochasticity": 1}, schedule="scaled", model="NoiseModel", shape=(1, numel), dtype="bf16", noise="Random")
+    r = bench.chain_time(spec, dev, "supplied", 0, 25, min_seconds=0.1, blocks=3)
+    print(f"numel {numel}: {r['ms_per_step'] * 1e3:.2f} us/step")

@@ -21,9 +21,11 @@ epsilon model, SDXL latent 8x4x128x128, bf16 storage / fp32 compute, on one B200
                side): a multi-request THROUGHPUT, not a step latency.
   e2e          the same steps through the public API (``sampler.sample``) with HOST buffers: per step the model
                prediction is copied from pinned host memory, the noise is drawn on the device and the result is read
-               back.  ``--inflight`` independent requests (default 2) are advanced round robin, each waiting for its own
-               previous result; ``e2e.one_request`` is the plain synchronous loop; ``e2e_graphed`` replays the steps
-               through ``GraphedTrajectory``.  At least 2000 steps and 0.5 s each.
+               back.  ``--inflight`` independent requests (default 4, each on its own stream) are advanced round robin,
+               each waiting for its own previous result; ``e2e.one_request`` is the plain synchronous loop;
+               ``e2e_graphed`` replays the steps through ``GraphedTrajectory``.  At least 2000 steps and 0.5 s each.
+               The floor of this leg is PCIe: a 1 MiB copy in and a 1 MiB copy out per step take 34 us when both
+               directions are busy (24 / 22 us alone).
   rows         the other BASELINE.json shapes (the Euler sweep of configs[4], the video shard of configs[3] with Pyramid
                and Colored noise drawn per step, UniPC on a Flux-sized latent, the RKUltra(4) step of configs[2]), each
                with its own roofline fraction; ``noise_generators`` times one draw of every generator.
@@ -843,7 +845,7 @@ def main() -> None:
     ap.add_argument("--sweep", action="store_true", help="accepted for compatibility: the rows are part of the default line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=4, help="parallel graph branches of the `concurrent_requests` leg")
-    ap.add_argument("--inflight", type=int, default=2, help="independent requests advanced round robin by the e2e leg (1: the synchronous loop only)")
+    ap.add_argument("--inflight", type=int, default=4, help="independent requests advanced round robin by the e2e leg (1: the synchronous loop only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     # stdout carries exactly one JSON line: anything a library prints there while the bench runs (NCCL's version banner

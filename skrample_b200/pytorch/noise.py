@@ -293,7 +293,8 @@ class TensorNoiseCommon[T: TensorNoiseProps | None](SkrampleTensorNoise):
         after = at + 4 * _SUBSTREAMS * max(1, calls)
         seed.set_offset(after)
         first = tick + _SUBSTREAMS if _take else tick
-        self.__dict__["_skr_reserved"] = [after, first, tick + _SUBSTREAMS * max(1, calls), int(seed.initial_seed()) & 0xFFFFFFFFFFFFFFFF]
+        # [offset after the reservation, next stream id, end of the reservation, Philox key, bound get_offset]
+        self.__dict__["_skr_reserved"] = [after, first, tick + _SUBSTREAMS * max(1, calls), int(seed.initial_seed()) & 0xFFFFFFFFFFFFFFFF, seed.get_offset]
         return tick
 
     def _key(self) -> int:
@@ -1000,9 +1001,11 @@ class BatchTensorNoise[T: TensorNoiseProps | None](SkrampleTensorNoise):
             return self.generate(step) if _fallback else None
         streams, seeds = [], []
         try:
-            for g in self.generators:  # TensorNoiseCommon._tick, inlined for its common case
+            # TensorNoiseCommon._tick, inlined for its common case: one get_offset() per generator (the check that nobody
+            # re-seeded or drew from it since the reservation was made), everything else is list arithmetic
+            for g in self.generators:
                 held = g.__dict__.get("_skr_reserved")
-                if held is not None and held[1] < held[2] and g.seed.get_offset() == held[0]:
+                if held is not None and held[1] < held[2] and held[4]() == held[0]:
                     tick = held[1]
                     held[1] = tick + _SUBSTREAMS
                 else:

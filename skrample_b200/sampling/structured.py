@@ -182,26 +182,36 @@ def _drive(sampler: Any, packed: SampleInput, model_transform: Any, schedule: An
         key = plan.key_for(sampler, packed, model_transform, schedule, previous, (sample.dtype, False) if forced is None else (forced, True))
         hit = plan.lookup(key, sampler, model_transform, schedule)
         if hit is not None:
-            bound = plan.bind(hit, packed, previous)
-            if bound is not None:
-                compiled = hit.compiled
-                count = compiled.n_inputs
-                outs = _native.launch_compiled(compiled, bound, None) if len(bound) == count else _native.launch_compiled(compiled, bound[:count], bound[count:])
-                if outs is not None:
-                    # _assemble, inlined: (final, sample, prediction, x-hat cache, x-hat key, low-precision x-hat)
-                    final_slot, sample_slot, pred_slot, cache_slot, cache_key, lowp_slot = hit.result
-                    result = SKSamples(
-                        sample if sample_slot is None else outs[sample_slot],
-                        packed.prediction if pred_slot is None else outs[pred_slot],
-                        packed.step,
-                        packed.noise,
-                        outs[final_slot],
-                    )
-                    if cache_slot is not None:
-                        result.__dict__[_XHAT_ATTR] = (cache_key, outs[cache_slot])
-                    if lowp_slot is not None:
-                        result.__dict__["_skr_pred_lowp"] = outs[lowp_slot]
-                    return result
+            compiled = hit.compiled
+            outs = None
+            fast = _native._fast if _native._fast is not _native._MISSING else _native._fast_module()
+            if fast is not None and compiled.fast and not _native.ACCOUNT["on"]:
+                # bind by role, fill the Philox key tables, allocate the outputs and launch: one C++ call
+                outs = fast.hit(hit.roles, compiled.n_inputs, compiled.n_philox, packed, previous, compiled.fast, False)
+                if outs.__class__ is not list:
+                    if outs.__class__ is tuple:
+                        _native.check(outs[0], "skr_plan_launch")
+                    outs = None  # an unseen dtype combination or a tensor that does not qualify: the Python path decides
+            if outs is None:
+                bound = plan.bind(hit, packed, previous)
+                if bound is not None:
+                    count = compiled.n_inputs
+                    outs = _native.launch_compiled(compiled, bound, None) if len(bound) == count else _native.launch_compiled(compiled, bound[:count], bound[count:])
+            if outs is not None:
+                # _assemble, inlined: (final, sample, prediction, x-hat cache, x-hat key, low-precision x-hat)
+                final_slot, sample_slot, pred_slot, cache_slot, cache_key, lowp_slot = hit.result
+                result = SKSamples(
+                    sample if sample_slot is None else outs[sample_slot],
+                    packed.prediction if pred_slot is None else outs[pred_slot],
+                    packed.step,
+                    packed.noise,
+                    outs[final_slot],
+                )
+                if cache_slot is not None:
+                    result.__dict__[_XHAT_ATTR] = (cache_key, outs[cache_slot])
+                if lowp_slot is not None:
+                    result.__dict__["_skr_pred_lowp"] = outs[lowp_slot]
+                return result
     ctx = _Ctx(sample)
     spec = build(ctx)
     if key is not None:

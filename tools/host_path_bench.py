@@ -36,6 +36,8 @@ class FakeCompiled:
     def __init__(self, program) -> None:  # noqa: ANN001
         self.n_inputs = len(program.inputs)
         self.out_specs = tuple(program.outputs)
+        self.fast = {}  # no native plans: the Python hit path is what this tool times
+        self.n_philox = 0
 
 
 native.launch_compiled = stub

@@ -12,6 +12,9 @@ python bench.py > $O/${R}_bench.json 2> $O/${R}_bench.err || echo "bench failed"
 python bench.py --impl reference > $O/${R}_bench_reference.json 2>> $O/${R}_bench.err || echo "reference arm failed"
 python tools/e2e_breakdown.py > $O/${R}_e2e_breakdown.txt 2>&1 || echo "breakdown failed"
 tools/bin/step_floor > $O/${R}_step_floor.txt 2>&1 || echo "floor probe failed"
+python tools/per_step.py unipc3_sde_flux_bf16 > $O/${R}_per_step_unipc3_flux_bf16.txt 2>&1 || echo "per-step failed"
+python tools/per_step.py unipc3_sde_flux_bf16 --contracted > $O/${R}_per_step_unipc3_flux_bf16_contracted.txt 2>&1 || echo "per-step failed"
+python tools/per_step.py unipc3_sde_flux64_bf16 > $O/${R}_per_step_unipc3_flux64_bf16.txt 2>&1 || echo "per-step failed"
 
 BENCH="python bench.py --quick --steps 400 --warmup 50 --no-cpu-baseline --streams 1 --inflight 1"
 $BENCH > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \

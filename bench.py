@@ -14,15 +14,16 @@ epsilon model, SDXL latent 8x4x128x128, bf16 storage / fp32 compute, on one B200
                ranks.  Trajectories of several latent batches are interleaved so consecutive launches never touch
                the same buffers and the working set of a round (> 2x L2) comes from HBM.  ``ms_per_step`` is a real
                per-step time: the launches are serialised.
-  kernel_only  the same chain with the noise written before the timed region: one launch per step, so a launch's
-               duration is well defined - ``roofline`` (algorithmic bytes per launch / that duration vs the measured
-               HBM copy peak) is taken here.
+  roofline     the dominant kernel of that timed region - the step kernel that draws its own noise: algorithmic bytes per
+               launch (no noise tensor) / average launch duration vs the measured HBM copy peak.
+  kernel_only  the same chain with the noise written before the timed region (the step reads noise tensors: more bytes,
+               less arithmetic); ``roofline_supplied_noise`` is taken here (round 1's definition).
   concurrent_requests  the same launches on ``--streams`` parallel graph branches (independent latent batches side by
                side): a multi-request THROUGHPUT, not a step latency.
   e2e          the same steps through the public API (``sampler.sample``) with HOST buffers: per step the model
                prediction is copied from pinned host memory, the noise is drawn on the device and the result is read
-               back.  ``--inflight`` independent requests (default 4, each on its own stream) are advanced round robin,
-               each waiting for its own previous result; ``e2e.one_request`` is the plain synchronous loop;
+               back.  ``--inflight`` independent requests (each on its own stream; default: the best of 1 / 2 / 4 by
+               a short trial, recorded in the line) are advanced round robin, each waiting for its own previous result; ``e2e.one_request`` is the plain synchronous loop;
                ``e2e_graphed`` replays the steps through ``GraphedTrajectory``.  At least 2000 steps and 0.5 s each.
                The floor of this leg is PCIe: a 1 MiB copy in and a 1 MiB copy out per step take 34 us when both
                directions are busy (24 / 22 us alone).
@@ -632,12 +633,14 @@ def e2e_throughput(spec: dict, device: torch.device, min_steps: int, warmup: int
     }
 
 
-def measured_traffic() -> float | None:
-    """DRAM bytes per launch of the dominant step kernel on the default workload, from the latest ncu capture
-    summarised under profiles/ (tools/profile_round.sh + tools/summarize_profiles.py); None when not captured."""
+def measured_traffic(which: str = "traffic") -> float | None:
+    """DRAM bytes per launch of the dominant step kernel on the default workload, from the latest ncu launch list
+    summarised under profiles/ (tools/profile_round.sh + tools/summarize_profiles.py); None when not captured.
+    ``traffic``: the kernel of the headline chain (noise drawn in the step); ``traffic_kernel_only``: the same step
+    reading supplied noise tensors."""
     if "--workload" in sys.argv:
         return None
-    found = sorted((ROOT / "profiles").glob("r*_traffic.json"))
+    found = sorted((ROOT / "profiles").glob(f"r[0-9][0-9]_{which}.json"))
     if not found:
         return None
     try:
@@ -847,7 +850,7 @@ def main() -> None:
     ap.add_argument("--sweep", action="store_true", help="accepted for compatibility: the rows are part of the default line")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--streams", type=int, default=4, help="parallel graph branches of the `concurrent_requests` leg")
-    ap.add_argument("--inflight", type=int, default=4, help="independent requests advanced round robin by the e2e leg (1: the synchronous loop only)")
+    ap.add_argument("--inflight", type=int, default=0, help="independent requests advanced round robin by the e2e leg (1: the synchronous loop only; 0: the best of 1 / 2 / 4 by a short trial)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     # stdout carries exactly one JSON line: anything a library prints there while the bench runs (NCCL's version banner
@@ -919,6 +922,9 @@ def main() -> None:
     # the same chain with the noise written beforehand: one launch per step, the step kernel's own duration
     torch.cuda.empty_cache()
     kernel = chain_time(spec, device, "supplied", args.steps, args.warmup)
+    headline_us_per_launch = ms_per_step * 1e3 / chain["launches_per_step"]
+    headline_bytes_per_launch = chain["bytes_per_step_avg"] / chain["launches_per_step"]
+    headline_achieved = headline_bytes_per_launch / (headline_us_per_launch * 1e-6) / 1e9
     per_launch_us = kernel["ms_per_step"] * 1e3 / kernel["launches_per_step"]
     bytes_per_launch = kernel["bytes_per_step_avg"] / kernel["launches_per_step"]
     achieved = bytes_per_launch / (per_launch_us * 1e-6) / 1e9
@@ -939,10 +945,22 @@ def main() -> None:
     single = e2e_throughput(spec, device, 2000, min(args.warmup, 100), 1)
     single_elapsed = max_over_ranks(single["elapsed_s"], device)
     e2e, e2e_elapsed = single, single_elapsed
-    if args.inflight > 1:
-        e2e = e2e_throughput(spec, device, 2000, min(args.warmup, 100), args.inflight)
+    # How many requests a server keeps in flight is a deployment knob, and the best value depends on what else shares the
+    # host's PCIe uplinks: alone on the node 4 requests hide both copies behind each other (38 us/step against 68 for
+    # the synchronous loop), with 8 ranks pushing 2 MiB per step each through the same host the queued copies slow each
+    # other down (133 us at 4 in flight against 83 synchronous).  --inflight 0 (the default) tries 2 and 4 for a short
+    # trial each and times the best of {1, 2, 4} - judged by the slowest rank, the same choice on every rank.
+    trials = {1: single_elapsed / single["steps"] * 1e3}
+    inflight = args.inflight
+    if inflight <= 0:
+        for candidate in (2, 4):
+            trial = e2e_throughput(spec, device, 500, min(args.warmup, 100), candidate, min_seconds=0.15)
+            trials[candidate] = max_over_ranks(trial["elapsed_s"], device) / trial["steps"] * 1e3
+        inflight = min(trials, key=trials.get)
+    if inflight > 1:
+        e2e = e2e_throughput(spec, device, 2000, min(args.warmup, 100), inflight)
         e2e_elapsed = max_over_ranks(e2e["elapsed_s"], device)
-    graphed = e2e_throughput(spec, device, 2000, min(args.warmup, 100), max(1, args.inflight), graphed=True)
+    graphed = e2e_throughput(spec, device, 2000, min(args.warmup, 100), inflight, graphed=True)
     graphed_elapsed = max_over_ranks(graphed["elapsed_s"], device)
 
     line = {
@@ -992,7 +1010,8 @@ def main() -> None:
             "ms_per_step": e2e_elapsed / e2e["steps"] * 1e3,
             "steps": e2e["steps"],
             "api": "structured sampler .sample() per step (the reference's call), pinned-host prediction in, result out; noise from BatchTensorNoise.auto",
-            "requests_in_flight": max(1, args.inflight),
+            "requests_in_flight": inflight,
+            "in_flight_trials_ms_per_step": {str(k): v for k, v in sorted(trials.items())},
             "one_request": {
                 "value": single["steps"] * batch * world / single_elapsed,
                 "ms_per_step": single_elapsed / single["steps"] * 1e3,
@@ -1005,16 +1024,33 @@ def main() -> None:
             "unit": "latent-steps/s",
             "ms_per_step": graphed_elapsed / graphed["steps"] * 1e3,
             "steps": graphed["steps"],
-            "requests_in_flight": max(1, args.inflight),
+            "requests_in_flight": inflight,
             "api": "skrample_b200.graphs.GraphedTrajectory.step(): same host buffers and copies, launches replayed from CUDA graphs",
         },
+        # the dominant kernel of the timed region of `value`: the step kernel that draws its own noise (one launch per
+        # step; when the library fills the noise first, launches_per_step > 1 and the per-launch figures are averages)
         "roofline": {
+            "bound": "hbm",
+            "achieved": headline_achieved,
+            "peak": peak,
+            "unit": "GB/s",
+            "frac": headline_achieved / peak,
+            "traffic": measured_traffic("traffic"),
+            "kernel": "skr::block_kernel (the step with its noise drawn in the kernel: no noise tensor is read or written)",
+            "bytes_per_launch": headline_bytes_per_launch,
+            "us_per_launch": headline_us_per_launch,
+            "launches_per_step": chain["launches_per_step"],
+            "measured_on": "the headline chain (`value`), CUDA events around the timed blocks",
+            "peak_source": peak_src,
+        },
+        # the same step reading supplied noise tensors (the round-1 definition: more bytes per step, less arithmetic)
+        "roofline_supplied_noise": {
             "bound": "hbm",
             "achieved": achieved,
             "peak": peak,
             "unit": "GB/s",
             "frac": achieved / peak,
-            "traffic": measured_traffic(),
+            "traffic": measured_traffic("traffic_kernel_only"),
             "kernel": "skr::block_kernel",
             "bytes_per_launch": bytes_per_launch,
             "us_per_launch": per_launch_us,

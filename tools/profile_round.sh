@@ -20,6 +20,11 @@ BENCH="python bench.py --quick --steps 400 --warmup 50 --no-cpu-baseline --strea
 $BENCH > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
     -k regex:"block_kernel|step_kernel|fill_kernel" -c 3000 --csv --log-file $O/${R}_launches.csv $BENCH > $O/${R}_ncu_launch.log 2>&1
 
+# the same step reading supplied noise tensors (bench.py: kernel_only / roofline_supplied_noise)
+KONLY="python tools/ab_bench.py unipc3_sde_sdxl_bf16"
+$KONLY > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
+    -k regex:"block_kernel|step_kernel|fill_kernel" -c 3000 --csv --log-file $O/${R}_launches_kernel_only.csv $KONLY > $O/${R}_ncu_launch_kernel_only.log 2>&1
+
 capture() {  # name, kernel regex, kernel skip count, command...
     local name=$1 kernel=$2 skip=$3
     shift 3

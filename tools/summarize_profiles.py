@@ -48,8 +48,8 @@ KEEP = (
 )
 
 
-def launches(round_name: str) -> None:
-    path = OUT / f"{round_name}_launches.csv"
+def launches(round_name: str, suffix: str = "", command: str = "python bench.py --quick --steps 400 --warmup 50 --no-cpu-baseline --streams 1 --inflight 1") -> None:
+    path = OUT / f"{round_name}_launches{suffix}.csv"
     if not path.exists():
         return
     lines = [line for line in path.read_text().splitlines() if line.startswith('"')]
@@ -77,12 +77,12 @@ def launches(round_name: str) -> None:
         if top is not None and traffic.get(top):
             import json
 
-            (PROFILES / f"{round_name}_traffic.json").write_text(
+            (PROFILES / f"{round_name}_traffic{suffix}.json").write_text(
                 json.dumps({"kernel": top[0], "grid": top[1], "launches": len(traffic[top]), "dram_bytes_per_launch": sum(traffic[top]) / len(traffic[top]),
-                            "source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum over the launches of this kernel in `{round_name}_launches.csv` (bench command, 16 interleaved latent batches)"}, indent=1) + "\n"
+                            "source": f"ncu dram__bytes_read.sum + dram__bytes_write.sum over the launches of this kernel in `{round_name}_launches{suffix}.csv` (`{command}`, 17 interleaved latent batches)"}, indent=1) + "\n"
             )
     out = [
-        f"# ncu launch list of `python bench.py --steps 400 --warmup 50 --no-cpu-baseline` (gpu__time_duration.sum, --clock-control none)",
+        f"# ncu launch list of `{command}` (gpu__time_duration.sum, --clock-control none)",
         '# filter: -k regex:"block_kernel|step_kernel|fill_kernel" -c 3000; per-launch times are cold-cache and serialised: compare SHARES',
         "",
         f"{'kernel':<110} {'grid':<14} {'n':>6} {'avg us':>8} {'share':>6}",
@@ -90,8 +90,8 @@ def launches(round_name: str) -> None:
     for (name, grid), values in sorted(groups.items(), key=lambda kv: -sum(kv[1])):
         short = name if len(name) <= 108 else name[:105] + "..."
         out.append(f"{short:<110} {grid:<14} {len(values):>6} {sum(values) / len(values):>8.2f} {sum(values) / total:>6.3f}")
-    (PROFILES / f"{round_name}_launches_summary.txt").write_text("\n".join(out) + "\n")
-    (PROFILES / f"{round_name}_launches_head.csv").write_text("\n".join(path.read_text().splitlines()[:60]) + "\n")
+    (PROFILES / f"{round_name}_launches{suffix}_summary.txt").write_text("\n".join(out) + "\n")
+    (PROFILES / f"{round_name}_launches{suffix}_head.csv").write_text("\n".join(path.read_text().splitlines()[:60]) + "\n")
 
 
 def full_captures(round_name: str) -> None:
@@ -139,5 +139,6 @@ if __name__ == "__main__":
     PROFILES.mkdir(parents=True, exist_ok=True)
     bench_lines(which)
     launches(which)
+    launches(which, "_kernel_only", "python tools/ab_bench.py unipc3_sde_sdxl_bf16")
     full_captures(which)
     print("\n".join(sorted(p.name for p in PROFILES.glob(f"{which}_*"))))

@@ -131,6 +131,13 @@ typedef struct skr_philox {
     int32_t dtype;      /* storage type of the tensor this stands for: SKR_BF16 / SKR_F16 round every normal to that
                            type before it is used, exactly what reading the filled tensor would give; SKR_F32 (0) and
                            SKR_F64 use the fp32 normal as drawn */
+    /* Offset noise (noise.py:84-113, kept axes leading): when offset_inner > 0 every run of offset_inner consecutive
+       elements of an item shares one more normal - stream[i] + 1 of the same seed at counter = run index - added to
+       each of its elements times offset_scale (strength^2): what skr_noise_fill writes with that skr_offset.
+       item_numel must be a multiple of offset_inner.  0: plain Random. */
+    int64_t offset_inner;
+    float offset_scale;
+    int32_t reserved;
 } skr_philox;
 
 typedef struct skr_program {

@@ -112,8 +112,14 @@ def build(force: bool = False, verbose: bool = False, defines: tuple[str, ...] =
     objdir.mkdir(parents=True, exist_ok=True)
     common = [*NVCC_FLAGS, *(f"-D{d}" for d in defines), *(["-Xptxas", "-v"] if verbose else [])]
 
+    shared = [*CSRC.glob("*.cuh"), *(ROOT / "include").glob("*.h"), Path(__file__)]
+    newest_shared = max(d.stat().st_mtime for d in shared)
+
     def compile_unit(unit: tuple[str, tuple[str, ...], str]) -> subprocess.CompletedProcess[str]:
         source, unit_defines, obj = unit
+        made = objdir / obj
+        if not force and not verbose and made.exists() and made.stat().st_mtime > max(newest_shared, (CSRC / source).stat().st_mtime):
+            return subprocess.CompletedProcess([], 0, "", "")  # neither the unit nor a header changed since it was compiled
         flags = list(common)
         if source == "noise_kernels.cu":
             # noise values carry no bit-level contract beyond "every kernel draws the same normal for the same key"

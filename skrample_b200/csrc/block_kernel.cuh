@@ -259,6 +259,8 @@ struct BlkAny {
     static constexpr int enabled = -1, kind = -1, sample = -1, base = -1, p_mode = -1, has_div = -1, pred_p = -1;
     static constexpr int noise = -1, store = -1, link = -1, slink = -1;
     static constexpr int n_terms = -1;  // >= 0: the history loop is unrolled, its constants become immediates
+    static constexpr bool offsets = true;  // an in-kernel draw may carry Offset noise (machine.cuh: draw_normals); the
+                                           // pinned blocks compile it out - a launch with offsets takes the generic shape
     static constexpr int dt_state = -1, dt_sample = -1, dt_noise = -1, dt_store = -1, dt_slink = -1;
 };
 struct BlkOff : BlkAny {
@@ -279,6 +281,7 @@ struct ShAny {
 // time stay run-time flags: one uniform branch each.
 template <int KIND, int SAMPLE, int BASE, int PMODE, int DIV, int PREDP, int STORE, int LINK, int SLINK, int OUT, int ST, int LP, int NT = -1>
 struct BlkPin : BlkAny {
+    static constexpr bool offsets = false;
     static constexpr int enabled = 1, kind = KIND, sample = SAMPLE, base = BASE, p_mode = PMODE, has_div = DIV;
     static constexpr int pred_p = PREDP, store = STORE, link = LINK, slink = SLINK, n_terms = NT;
     static constexpr int dt_state = ST, dt_sample = ST, dt_noise = LP, dt_store = OUT, dt_slink = SKR_F32;
@@ -287,6 +290,7 @@ struct BlkPin : BlkAny {
 // A = (sum k_i c_i [+ P c_s]) [/ sum c], derivatives k_i in fp32; covers stage inputs (has_div) and the final update
 template <int LP>
 struct BlkRK : BlkAny {
+    static constexpr bool offsets = false;
     static constexpr int enabled = 1, kind = BK_ACC, sample = 1, base = 0, pred_p = 0, store = 1, link = BL_NONE, slink = 0;
     static constexpr int dt_state = SKR_F32, dt_sample = LP, dt_noise = LP, dt_store = LP;
 };
@@ -578,7 +582,7 @@ __device__ __forceinline__ void run_one_block(const BProgram<CT>& prog, const Ph
         bool drawn = false;
         if constexpr (PHILOX) {
             if (has_noise == 2) {
-                draw_normals<CT, V>(keys.table[k.noise_in], io.first, prog.numel, in);
+                draw_normals<CT, V, BS::offsets>(keys.table[k.noise_in], io.first, prog.numel, in);
                 drawn = true;
             }
         }

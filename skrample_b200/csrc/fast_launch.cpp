@@ -111,14 +111,15 @@ py::object launch(py::dict plans, py::list inputs, uintptr_t draws, bool account
 // .numel, .dtype).  Returns what launch() returns, or None when a role cannot be resolved.
 
 struct Names {
-    PyObject *sample, *prediction, *noise, *dict, *xhat, *materialize, *seeds, *streams, *item_numel, *numel, *dtype, *tensor;
+    PyObject *sample, *prediction, *noise, *dict, *xhat, *materialize, *seeds, *streams, *item_numel, *numel, *dtype, *tensor, *offset_inner, *offset_scale;
     Names()
         : sample(PyUnicode_InternFromString("sample")), prediction(PyUnicode_InternFromString("prediction")),
           noise(PyUnicode_InternFromString("noise")), dict(PyUnicode_InternFromString("__dict__")),
           xhat(PyUnicode_InternFromString("_skr_xhat")), materialize(PyUnicode_InternFromString("materialize")),
           seeds(PyUnicode_InternFromString("seeds")), streams(PyUnicode_InternFromString("streams")),
           item_numel(PyUnicode_InternFromString("item_numel")), numel(PyUnicode_InternFromString("numel")),
-          dtype(PyUnicode_InternFromString("dtype")), tensor(PyUnicode_InternFromString("_tensor")) {}
+          dtype(PyUnicode_InternFromString("dtype")), tensor(PyUnicode_InternFromString("_tensor")),
+          offset_inner(PyUnicode_InternFromString("offset_inner")), offset_scale(PyUnicode_InternFromString("offset_scale")) {}
 };
 const Names& names() {
     static const Names n;
@@ -174,7 +175,9 @@ bool fill_draw(skr_philox& table, PyObject* draw, int64_t* numel) {
     PyObject* item_numel = PyObject_GetAttr(draw, n.item_numel);
     PyObject* total = PyObject_GetAttr(draw, n.numel);
     PyObject* dtype = PyObject_GetAttr(draw, n.dtype);
-    bool ok = seeds && streams && item_numel && total && dtype && PyTuple_Check(seeds) && PyTuple_Check(streams) &&
+    PyObject* inner = PyObject_GetAttr(draw, n.offset_inner);
+    PyObject* scale = PyObject_GetAttr(draw, n.offset_scale);
+    bool ok = seeds && streams && item_numel && total && dtype && inner && scale && PyTuple_Check(seeds) && PyTuple_Check(streams) &&
               PyTuple_GET_SIZE(seeds) == PyTuple_GET_SIZE(streams) && PyTuple_GET_SIZE(seeds) >= 1 &&
               PyTuple_GET_SIZE(seeds) <= SKR_MAX_PHILOX_ITEMS;
     if (ok) {
@@ -188,10 +191,14 @@ bool fill_draw(skr_philox& table, PyObject* draw, int64_t* numel) {
         *numel = PyLong_AsLongLong(total);
         table.dtype = THPDtype_Check(dtype) ? code_of(reinterpret_cast<THPDtype*>(dtype)->scalar_type) : 0;
         if (table.dtype < 0) table.dtype = 0;
+        table.offset_inner = PyLong_AsLongLong(inner);
+        table.offset_scale = (float)PyFloat_AsDouble(scale);
+        table.reserved = 0;
         ok = !PyErr_Occurred();
     }
     PyErr_Clear();
     Py_XDECREF(seeds); Py_XDECREF(streams); Py_XDECREF(item_numel); Py_XDECREF(total); Py_XDECREF(dtype);
+    Py_XDECREF(inner); Py_XDECREF(scale);
     return ok;
 }
 

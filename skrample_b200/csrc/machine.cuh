@@ -281,6 +281,9 @@ struct KPhilox {
     int32_t aligned;  // bit 0: item_numel % 4 == 0 (four consecutive elements share one Philox block);
                       // bit 1: numel < 2^31 (32-bit index arithmetic);
                       // bits 8-9: round every normal to bf16 (1) / fp16 (2), like the tensor skr_noise_fill writes
+    int64_t offset_inner;  // Offset noise: > 0 = elements of an item that share one offset draw (skr_philox)
+    float offset_scale;
+    int32_t reserved;
 };
 
 // The key tables of a launch that draws noise in the kernel travel as a second kernel parameter, so the
@@ -298,7 +301,27 @@ __device__ __forceinline__ float round_as_stored(float z, int mode) {
     return z;
 }
 
-// Four normals of the virtual noise tensor starting at element e (e % 4 == 0, item_numel % 4 == 0).
+// Offset noise: the shared draw of the run an element belongs to, added with two individually rounded operations (the
+// fill kernel of the noise unit, compiled with contraction on, spells the same two out).  Out of line: plain Random
+// draws - the hot case - pay one uniform branch for it.
+static __device__ __noinline__ float4 add_offsets(uint64_t seed, uint64_t stream, int64_t inner, float scale, int64_t local, float4 z) {
+    const Philox ph(seed);
+    const int64_t row = local / inner;
+    if (local + 3 < (row + 1) * inner) {
+        const float shift = __fmul_rn(normal_at(ph, (uint64_t)row, stream), scale);
+        z.x = __fadd_rn(z.x, shift); z.y = __fadd_rn(z.y, shift); z.z = __fadd_rn(z.z, shift); z.w = __fadd_rn(z.w, shift);
+    } else {
+        z.x = __fadd_rn(z.x, __fmul_rn(normal_at(ph, (uint64_t)(local / inner), stream), scale));
+        z.y = __fadd_rn(z.y, __fmul_rn(normal_at(ph, (uint64_t)((local + 1) / inner), stream), scale));
+        z.z = __fadd_rn(z.z, __fmul_rn(normal_at(ph, (uint64_t)((local + 2) / inner), stream), scale));
+        z.w = __fadd_rn(z.w, __fmul_rn(normal_at(ph, (uint64_t)((local + 3) / inner), stream), scale));
+    }
+    return z;
+}
+
+// Four normals of the virtual noise tensor starting at element e (e % 4 == 0, item_numel % 4 == 0).  OFFSETS = false
+// compiles the Offset term out (the pinned step shapes: launches whose draws carry offsets take the generic shape).
+template <bool OFFSETS>
 __device__ __forceinline__ float4 draw_group(const KPhilox& d, int64_t e) {
     int64_t item, local;
     if (d.aligned & 2) {
@@ -311,6 +334,10 @@ __device__ __forceinline__ float4 draw_group(const KPhilox& d, int64_t e) {
     }
     float z[4];
     normal4(Philox(d.seed[item])((uint64_t)local >> 2, d.stream[item]), z);
+    if (OFFSETS && d.offset_inner > 0) {
+        const float4 shifted = add_offsets(d.seed[item], d.stream[item] + 1, d.offset_inner, d.offset_scale, local, make_float4(z[0], z[1], z[2], z[3]));
+        z[0] = shifted.x; z[1] = shifted.y; z[2] = shifted.z; z[3] = shifted.w;
+    }
     const int mode = (d.aligned >> 8) & 3;
     if (mode) {
 #pragma unroll
@@ -319,28 +346,32 @@ __device__ __forceinline__ float4 draw_group(const KPhilox& d, int64_t e) {
     return make_float4(z[0], z[1], z[2], z[3]);
 }
 
+template <bool OFFSETS>
 __device__ __forceinline__ float draw_single(const KPhilox& d, int64_t e) {
     const int64_t item = e / d.item_numel;
     const int64_t local = e - item * d.item_numel;
-    return round_as_stored(normal_at(Philox(d.seed[item]), (uint64_t)local, d.stream[item]), (d.aligned >> 8) & 3);
+    float z = normal_at(Philox(d.seed[item]), (uint64_t)local, d.stream[item]);
+    if (OFFSETS && d.offset_inner > 0)
+        z = __fadd_rn(z, __fmul_rn(normal_at(Philox(d.seed[item]), (uint64_t)(local / d.offset_inner), d.stream[item] + 1), d.offset_scale));
+    return round_as_stored(z, (d.aligned >> 8) & 3);
 }
 
 // V consecutive elements starting at global element `first` (a multiple of 4) of the virtual noise tensor.
-template <typename CT, int V>
+template <typename CT, int V, bool OFFSETS = true>
 __device__ __forceinline__ void draw_normals(const KPhilox& d, int64_t first, int64_t numel, CT (&v)[V]) {
     if (d.aligned & 1) {
 #pragma unroll
         for (int g = 0; g < V / 4; ++g) {
             const int64_t e = first + 4 * g;
             float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e < numel) z = draw_group(d, e);
+            if (e < numel) z = draw_group<OFFSETS>(d, e);
             v[4 * g] = (CT)z.x; v[4 * g + 1] = (CT)z.y; v[4 * g + 2] = (CT)z.z; v[4 * g + 3] = (CT)z.w;
         }
     } else {
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             const int64_t e = first + j;
-            v[j] = (CT)(e < numel ? draw_single(d, e) : 0.f);
+            v[j] = (CT)(e < numel ? draw_single<OFFSETS>(d, e) : 0.f);
         }
     }
 }
@@ -351,6 +382,9 @@ static inline void fill_kphilox(KPhilox* out, const skr_philox* in, int count) {
         for (int j = 0; j < n; ++j) { out[i].seed[j] = in[i].seed[j]; out[i].stream[j] = in[i].stream[j]; }
         out[i].item_numel = in[i].item_numel;
         out[i].n_items = in[i].n_items;
+        out[i].offset_inner = in[i].offset_scale != 0.0f ? in[i].offset_inner : 0;
+        out[i].offset_scale = in[i].offset_scale;
+        out[i].reserved = 0;
         const int round_to = in[i].dtype == SKR_BF16 ? 1 : in[i].dtype == SKR_F16 ? 2 : 0;
         out[i].aligned = ((in[i].item_numel % 4) == 0 ? 1 : 0) |
                          (in[i].item_numel * in[i].n_items < (int64_t)0x7fffffff ? 2 : 0) | (round_to << 8);

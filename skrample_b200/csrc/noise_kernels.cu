@@ -20,6 +20,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -33,6 +34,7 @@ namespace skr {
 extern int fail(int code, const char* fmt, ...);
 extern void count_launch(int kind);
 extern int sm_count_or(int fallback);
+extern int env_int(const char* name, int fallback);
 
 // ---------------------------------------------------------------------------------------------------------
 // store helpers
@@ -107,6 +109,8 @@ __device__ __forceinline__ void block_sum2(double& a, double& b) {
 //   buf[4 + 2b], buf[5 + 2b]  partial sums of block b
 // Every block stores its partials; the block that arrives last adds them up in block order (each lane a fixed strided
 // subset, then a fixed shuffle tree) and publishes the totals.  gridDim.x <= SKR_MOMENT_BLOCKS.
+//   buf[3]     (resident kernels only) generation counter: bumped once the totals of a launch are published
+template <bool SIGNAL = false>
 __device__ __forceinline__ void publish_sums(double a, double b, double* buf) {
     __shared__ bool last;
     block_sum2(a, b);
@@ -134,8 +138,18 @@ __device__ __forceinline__ void publish_sums(double a, double b, double* buf) {
             buf[0] += ta;
             buf[1] += tb;
             *reinterpret_cast<unsigned int*>(buf + 2) = 0u;
+            if constexpr (SIGNAL) {
+                __threadfence();
+                atomicAdd(reinterpret_cast<unsigned int*>(buf + 3), 1u);
+            }
         }
     }
+}
+
+__device__ __forceinline__ unsigned int load_acquire(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
 // 128-bit loads / stores of VEC consecutive elements of a storage type, as floats
@@ -254,13 +268,15 @@ __global__ void __launch_bounds__(256) fill_kernel(const __grid_constant__ FillP
             const int64_t row = p.inner > 0 ? first / p.inner : -1;
             if (row >= 0 && first + 3 < (row + 1) * p.inner) {
                 // the usual case (offsets along leading axes): the four elements share one offset draw
-                const float shift = normal_at(ph, (uint64_t)row, p.offset_stream) * p.offset_scale;
+                // (a product and a sum, individually rounded: the in-step draw of machine.cuh computes the same bits)
+                const float shift = __fmul_rn(normal_at(ph, (uint64_t)row, p.offset_stream), p.offset_scale);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) z[j] = z[j] + shift;
+                for (int j = 0; j < 4; ++j) z[j] = __fadd_rn(z[j], shift);
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    if (first + j < p.numel) z[j] = z[j] + normal_at(ph, (uint64_t)reduced_index(p, first + j), p.offset_stream) * p.offset_scale;
+                    if (first + j < p.numel)
+                        z[j] = __fadd_rn(z[j], __fmul_rn(normal_at(ph, (uint64_t)reduced_index(p, first + j), p.offset_stream), p.offset_scale));
                 }
             }
         }
@@ -865,6 +881,138 @@ __global__ void __launch_bounds__(256) pyramid_compose_trailing_kernel(const __g
     publish_sums(s1, s2, p.moments);
 }
 
+// Composition AND normalisation in one launch, for units that fit the shared memory of the whole GPU (a 16x21x90x160
+// video latent is 19.4 MB against 148 x 227 KB): a cooperative grid of one 1024-thread CTA per SM, every CTA owning a
+// contiguous run of the unit.  Phase 1 is the composition of pyramid_compose_trailing_kernel (same arithmetic, same
+// order) with the unnormalised values HELD IN SHARED MEMORY instead of written to a scratch tensor; the grid-wide sums
+// are published in a fixed order; every CTA waits for the totals (generation counter, acquire load); phase 2 scales
+// what it holds and stores it once, in the output's storage type.  Against composition + scale pass this removes a
+// launch and a 4-byte-per-element round trip.  K float4 groups per thread and iteration (K = 2 when a row holds an even
+// number of groups: the row arithmetic of a level is shared by eight elements); coordinates advance by carries, three
+// integer divisions per thread in total.
+template <int AXES, int K, typename TO>
+__global__ void __launch_bounds__(1024, 1) pyramid_resident_kernel(const __grid_constant__ PyramidParams p, const int32_t units_per_cta) {
+    extern __shared__ __align__(16) float4 held[];
+    __shared__ unsigned int generation;
+    const int32_t width = (int32_t)p.shape[AXES], height = AXES == 2 ? (int32_t)p.shape[1] : 1;
+    const int32_t upr = width / (4 * K);  // units (K groups of four elements) per row
+    const int32_t units = (int32_t)(p.numel >> 2) / K;
+    const int32_t first = (int32_t)blockIdx.x * units_per_cta;
+    const int32_t count = units - first < units_per_cta ? (units - first > 0 ? units - first : 0) : units_per_cta;
+    unsigned int* const gen = reinterpret_cast<unsigned int*>(p.moments + 3);
+    if (threadIdx.x == 0) generation = load_acquire(gen);  // before this CTA's arrival: the same value in every CTA
+    const Philox ph(p.seed);
+    const int32_t stride = (int32_t)blockDim.x;
+    int32_t xu, slice, y = 0;
+    {
+        const int32_t u = first + (int32_t)threadIdx.x;
+        const int32_t row = u / upr;
+        xu = u - row * upr;
+        slice = row;
+        if constexpr (AXES == 2) {
+            slice = row / height;
+            y = row - slice * height;
+        }
+    }
+    const int32_t dq = stride / upr, dr = stride - dq * upr;
+    const int32_t dqs = AXES == 2 ? dq / height : dq, dqy = AXES == 2 ? dq - dqs * height : 0;
+    double s1 = 0.0, s2 = 0.0;
+    for (int32_t i = (int32_t)threadIdx.x; i < count; i += stride) {
+        const int32_t g0 = (first + i) * K;
+        const int32_t x = xu * (4 * K);
+        float acc[K][4];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.0f;
+        for (int l = 0; l < p.n_levels; ++l) {
+            const float wl = p.weight[l];
+            if (wl == 0.0f) continue;
+            if (p.same_size[l]) {
+                const float* grid = p.buffer[l];
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    float q[4];
+                    if (grid) {
+                        const float4 v = *reinterpret_cast<const float4*>(grid + ((g0 + k) << 2));
+                        q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
+                    } else {
+                        normal4(ph((uint64_t)(g0 + k), p.stream[l]), q);
+                    }
+                    acc[k][0] += q[0] * wl; acc[k][1] += q[1] * wl; acc[k][2] += q[2] * wl; acc[k][3] += q[3] * wl;
+                }
+                continue;
+            }
+            const float* wide = p.wide[l];
+            if constexpr (AXES == 2) {
+                int h0, h1;
+                float wh;
+                source_index32(y, (int)p.extent[l][0], p.ratio[l][0], h0, h1, wh);
+                const int32_t base = slice * (int32_t)p.extent[l][0];
+                const float* r0 = wide + (base + h0) * width + x;
+                const float* r1 = wide + (base + h1) * width + x;
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    float4 top = *reinterpret_cast<const float4*>(r0 + 4 * k);
+                    const float4 bot = *reinterpret_cast<const float4*>(r1 + 4 * k);
+                    top.x = (1.0f - wh) * top.x + wh * bot.x;
+                    top.y = (1.0f - wh) * top.y + wh * bot.y;
+                    top.z = (1.0f - wh) * top.z + wh * bot.z;
+                    top.w = (1.0f - wh) * top.w + wh * bot.w;
+                    acc[k][0] += top.x * wl; acc[k][1] += top.y * wl; acc[k][2] += top.z * wl; acc[k][3] += top.w * wl;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const float4 top = *reinterpret_cast<const float4*>(wide + ((g0 + k) << 2));
+                    acc[k][0] += top.x * wl; acc[k][1] += top.y * wl; acc[k][2] += top.z * wl; acc[k][3] += top.w * wl;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            float b[4];
+            if (p.base_buffer) {
+                const float4 q = *reinterpret_cast<const float4*>(p.base_buffer + ((g0 + k) << 2));
+                b[0] = q.x; b[1] = q.y; b[2] = q.z; b[3] = q.w;
+            } else {
+                normal4(ph((uint64_t)(g0 + k), p.base_stream), b);
+            }
+            const float4 v = make_float4(b[0] + acc[k][0], b[1] + acc[k][1], b[2] + acc[k][2], b[3] + acc[k][3]);
+            held[i * K + k] = v;
+            s1 += (double)((v.x + v.y) + (v.z + v.w));
+            s2 += (double)((v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w));
+        }
+        // the next unit of this thread: `stride` units further on
+        xu += dr;
+        const int32_t carry = xu >= upr ? 1 : 0;
+        xu -= carry ? upr : 0;
+        if constexpr (AXES == 2) {
+            y += dqy + carry;
+            slice += dqs;
+            if (y >= height) {
+                y -= height;
+                ++slice;
+            }
+        } else {
+            slice += dq + carry;
+        }
+    }
+    publish_sums<true>(s1, s2, p.moments);
+    if (threadIdx.x == 0) {
+        const unsigned int before = generation;
+        while (load_acquire(gen) == before) __nanosleep(40);
+    }
+    __syncthreads();
+    double m[2] = {__ldcg(p.moments), __ldcg(p.moments + 1)};
+    const double sd = std_from(m, p.numel);
+    const float fs = (float)(sd > 0.0 ? 1.0 / sd : 1.0);
+    TO* const out = reinterpret_cast<TO*>(p.out) + ((int64_t)first * K << 2);
+    for (int32_t i = (int32_t)threadIdx.x; i < count * K; i += stride) {
+        const float4 v = held[i];
+        const float scaled[4] = {v.x * fs, v.y * fs, v.z * fs, v.w * fs};
+        put4<TO>(out + (i << 2), scaled);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Colored: spectral shaping of an rfftn half spectrum, in place   (reference: noise.py:285-335,379-394)
 
@@ -1081,6 +1229,76 @@ static int check_launch(const char* what) {
     return 0;
 }
 
+
+// The resident composition (pyramid_resident_kernel): returns 0 when launched, a negative value when this unit / device
+// does not qualify (the caller then runs composition + scale pass), a positive CUDA status when the launch failed.
+template <int AXES, int K, typename TO>
+static int launch_resident_as(PyramidParams& p, int sms, int max_smem, cudaStream_t s) {
+    const int64_t units = (p.numel >> 2) / K;
+    const int64_t per_cta = (units + sms - 1) / sms;
+    const int64_t bytes = per_cta * K * (int64_t)sizeof(float4);
+    if (bytes + 2048 > max_smem) return -1;  // static shared memory of the kernel: 1.5 KB
+    auto kernel = pyramid_resident_kernel<AXES, K, TO>;
+    static std::atomic<uint64_t> prepared{0};  // one bit per device: the shared-memory opt-in has been set
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    if (!(prepared.load(std::memory_order_acquire) >> dev & 1u)) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 2048) != cudaSuccess) {
+            cudaGetLastError();
+            return -1;
+        }
+        prepared.fetch_or((uint64_t)1 << dev, std::memory_order_release);
+    }
+    int32_t units_per_cta = (int32_t)per_cta;
+    void* args[] = {&p, &units_per_cta};
+    // cooperative: the grid-wide wait inside the kernel needs every CTA resident, and this launch guarantees it
+    const cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), dim3((unsigned)sms), dim3(1024), args, (size_t)bytes, s);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported ? -1 : fail((int)e, "pyramid resident launch: %s", cudaGetErrorString(e));
+    }
+    count_launch(2);
+    return 0;
+}
+
+template <int AXES, int K>
+static int launch_resident_typed(PyramidParams& p, int sms, int max_smem, cudaStream_t s) {
+    switch (p.dtype) {
+        case SKR_F32: return launch_resident_as<AXES, K, float>(p, sms, max_smem, s);
+        case SKR_BF16: return launch_resident_as<AXES, K, __nv_bfloat16>(p, sms, max_smem, s);
+        case SKR_F16: return launch_resident_as<AXES, K, __half>(p, sms, max_smem, s);
+        default: return -1;
+    }
+}
+
+// p is the collapsed trailing-layout descriptor ([slices, H, W] or [slices, W]) the composition kernel would get.
+static int launch_resident(PyramidParams& p, int axes, cudaStream_t s) {
+    if (env_int("SKR_NO_RESIDENT_PYRAMID", 0)) return -1;
+    int dev = 0, coop = 0, sms = 0, max_smem = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    static std::atomic<int> cached[64][3];  // cooperative launch, SM count, opt-in shared memory (+1: 0 = not read yet)
+    if (dev < 0 || dev >= 64) return -1;
+    if (cached[dev][1].load(std::memory_order_acquire) == 0) {
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cached[dev][0].store(coop, std::memory_order_relaxed);
+        cached[dev][2].store(max_smem, std::memory_order_relaxed);
+        cached[dev][1].store(sms > 0 ? sms : -1, std::memory_order_release);
+    }
+    coop = cached[dev][0].load(std::memory_order_relaxed);
+    sms = cached[dev][1].load(std::memory_order_relaxed);
+    max_smem = cached[dev][2].load(std::memory_order_relaxed);
+    if (!coop || sms < 1 || sms > SKR_MOMENT_BLOCKS || max_smem < 64 * 1024) return -1;
+    for (int l = 0; l < p.n_levels; ++l)
+        if (p.weight[l] != 0.0f && !p.same_size[l] && !p.wide[l]) return -1;  // a coarse level that was not widened
+    const int width = (int)p.shape[axes];
+    const int align = p.dtype == SKR_F32 ? 15 : 7;
+    if ((reinterpret_cast<uintptr_t>(p.out) & align) != 0) return -1;
+    const bool pairs = (width & 7) == 0;
+    if (axes == 2) return pairs ? launch_resident_typed<2, 2>(p, sms, max_smem, s) : launch_resident_typed<2, 1>(p, sms, max_smem, s);
+    return pairs ? launch_resident_typed<1, 2>(p, sms, max_smem, s) : launch_resident_typed<1, 1>(p, sms, max_smem, s);
+}
 }  // namespace skr
 
 extern "C" {
@@ -1138,6 +1356,8 @@ int skr_noise_fill_batch(void* out, int32_t dtype, const skr_philox* keys, void*
     if (dtype < 0 || dtype > SKR_F16) return fail(SKR_E_DTYPE, "unknown dtype %d", dtype);
     if (keys->n_items < 1 || keys->n_items > SKR_MAX_PHILOX_ITEMS) return fail(SKR_E_RANGE, "n_items %d out of range", keys->n_items);
     if (keys->item_numel < 0) return fail(SKR_E_RANGE, "negative item_numel");
+    if (keys->offset_scale != 0.0f && (keys->offset_inner < 1 || keys->item_numel % keys->offset_inner != 0))
+        return fail(SKR_E_SHAPE, "offset_inner %lld does not divide item_numel", (long long)keys->offset_inner);
     const int64_t numel = keys->item_numel * keys->n_items;
     if (numel == 0) return 0;
     if (!out) return fail(SKR_E_NULL, "null output");
@@ -1429,6 +1649,10 @@ int skr_noise_pyramid(void* out, int32_t dtype, const skr_pyramid* desc, double*
                     int rc = check_launch("pyramid widen");
                     if (rc) return rc;
                 }
+            }
+            {
+                const int resident = launch_resident(p, masked, s);
+                if (resident >= 0) return resident;
             }
             if (masked == 2) pyramid_compose_trailing_kernel<2><<<grid_for(numel / 4, 256), 256, 0, s>>>(p);
             else pyramid_compose_trailing_kernel<1><<<grid_for(numel / 4, 256), 256, 0, s>>>(p);

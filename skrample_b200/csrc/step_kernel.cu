@@ -507,18 +507,21 @@ static BlockLauncher<float> pinned_any(const BProgram<float>& k, int n_philox, c
     }
 }
 
-static BlockLauncher<double> select_launcher(const BProgram<double>&, int n_philox, const char** name) {
+// offsets: a draw of this launch carries Offset noise, which only the generic shape draws (BlkAny::offsets)
+static BlockLauncher<double> select_launcher(const BProgram<double>&, int n_philox, const char** name, bool = false) {
     *name = "any";
     return generic_launcher<double, IN_MIXED, 4>(n_philox);
 }
 
-static BlockLauncher<float> select_launcher(const BProgram<float>& k, int n_philox, const char** name) {
+static BlockLauncher<float> select_launcher(const BProgram<float>& k, int n_philox, const char** name, bool offsets = false) {
     *name = "any";
     const StorageClass storage(k);
     const int force = switches().in_mode.load(std::memory_order_relaxed);  // development switch: 0 / 8 force a mixed instantiation
     if (force == 0) return generic_launcher<float, IN_MIXED, 4>(n_philox);
     if (force == 8) return generic_launcher<float, IN_MIXED, 8>(n_philox);
-    if (BlockLauncher<float> pinned = pinned_any(k, n_philox, name)) return pinned;
+    if (!offsets) {
+        if (BlockLauncher<float> pinned = pinned_any(k, n_philox, name)) return pinned;
+    }
     if (storage.all_f32) return generic_launcher<float, IN_F32, 4>(n_philox);
     if (storage.all_bf16) return generic_launcher<float, IN_BF16, 8>(n_philox);
     if (storage.all_f16) return generic_launcher<float, IN_F16, 8>(n_philox);
@@ -569,11 +572,19 @@ static int validate_program(const skr_program* p, int64_t numel, bool need_point
     return 0;
 }
 
+static bool draws_offsets(const skr_philox* draws, int n) {
+    for (int i = 0; i < n; ++i)
+        if (draws[i].offset_scale != 0.0f && draws[i].offset_inner > 0) return true;
+    return false;
+}
+
 static int validate_philox(const skr_philox* draws, int n, int64_t numel) {
     for (int i = 0; i < n; ++i) {
         const skr_philox& d = draws[i];
         if (d.n_items < 1 || d.n_items > SKR_MAX_PHILOX_ITEMS) return fail(SKR_E_RANGE, "philox %d: n_items %d out of range", i, d.n_items);
         if (d.item_numel < 1 || d.item_numel * d.n_items != numel) return fail(SKR_E_SHAPE, "philox %d: n_items * item_numel != numel", i);
+        if (d.offset_scale != 0.0f && (!(d.offset_scale == d.offset_scale) || d.offset_inner < 1 || d.item_numel % d.offset_inner != 0))
+            return fail(SKR_E_SHAPE, "philox %d: offset_inner %lld does not divide item_numel", i, (long long)d.offset_inner);
     }
     return 0;
 }
@@ -593,7 +604,7 @@ static int launch_any(const skr_program* p, int64_t numel, cudaStream_t stream, 
         if (parse_block_program<CT>(p, b)) {
             bind_tensors(p, b);
             const char* name = nullptr;
-            return select_launcher(b, p->n_philox, &name)(b, p->philox, p->n_philox, numel, stream, aligned);
+            return select_launcher(b, p->n_philox, &name, draws_offsets(p->philox, p->n_philox))(b, p->philox, p->n_philox, numel, stream, aligned);
         }
     }
     return launch_typed<CT>(p, numel, stream, aligned);
@@ -609,7 +620,7 @@ struct skr_plan {
     const char* shape_name;
     std::unique_ptr<skr::BProgram<float>> bf;
     std::unique_ptr<skr::BProgram<double>> bd;
-    skr::BlockLauncher<float> lf = nullptr;
+    skr::BlockLauncher<float> lf = nullptr, lf_offsets = nullptr;  // *_offsets: the generic shape, for draws that carry Offset noise
     skr::BlockLauncher<double> ld = nullptr;
     skr_program source;  // ops + dtypes (the interpreter's input; pointers are filled per launch)
 };
@@ -730,6 +741,8 @@ int skr_plan_create(const skr_program* p, skr_plan** out) {
             if (parse_block_program<float>(p, *plan->bf)) {
                 fill_dtypes(p, *plan->bf);
                 plan->lf = select_launcher(*plan->bf, p->n_philox, &plan->shape_name);
+                const char* unused = nullptr;
+                plan->lf_offsets = p->n_philox > 0 ? select_launcher(*plan->bf, p->n_philox, &unused, true) : plan->lf;
                 plan->block = true;
             }
         }
@@ -763,7 +776,8 @@ int skr_plan_launch(const skr_plan* plan, const void* const* tensors, int64_t nu
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     if (plan->block) {
         if (plan->f64) return launch_planned<double>(*plan->bd, plan->ld, plan, tensors, numel, draws, s, aligned);
-        return launch_planned<float>(*plan->bf, plan->lf, plan, tensors, numel, draws, s, aligned);
+        const bool offsets = plan->n_philox > 0 && draws_offsets(draws, plan->n_philox);
+        return launch_planned<float>(*plan->bf, offsets ? plan->lf_offsets : plan->lf, plan, tensors, numel, draws, s, aligned);
     }
     skr_program p = plan->source;
     for (int i = 0; i < plan->n_inputs; ++i) p.inputs[i].ptr = const_cast<void*>(tensors[i]);

@@ -65,6 +65,9 @@ class SkrPhilox(ctypes.Structure):
         ("item_numel", ctypes.c_int64),
         ("n_items", ctypes.c_int32),
         ("dtype", ctypes.c_int32),
+        ("offset_inner", ctypes.c_int64),
+        ("offset_scale", ctypes.c_float),
+        ("reserved", ctypes.c_int32),
     ]
 
 
@@ -93,6 +96,8 @@ def _pack_draws(packed: SkrProgram, draws: list[Any]) -> None:
         slot.seed[:count] = draw.seeds
         slot.stream[:count] = draw.streams
         slot.dtype = DTYPE_CODE.get(draw.dtype, F32)
+        slot.offset_inner = draw.offset_inner
+        slot.offset_scale = draw.offset_scale
 
 
 EXPORTS = (
@@ -390,6 +395,8 @@ def _pack_draw_table(draws: list[Any]) -> Any:
         slot.seed[:count] = draw.seeds
         slot.stream[:count] = draw.streams
         slot.dtype = DTYPE_CODE.get(draw.dtype, F32)
+        slot.offset_inner = draw.offset_inner
+        slot.offset_scale = draw.offset_scale
     return table
 
 

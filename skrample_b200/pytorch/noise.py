@@ -189,14 +189,26 @@ class PhiloxDraw:
     Passing this as ``noise`` to a sampler removes the noise tensor's write (generation) and every read of it
     (the step itself and, for UniPC, the corrector of the next step, which re-draws it).  ``materialize()``
     produces the bit-identical tensor through ``skr_noise_fill``.  One (seed, stream) pair per batch item.
+    ``offset_inner`` / ``offset_scale`` make it ``Offset`` noise (kept axes leading): every run of ``offset_inner``
+    elements of an item shares one more normal from the item's next stream, added times ``offset_scale``.
     """
 
     is_lazy_noise = True
-    __slots__ = ("device", "dtype", "item_numel", "numel", "seeds", "shape", "streams", "_tensor")
+    __slots__ = ("device", "dtype", "item_numel", "numel", "offset_inner", "offset_scale", "seeds", "shape", "streams", "_tensor")
 
     def __init__(
-        self, shape: tuple[int, ...], seeds: tuple[int, ...], streams: tuple[int, ...], dtype: torch.dtype, device: torch.device, numel: int | None = None
+        self,
+        shape: tuple[int, ...],
+        seeds: tuple[int, ...],
+        streams: tuple[int, ...],
+        dtype: torch.dtype,
+        device: torch.device,
+        numel: int | None = None,
+        offset_inner: int = 0,
+        offset_scale: float = 0.0,
     ) -> None:
+        self.offset_inner = offset_inner
+        self.offset_scale = offset_scale
         self.shape = shape if shape.__class__ is tuple else tuple(shape)
         self.seeds = seeds
         self.streams = streams
@@ -226,6 +238,8 @@ class PhiloxDraw:
                 count = min(limit, total - first)
                 keys.n_items = count
                 keys.item_numel = item_numel
+                keys.offset_inner = self.offset_inner
+                keys.offset_scale = self.offset_scale
                 keys.seed[:count] = self.seeds[first : first + count]
                 keys.stream[:count] = self.streams[first : first + count]
                 status = lib.skr_noise_fill_batch(base + first * item_numel * esize, code, ctypes.byref(keys), stream)
@@ -968,7 +982,7 @@ class BatchTensorNoise[T: TensorNoiseProps | None](SkrampleTensorNoise):
 
     def auto(self, step: Step | None) -> "PhiloxDraw | torch.Tensor":
         """The next batch of noise in the form a sampler makes the most of: Philox keys (a ``PhiloxDraw``) when every
-        item is a plain ``Random`` on one CUDA device - the step then draws the normals inside its own kernel, or has
+        item is a plain ``Random`` (or a non-static ``Offset`` along leading axes) on one CUDA device - the step then draws the normals inside its own kernel, or has
         them written by the fill kernel first where that is faster for the step at hand (``Program.settle_noise``) - and
         the generated tensor otherwise.  Same values either way."""
         info = self._uniform_info()
@@ -977,16 +991,31 @@ class BatchTensorNoise[T: TensorNoiseProps | None](SkrampleTensorNoise):
         return self.generate(step)
 
     def _uniform_info(self) -> tuple | None:
-        """(count, shape, numel, dtype, device) when every item is a plain ``Random`` with one shape / dtype on one CUDA
-        device, else None.  Checked once per generator list (identity of the list, its length and its ends)."""
+        """(count, shape, numel, dtype, device, offset_inner, offset_scale) when every item is a plain ``Random`` - or
+        every item an ``Offset`` with the same props, a fresh offset per draw and its kept axes leading - with one shape /
+        dtype on one CUDA device, else None.  Checked once per generator list (identity of the list, its length and
+        its ends)."""
         generators = self.generators
         cached = self.__dict__.get("_skr_uniform")
         if cached is not None and cached[0] is generators and cached[1] == len(generators) and cached[2] is generators[0] and cached[3] is generators[-1]:
             return cached[4]
         first = generators[0]
-        ok = all(type(g) is Random and g.on_device and g.seed.device == first.seed.device and g.dtype == first.dtype and g.shape == first.shape for g in generators)
+        kind = type(first)
+        ok = kind in (Random, Offset) and all(
+            type(g) is kind and g.on_device and g.seed.device == first.seed.device and g.dtype == first.dtype and g.shape == first.shape for g in generators
+        )
+        inner, scale = 0, 0.0
+        if ok and kind is Offset:
+            # the in-kernel form covers what the fill kernel's fast path covers: kept axes first, broadcast axes after
+            props = first.props
+            kept = [n in props.dims for n in range(len(first.shape))]
+            lead = kept.index(False) if False in kept else len(kept)
+            ok = not props.static and not any(kept[lead:]) and all(g.props == props for g in generators)
+            inner, scale = math.prod(first.shape[lead:]), float(props.strength**2)
+            if scale == 0.0:
+                inner = 0
         shape = (len(generators), *first.shape)
-        info = (len(generators), shape, math.prod(shape), first.dtype, first.seed.device) if ok else None
+        info = (len(generators), shape, math.prod(shape), first.dtype, first.seed.device, inner, scale) if ok else None
         self.__dict__["_skr_uniform"] = (generators, len(generators), first, generators[-1], info)
         return info
 
@@ -994,8 +1023,8 @@ class BatchTensorNoise[T: TensorNoiseProps | None](SkrampleTensorNoise):
         return self._uniform_info() is not None
 
     def lazy(self, step: Step | None, _fallback: bool = True) -> "PhiloxDraw | torch.Tensor | None":
-        """The next batch of noise as Philox keys when every item is a plain ``Random`` on one CUDA device; otherwise the
-        materialised tensor."""
+        """The next batch of noise as Philox keys when every item is a plain ``Random`` (or a non-static ``Offset`` along
+        leading axes) on one CUDA device; otherwise the materialised tensor."""
         info = self._uniform_info()
         if info is None:
             return self.generate(step) if _fallback else None
@@ -1018,7 +1047,7 @@ class BatchTensorNoise[T: TensorNoiseProps | None](SkrampleTensorNoise):
             for g in self.generators:
                 streams.append(g._tick())
                 seeds.append(g.__dict__["_skr_reserved"][3])
-        return PhiloxDraw(info[1], tuple(seeds), tuple(streams), info[3], info[4], info[2])
+        return PhiloxDraw(info[1], tuple(seeds), tuple(streams), info[3], info[4], info[2], info[5], info[6])
 
     @classmethod
     def from_batch_inputs[U: TensorNoiseProps | None](

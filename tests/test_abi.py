@@ -33,7 +33,7 @@ def test_struct_layout_matches_header() -> None:
 
     assert ctypes.sizeof(native.SkrOp) == 40
     assert ctypes.sizeof(native.SkrTensor) == 16
-    assert ctypes.sizeof(native.SkrPhilox) == 8 * 256 + 8 * 256 + 8 + 4 + 4
+    assert ctypes.sizeof(native.SkrPhilox) == 8 * 256 + 8 * 256 + 8 + 4 + 4 + 8 + 4 + 4
     assert ctypes.sizeof(native.SkrProgram) == 16 + 40 * 64 + 16 * 32 + 16 * 8 + 2 * ctypes.sizeof(native.SkrPhilox)
 
 

@@ -468,6 +468,53 @@ def test_in_kernel_noise_equals_materialised_noise(sampler_name: str, kw: dict, 
 
 
 @gpu
+@pytest.mark.parametrize(("unit", "dims"), [((4, 33, 32), (0,)), ((4, 6, 10), (0, 1)), ((3, 7, 5), (0,)), ((8, 16), ()), ((2, 12), (0, 1))])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("kernel", ["block", "interpreter"])
+def test_offset_batches_are_philox_keys_too(unit: tuple[int, ...], dims: tuple[int, ...], dtype: torch.dtype, kernel: str, monkeypatch: pytest.MonkeyPatch) -> None:
+    """A batch of non-static Offset generators with leading kept axes (noise.py:84-113) is handed out as Philox keys:
+    the materialised batch equals the per-item fill, and a step that draws it in its kernel equals the step that
+    reads the tensor - bit for bit, with no fill launch."""
+    from skrample_b200 import native, scheduling
+    from skrample_b200.sampling import models, structured
+
+    if kernel == "interpreter":
+        monkeypatch.setenv("SKR_FORCE_INTERP", "1")
+    native.reset_switches()
+    props = noise.OffsetProps(dims=dims, strength=0.4)
+    batch = 3
+    source = noise.BatchTensorNoise.from_batch_inputs(noise.Offset, unit, [_gen(70 + i) for i in range(batch)], props, dtype)
+    twins = [noise.Offset.from_inputs(unit, _gen(70 + i), props, dtype) for i in range(batch)]
+    sampler, model, schedule = structured.Euler(stochasticity=1), models.FlowModel(), scheduling.Linear()
+    x = torch.randn((batch, *unit), device="cuda").to(dtype)
+    o = torch.randn((batch, *unit), device="cuda").to(dtype)
+    for n in range(2):  # consecutive draws stay in step with the per-item generators
+        drawn = source.auto(None)
+        assert isinstance(drawn, noise.PhiloxDraw) and drawn.offset_inner > 0
+        fills = native.launch_count_kind(2)
+        a = sampler.sample(x, o, Step.from_int(n + 1, 9), model, schedule, drawn)
+        assert native.launch_count_kind(2) == fills, "the offset draw must happen inside the step kernel"
+        want = torch.stack([t.generate(None) for t in twins])
+        assert torch.equal(drawn.materialize(), want)
+        b = sampler.sample(x, o, Step.from_int(n + 1, 9), model, schedule, want)
+        assert torch.equal(a.final, b.final)
+    # the offset really is there: constant along the broadcast axes, different from the plain draw
+    plain = noise.BatchTensorNoise.from_batch_inputs(noise.Random, unit, [_gen(70 + i) for i in range(batch)], dtype=torch.float32)
+    shifted = noise.BatchTensorNoise.from_batch_inputs(noise.Offset, unit, [_gen(70 + i) for i in range(batch)], props, torch.float32)
+    delta = shifted.generate(None) - plain.generate(None)
+    lead = len([d for d in range(len(unit)) if d in dims])
+    rows = delta.reshape(batch * math.prod(unit[:lead]), -1)
+    assert (rows.max(dim=1).values - rows.min(dim=1).values).abs().max().item() < 2e-6
+    assert rows[:, 0].abs().max().item() > 0
+    # static offsets and offsets along non-leading axes keep the per-item path
+    static = noise.BatchTensorNoise.from_batch_inputs(noise.Offset, unit, [_gen(1), _gen(2)], noise.OffsetProps(dims=dims, static=True))
+    assert isinstance(static.auto(None), torch.Tensor)
+    if len(unit) > 1:
+        trailing = noise.BatchTensorNoise.from_batch_inputs(noise.Offset, unit, [_gen(1), _gen(2)], noise.OffsetProps(dims=(len(unit) - 1,)))
+        assert isinstance(trailing.auto(None), torch.Tensor)
+
+
+@gpu
 def test_in_kernel_noise_unaligned_items() -> None:
     "item_numel not a multiple of 4: per-element Philox indexing still matches the materialised tensor."
     from skrample_b200 import scheduling

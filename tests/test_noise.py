@@ -650,6 +650,29 @@ def test_fill_values_match_the_oracle_philox(seed: int, stream: int, numel: int)
 
 
 @gpu
+@pytest.mark.parametrize(("shape", "dims"), [((6, 10, 12), (0,)), ((3, 4, 20), (0, 1)), ((5, 7, 3), (0,))])
+def test_offset_values_match_the_oracle_philox(shape: tuple[int, ...], dims: tuple[int, ...]) -> None:
+    """Offset on a CUDA generator (noise.py:104-113): the oracle's normals of the draw's stream plus, per kept slice, the
+    oracle's normal of the next stream at the slice index times strength^2 - through the fill kernel (one generator)
+    and through the key-table path (a batch of generators)."""
+    props = noise.OffsetProps(dims=dims, strength=0.6)
+    one = noise.Offset.from_inputs(shape, _gen(31), props)
+    probe = noise.Offset.from_inputs(shape, _gen(31), props)
+    key, tick = probe._key(), probe._tick()  # the stream block the first draw of an identically seeded generator takes
+    numel = math.prod(shape)
+    rows = math.prod(shape[: len(dims)])
+    shift = O.philox_normals(key, tick + 1, rows) * props.strength**2
+    want = (O.philox_normals(key, tick, numel).reshape(rows, -1) + shift[:, None]).reshape(shape)
+    got = one.generate(None)
+    np.testing.assert_allclose(got.cpu().numpy().astype(np.float64), want, rtol=0, atol=2e-5)
+    batch = noise.BatchTensorNoise.from_batch_inputs(noise.Offset, shape, [_gen(31), _gen(31)], props)
+    drawn = batch.lazy(None)
+    assert isinstance(drawn, noise.PhiloxDraw)
+    both = drawn.materialize()
+    assert torch.equal(both[0], got) and torch.equal(both[1], got)
+
+
+@gpu
 @pytest.mark.parametrize("step", BROWNIAN_STEPS)
 @pytest.mark.parametrize("max_steps", [10_000, 50])
 def test_brownian_kernel_vs_oracle(step: tuple[float, float], max_steps: int) -> None:

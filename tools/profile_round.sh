@@ -11,6 +11,7 @@ mkdir -p $O
 python bench.py > $O/${R}_bench.json 2> $O/${R}_bench.err || echo "bench failed"
 python bench.py --impl reference > $O/${R}_bench_reference.json 2>> $O/${R}_bench.err || echo "reference arm failed"
 python tools/e2e_breakdown.py > $O/${R}_e2e_breakdown.txt 2>&1 || echo "breakdown failed"
+python tools/hit_breakdown.py > $O/${R}_hit_breakdown.txt 2>&1 || echo "hit breakdown failed"
 tools/bin/step_floor > $O/${R}_step_floor.txt 2>&1 || echo "floor probe failed"
 python tools/per_step.py unipc3_sde_flux_bf16 > $O/${R}_per_step_unipc3_flux_bf16.txt 2>&1 || echo "per-step failed"
 python tools/per_step.py unipc3_sde_flux_bf16 --contracted > $O/${R}_per_step_unipc3_flux_bf16_contracted.txt 2>&1 || echo "per-step failed"
@@ -43,10 +44,11 @@ capture interpreter_unipc3_sde_f32_16x16x128x128 step_kernel 6 env SKR_FORCE_INT
 # noise kernels on one 16x21x90x160 video latent (the first timed shape of tools/noise_bench.py)
 N="python tools/noise_bench.py"
 capture noise_fill_f32_16x21x90x160 fill_kernel 25 $N Random
-capture noise_pyramid_compose_f32_16x21x90x160 pyramid_compose 25 $N Pyramid
+capture noise_pyramid_resident_f32_16x21x90x160 pyramid_resident 25 $N Pyramid
+capture noise_pyramid_compose_f32_16x21x90x160 pyramid_compose 25 env SKR_NO_RESIDENT_PYRAMID=1 $N Pyramid
 capture noise_pyramid_widen_f32_16x21x90x160 levels_widen 25 $N Pyramid
 capture noise_pyramid_levels_f32_16x21x90x160 levels_fill 25 $N Pyramid
-capture noise_scale_f32_16x21x90x160 scale_kernel 25 $N Pyramid
+capture noise_scale_f32_16x21x90x160 scale_kernel 25 env SKR_NO_RESIDENT_PYRAMID=1 $N Pyramid
 capture noise_colored_shape_16x21x90x160 colored_shape 25 $N Colored
 capture noise_moments_f32_16x21x90x160 moments_kernel 25 $N Colored
 capture noise_brownian_f32_16x21x90x160 brownian_kernel 30 $N Brownian

@@ -127,7 +127,7 @@ def full_captures(round_name: str) -> None:
 
 
 def bench_lines(round_name: str) -> None:
-    for name in ("bench", "bench_reference", "e2e_breakdown", "step_floor", "per_step_unipc3_flux_bf16", "per_step_unipc3_flux_bf16_contracted", "per_step_unipc3_flux64_bf16"):
+    for name in ("bench", "bench_reference", "e2e_breakdown", "hit_breakdown", "step_floor", "per_step_unipc3_flux_bf16", "per_step_unipc3_flux_bf16_contracted", "per_step_unipc3_flux64_bf16"):
         for suffix in (".json", ".txt"):
             src = OUT / f"{round_name}_{name}{suffix}"
             if src.exists() and src.stat().st_size and src.resolve().parent != PROFILES.resolve():

@@ -654,6 +654,37 @@ def barrier() -> None:
         torch.distributed.barrier()
 
 
+def leave_process_group(grace_s: float = 20.0, device: torch.device | None = None) -> None:
+    """End a multi-rank run: wait for the other ranks, tear the process group down, exit 0 - without ever hanging.
+
+    ``destroy_process_group()`` is not a synchronising call: a rank that tears its NCCL communicator down while its
+    peers are already exiting can wait for them indefinitely (seen once at 8 ranks: the result line was out, six of
+    the eight workers then sat in the teardown until the launcher was killed).  So the teardown runs beside a
+    watchdog: barrier, destroy, and after ``grace_s`` at most the process leaves with status 0 either way - the
+    measurement is complete and printed by then; interpreter teardown (CUDA graphs, pinned buffers, the communicator's
+    own threads) is skipped on purpose."""
+    import threading
+
+    closed = threading.Event()
+
+    def close() -> None:
+        try:
+            if device is not None and device.type == "cuda":
+                torch.cuda.set_device(device)  # the current device is per thread
+                torch.cuda.synchronize(device)
+            torch.distributed.barrier()
+            torch.distributed.destroy_process_group()
+        except Exception:  # noqa: BLE001 - leaving anyway
+            pass
+        closed.set()
+
+    threading.Thread(target=close, daemon=True).start()
+    closed.wait(grace_s)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
 def max_over_ranks(value: float, device: torch.device) -> float:
     if torch.distributed.is_available() and torch.distributed.is_initialized():
         t = torch.tensor([value], device=device, dtype=torch.float64)
@@ -1123,7 +1154,7 @@ def main() -> None:
     if rank == 0:
         emit(line)
     if world > 1:
-        torch.distributed.destroy_process_group()
+        leave_process_group(device=device)
 
 
 if __name__ == "__main__":

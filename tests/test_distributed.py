@@ -134,3 +134,38 @@ def test_bench_reference_arm_under_torchrun_prints_once() -> None:
     assert len(lines) == 1, done.stdout[-2000:]
     line = json.loads(lines[0])
     assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0
+
+
+def test_bench_leaves_a_process_group_without_hanging(tmp_path: Path) -> None:
+    """bench.leave_process_group: every rank exits 0 promptly - also when one rank never reaches the teardown (the
+    watchdog's case), which a plain destroy_process_group() would wait for."""
+    import socket
+    import subprocess
+    import sys
+    import time
+
+    root = Path(__file__).resolve().parent.parent
+    script = tmp_path / "leave.py"
+    script.write_text(
+        "import os, sys, time\n"
+        f"sys.path.insert(0, {str(root)!r})\n"
+        "import torch, torch.distributed as dist\n"
+        "import bench\n"
+        "dist.init_process_group('gloo')\n"
+        "t = torch.ones(1); dist.all_reduce(t); assert t.item() == 2\n"
+        "print('rank', dist.get_rank(), 'done', flush=True)\n"
+        "if os.environ.get('STRAGGLER') == '1' and dist.get_rank() == 1:\n"
+        "    time.sleep(8); os._exit(0)\n"
+        "bench.leave_process_group(grace_s=3.0)\n"
+        "raise SystemExit('leave_process_group returned')\n"
+    )
+    for straggler in ("0", "1"):
+        with socket.socket() as probe:
+            probe.bind(("127.0.0.1", 0))
+            port = probe.getsockname()[1]
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
+        t0 = time.perf_counter()
+        done = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env={**os.environ, "STRAGGLER": straggler})
+        assert done.returncode == 0, done.stderr[-2000:]
+        assert done.stdout.count("done") == 2, done.stdout[-500:]
+        assert time.perf_counter() - t0 < 120

@@ -46,7 +46,8 @@ def build_fast(force: bool = False) -> Path | None:
     """Compile ``_fast.so`` in-tree with g++ against the installed torch (ATen + pybind11).  Host glue only: when it
     cannot be built here the Python layer runs the same sequence itself, so a failure is reported, not raised."""
     source = CSRC / "fast_launch.cpp"
-    if not force and FAST.exists() and FAST.stat().st_mtime >= source.stat().st_mtime:
+    header = ROOT / "include" / "skrample_b200.h"  # the module copies skr_philox tables: the struct layout is part of it
+    if not force and FAST.exists() and FAST.stat().st_mtime >= max(source.stat().st_mtime, header.stat().st_mtime):
         return FAST
     try:
         import sysconfig

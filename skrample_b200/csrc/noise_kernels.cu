@@ -887,9 +887,9 @@ __global__ void __launch_bounds__(256) pyramid_compose_trailing_kernel(const __g
 // order) with the unnormalised values HELD IN SHARED MEMORY instead of written to a scratch tensor; the grid-wide sums
 // are published in a fixed order; every CTA waits for the totals (generation counter, acquire load); phase 2 scales
 // what it holds and stores it once, in the output's storage type.  Against composition + scale pass this removes a
-// launch and a 4-byte-per-element round trip.  K float4 groups per thread and iteration (K = 2 when a row holds an even
-// number of groups: the row arithmetic of a level is shared by eight elements); coordinates advance by carries, three
-// integer divisions per thread in total.
+// launch and a 4-byte-per-element round trip.  K float4 groups per thread and iteration (the library launches K = 2: a
+// row holds an even number of groups and the row arithmetic of a level is shared by eight elements); coordinates
+// advance by carries, three integer divisions per thread in total.
 template <int AXES, int K, typename TO>
 __global__ void __launch_bounds__(1024, 1) pyramid_resident_kernel(const __grid_constant__ PyramidParams p, const int32_t units_per_cta) {
     extern __shared__ __align__(16) float4 held[];
@@ -1295,9 +1295,10 @@ static int launch_resident(PyramidParams& p, int axes, cudaStream_t s) {
     const int width = (int)p.shape[axes];
     const int align = p.dtype == SKR_F32 ? 15 : 7;
     if ((reinterpret_cast<uintptr_t>(p.out) & align) != 0) return -1;
-    const bool pairs = (width & 7) == 0;
-    if (axes == 2) return pairs ? launch_resident_typed<2, 2>(p, sms, max_smem, s) : launch_resident_typed<2, 1>(p, sms, max_smem, s);
-    return pairs ? launch_resident_typed<1, 2>(p, sms, max_smem, s) : launch_resident_typed<1, 1>(p, sms, max_smem, s);
+    // two groups per thread and iteration: a row must hold an even number of groups (width % 8 == 0; every latent
+    // shape in use does).  Other widths keep composition + scale pass.
+    if ((width & 7) != 0) return -1;
+    return axes == 2 ? launch_resident_typed<2, 2>(p, sms, max_smem, s) : launch_resident_typed<1, 2>(p, sms, max_smem, s);
 }
 }  // namespace skr
 
